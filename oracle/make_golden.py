@@ -1,0 +1,245 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on the CPU.
+
+Run in the authoring container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+For every case it (1) runs the reference's own EncoderTransformer / Transformer / rot_pose_beta_to_mesh,
+(2) runs the oracle restatement (oracle/head_oracle.py, oracle/mano_oracle.py) on the same inputs,
+(3) asserts they agree, and (4) stores the reference outputs (full tensors where small, per-tensor
+checksums + strided samples where large) together with input checksums.  Inputs and weights are
+regenerated from seeds by scat_b200/synth.py (numpy PCG64), so fixtures stay small.
+
+Shims needed to import the reference offline without a GPU: Tensor.cuda -> identity,
+model_zoo.load_url -> {}; the backbone is replaced by a stub that returns the synthetic seam tensors.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import random
+import sys
+import tempfile
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from scat_b200 import synth  # noqa: E402
+from oracle import head_oracle, mano_oracle  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _import_reference_head():
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import torch.utils.model_zoo as mz
+    mz.load_url = lambda *a, **k: {}
+    from models import hand_net, vision_transformer
+    return hand_net, vision_transformer
+
+
+class _StubBackbone(torch.nn.Module):
+    """Stands in for resnet50: returns (main_feat, x1-like, x2, None, None) (resnet.py:162)."""
+
+    def __init__(self):
+        super().__init__()
+        self.main_feat = None
+        self.x2 = None
+
+    def forward(self, _img):
+        return self.main_feat, self.x2[:, :1, :1, :1], self.x2, None, None
+
+
+def summary(t: torch.Tensor, n_samples: int = 64):
+    """Checksum record for a tensor too large to store: [sum, abs-sum, sum of squares] in float64
+    plus a strided sample."""
+    f = t.detach().double().reshape(-1)
+    stride = max(1, f.numel() // n_samples)
+    idx = torch.arange(0, f.numel(), stride)[:n_samples]
+    return (np.array([f.sum().item(), f.abs().sum().item(), f.square().sum().item()]),
+            idx.numpy().astype(np.int64), f[idx].numpy())
+
+
+def run_head_case(hand_net, name, *, B, heads, iteration, pos_embed, mask_rate, pl_reg, mask_seed,
+                  w_seed=20211011, in_seed=0, regime="unit", mean_kind="hand", backward=True):
+    opt = SimpleNamespace(vit_heads=heads, pl_reg=pl_reg, iteration=iteration, pos_embed=pos_embed,
+                          mask_rate=mask_rate)
+    mean = torch.from_numpy(synth.make_mean_params(mean_kind))
+    torch.manual_seed(0)
+    net = hand_net.EncoderTransformer(opt, mean).train()
+    W = synth.make_head_weights(heads, w_seed, regime)
+    sd = net.state_dict()
+    for k, v in W.items():
+        assert tuple(sd[k].shape) == v.shape, (k, sd[k].shape, v.shape)
+        sd[k].copy_(torch.from_numpy(v))
+    stub = _StubBackbone()
+    net.main_encoder = stub
+    x2_np, mf_np, lab_np = synth.make_head_inputs(B, in_seed)
+    x2 = torch.from_numpy(x2_np).requires_grad_(True)
+    mf = torch.from_numpy(mf_np).requires_grad_(True)
+    labels = torch.from_numpy(lab_np)
+    stub.x2, stub.main_feat = x2, mf
+
+    random.seed(mask_seed)
+    outs = net(torch.zeros(B, 3, 8, 8))
+    pred, fv = outs[0], outs[1]
+    pl = outs[2] if pl_reg else None
+    # what indices did the reference draw?  replay the host RNG (hand_net.py:370-372)
+    random.seed(mask_seed)
+    mask_idx = synth.mask_indices(mask_rate)
+
+    rec = dict(B=B, heads=heads, iteration=iteration, pos_embed=int(pos_embed), mask_rate=mask_rate,
+               pl_reg=int(pl_reg), mask_seed=mask_seed, w_seed=w_seed, in_seed=in_seed,
+               regime=regime, mean_kind=mean_kind, mask_idx=np.array(mask_idx, dtype=np.int64),
+               pred=pred.detach().numpy(), feat_visual=fv.detach().numpy().copy())
+    for nm, arr in (("x2", x2_np), ("main_feat", mf_np), ("labels", lab_np)):
+        rec["in_" + nm + "_sum"] = np.array([arr.astype(np.float64).sum(), np.abs(arr.astype(np.float64)).sum()])
+    rec["w_sum"] = np.array([sum(float(np.abs(v.astype(np.float64)).sum()) for v in W.values())])
+    if pl_reg:
+        rec["pl"] = pl.detach().numpy()
+        assert not pl.requires_grad
+
+    # oracle vs reference, forward
+    P = {k: torch.from_numpy(v) for k, v in W.items()}
+    o = head_oracle.head_forward(P, torch.from_numpy(x2_np).requires_grad_(True), torch.from_numpy(mf_np),
+                                 mean, heads=heads, iteration=iteration, pos_embed=pos_embed,
+                                 mask_idx=mask_idx, pl_reg=pl_reg)
+    d_pred = (o[0] - pred).abs().max().item()
+    d_fv = (o[1] - fv).abs().max().item()
+    assert d_pred <= 1e-5 * max(1.0, pred.abs().max().item()), (name, d_pred)
+    assert d_fv <= 1e-5 * max(1.0, fv.abs().max().item()), (name, d_fv)
+    diffs = dict(pred=d_pred, feat_visual=d_fv)
+    if pl_reg:
+        d_pl = (o[2] - pl).abs().max().item()
+        assert d_pl <= 1e-5 * max(1e-3, pl.abs().max().item()), (name, d_pl)
+        diffs["pl"] = d_pl
+
+    if backward:
+        # train-step body restated from train.py:165-206 (file itself unimportable offline)
+        loss, l3, l2, lpl = head_oracle.train_loss(pred, labels, pl)
+        loss.backward()
+        rec["loss"] = np.array([loss.item(), l3.item(), l2.item(), lpl.item()])
+        rec["main_feat_grad"] = mf.grad.numpy()
+        s, i, v = summary(x2.grad)
+        rec["x2_grad_sum"], rec["x2_grad_idx"], rec["x2_grad_val"] = s, i, v
+        named = dict(net.named_parameters())
+        ostep = head_oracle.train_step(P, torch.from_numpy(x2_np), torch.from_numpy(mf_np), labels, mean,
+                                       heads=heads, iteration=iteration, pos_embed=pos_embed,
+                                       mask_idx=mask_idx, pl_reg=pl_reg)
+        assert abs(ostep["loss"].item() - loss.item()) <= 1e-5 * abs(loss.item()), (name, "loss")
+        worst = 0.0
+        for k in W:
+            g = named[k].grad
+            g = torch.zeros_like(named[k]) if g is None else g
+            s, i, v = summary(g)
+            rec["g_sum/" + k], rec["g_idx/" + k], rec["g_val/" + k] = s, i, v
+            den = g.abs().max().item() + 1e-30
+            worst = max(worst, (ostep["grads"][k] - g).abs().max().item() / den)
+        assert worst < 2e-4, (name, "param grads", worst)
+        dx = (ostep["x2_grad"] - x2.grad).abs().max().item() / (x2.grad.abs().max().item() + 1e-30)
+        assert dx < 2e-4, (name, "x2 grad", dx)
+        diffs["grads_rel"] = worst
+        diffs["x2_grad_rel"] = dx
+    rec["oracle_vs_reference"] = np.array([diffs.get(k, 0.0) for k in ("pred", "feat_visual", "pl", "grads_rel", "x2_grad_rel")])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(f"[golden] {name}: mask={mask_idx} oracle-vs-reference {diffs}")
+
+
+def run_token_case(vision_transformer, hand_net, name, *, B, n, dim, heads, mask_rate, mask_seed, in_seed=3):
+    """Config 4: the HRNet-variant token path up to feat.mean(dim=1) (hand_net.py:193-203)."""
+    torch.manual_seed(0)
+    tr = vision_transformer.Transformer(dim=dim, depth=3, heads=heads, dim_head=64, mlp_dim=2 * dim, dropout=0.0)
+    pos = hand_net.PositionalEncoding(dim, max_len=n)
+    W = synth.make_token_weights(dim, heads)
+    for k, p in tr.named_parameters():
+        p.data.copy_(torch.from_numpy(W["transformer." + k]))
+    tok = torch.from_numpy(synth.make_token_inputs(B, n, dim, in_seed))
+    random.seed(mask_seed)
+    masked = list(range(n))
+    random.shuffle(masked)
+    masked = masked[: int(mask_rate * n)]
+    feat = pos(tok)
+    feat[:, masked, :] = torch.from_numpy(W["mask_token"])
+    out = tr(feat, None)
+    mean = out.mean(dim=1)
+    P = {k: torch.from_numpy(v) for k, v in W.items()}
+    o_out, o_mean = head_oracle.token_transformer_forward(P, tok, heads=heads, mask_idx=masked)
+    d = (o_out - out).abs().max().item()
+    assert d < 1e-5 * max(1.0, out.abs().max().item()), d
+    rec = dict(B=B, n=n, dim=dim, heads=heads, mask_idx=np.array(masked, dtype=np.int64), in_seed=in_seed,
+               out=out.detach().numpy(), mean=mean.detach().numpy(), pe_row1=pos.pe[0, 1, :8].numpy(),
+               tok_sum=np.array([tok.double().sum().item()]))
+    rec["w_sum"] = np.array([sum(float(np.abs(v.astype(np.float64)).sum()) for v in W.values())])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(f"[golden] {name}: oracle-vs-reference {d:.3e}")
+
+
+def run_mano_case(name, B=6):
+    """MANO LBS: import models.mano from a temp cwd holding a synthetic MANO_RIGHT.pkl (mano.py:220)."""
+    import scipy.sparse as sp
+    asset = synth.make_mano_asset()
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, "extra_data"))
+    dd = dict(asset)
+    dd["J_regressor"] = sp.csc_matrix(asset["J_regressor"])
+    with open(os.path.join(tmp, "extra_data", "MANO_RIGHT.pkl"), "wb") as f:
+        pickle.dump(dd, f)
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        sys.path.insert(0, REF)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        from models import mano as ref_mano
+    finally:
+        os.chdir(cwd)
+    rots, poses, betas = synth.make_mano_inputs(B, 0)
+    rots[1] = 0.0                       # exercises the theta -> 0 limit of the global rotation
+    poses[2] = -asset["hands_mean"]     # all local rotations exactly zero -> NaN in the reference's n = r/theta
+    out = ref_mano.rot_pose_beta_to_mesh(torch.from_numpy(rots), torch.from_numpy(poses), torch.from_numpy(betas))
+    out = out.detach().numpy()
+    o = mano_oracle.rot_pose_beta_to_mesh(rots, poses, betas, asset)
+    finite = np.isfinite(out).all(axis=(1, 2))
+    d = np.abs(o[finite] - out[finite]).max()
+    assert d < 2e-5, d
+    assert (np.isfinite(o).all(axis=(1, 2)) == finite).all(), "oracle must reproduce the reference's NaN rows"
+    o64 = mano_oracle.rot_pose_beta_to_mesh(rots.astype(np.float64), poses.astype(np.float64),
+                                            betas.astype(np.float64), {k: np.asarray(v, dtype=np.float64) if k != "kintree_table" and k != "f" else v for k, v in asset.items()})
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), rots=rots, poses=poses, betas=betas, out=out,
+                        finite=finite, out_fp64_oracle=o64.astype(np.float64))
+    print(f"[golden] {name}: oracle-vs-reference {d:.3e}; finite rows {finite.tolist()}")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    hand_net, vt = _import_reference_head()
+    # analytic anchors
+    random.seed(0)
+    assert synth.mask_indices(0.2) == [10, 19, 17, 14]
+    random.seed(1)
+    assert synth.mask_indices(0.2) == [20, 17, 19, 11]
+    pe_ref = hand_net.PositionalEncoding(784, max_len=21).pe
+    assert torch.equal(pe_ref, head_oracle.positional_encoding(21, 784))
+    np.savez_compressed(os.path.join(GOLD, "pos_encoding.npz"), pe=pe_ref.numpy())
+
+    run_head_case(hand_net, "head_kat_b2", B=2, heads=8, iteration=3, pos_embed=True, mask_rate=0.2,
+                  pl_reg=True, mask_seed=0)
+    run_head_case(hand_net, "head_b3_mask50", B=3, heads=8, iteration=3, pos_embed=True, mask_rate=0.5,
+                  pl_reg=True, mask_seed=1, in_seed=1, regime="hand")
+    run_head_case(hand_net, "head_b2_nope_alias", B=2, heads=8, iteration=2, pos_embed=False, mask_rate=0.2,
+                  pl_reg=True, mask_seed=2, in_seed=2)
+    run_head_case(hand_net, "head_b2_h4_it1_nomask", B=2, heads=4, iteration=1, pos_embed=True, mask_rate=0.0,
+                  pl_reg=False, mask_seed=3, in_seed=3)
+    run_head_case(hand_net, "head_b2_mask90", B=2, heads=8, iteration=3, pos_embed=True, mask_rate=0.9,
+                  pl_reg=True, mask_seed=4, in_seed=4)
+    run_token_case(vt, hand_net, "tokens_n128_d196", B=2, n=128, dim=196, heads=8, mask_rate=0.2, mask_seed=5)
+    run_mano_case("mano_lbs")
+
+
+if __name__ == "__main__":
+    main()

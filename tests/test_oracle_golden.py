@@ -1,0 +1,115 @@
+"""CPU: the oracle restatement against the fixtures generated from the unmodified reference.
+
+Fixtures: tests/golden/*.npz written by oracle/make_golden.py (reference imported from /root/reference
+in the authoring container).  fp32 CPU results are reproducible to round-off across thread counts, so
+tolerances are a few ulp-scale multiples rather than exact equality.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import head_oracle, mano_oracle
+from scat_b200 import synth
+
+HEAD_CASES = ["head_kat_b2", "head_b3_mask50", "head_b2_nope_alias", "head_b2_h4_it1_nomask", "head_b2_mask90"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_analytic_anchors(golden_dir):
+    # mask draws and positional-encoding values pinned from the reference
+    random.seed(0)
+    assert synth.mask_indices(0.2) == [10, 19, 17, 14]
+    random.seed(1)
+    assert synth.mask_indices(0.2) == [20, 17, 19, 11]
+    for rate, n in ((0.05, 0), (0.1, 2), (0.2, 4), (0.5, 10), (0.9, 18), (0.95, 0)):
+        assert len(synth.mask_indices(rate)) == n
+    pe = head_oracle.positional_encoding(21, 784)
+    assert np.array_equal(pe.numpy(), _load(golden_dir, "pos_encoding")["pe"])
+    np.testing.assert_allclose(pe[0, 0, :4].numpy(), [0, 1, 0, 1], atol=0)
+    np.testing.assert_allclose(pe[0, 1, :4].numpy(), [0.8415, 0.5403, 0.8287, 0.5597], atol=5e-5)
+
+
+@pytest.mark.parametrize("name", HEAD_CASES)
+def test_head_oracle_matches_reference_fixture(golden_dir, name):
+    g = _load(golden_dir, name)
+    B, heads, it = int(g["B"]), int(g["heads"]), int(g["iteration"])
+    pos_embed, pl_reg = bool(g["pos_embed"]), bool(g["pl_reg"])
+    W = synth.make_head_weights(heads, int(g["w_seed"]), str(g["regime"]))
+    x2, mf, labels = synth.make_head_inputs(B, int(g["in_seed"]))
+    # the regenerated inputs must be the bytes the fixture was made from
+    assert abs(x2.astype(np.float64).sum() - g["in_x2_sum"][0]) < 1e-6 * abs(g["in_x2_sum"][0])
+    assert abs(np.abs(mf.astype(np.float64)).sum() - g["in_main_feat_sum"][1]) < 1e-9 * g["in_main_feat_sum"][1]
+    assert abs(sum(float(np.abs(v.astype(np.float64)).sum()) for v in W.values()) - g["w_sum"][0]) < 1e-9 * g["w_sum"][0]
+    random.seed(int(g["mask_seed"]))
+    mask_idx = synth.mask_indices(float(g["mask_rate"]))
+    assert mask_idx == g["mask_idx"].tolist()          # bit-exact index draw
+
+    P = {k: torch.from_numpy(v) for k, v in W.items()}
+    mean = torch.from_numpy(synth.make_mean_params(str(g["mean_kind"])))
+    step = head_oracle.train_step(P, torch.from_numpy(x2), torch.from_numpy(mf), torch.from_numpy(labels), mean,
+                                  heads=heads, iteration=it, pos_embed=pos_embed, mask_idx=mask_idx, pl_reg=pl_reg)
+    assert _rel(step["pred"], g["pred"]) < 2e-6
+    assert _rel(step["feat_visual"], g["feat_visual"]) < 2e-6
+    assert np.all(step["pred"].numpy()[:, 6:9] == 0.0)                       # joint 1 == 0 exactly
+    if pl_reg:
+        assert _rel(step["pl"], g["pl"]) < 2e-5
+        if pos_embed and len(mask_idx):
+            assert np.all(step["pl"].numpy().reshape(B, 21, -1)[:, mask_idx] == 0.0)   # masked tokens: zero VJP
+    np.testing.assert_allclose(step["loss"].item(), g["loss"][0], rtol=2e-6)
+    assert _rel(step["main_feat_grad"], g["main_feat_grad"]) < 2e-5
+    xg = step["x2_grad"].double().reshape(-1).numpy()
+    assert _rel(xg[g["x2_grad_idx"]], g["x2_grad_val"]) < 2e-5
+    np.testing.assert_allclose(np.abs(xg).sum(), g["x2_grad_sum"][1], rtol=1e-5)
+    for k in W:
+        gg = step["grads"][k].double().reshape(-1).numpy()
+        ref_abs = g["g_sum/" + k][1]
+        np.testing.assert_allclose(np.abs(gg).sum(), ref_abs, rtol=2e-5, atol=1e-12, err_msg=k)
+        scale = np.abs(gg).max() + 1e-30
+        assert np.abs(gg[g["g_idx/" + k]] - g["g_val/" + k]).max() <= 2e-5 * scale, k
+
+
+def test_fp64_oracle_close_to_fp32(golden_dir):
+    g = _load(golden_dir, "head_kat_b2")
+    W = synth.make_head_weights(8)
+    x2, mf, _ = synth.make_head_inputs(2, 0)
+    P = {k: torch.from_numpy(v).double() for k, v in W.items()}
+    mean = torch.from_numpy(synth.make_mean_params("hand")).double()
+    out = head_oracle.head_forward(P, torch.from_numpy(x2).double(), torch.from_numpy(mf).double(), mean,
+                                   mask_idx=g["mask_idx"].tolist())
+    assert _rel(out[0], g["pred"]) < 1e-5
+
+
+def test_token_transformer_fixture(golden_dir):
+    g = _load(golden_dir, "tokens_n128_d196")
+    B, n, dim, heads = int(g["B"]), int(g["n"]), int(g["dim"]), int(g["heads"])
+    W = synth.make_token_weights(dim, heads)
+    P = {k: torch.from_numpy(v) for k, v in W.items()}
+    tok = torch.from_numpy(synth.make_token_inputs(B, n, dim, int(g["in_seed"])))
+    out, mean = head_oracle.token_transformer_forward(P, tok, heads=heads, mask_idx=g["mask_idx"].tolist())
+    assert _rel(out, g["out"]) < 2e-6
+    assert _rel(mean, g["mean"]) < 2e-6
+
+
+def test_mano_oracle_fixture(golden_dir):
+    g = _load(golden_dir, "mano_lbs")
+    asset = synth.make_mano_asset()
+    out = mano_oracle.rot_pose_beta_to_mesh(g["rots"], g["poses"], g["betas"], asset)
+    assert out.shape == (g["rots"].shape[0], 799, 3)
+    assert np.abs(out - g["out"]).max() < 2e-6
+    assert np.all(out[:, 1] == 0.0)            # root joint (index 1) is the origin, mano.py:386-388
+    a64 = {k: (np.asarray(v, dtype=np.float64) if v.dtype.kind == "f" else v) for k, v in asset.items()}
+    o64 = mano_oracle.rot_pose_beta_to_mesh(g["rots"].astype(np.float64), g["poses"].astype(np.float64),
+                                            g["betas"].astype(np.float64), a64)
+    assert np.abs(o64 - g["out_fp64_oracle"]).max() < 1e-12
