@@ -1,0 +1,180 @@
+/*
+ * scat_b200 C ABI  --  B200 (sm_100a) kernels for SCAT's reg_transformer hand-pose head.
+ *
+ * The reference (tomguluson92/SCAT) is pure Python/PyTorch and defines no native interface; the
+ * boundary its hot path sits behind is the nn.Module `EncoderTransformer` (models/hand_net.py:315-398).
+ * This header is the C-ABI a maintainer binds (ctypes) to replace the ATen calls
+ * on that path.  Each entry cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t or a negative SCAT_ERR_* code;
+ *     nothing throws; scat_last_error_string() describes the last failure on the calling thread.
+ *   - all tensor arguments are DEVICE pointers to contiguous fp32 (int32 for indices) unless a
+ *     leading dimension is given; the caller owns every buffer including the workspace.
+ *   - no function allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so call sequences can be captured into a CUDA graph.
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails with a CUDA error.
+ */
+#ifndef SCAT_B200_H_
+#define SCAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAT_B200_ABI_VERSION 1
+
+#define SCAT_ERR_BAD_ARG     (-1)
+#define SCAT_ERR_WORKSPACE   (-2)
+#define SCAT_ERR_UNSUPPORTED (-3)
+
+/* arithmetic of the large GEMMs; the regressor and the last feed-forward are always fp32 */
+#define SCAT_PREC_FP32 0   /* CUDA-core FFMA everywhere ("parity mode")                         */
+#define SCAT_PREC_TF32 1   /* tcgen05 kind::tf32, operands stay fp32 in HBM, fp32 accumulate    */
+#define SCAT_PREC_BF16 2   /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate             */
+
+/* GEMM epilogues (scat_gemm) */
+#define SCAT_EPI_NONE       0
+#define SCAT_EPI_BIAS       1
+#define SCAT_EPI_BIAS_RESID 2
+#define SCAT_EPI_BIAS_GELU  3
+#define SCAT_EPI_DGELU      4
+#define SCAT_EPI_RESID      5
+
+/* Number of parameter tensors of the head, in the reference's state_dict order (hand_net.py:329-353):
+ *   0 mask_token[dim]  1 conv1x1_channel_reduction.weight[T,C]
+ *   layer i=0,1 (base 2+11i): norm_a.w norm_a.b to_qkv.w[3*64h,d] to_out.w[d,64h] to_out.b
+ *                             norm_f.w norm_f.b fc1.w[3d/4,d] fc1.b fc2.w[d/2,3d/4] fc2.b
+ *   layer 2 (base 24):        norm_a.w norm_a.b to_qkv.w to_out.w to_out.b fc1.w fc1.b fc2.w[3,hid] fc2.b
+ *   33 regressor.weight[66,1090]  34 regressor.bias[66] */
+#define SCAT_HEAD_NUM_PARAMS 35
+
+typedef struct ScatHeadDesc {
+    int32_t batch;          /* B (may vary call to call: train.py:143-150 filters empty images)     */
+    int32_t n_tokens;       /* 21  (hand_net.py:328)                                                */
+    int32_t channels;       /* 512 (x2 channels, hand_net.py:329); 0 = token input, no conv         */
+    int32_t token_dim;      /* 784 = 28*28 (hand_net.py:331)                                        */
+    int32_t heads;          /* opt.vit_heads                                                        */
+    int32_t iteration;      /* opt.iteration; 0 with main_feat_dim=0 = no regressor (token path)    */
+    int32_t pos_embed;      /* opt.pos_embed                                                        */
+    int32_t n_masked;       /* int(mask_rate*n_tokens) if 0.1<=mask_rate<=0.9 else 0                */
+    int32_t pl_reg;         /* opt.pl_reg: also return d(sum feat_out)/d feat_visual                */
+    int32_t precision;      /* SCAT_PREC_*                                                          */
+    int32_t main_feat_dim;  /* 1024 (resnet fc1)                                                    */
+    int32_t n_out;          /* 66 = 3 camera + 63 joint coordinates                                 */
+} ScatHeadDesc;
+
+int         scat_abi_version(void);
+const char* scat_last_error_string(void);
+/* number of CUDA kernels this library has launched (or captured into a graph) since load */
+uint64_t    scat_launch_count(void);
+
+/* ---- whole-head entry points ---------------------------------------------------------------- */
+
+/* bytes of caller-owned workspace for scat_head_forward/backward/train_step with this descriptor */
+size_t scat_head_workspace_bytes(const ScatHeadDesc* desc);
+
+/* EncoderTransformer.forward after the backbone (hand_net.py:363-398).
+ *   params[35]     device pointers, order above;  pe[T,dim] = positionalEncoding.pe[0];
+ *   mean_params[66]; mask_idx[n_masked] int32 token indices drawn on the host (hand_net.py:370-372)
+ *   x2[B,C,28,28], main_feat[B,1024]  ->  pred_params[B,66], feat_visual[B,T,28,28], pl_term[B,T,28,28]
+ *   (pl_term may be NULL iff !pl_reg).  With pos_embed==0 and masking the reference overwrites
+ *   feat_visual in place (hand_net.py:364,373); that aliasing is reproduced. */
+int scat_head_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                      const float* mean_params, const int32_t* mask_idx, const float* x2,
+                      const float* main_feat, float* pred_params, float* feat_visual, float* pl_term,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above (what loss.backward() does at train.py:206) from the forward's workspace.
+ *   feat_visual: the forward's output (only read when pos_embed==0, where it IS the token matrix)
+ *   grad_pred[B,66] (required), grad_feat_visual[B,T,784] (NULL = zero)
+ *   grads[35] device pointers to receive parameter gradients (overwritten, not accumulated),
+ *   x2_grad[B,C,784] / main_feat_grad[B,1024]: NULL to skip. */
+int scat_head_backward(const ScatHeadDesc* desc, const float* const* params, const int32_t* mask_idx,
+                       const float* x2, const float* main_feat, const float* feat_visual,
+                       const float* grad_pred, const float* grad_feat_visual, float* const* grads,
+                       float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* projection + losses + d loss / d pred_params (train.py:112-120,165-203).
+ *   labels[B,ld_labels] (63 3D + 42 2D first), pl_term NULL = no path-length term,
+ *   losses[4] = {loss, l_3d, l_2d, l_pl} (device), grad_pred[B,66] scaled by grad_scale (1/world for DP),
+ *   scratch: >= B floats. */
+int scat_proj_loss(int32_t batch, int32_t n_tokens, int32_t token_dim, const float* pred_params,
+                   const float* labels, int32_t ld_labels, const float* pl_term, float l_weight_3d,
+                   float l_weight_2d, float grad_scale, float* losses, float* grad_pred, float* scratch,
+                   void* stream);
+
+/* One fused training-step body (train.py:159-206): forward, path-length VJP, losses, backward. */
+int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                         const float* mean_params, const int32_t* mask_idx, const float* x2,
+                         const float* main_feat, const float* labels, int32_t ld_labels,
+                         float l_weight_3d, float l_weight_2d, float grad_scale, float* pred_params,
+                         float* feat_visual, float* pl_term, float* losses, float* const* grads,
+                         float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* Token-only transformer (HRNet-variant path up to feat.mean(dim=1), hand_net.py:193-203):
+ *   tokens[B,n,dim] -> out[B,n,3], mean[B,3].  desc.channels = 0, desc.iteration = 0. */
+int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                        const int32_t* mask_idx, const float* tokens, float* out, float* mean,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- single operators (used by the unit tests and by other callers of the same kernels) ------ */
+
+/* C[M,N] = epilogue(sum_k A(m,k) B(n,k)),  A(m,k)=A[m*sam+k*sak], B(n,k)=B[n*sbn+k*sbk]
+ * replaces nn.Linear forward / backward (vision_transformer.py:33-35,53-55). */
+int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
+              int32_t ldc, int32_t M, int32_t N, int32_t K, int32_t epilogue, const float* bias,
+              const float* aux_in, int32_t ld_aux_in, float* aux_out, int32_t ld_aux_out,
+              int32_t accumulate, int32_t precision, void* stream);
+
+/* hand_net.py:363-373 */
+int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
+                          const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
+                          float* tokens_out, int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens,
+                          void* stream);
+/* backward of the conv: d_tokens[B,T,hw] -> x2_grad (NULL to skip), conv_w_grad[T,C], mask_token_grad[hw];
+ * scratch: scat_conv_bwd_scratch_floats() floats */
+size_t scat_conv_bwd_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens);
+int scat_conv_bwd(const float* d_tokens, const float* x2, const float* conv_w, const int32_t* mask_idx,
+                  int32_t n_masked, float* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
+                  int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens, void* stream);
+
+/* vision_transformer.py:23,26 */
+int scat_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                       int32_t rows, int32_t dim, void* stream);
+int scat_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* resid, float* dx, float* dgamma, float* dbeta, int32_t rows, int32_t dim,
+                       void* stream);
+
+/* vision_transformer.py:61-77: qkv[B*n,3*64h] -> o[B*n,64h], p[B,h,n,n] */
+int scat_attention_fwd(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream);
+int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
+                       int32_t heads, void* stream);
+
+/* hand_net.py:379-393 (root_relative=1, n_out=66) and hand_net.py:53-57 (root_relative=0, n_out=61).
+ * states[B,iteration,n_out] may be NULL when no backward follows. */
+int scat_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* w,
+                       const float* b, float* pred, float* states, int32_t batch, int32_t feat_dim, int32_t n_out,
+                       int32_t iteration, int32_t root_relative, void* stream);
+
+/* MANO linear blend skinning, models/mano.py:280-391 (rot_pose_beta_to_mesh).
+ * asset (as in MANO_RIGHT.pkl, row-major fp32): v_template[778,3] shapedirs[778,3,10] posedirs[778,3,135]
+ * J_regressor[16,778] (dense) weights[778,16] hands_mean[45].
+ * scat_lbs_prepare fills derived[scat_lbs_derived_floats()] once per asset (regressed template joints and
+ * vertex-contiguous copies of the blend-shape tables); scat_lbs_fwd then maps
+ * rots[B,3] poses[B,45] betas[B,10] -> out[B,799,3] (21 joints then 778 vertices, joint 1 at the origin). */
+size_t scat_lbs_derived_floats(void);
+int scat_lbs_prepare(const float* v_template, const float* shapedirs, const float* posedirs,
+                     const float* j_regressor, const float* weights, float* derived, void* stream);
+int scat_lbs_fwd(const float* derived, const float* hands_mean, const float* rots, const float* poses,
+                 const float* betas, float* out, int32_t batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAT_B200_H_ */

@@ -1,0 +1,75 @@
+// Shared device/host helpers for the scat_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace scat {
+
+// ---- error plumbing: every C-ABI entry returns 0 or a negative/`cudaError_t` code, never throws ----
+void set_last_error(const char* fmt, ...);
+const char* last_error();
+
+#define SCAT_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            scat::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                                 cudaGetErrorString(_e));                                      \
+            return (int)_e;                                                                    \
+        }                                                                                      \
+    } while (0)
+
+// every kernel launch goes through this macro, so the counter is an exact count of launched kernels
+extern unsigned long long g_launch_count;
+#define SCAT_CHECK_LAUNCH()                      \
+    do {                                         \
+        ++scat::g_launch_count;                  \
+        SCAT_CHECK_CUDA(cudaGetLastError());     \
+    } while (0)
+
+#define SCAT_REQUIRE(cond, code, ...)                                                          \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            scat::set_last_error(__VA_ARGS__);                                                 \
+            return (code);                                                                     \
+        }                                                                                      \
+    } while (0)
+
+#define SCAT_PROPAGATE(expr)                                                                   \
+    do {                                                                                       \
+        int _rc = (expr);                                                                      \
+        if (_rc != 0) return _rc;                                                              \
+    } while (0)
+
+constexpr int kErrBadArg = -1;
+constexpr int kErrWorkspace = -2;
+constexpr int kErrUnsupported = -3;
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// exact (erf) GELU, the nn.GELU() default used by vision_transformer.py:33
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+#endif
+
+}  // namespace scat

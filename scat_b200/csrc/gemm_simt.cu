@@ -1,0 +1,163 @@
+// fp32 CUDA-core GEMM with strided operands and fused epilogues ("parity mode", and the path for
+// shapes the tensor-core kernel does not take: N=3, N=147/K=147 last feed-forward, regressor grads).
+//
+// Replaces the cuBLAS calls behind nn.Linear on the reference's path (vision_transformer.py:33-35,53-55)
+// and their autograd backward.  C = epilogue(A * B^T) with A(m,k) and B(n,k) addressed through
+// (row, col) strides so forward / dgrad / wgrad are the same kernel (see kernels.h).
+#include "kernels.h"
+
+namespace scat {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, THREADS = 256, PAD = 4;
+
+struct Frag { float v[4]; };
+
+// Load a [64 x 16] (rows x k) operand tile into registers.  Two thread->element maps so that the
+// unit-stride direction is the fastest-varying one across a warp (coalesced either way).
+template <bool ROW_CONTIG_K>
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, long long s_row, long long s_k, int row0,
+                                          int k0, int rows, int K, int tid, Frag& f) {
+    if (ROW_CONTIG_K) {
+        const int r = row0 + (tid >> 2);
+        const int k = k0 + (tid & 3) * 4;
+        const float* p = P + (long long)r * s_row + (long long)k * s_k;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f.v[i] = (r < rows && k + i < K) ? __ldg(p + i * s_k) : 0.f;
+    } else {
+        const int k = k0 + (tid >> 4);
+        const int r = row0 + (tid & 15) * 4;
+        const float* p = P + (long long)r * s_row + (long long)k * s_k;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f.v[i] = (k < K && r + i < rows) ? __ldg(p + i * s_row) : 0.f;
+    }
+}
+
+template <bool ROW_CONTIG_K>
+__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], int tid, const Frag& f) {
+    if (ROW_CONTIG_K) {
+        const int r = tid >> 2, k = (tid & 3) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) S[k + i][r] = f.v[i];
+    } else {
+        const int k = tid >> 4, r = (tid & 15) * 4;
+        *reinterpret_cast<float4*>(&S[k][r]) = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+    }
+}
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[BK][BM + PAD];
+    __shared__ __align__(16) float Bs[BK][BN + PAD];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    Frag fa, fb;
+    load_tile<A_K>(g.A, g.sam, g.sak, m0, 0, g.M, g.K, tid, fa);
+    load_tile<B_K>(g.B, g.sbn, g.sbk, n0, 0, g.N, g.K, tid, fb);
+    const int nk = (g.K + BK - 1) / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        store_tile<A_K>(As, tid, fa);
+        store_tile<B_K>(Bs, tid, fb);
+        __syncthreads();
+        if (kt + 1 < nk) {
+            load_tile<A_K>(g.A, g.sam, g.sak, m0, (kt + 1) * BK, g.M, g.K, tid, fa);
+            load_tile<B_K>(g.B, g.sbn, g.sbk, n0, (kt + 1) * BK, g.N, g.K, tid, fb);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            switch (g.epilogue) {
+                case EPI_BIAS: v += g.bias[n]; break;
+                case EPI_BIAS_RESID: v += g.bias[n] + g.aux_in[(long long)m * g.ld_aux_in + n]; break;
+                case EPI_BIAS_GELU: {
+                    v += g.bias[n];
+                    g.aux_out[(long long)m * g.ld_aux_out + n] = v;
+                    v = gelu_erf(v);
+                } break;
+                case EPI_DGELU: v *= gelu_erf_grad(g.aux_in[(long long)m * g.ld_aux_in + n]); break;
+                case EPI_RESID: v += g.aux_in[(long long)m * g.ld_aux_in + n]; break;
+                default: break;
+            }
+            float* c = g.C + (long long)m * g.ldc + n;
+            *c = g.accumulate ? (*c + v) : v;
+        }
+    }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N, float* __restrict__ out,
+                              int accumulate) {
+    // block = 32 columns x 8 row-lanes; grid.x over column groups; deterministic (no atomics)
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < N)
+        for (int m = threadIdx.y; m < M; m += 8) s += X[(long long)m * ld + c];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        out[c] = accumulate ? out[c] + t : t;
+    }
+}
+
+}  // namespace
+
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
+    SCAT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, kErrBadArg, "gemm: bad shape %d %d %d", g.M, g.N, g.K);
+    SCAT_REQUIRE(g.A && g.B && g.C, kErrBadArg, "gemm: null operand");
+    if (g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_BIAS_GELU)
+        SCAT_REQUIRE(g.bias != nullptr, kErrBadArg, "gemm: epilogue %d needs bias", g.epilogue);
+    if (g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_DGELU || g.epilogue == EPI_RESID)
+        SCAT_REQUIRE(g.aux_in != nullptr, kErrBadArg, "gemm: epilogue %d needs aux_in", g.epilogue);
+    if (g.epilogue == EPI_BIAS_GELU)
+        SCAT_REQUIRE(g.aux_out != nullptr, kErrBadArg, "gemm: epilogue %d needs aux_out", g.epilogue);
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+    const bool a_k = (g.sak == 1) || (g.sam != 1);
+    const bool b_k = (g.sbk == 1) || (g.sbn != 1);
+    if (a_k && b_k) gemm_simt_kernel<true, true><<<grid, THREADS, 0, stream>>>(g);
+    else if (a_k && !b_k) gemm_simt_kernel<true, false><<<grid, THREADS, 0, stream>>>(g);
+    else if (!a_k && b_k) gemm_simt_kernel<false, true><<<grid, THREADS, 0, stream>>>(g);
+    else gemm_simt_kernel<false, false><<<grid, THREADS, 0, stream>>>(g);
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream) {
+    SCAT_REQUIRE(X && out && M > 0 && N > 0, kErrBadArg, "colsum: bad args");
+    colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, stream>>>(X, ld, M, N, out, accumulate);
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace scat

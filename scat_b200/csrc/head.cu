@@ -1,0 +1,505 @@
+// Orchestration of the reg_transformer head on one GPU and the C ABI of include/scat_b200.h.
+//
+// The forward follows EncoderTransformer.forward after the backbone (hand_net.py:363-398) and
+// Transformer.forward (vision_transformer.py:97-101); the backward is the autograd graph of that code
+// written out by hand.  All activations needed by the backward live in a
+// caller-owned workspace laid out by HeadPlan; nothing here allocates or synchronises.
+#include <stdarg.h>
+
+#include "../../include/scat_b200.h"
+#include "kernels.h"
+
+namespace scat {
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+unsigned long long g_launch_count = 0;
+
+int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
+    if (precision != PREC_FP32 && gemm_tc_supported(g)) return launch_gemm_tc(g, precision, stream);
+    return launch_gemm_simt(g, stream);
+}
+
+namespace {
+
+constexpr int kDepth = 3;   // hand_net.py:331 depth=3 (opt.vit_depth is ignored by the reference)
+constexpr int kDimHead = 64;
+
+enum ParamIdx {
+    P_MASK_TOKEN = 0, P_CONV_W = 1,
+    // per layer offsets
+    L_NA_W = 0, L_NA_B = 1, L_QKV_W = 2, L_OUT_W = 3, L_OUT_B = 4,
+    L_NF_W = 5, L_NF_B = 6, L_FC1_W = 7, L_FC1_B = 8, L_FC2_W = 9, L_FC2_B = 10,
+    // last layer has no feed-forward norm
+    LL_FC1_W = 5, LL_FC1_B = 6, LL_FC2_W = 7, LL_FC2_B = 8,
+    P_REG_W = 33, P_REG_B = 34,
+};
+inline int layer_base(int l) { return 2 + 11 * l; }
+
+struct LayerPlan {
+    int d, hid, out, ldh;
+    size_t X, Na, mean_a, rstd_a, QKV, P, O, X1, Nf, mean_f, rstd_f, Z, H;   // float offsets
+    bool last;
+    int p_na_w, p_na_b, p_qkv, p_out_w, p_out_b, p_nf_w, p_nf_b, p_fc1_w, p_fc1_b, p_fc2_w, p_fc2_b;
+};
+
+struct HeadPlan {
+    int B, T, C, D, heads, inner, M, it, F, NP;
+    LayerPlan L[kDepth];
+    size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dX, dFv, conv_scratch, pl_scratch,
+        g_pred, ones, total;
+};
+
+size_t take(size_t& cur, size_t n) {
+    const size_t at = cur;
+    cur += (n + 63) / 64 * 64;   // 256-byte granules keep every buffer float4 / TMA aligned
+    return at;
+}
+
+int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
+    SCAT_REQUIRE(d.batch > 0 && d.n_tokens > 0 && d.n_tokens <= 128 && d.token_dim > 0 && d.heads > 0, kErrBadArg,
+                 "desc: bad batch/n_tokens/token_dim/heads (%d %d %d %d)", d.batch, d.n_tokens, d.token_dim, d.heads);
+    SCAT_REQUIRE(d.token_dim % 4 == 0 && d.token_dim <= 1024, kErrUnsupported,
+                 "desc: token_dim %d must be a multiple of 4 and <= 1024", d.token_dim);
+    SCAT_REQUIRE(d.n_masked >= 0 && d.n_masked <= d.n_tokens, kErrBadArg, "desc: n_masked %d", d.n_masked);
+    SCAT_REQUIRE(d.precision >= PREC_FP32 && d.precision <= PREC_BF16, kErrBadArg, "desc: precision %d", d.precision);
+    p.B = d.batch; p.T = d.n_tokens; p.C = d.channels; p.D = d.token_dim; p.heads = d.heads;
+    p.inner = kDimHead * d.heads; p.M = d.batch * d.n_tokens; p.it = d.iteration; p.F = d.main_feat_dim; p.NP = d.n_out;
+    size_t cur = 0;
+    const size_t M = (size_t)p.M;
+    int dim = d.token_dim, dmax = d.token_dim, ldh_max = 0;
+    for (int l = 0; l < kDepth; ++l) {
+        LayerPlan& L = p.L[l];
+        L.last = (l == kDepth - 1);
+        L.d = dim; L.hid = (dim * 3) / 4; L.out = L.last ? 3 : dim / 2; L.ldh = (L.hid + 3) / 4 * 4;
+        ldh_max = L.ldh > ldh_max ? L.ldh : ldh_max;
+        L.X = take(cur, M * dim);
+        L.Na = take(cur, M * dim);
+        L.mean_a = take(cur, M); L.rstd_a = take(cur, M);
+        L.QKV = take(cur, M * 3 * p.inner);
+        L.P = take(cur, (size_t)p.B * p.heads * p.T * p.T);
+        L.O = take(cur, M * p.inner);
+        L.X1 = take(cur, M * dim);
+        if (!L.last) { L.Nf = take(cur, M * dim); L.mean_f = take(cur, M); L.rstd_f = take(cur, M); }
+        else { L.Nf = L.X1; L.mean_f = L.rstd_f = 0; }
+        L.Z = take(cur, M * L.ldh);
+        L.H = take(cur, M * L.ldh);
+        const int base = layer_base(l);
+        L.p_na_w = base + L_NA_W; L.p_na_b = base + L_NA_B; L.p_qkv = base + L_QKV_W; L.p_out_w = base + L_OUT_W;
+        L.p_out_b = base + L_OUT_B;
+        if (!L.last) {
+            L.p_nf_w = base + L_NF_W; L.p_nf_b = base + L_NF_B; L.p_fc1_w = base + L_FC1_W; L.p_fc1_b = base + L_FC1_B;
+            L.p_fc2_w = base + L_FC2_W; L.p_fc2_b = base + L_FC2_B;
+        } else {
+            L.p_nf_w = L.p_nf_b = -1; L.p_fc1_w = base + LL_FC1_W; L.p_fc1_b = base + LL_FC1_B;
+            L.p_fc2_w = base + LL_FC2_W; L.p_fc2_b = base + LL_FC2_B;
+        }
+        if (!L.last) dim /= 2;
+    }
+    p.feat_out = take(cur, M * 3);
+    const int it = p.it > 0 ? p.it : 1, NP = p.NP > 0 ? p.NP : 1;
+    p.states = take(cur, (size_t)p.B * it * NP);
+    p.gsum = take(cur, (size_t)p.B * NP);
+    p.gsteps = take(cur, (size_t)p.B * it * NP);
+    p.dfeat = take(cur, M * 3);
+    p.ones = take(cur, M * 3);
+    p.g_pred = take(cur, (size_t)p.B * NP);
+    p.dZ = take(cur, M * ldh_max);
+    p.dNf = take(cur, M * dmax);
+    p.dX1 = take(cur, M * dmax);
+    p.dO = take(cur, M * p.inner);
+    p.dQKV = take(cur, M * 3 * p.inner);
+    p.dNa = take(cur, M * dmax);
+    p.dX = take(cur, M * dmax);
+    p.dFv = take(cur, M * dmax);
+    p.conv_scratch = take(cur, p.C > 0 ? conv_wgrad_scratch_floats(p.C, p.T) : 64);
+    p.pl_scratch = take(cur, (size_t)p.B);
+    p.total = cur;
+    return 0;
+}
+
+__global__ void fill_kernel(float* p, float v, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
+}
+__global__ void token_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int n) {
+    // out[b, c] = mean_t X[b, t, c], c < 3  (hand_net.py:203)
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c >= 3) return;
+    float s = 0.f;
+    for (int t = 0; t < n; ++t) s += X[((long long)b * n + t) * 3 + c];
+    out[b * 3 + c] = s / (float)n;
+}
+
+// ---- forward through the transformer (vision_transformer.py:97-101) --------------------------------
+int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st,
+                        float* X0_override) {
+    const int M = p.M;
+    for (int l = 0; l < kDepth; ++l) {
+        const LayerPlan& L = p.L[l];
+        float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
+        // PreNorm + Attention + Residual (:18,:26,:59-79)
+        SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, L.d, ws + L.mean_a,
+                                            ws + L.rstd_a, M, L.d, st));
+        GemmArgs g;
+        g.A = ws + L.Na; g.sam = L.d; g.sak = 1; g.B = W[L.p_qkv]; g.sbn = L.d; g.sbk = 1;
+        g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d;
+        SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, st));
+        g = GemmArgs();
+        g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = W[L.p_out_w]; g.sbn = p.inner; g.sbk = 1;
+        g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner;
+        g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
+        SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        // (PreNorm +) FeedForward, no residual (:44,:94 / :89)
+        if (!L.last)
+            SCAT_PROPAGATE(launch_layernorm_fwd(ws + L.X1, L.d, W[L.p_nf_w], W[L.p_nf_b], ws + L.Nf, L.d,
+                                                ws + L.mean_f, ws + L.rstd_f, M, L.d, st));
+        const int ffprec = L.last ? PREC_FP32 : prec;   // last FF stays fp32
+        g = GemmArgs();
+        g.A = ws + L.Nf; g.sam = L.d; g.sak = 1; g.B = W[L.p_fc1_w]; g.sbn = L.d; g.sbk = 1;
+        g.C = ws + L.H; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.d;
+        g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh;
+        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
+        g = GemmArgs();
+        g.A = ws + L.H; g.sam = L.ldh; g.sak = 1; g.B = W[L.p_fc2_w]; g.sbn = L.hid; g.sbk = 1;
+        g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid;
+        g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
+        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+    }
+    return 0;
+}
+
+// ---- reverse sweep: d/dX0 of <up, feat_out>, optionally with parameter gradients ---------------------
+// up: [M,3] cotangent of the transformer output.  Result lands in ws + p.dX ([M, D]).
+int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
+                         int prec, const float* up, cudaStream_t st, const float* X0_override) {
+    const int M = p.M;
+    const float* dY = up;
+    for (int l = kDepth - 1; l >= 0; --l) {
+        const LayerPlan& L = p.L[l];
+        const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
+        const int ffprec = L.last ? PREC_FP32 : prec;
+        GemmArgs g;
+        if (G) {
+            // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
+            g.A = dY; g.sam = 1; g.sak = L.out; g.B = ws + L.H; g.sbn = 1; g.sbk = L.ldh;
+            g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M;
+            SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 0, st));
+        }
+        // dZ = (dY W2) * gelu'(Z)
+        g = GemmArgs();
+        g.A = dY; g.sam = L.out; g.sak = 1; g.B = W[L.p_fc2_w]; g.sbn = 1; g.sbk = L.hid;
+        g.C = ws + p.dZ; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.out;
+        g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh;
+        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        if (G) {
+            // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
+            g = GemmArgs();
+            g.A = ws + p.dZ; g.sam = 1; g.sak = L.ldh; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.d;
+            g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M;
+            SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+            SCAT_PROPAGATE(launch_colsum(ws + p.dZ, L.ldh, M, L.hid, G[L.p_fc1_b], 0, st));
+        }
+        // dNf = dZ W1
+        g = GemmArgs();
+        g.A = ws + p.dZ; g.sam = L.ldh; g.sak = 1; g.B = W[L.p_fc1_w]; g.sbn = 1; g.sbk = L.d;
+        g.C = ws + p.dNf; g.ldc = L.d; g.M = M; g.N = L.d; g.K = L.hid;
+        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        const float* dX1 = ws + p.dNf;
+        if (!L.last) {
+            SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
+                                                ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d,
+                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, M, L.d, st));
+            dX1 = ws + p.dX1;
+        }
+        if (G) {
+            // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1)
+            g = GemmArgs();
+            g.A = dX1; g.sam = 1; g.sak = L.d; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner;
+            g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M;
+            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 0, st));
+        }
+        // dO = dX1 Wo
+        g = GemmArgs();
+        g.A = dX1; g.sam = L.d; g.sak = 1; g.B = W[L.p_out_w]; g.sbn = 1; g.sbk = p.inner;
+        g.C = ws + p.dO; g.ldc = p.inner; g.M = M; g.N = p.inner; g.K = L.d;
+        SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B, p.T, p.heads, st));
+        if (G) {
+            // dWqkv[3inner,d] = dQKV^T Na
+            g = GemmArgs();
+            g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = L.d;
+            g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M;
+            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        }
+        // dNa = dQKV Wqkv
+        g = GemmArgs();
+        g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = W[L.p_qkv]; g.sbn = 1; g.sbk = L.d;
+        g.C = ws + p.dNa; g.ldc = L.d; g.M = M; g.N = L.d; g.K = 3 * p.inner;
+        SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18)
+        SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
+                                            L.d, ws + p.dX, L.d, G ? G[L.p_na_w] : nullptr,
+                                            G ? G[L.p_na_b] : nullptr, M, L.d, st));
+        dY = ws + p.dX;
+    }
+    return 0;
+}
+
+int check_ws(const HeadPlan& p, void* ws, size_t bytes) {
+    SCAT_REQUIRE(ws != nullptr, kErrWorkspace, "workspace is null");
+    SCAT_REQUIRE(bytes >= p.total * sizeof(float), kErrWorkspace, "workspace too small: %zu < %zu bytes", bytes,
+                 p.total * sizeof(float));
+    SCAT_REQUIRE(((uintptr_t)ws & 255) == 0, kErrWorkspace, "workspace must be 256-byte aligned");
+    return 0;
+}
+
+int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, const float* mean_params,
+                 const int32_t* mask_idx, const float* x2, const float* main_feat, float* pred, float* fv, float* pl,
+                 void* workspace, size_t ws_bytes, cudaStream_t st) {
+    HeadPlan p;
+    SCAT_PROPAGATE(make_plan(d, p));
+    SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
+    SCAT_REQUIRE(d.channels > 0 && d.n_out == 66 && d.n_tokens == 21, kErrUnsupported,
+                 "head_forward: needs channels>0, n_out=66, n_tokens=21");
+    SCAT_REQUIRE(W && x2 && main_feat && pred && fv && mean_params, kErrBadArg, "head_forward: null tensor");
+    SCAT_REQUIRE(!d.pl_reg || pl, kErrBadArg, "head_forward: pl_reg set but pl_term is null");
+    SCAT_REQUIRE(!d.pos_embed || pe, kErrBadArg, "head_forward: pos_embed set but pe is null");
+    float* ws = (float*)workspace;
+    // with pos_embed == 0 the reference's token matrix is a view of feat_visual (hand_net.py:364): alias it
+    float* X0 = d.pos_embed ? ws + p.L[0].X : fv;
+    SCAT_PROPAGATE(launch_conv_pe_mask_fwd(x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed, fv,
+                                           X0, p.B, p.C, p.D, p.T, st));
+    SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
+    SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
+                                        ws + p.states, p.B, p.F, p.NP, p.it, 1, st));
+    if (d.pl_reg) {
+        // autograd.grad(sum(feat_out), feat_visual) (hand_net.py:396): dgrad-only sweep with a ones cotangent
+        fill_kernel<<<64, 256, 0, st>>>(ws + p.ones, 1.0f, (long long)p.M * 3);
+        SCAT_CHECK_LAUNCH();
+        SCAT_PROPAGATE(transformer_backward(p, W, nullptr, ws, d.precision, ws + p.ones, st, d.pos_embed ? nullptr : fv));
+        // masked tokens do not depend on feat_visual (zero rows) unless the overwrite aliased feat_visual itself
+        SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, d.pos_embed ? 0 : 1, pl, nullptr, p.B, p.T, p.D, st));
+    }
+    return 0;
+}
+
+int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* mask_idx, const float* x2,
+                  const float* main_feat, const float* g_pred, const float* g_fv, float* const* G, float* x2_grad,
+                  float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias) {
+    HeadPlan p;
+    SCAT_PROPAGATE(make_plan(d, p));
+    SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
+    SCAT_REQUIRE(W && G && x2 && main_feat && g_pred, kErrBadArg, "head_backward: null tensor");
+    SCAT_REQUIRE(d.pos_embed || fv_alias, kErrBadArg, "head_backward: pos_embed==0 needs the forward's feat_visual");
+    float* ws = (float*)workspace;
+    // regressor + root-relative backward
+    SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], ws + p.dfeat, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
+                                        p.NP, p.it, 1, st));
+    {
+        const int ldw = p.F + p.NP;
+        GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
+        g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
+        g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B;
+        SCAT_PROPAGATE(launch_gemm_simt(g, st));
+        if (p.it > 0) {   // dWr[:, F:] = sum over samples and steps of g_step (x) state
+            g = GemmArgs();
+            g.A = ws + p.gsteps; g.sam = 1; g.sak = p.NP; g.B = ws + p.states; g.sbn = 1; g.sbk = p.NP;
+            g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it;
+            SCAT_PROPAGATE(launch_gemm_simt(g, st));
+        } else {
+            SCAT_CHECK_CUDA(cudaMemset2DAsync(G[P_REG_W] + p.F, ldw * sizeof(float), 0, p.NP * sizeof(float), p.NP, st));
+        }
+        SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 0, st));
+    }
+    // LayerNorm affine grads are accumulated with atomics: clear them first
+    for (int l = 0; l < kDepth; ++l) {
+        const LayerPlan& L = p.L[l];
+        SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_na_w], 0, L.d * sizeof(float), st));
+        SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_na_b], 0, L.d * sizeof(float), st));
+        if (!L.last) {
+            SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_nf_w], 0, L.d * sizeof(float), st));
+            SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_nf_b], 0, L.d * sizeof(float), st));
+        }
+    }
+    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, ws + p.dfeat, st, d.pos_embed ? nullptr : fv_alias));
+    // through masking / positional encoding into the conv output
+    SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st));
+    if (d.n_masked == 0) SCAT_CHECK_CUDA(cudaMemsetAsync(G[P_MASK_TOKEN], 0, p.D * sizeof(float), st));
+    if (g_fv != nullptr) {
+        add_inplace_kernel<<<148 * 4, 256, 0, st>>>(ws + p.dFv, g_fv, (long long)p.M * p.D);
+        SCAT_CHECK_LAUNCH();
+    }
+    if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], x2_grad, p.B, p.C, p.D, p.T, st));
+    SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
+    return 0;
+}
+
+}  // namespace
+}  // namespace scat
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace scat;
+
+extern "C" {
+
+int scat_abi_version(void) { return SCAT_B200_ABI_VERSION; }
+const char* scat_last_error_string(void) { return last_error(); }
+uint64_t scat_launch_count(void) { return g_launch_count; }
+
+size_t scat_head_workspace_bytes(const ScatHeadDesc* desc) {
+    if (!desc) return 0;
+    HeadPlan p;
+    if (make_plan(*desc, p) != 0) return 0;
+    return p.total * sizeof(float);
+}
+
+int scat_head_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const float* mean_params,
+                      const int32_t* mask_idx, const float* x2, const float* main_feat, float* pred_params,
+                      float* feat_visual, float* pl_term, void* workspace, size_t workspace_bytes, void* stream) {
+    SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
+    return head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual, pl_term,
+                        workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int scat_head_backward(const ScatHeadDesc* desc, const float* const* params, const int32_t* mask_idx, const float* x2,
+                       const float* main_feat, const float* feat_visual, const float* grad_pred,
+                       const float* grad_feat_visual, float* const* grads, float* x2_grad, float* main_feat_grad,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
+    return head_backward(*desc, params, mask_idx, x2, main_feat, grad_pred, grad_feat_visual, grads, x2_grad,
+                         main_feat_grad, workspace, workspace_bytes, (cudaStream_t)stream, feat_visual);
+}
+
+int scat_proj_loss(int32_t batch, int32_t n_tokens, int32_t token_dim, const float* pred_params, const float* labels,
+                   int32_t ld_labels, const float* pl_term, float l_weight_3d, float l_weight_2d, float grad_scale,
+                   float* losses, float* grad_pred, float* scratch, void* stream) {
+    return launch_proj_loss(pred_params, labels, ld_labels, pl_term, n_tokens * token_dim, n_tokens, l_weight_3d,
+                            l_weight_2d, grad_scale, losses, grad_pred, scratch, batch, (cudaStream_t)stream);
+}
+
+int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                         const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                         const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d, float grad_scale,
+                         float* pred_params, float* feat_visual, float* pl_term, float* losses, float* const* grads,
+                         float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream) {
+    SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    SCAT_PROPAGATE(head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual,
+                                pl_term, workspace, workspace_bytes, st));
+    HeadPlan p;
+    SCAT_PROPAGATE(make_plan(*desc, p));
+    float* ws = (float*)workspace;
+    SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, desc->pl_reg ? pl_term : nullptr, p.T * p.D, p.T,
+                                    l_weight_3d, l_weight_2d, grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch,
+                                    p.B, st));
+    return head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
+                         main_feat_grad, workspace, workspace_bytes, st, feat_visual);
+}
+
+int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const int32_t* mask_idx,
+                        const float* tokens, float* out, float* mean, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    SCAT_REQUIRE(desc && params && tokens && out, kErrBadArg, "tokens_forward: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    HeadPlan p;
+    SCAT_PROPAGATE(make_plan(*desc, p));
+    SCAT_PROPAGATE(check_ws(p, workspace, workspace_bytes));
+    float* ws = (float*)workspace;
+    SCAT_PROPAGATE(launch_pe_mask_tokens(tokens, pe, params[P_MASK_TOKEN], mask_idx, desc->n_masked, desc->pos_embed,
+                                         ws + p.L[0].X, p.B, p.T, p.D, st));
+    SCAT_PROPAGATE(transformer_forward(p, params, ws, desc->precision, st, nullptr));
+    SCAT_CHECK_CUDA(cudaMemcpyAsync(out, ws + p.feat_out, (size_t)p.M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (mean != nullptr) {
+        token_mean_kernel<<<p.B, 32, 0, st>>>(ws + p.feat_out, mean, p.T);
+        SCAT_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// ---- single operators ----------------------------------------------------------------------------
+int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int32_t ldc,
+              int32_t M, int32_t N, int32_t K, int32_t epilogue, const float* bias, const float* aux_in,
+              int32_t ld_aux_in, float* aux_out, int32_t ld_aux_out, int32_t accumulate, int32_t precision,
+              void* stream) {
+    GemmArgs g;
+    g.A = A; g.sam = sam; g.sak = sak; g.B = B; g.sbn = sbn; g.sbk = sbk; g.C = C; g.ldc = ldc;
+    g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
+    g.aux_out = aux_out; g.ld_aux_out = ld_aux_out; g.accumulate = accumulate;
+    if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
+    SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
+                 "scat_gemm: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
+    return launch_gemm_tc(g, precision, (cudaStream_t)stream);
+}
+
+int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
+                          const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
+                          float* tokens_out, int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens,
+                          void* stream) {
+    return launch_conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, n_masked, pos_embed, feat_visual, tokens_out,
+                                   batch, channels, hw, n_tokens, (cudaStream_t)stream);
+}
+
+size_t scat_conv_bwd_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens) {
+    return conv_wgrad_scratch_floats(channels, n_tokens) + (size_t)batch * n_tokens * hw;
+}
+
+int scat_conv_bwd(const float* d_tokens, const float* x2, const float* conv_w, const int32_t* mask_idx,
+                  int32_t n_masked, float* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
+                  int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SCAT_REQUIRE(scratch, kErrBadArg, "conv_bwd: scratch is null");
+    float* dFv = scratch + conv_wgrad_scratch_floats(channels, n_tokens);
+    SCAT_PROPAGATE(launch_mask_bwd(d_tokens, mask_idx, n_masked, 0, dFv, mask_token_grad, batch, n_tokens, hw, st));
+    if (x2_grad) SCAT_PROPAGATE(launch_conv_dgrad(dFv, conv_w, x2_grad, batch, channels, hw, n_tokens, st));
+    return launch_conv_wgrad(dFv, x2, conv_w_grad, scratch, batch, channels, hw, n_tokens, st);
+}
+
+int scat_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                       int32_t rows, int32_t dim, void* stream) {
+    return launch_layernorm_fwd(x, dim, gamma, beta, y, dim, mean, rstd, rows, dim, (cudaStream_t)stream);
+}
+
+int scat_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* resid, float* dx, float* dgamma, float* dbeta, int32_t rows, int32_t dim,
+                       void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dgamma) {
+        SCAT_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, dim * sizeof(float), st));
+        SCAT_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, dim * sizeof(float), st));
+    }
+    return launch_layernorm_bwd(dy, dim, x, dim, gamma, mean, rstd, resid, dim, dx, dim, dgamma, dbeta, rows, dim, st);
+}
+
+int scat_attention_fwd(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream) {
+    return launch_attention_fwd(qkv, o, p, batch, n, heads, (cudaStream_t)stream);
+}
+
+int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
+                       int32_t heads, void* stream) {
+    return launch_attention_bwd(qkv, p, d_o, d_qkv, batch, n, heads, (cudaStream_t)stream);
+}
+
+int scat_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* w,
+                       const float* b, float* pred, float* states, int32_t batch, int32_t feat_dim, int32_t n_out,
+                       int32_t iteration, int32_t root_relative, void* stream) {
+    return launch_regressor_fwd(main_feat, feat_out, mean_params, w, b, pred, states, batch, feat_dim, n_out, iteration,
+                                root_relative, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Internal host-side launcher API shared by the .cu translation units.  Not part of the C ABI
+// (see include/scat_b200.h for that); everything here takes raw device pointers and a stream and
+// never allocates or synchronises, so a caller may capture any sequence into a CUDA graph.
+#pragma once
+#include "common.cuh"
+
+namespace scat {
+
+// ------------------------------------------------------------------------------------------
+// GEMM:  C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )   with fully strided operands
+//   A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]
+//   forward  y = x W^T      : A=x (sam=ldx,sak=1)    B=W  (sbn=ldw,sbk=1)      "K-major / K-major"
+//   dgrad    dx = dy W      : A=dy (sam=ld,sak=1)    B=W  (sbn=1,  sbk=ldw)    "K-major / MN-major"
+//   wgrad    dW = dy^T x    : A=dy (sam=1, sak=ld)   B=x  (sbn=1,  sbk=ldx)    "MN-major / MN-major"
+// ------------------------------------------------------------------------------------------
+enum Epilogue : int {
+    EPI_NONE = 0,        // C = acc
+    EPI_BIAS = 1,        // C = acc + bias[n]
+    EPI_BIAS_RESID = 2,  // C = acc + bias[n] + aux_in[m,n]
+    EPI_BIAS_GELU = 3,   // z = acc + bias[n]; aux_out[m,n] = z; C = gelu(z)
+    EPI_DGELU = 4,       // C = acc * gelu'(aux_in[m,n])
+    EPI_RESID = 5,       // C = acc + aux_in[m,n]
+};
+
+enum Precision : int {
+    PREC_FP32 = 0,  // CUDA-core FFMA, fp32 throughout (parity mode)
+    PREC_TF32 = 1,  // tcgen05 kind::tf32, fp32 storage, fp32 accumulate in TMEM
+    PREC_BF16 = 2,  // tcgen05 kind::f16 (bf16 operands), fp32 accumulate
+};
+
+struct GemmArgs {
+    const float* A = nullptr; long long sam = 0, sak = 0;
+    const float* B = nullptr; long long sbn = 0, sbk = 0;
+    float* C = nullptr; int ldc = 0;
+    int M = 0, N = 0, K = 0;
+    int epilogue = EPI_NONE;
+    const float* bias = nullptr;
+    const float* aux_in = nullptr; int ld_aux_in = 0;
+    float* aux_out = nullptr; int ld_aux_out = 0;
+    int accumulate = 0;  // C += epilogue(...)
+};
+
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// tcgen05 path; returns kErrUnsupported if the operand strides cannot be expressed as TMA tensor maps
+int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream);
+bool gemm_tc_supported(const GemmArgs& g);
+int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream);  // dispatch on precision/shape
+
+// column sums: out[n] (+)= sum_m X[m*ld + n]
+int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// 1x1 conv + positional encoding + token masking (hand_net.py:363-373)
+// ------------------------------------------------------------------------------------------
+int launch_conv_pe_mask_fwd(const float* x2, const float* Wc, const float* pe, const float* mask_token,
+                            const int32_t* mask_idx, int n_masked, int pos_embed, float* feat_visual, float* X0,
+                            int B, int C, int HW, int T, cudaStream_t stream);
+// dFv = dX0 with masked token rows zeroed (unless keep_masked); d mask_token = sum over b, masked t of dX0
+int launch_mask_bwd(const float* dX0, const int32_t* mask_idx, int n_masked, int keep_masked, float* dFv,
+                    float* d_mask_token, int B, int T, int HW, cudaStream_t stream);
+int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, int C, int HW, int T,
+                      cudaStream_t stream);
+size_t conv_wgrad_scratch_floats(int C, int T);
+int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scratch, int B, int C, int HW, int T,
+                      cudaStream_t stream);
+// token-only front end (config 4): X0 = tokens (+pe) with masked rows replaced
+int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mask_token, const int32_t* mask_idx,
+                          int n_masked, int pos_embed, float* X0, int B, int T, int D, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (vision_transformer.py:23,26; eps 1e-5, affine)
+// ------------------------------------------------------------------------------------------
+int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
+                         float* mean, float* rstd, int M, int D, cudaStream_t stream);
+// dX = LN'(dY) (+ resid); dgamma/dbeta accumulated with atomics when non-null (must be pre-zeroed)
+int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
+                         const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
+                         float* dbeta, int M, int D, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// softmax attention over n tokens, heads of 64 (vision_transformer.py:61-77)
+//   QKV [B*n, 3*inner] (q | k | v, head g = columns g*64..g*64+63), O [B*n, inner], P [B,h,n,n]
+// ------------------------------------------------------------------------------------------
+int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, cudaStream_t stream);
+int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+                         cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// autoregressive regressor (hand_net.py:379-393) and its backward
+// ------------------------------------------------------------------------------------------
+// pred0 = mean + [0,0,0,feat_out]; `iteration` x pred += [mf|pred] Wr^T + br; root-relative joints.
+// states [B, iteration, P] keeps pred before each step (for backward).  P = n_out (66), F = feature width.
+int launch_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* Wr,
+                         const float* br, float* pred, float* states, int B, int F, int P, int iteration,
+                         int root_relative, cudaStream_t stream);
+// g_pred [B,P] -> d_feat_out [B,P-3], d_main_feat [B,F] (nullable), gsum [B,P], gsteps [B,iteration,P]
+int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out, float* d_main_feat, float* gsum,
+                         float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// projection + losses (train.py:112-120,165-203) with closed-form gradient w.r.t. pred_params
+// ------------------------------------------------------------------------------------------
+// losses[4] = {loss, l_3d, l_2d, l_pl}; pl_term may be null (then l_pl = 0 and the 10*l_pl term is absent)
+int launch_proj_loss(const float* pred, const float* labels, int ld_labels, const float* pl_term, int pl_row_elems,
+                     int n_tokens, float w3d, float w2d, float grad_scale, float* losses, float* g_pred,
+                     float* pl_scratch, int B, cudaStream_t stream);
+
+// MANO linear blend skinning (mano.py:280-391) lives in lbs.cu with its own C-ABI wrappers.
+
+}  // namespace scat

@@ -1,0 +1,149 @@
+// LayerNorm forward / backward over token rows (vision_transformer.py:23,26: nn.LayerNorm(dim), eps=1e-5,
+// affine).  One warp per row, the row lives in registers; two-pass mean/variance like ATen's CPU kernel.
+#include "kernels.h"
+
+namespace scat {
+namespace {
+
+constexpr float kEps = 1e-5f;
+constexpr int LN_WARPS = 8;
+
+template <int NPL>  // elements per lane (row length <= 32*NPL)
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ Y, int ldy, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int M, int D) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* x = X + (long long)row * ldx;
+    float v[NPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const int c = i * 32 + lane;
+        v[i] = c < D ? x[c] : 0.f;
+        s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const int c = i * 32 + lane;
+        const float d = c < D ? v[i] - mean : 0.f;
+        q = fmaf(d, d, q);
+    }
+    const float var = warp_sum(q) / (float)D;
+    const float rstd = 1.0f / sqrtf(var + kEps);
+    float* y = Y + (long long)row * ldy;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const int c = i * 32 + lane;
+        if (c < D) y[c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ resid, int ldr, float* __restrict__ dX, int lddx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D) {
+    __shared__ float red[LN_WARPS][32 * NPL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float gam[NPL], dg[NPL], db[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const int c = i * 32 + lane;
+        gam[i] = c < D ? gamma[c] : 0.f;
+        dg[i] = 0.f;
+        db[i] = 0.f;
+    }
+    const float invD = 1.0f / (float)D;
+    for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+        const float mu = mean[row], rs = rstd[row];
+        const float* x = X + (long long)row * ldx;
+        const float* dy = dY + (long long)row * lddy;
+        float xh[NPL], g[NPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int c = i * 32 + lane;
+            const float xv = c < D ? x[c] : mu;
+            const float dv = c < D ? dy[c] : 0.f;
+            xh[i] = (xv - mu) * rs;
+            g[i] = dv * gam[i];
+            s1 += g[i];
+            s2 = fmaf(g[i], xh[i], s2);
+            dg[i] = fmaf(dv, xh[i], dg[i]);
+            db[i] += dv;
+        }
+        s1 = warp_sum(s1) * invD;
+        s2 = warp_sum(s2) * invD;
+        float* dx = dX + (long long)row * lddx;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int c = i * 32 + lane;
+            if (c < D) {
+                float o = rs * (g[i] - s1 - xh[i] * s2);
+                if (resid != nullptr) o += resid[(long long)row * ldr + c];
+                dx[c] = o;
+            }
+        }
+    }
+    if (dgamma == nullptr) return;   // dgrad-only pass (path-length VJP)
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) red[warp][i * 32 + lane] = dg[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+        atomicAdd(dgamma + c, s);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) red[warp][i * 32 + lane] = db[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+        atomicAdd(dbeta + c, s);
+    }
+}
+
+}  // namespace
+
+int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
+                         float* mean, float* rstd, int M, int D, cudaStream_t stream) {
+    SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm: D=%d not in [1,1024]", D);
+    const int grid = ceil_div(M, LN_WARPS);
+    if (D <= 256) layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D);
+    else if (D <= 512) layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D);
+    else layernorm_fwd_kernel<32><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D);
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
+                         const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
+                         float* dbeta, int M, int D, cudaStream_t stream) {
+    SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm bwd: D=%d not in [1,1024]", D);
+    SCAT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), kErrBadArg, "layernorm bwd: dgamma/dbeta must both be set or null");
+    const int grid = min(ceil_div(M, LN_WARPS), 148 * 2);
+#define SCAT_LN_BWD(NPL) layernorm_bwd_kernel<NPL><<<grid, LN_WARPS * 32, 0, stream>>>( \
+        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D)
+    if (D <= 256) SCAT_LN_BWD(8);
+    else if (D <= 512) SCAT_LN_BWD(16);
+    else SCAT_LN_BWD(32);
+#undef SCAT_LN_BWD
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace scat

@@ -1,0 +1,59 @@
+"""Host mirror of the reference's models/mano.py:280-391 over the fused LBS kernel.
+
+``ManoLayer(asset)`` uploads a MANO-shaped asset (keys as in MANO_RIGHT.pkl: v_template, shapedirs, posedirs,
+J_regressor (dense or scipy sparse), weights, hands_mean) once, derives the vertex-contiguous tables on the
+GPU and exposes ``rot_pose_beta_to_mesh(rots, poses, betas) -> [B, 21+778, 3]`` with the reference's argument
+meaning (no PCA: poses are 45 axis-angle values added to hands_mean; local root rotation forced to 0;
+joints = 16 chain joints + 5 fingertip vertices; everything relative to joint 1).  Forward only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+class ManoLayer:
+    def __init__(self, asset: dict, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("scat_b200.mano needs a CUDA device; there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        lib = _lib.load()
+
+        def up(key, shape):
+            a = asset[key]
+            if hasattr(a, "todense"):
+                a = np.asarray(a.todense())
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(self.device)
+            if tuple(t.shape) != shape:
+                raise ValueError(f"MANO asset {key}: expected {shape}, got {tuple(t.shape)}")
+            return t.contiguous()
+
+        self.v_template = up("v_template", (778, 3))
+        self.shapedirs = up("shapedirs", (778, 3, 10))
+        self.posedirs = up("posedirs", (778, 3, 135))
+        self.J_regressor = up("J_regressor", (16, 778))
+        self.weights = up("weights", (778, 16))
+        self.hands_mean = up("hands_mean", (45,))
+        self.derived = torch.empty(lib.scat_lbs_derived_floats(), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib.scat_lbs_prepare(ptr(self.v_template), ptr(self.shapedirs), ptr(self.posedirs),
+                                       ptr(self.J_regressor), ptr(self.weights), ptr(self.derived), stream_ptr()),
+                  "scat_lbs_prepare")
+
+    def rot_pose_beta_to_mesh(self, rots, poses, betas, out=None):
+        lib = _lib.load()
+        for name, t, w in (("rots", rots, 3), ("poses", poses, 45), ("betas", betas, 10)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == w):
+                raise RuntimeError(f"scat_b200.mano: {name} must be a CUDA float32 [B,{w}] tensor")
+        B = rots.shape[0]
+        if out is None:
+            out = torch.empty(B, 799, 3, device=rots.device, dtype=torch.float32)
+        check(lib.scat_lbs_fwd(ptr(self.derived), ptr(self.hands_mean), ptr(rots.contiguous()),
+                               ptr(poses.contiguous()), ptr(betas.contiguous()), ptr(out), B, stream_ptr()),
+              "scat_lbs_fwd")
+        return out
+
+    __call__ = rot_pose_beta_to_mesh

@@ -1,0 +1,214 @@
+"""GPU parity of the whole reg_transformer head through the reference-shaped nn.Module and the C ABI.
+
+  * against the fixtures generated from the UNMODIFIED reference (tests/golden, oracle/make_golden.py);
+  * against the CPU oracle at BASELINE config 2 size (B=96, mask 0.2, pl_reg, iteration 3);
+  * size-independent properties at full size (joint 1 == 0, masked-token zeros, linearity of the VJP).
+
+Tolerances (north_star): fp32 parity mode 2e-5 relative on outputs / 2e-4 on gradients; TF32 path 1e-4
+relative on joints, 1e-3 relative (L2) on gradients; masking and indexing bit-exact.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from scat_b200 import synth
+from tests.util import build_net, load_golden, make_opt, oracle_step, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+HEAD_CASES = ["head_kat_b2", "head_b3_mask50", "head_b2_nope_alias", "head_b2_h4_it1_nomask", "head_b2_mask90"]
+
+
+def _run_module_step(net, x2, mf, labels, mask_seed):
+    """train.py:159-206 body through the drop-in module + autograd (loss via the CUDA loss kernel)."""
+    from scat_b200 import functional as SF
+    x2d = torch.from_numpy(x2).cuda().requires_grad_(True)
+    mfd = torch.from_numpy(mf).cuda().requires_grad_(True)
+    net.main_encoder.x2, net.main_encoder.main_feat = x2d, mfd
+    random.seed(mask_seed)
+    outs = net(torch.zeros(x2.shape[0], 3, 8, 8, device="cuda"))
+    pred, fv = outs[0], outs[1]
+    pl = outs[2] if net.pl else None
+    loss, parts = SF.proj_loss(pred, torch.from_numpy(labels).cuda(), pl)
+    net.zero_grad(set_to_none=True)
+    loss.backward()
+    return dict(pred=pred.detach(), fv=fv.detach(), pl=None if pl is None else pl.detach(), loss=loss.detach(),
+                parts=parts, x2_grad=x2d.grad, mf_grad=mfd.grad)
+
+
+@pytest.mark.parametrize("name", HEAD_CASES)
+def test_head_matches_reference_fixture_fp32(name):
+    g = load_golden(name)
+    B, heads, it = int(g["B"]), int(g["heads"]), int(g["iteration"])
+    opt = make_opt(heads, bool(g["pl_reg"]), it, bool(g["pos_embed"]), float(g["mask_rate"]))
+    W = synth.make_head_weights(heads, int(g["w_seed"]), str(g["regime"]))
+    net = build_net(opt, W, str(g["mean_kind"]), precision="fp32")
+    x2, mf, labels = synth.make_head_inputs(B, int(g["in_seed"]))
+    r = _run_module_step(net, x2, mf, labels, int(g["mask_seed"]))
+    assert net.last_mask == g["mask_idx"].tolist()                     # same host RNG draw as the reference
+    assert rel_max(r["pred"], g["pred"]) < 2e-5
+    assert torch.all(r["pred"][:, 6:9] == 0)                           # joint 1 is exactly the origin
+    assert rel_max(r["fv"], g["feat_visual"]) < 2e-5
+    idx = net.last_mask
+    if not opt.pos_embed and idx:                                      # aliased overwrite: rows ARE the mask token
+        assert torch.equal(r["fv"].view(B, 21, -1)[:, idx].cpu(),
+                           torch.from_numpy(W["mask_token"]).expand(B, len(idx), -1))
+    if opt.pl_reg:
+        assert rel_max(r["pl"], g["pl"]) < 1e-4
+        assert rel_l2(r["pl"], g["pl"]) < 2e-5
+        if opt.pos_embed and idx:
+            assert torch.all(r["pl"].view(B, 21, -1)[:, idx] == 0)     # masked tokens: exactly zero VJP rows
+    np.testing.assert_allclose(r["loss"].item(), g["loss"][0], rtol=5e-5)
+    assert rel_max(r["mf_grad"], g["main_feat_grad"]) < 2e-4
+    xg = r["x2_grad"].double().reshape(-1).cpu().numpy()
+    assert np.abs(xg[g["x2_grad_idx"]] - g["x2_grad_val"]).max() <= 2e-4 * np.abs(xg).max()
+    np.testing.assert_allclose(np.abs(xg).sum(), g["x2_grad_sum"][1], rtol=1e-4)
+    named = dict(net.named_parameters())
+    for k in W:
+        gg = named[k].grad
+        gg = torch.zeros_like(named[k]) if gg is None else gg
+        gg = gg.double().reshape(-1).cpu().numpy()
+        np.testing.assert_allclose(np.abs(gg).sum(), g["g_sum/" + k][1], rtol=2e-4, atol=1e-10, err_msg=k)
+        assert np.abs(gg[g["g_idx/" + k]] - g["g_val/" + k]).max() <= 2e-4 * (np.abs(gg).max() + 1e-30), k
+
+
+def _config2(precision, B=96, regime="unit", seed=11):
+    opt = make_opt(8, True, 3, True, 0.2)
+    W = synth.make_head_weights(8, regime=regime)
+    net = build_net(opt, W, "hand", precision=precision)
+    x2, mf, labels = synth.make_head_inputs(B, seed)
+    return opt, W, net, x2, mf, labels
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 2e-5, 2e-4), ("tf32", 1e-4, 1e-3)])
+def test_head_config2_against_oracle(precision, tol_out, tol_grad):
+    """BASELINE config 2 (B=96, mask 0.2, pl_reg, iteration 3) against the fp64 oracle."""
+    opt, W, net, x2, mf, labels = _config2(precision)
+    r = _run_module_step(net, x2, mf, labels, mask_seed=3)
+    o = oracle_step(W, x2, mf, labels, "hand", heads=8, iteration=3, pos_embed=True, mask_idx=net.last_mask,
+                    pl_reg=True, dtype=torch.float64)
+    assert rel_max(r["pred"], o["pred"]) < tol_out                     # joints + camera, north_star: 1e-4 relative
+    assert torch.all(r["pred"][:, 6:9] == 0)
+    assert rel_l2(r["fv"], o["feat_visual"]) < (2e-5 if precision == "fp32" else 2e-3)
+    assert rel_l2(r["pl"], o["pl"]) < (2e-5 if precision == "fp32" else 5e-3)
+    np.testing.assert_allclose(r["loss"].item(), o["loss"].item(), rtol=10 * tol_out)
+    assert rel_l2(r["mf_grad"], o["main_feat_grad"]) < tol_grad
+    assert rel_l2(r["x2_grad"], o["x2_grad"]) < tol_grad
+    named = dict(net.named_parameters())
+    worst = max(rel_l2(named[k].grad, o["grads"][k]) for k in W)
+    assert worst < tol_grad, worst
+
+
+def test_fused_train_step_equals_module_autograd():
+    """scat_head_train_step (one call, CUDA graph) == module forward + loss + autograd backward."""
+    from scat_b200.train_step import HeadTrainStep
+    opt, W, net, x2, mf, labels = _config2("fp32", B=8)
+    r = _run_module_step(net, x2, mf, labels, mask_seed=9)
+    ref_grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    for use_graph in (False, True):
+        ts = HeadTrainStep(net, 8, use_graph=use_graph)
+        ts.load_inputs(torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda(), torch.from_numpy(labels).cuda())
+        ts.set_mask(net.last_mask)
+        for _ in range(2):                                            # replays are idempotent
+            losses = ts.step()
+        torch.cuda.synchronize()
+        assert abs(losses[0].item() - r["loss"].item()) <= 1e-6 * abs(r["loss"].item())
+        assert torch.equal(ts.pred, r["pred"]) and torch.equal(ts.pl, r["pl"])
+        for k, p in net.named_parameters():
+            if k in ref_grads:
+                assert rel_max(p.grad, ref_grads[k]) < 1e-6, k
+        assert rel_max(ts.x2_grad, r["x2_grad"]) < 1e-6
+
+
+def test_full_size_properties_tf32():
+    """Size-independent checks at config-2 size on the default (TF32) path."""
+    opt, W, net, x2, mf, labels = _config2("tf32")
+    x2d, mfd = torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda()
+    random.seed(1)
+    pred, fv, pl = net.forward_features(mfd, x2d)
+    idx = net.last_mask
+    assert idx == [20, 17, 19, 11]
+    assert torch.all(pred[:, 6:9] == 0) and torch.isfinite(pred).all()
+    assert torch.all(pl.view(96, 21, -1)[:, idx] == 0) and not pl.requires_grad
+    # samples are independent: a batch of 96 equals two batches of 48 with the same mask
+    p1, f1, l1 = net.forward_features(mfd[:48], x2d[:48], mask_idx=idx)
+    p2, f2, l2 = net.forward_features(mfd[48:], x2d[48:], mask_idx=idx)
+    assert torch.equal(torch.cat([p1, p2]), pred) and torch.equal(torch.cat([f1, f2]), fv)
+    assert torch.equal(torch.cat([l1, l2]), pl)
+    # masked tokens do not see their input: perturbing x2 only changes feat_visual rows, not pred, if ALL tokens
+    # but the masked ones are unchanged -> check via conv linearity instead: fv(2*x2) == 2*fv(x2) exactly
+    p3, f3, _ = net.forward_features(mfd, 2.0 * x2d, mask_idx=idx)
+    assert torch.equal(f3, 2.0 * fv)
+
+
+def test_module_contract():
+    """state_dict keys / shapes, option handling and error behaviour of the drop-in module."""
+    opt = make_opt(8, True, 3, True, 0.2)
+    W = synth.make_head_weights(8)
+    net = build_net(opt, W, "hand", precision="fp32")
+    sd = net.state_dict()
+    for k, shape in synth.head_param_shapes(8).items():
+        assert tuple(sd[k].shape) == shape, k
+    assert tuple(sd["positionalEncoding.pe"].shape) == (1, 21, 784)
+    x2, mf, _ = synth.make_head_inputs(2, 0)
+    x2d, mfd = torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="does not require grad"):    # like the reference under no_grad
+            net.forward_features(mfd, x2d)
+    # host RNG consumption: exactly one shuffle of range(21) per forward when masking is active
+    random.seed(123)
+    net.forward_features(mfd, x2d)
+    after = random.random()
+    random.seed(123)
+    masked = list(range(21)); random.shuffle(masked)
+    assert after == random.random() and net.last_mask == masked[:4]
+    # masking also applies in eval mode (hand_net.py:369 has no self.training check)
+    net.pl = False
+    net.eval()
+    with torch.no_grad():
+        random.seed(7)
+        out = net.forward_features(mfd, x2d)
+    assert len(out) == 2 and len(net.last_mask) == 4
+    with pytest.raises(RuntimeError):
+        net.forward_features(mfd.cpu(), x2d.cpu())                          # no CPU path
+
+
+def test_token_transformer_config4_fixture():
+    """Config 4 (n=128 tokens x dim 196) up to feat.mean(dim=1) against the reference fixture."""
+    from scat_b200 import functional as SF
+    from scat_b200.vision_transformer import Transformer
+    from scat_b200.hand_net import PositionalEncoding
+    g = load_golden("tokens_n128_d196")
+    B, n, dim, heads = int(g["B"]), int(g["n"]), int(g["dim"]), int(g["heads"])
+    W = synth.make_token_weights(dim, heads)
+    tr = Transformer(dim=dim, depth=3, heads=heads, dim_head=64, mlp_dim=2 * dim)
+    tr.load_state_dict({k[len("transformer."):]: torch.from_numpy(v) for k, v in W.items() if k.startswith("transformer.")})
+    tr = tr.cuda()
+    pe = PositionalEncoding(dim, max_len=n).pe[0].cuda()
+    tok = torch.from_numpy(synth.make_token_inputs(B, n, dim, int(g["in_seed"]))).cuda()
+    idx = torch.tensor(g["mask_idx"].tolist(), dtype=torch.int32, device="cuda")
+    with torch.no_grad():
+        for prec, tol in (("fp32", 2e-5), ("tf32", 2e-3)):
+            out, mean = SF.token_transformer(tr, tok, mask_token=torch.from_numpy(W["mask_token"]).cuda().view(-1),
+                                             pe=pe, mask_idx=idx, precision=prec, return_mean=True)
+            assert rel_max(out, g["out"]) < tol, prec
+            assert rel_max(mean, g["mean"]) < tol, prec
+
+
+def test_data_parallel_shards_sum_to_full_batch():
+    """Two shards of 4 with grad_scale 1/2, summed, equal one batch of 8 (the all-reduce contract, on one GPU)."""
+    from scat_b200.train_step import HeadTrainStep
+    opt, W, net, x2, mf, labels = _config2("fp32", B=8)
+    x2d, mfd, lab = torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda(), torch.from_numpy(labels).cuda()
+    full = HeadTrainStep(net, 8, use_graph=False)
+    full.load_inputs(x2d, mfd, lab); full.set_mask([1, 5, 9, 13]); full.step()
+    g_full = full.bucket.flat.clone()
+    acc = torch.zeros_like(g_full)
+    for lo in (0, 4):
+        half = HeadTrainStep(net, 4, use_graph=False)
+        half.world = 2                                   # what dist.get_world_size() reports on 2 ranks
+        half.load_inputs(x2d[lo:lo + 4], mfd[lo:lo + 4], lab[lo:lo + 4]); half.set_mask([1, 5, 9, 13]); half.step(allreduce=False)
+        acc += half.bucket.flat
+    assert rel_l2(acc, g_full) < 1e-5

@@ -1,0 +1,197 @@
+"""GPU parity of the single operators behind the C ABI against CPU restatements (oracle / torch fp64).
+
+Tolerances: fp32 kernels are compared with float64 references at 2e-5 relative (summation-order noise of
+K<=2016 fp32 dot products); index/masking work is bit-exact.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import head_oracle
+from scat_b200 import synth
+from tests.util import rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return torch.from_numpy((scale * g.standard_normal(size=shape)).astype(np.float32))
+
+
+def _gelu_grad(z):
+    z = z.double().requires_grad_(True)
+    F.gelu(z).sum().backward()
+    return z.grad
+
+
+@pytest.mark.parametrize("M,N,K", [(2016, 1536, 784), (2016, 392, 588), (42, 3, 147), (2016, 147, 196), (63, 200, 37),
+                                   (1, 1, 1), (130, 70, 2016)])
+def test_gemm_forward_layout_and_epilogues(M, N, K):
+    from scat_b200 import functional as SF
+    a, w, bias, res = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.1), _rand(N, seed=3), _rand(M, N, seed=4)
+    ref = a.double() @ w.double().t()
+    ad, wd, bd, rd = a.cuda(), w.cuda(), bias.cuda(), res.cuda()
+    assert rel_max(SF.gemm(ad, wd), ref) < 2e-5
+    assert rel_max(SF.gemm(ad, wd, epilogue="bias", bias=bd), ref + bias.double()) < 2e-5
+    assert rel_max(SF.gemm(ad, wd, epilogue="bias_resid", bias=bd, aux_in=rd), ref + bias.double() + res.double()) < 2e-5
+    assert rel_max(SF.gemm(ad, wd, epilogue="resid", aux_in=rd), ref + res.double()) < 2e-5
+    y, z = SF.gemm(ad, wd, epilogue="bias_gelu", bias=bd)
+    assert rel_max(z, ref + bias.double()) < 2e-5
+    assert rel_max(y, F.gelu(ref + bias.double())) < 2e-5
+    assert rel_max(SF.gemm(ad, wd, epilogue="dgelu", aux_in=rd), ref * _gelu_grad(res)) < 2e-5
+    c0 = torch.ones(M, N, device="cuda")
+    assert rel_max(SF.gemm(ad, wd, out=c0, accumulate=True), ref + 1.0) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(2016, 784, 512), (300, 294, 196), (21, 3, 147)])
+def test_gemm_dgrad_and_wgrad_layouts(M, N, K):
+    """dx = dy W (B operand N-major) and dW = dy^T x (both operands M-major) through the same kernel."""
+    from scat_b200 import functional as SF
+    dy, w, x = _rand(M, N, seed=5), _rand(N, K, seed=6, scale=0.1), _rand(M, K, seed=7)
+    dyd, wd, xd = dy.cuda(), w.cuda(), x.cuda()
+    dx = SF.gemm(dyd, wd, a_strides=(N, 1), b_strides=(1, K), m=M, n=K, k=N)
+    assert rel_max(dx, dy.double() @ w.double()) < 2e-5
+    dw = SF.gemm(dyd, xd, a_strides=(1, N), b_strides=(1, K), m=N, n=K, k=M)
+    assert rel_max(dw, dy.double().t() @ x.double()) < 2e-5
+
+
+@pytest.mark.parametrize("rows,dim", [(2016, 784), (2016, 392), (2016, 196), (7, 49), (1, 1000)])
+def test_layernorm_fwd_bwd(rows, dim):
+    from scat_b200 import functional as SF
+    x, g, b, dy, res = (_rand(rows, dim, seed=1, scale=2.0) + 0.5, 1 + 0.1 * _rand(dim, seed=2), _rand(dim, seed=3),
+                        _rand(rows, dim, seed=4), _rand(rows, dim, seed=5))
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (dim,), gr, br, 1e-5)
+    yr.backward(dy.double())
+    y, mean, rstd = SF.layernorm_fwd(x.cuda(), g.cuda(), b.cuda())
+    assert rel_max(y, yr.detach()) < 5e-6
+    dx, dg, db = SF.layernorm_bwd(dy.cuda(), x.cuda(), g.cuda(), mean, rstd, resid=res.cuda())
+    assert rel_max(dx, xr.grad + res.double()) < 2e-5
+    assert rel_max(dg, gr.grad) < 2e-5
+    assert rel_max(db, br.grad) < 2e-5
+    dx2, dg2, _ = SF.layernorm_bwd(dy.cuda(), x.cuda(), g.cuda(), mean, rstd, param_grads=False)
+    assert dg2 is None and rel_max(dx2, xr.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,n,heads", [(96, 21, 8), (3, 21, 4), (2, 128, 8), (5, 1, 2), (2, 64, 3)])
+def test_attention_fwd_bwd(B, n, heads):
+    from scat_b200 import functional as SF
+    inner = 64 * heads
+    qkv = _rand(B * n, 3 * inner, seed=11)
+    d_o = _rand(B * n, inner, seed=12)
+    q = qkv.double().requires_grad_(True)
+    qq, kk, vv = q.view(B, n, 3 * inner).chunk(3, dim=-1)
+    sp = lambda t: t.reshape(B, n, heads, 64).permute(0, 2, 1, 3)
+    p_ref = (torch.matmul(sp(qq), sp(kk).transpose(-1, -2)) * 0.125).softmax(-1)
+    o_ref = torch.matmul(p_ref, sp(vv)).permute(0, 2, 1, 3).reshape(B * n, inner)
+    o, p = SF.attention_fwd(qkv.cuda(), B, n, heads)
+    assert rel_max(p, p_ref.detach()) < 1e-5
+    assert rel_max(o, o_ref.detach()) < 1e-5
+    if n <= 64:
+        o_ref.backward(d_o.double())
+        dqkv = SF.attention_bwd(qkv.cuda(), p, d_o.cuda(), B, n, heads)
+        assert rel_max(dqkv, q.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,mask_rate,pos_embed", [(3, 0.2, True), (2, 0.9, True), (2, 0.0, True), (2, 0.2, False),
+                                                   (5, 0.5, True)])
+def test_conv_pe_mask_fwd_bwd(B, mask_rate, pos_embed):
+    from scat_b200 import functional as SF
+    x2, _, _ = synth.make_head_inputs(B, 3)
+    W = synth.make_head_weights(8)
+    cw, mt = torch.from_numpy(W["conv1x1_channel_reduction.weight"]), torch.from_numpy(W["mask_token"])
+    pe = head_oracle.positional_encoding(21, 784)
+    random.seed(5)
+    idx = synth.mask_indices(mask_rate)
+    xr = torch.from_numpy(x2).double().requires_grad_(True)
+    cwr, mtr = cw.double().requires_grad_(True), mt.double().requires_grad_(True)
+    fv_ref = F.conv2d(xr, cwr)
+    tok_ref = fv_ref.view(B, 21, -1)
+    if pos_embed:
+        tok_ref = tok_ref + pe.double()
+    else:
+        tok_ref = tok_ref.clone()
+    if idx:
+        tok_ref[:, idx, :] = mtr
+    idx_dev = torch.tensor(idx, dtype=torch.int32, device="cuda") if idx else None
+    fv, tok = SF.conv_pe_mask_fwd(torch.from_numpy(x2).cuda(), cw.cuda().view(21, 512), pe[0].cuda(),
+                                  mt.cuda().view(-1), idx_dev, pos_embed)
+    keep = [t for t in range(21) if t not in idx]
+    assert rel_max(fv.view(B, 21, -1)[:, keep], fv_ref.detach().view(B, 21, -1)[:, keep]) < 1e-5
+    # masking / indexing is bit-exact: masked rows ARE the mask token, unmasked rows are fv (+ pe) exactly
+    if idx:
+        assert torch.equal(tok[:, idx, :].cpu(), mt.view(1, 1, -1).expand(B, len(idx), -1))
+    if pos_embed:
+        assert torch.equal(tok[:, keep].cpu(), (fv.view(B, 21, -1)[:, keep] + pe[0, keep].cuda()).cpu())
+        assert rel_max(fv, fv_ref.detach()) < 1e-5
+    else:
+        assert tok.data_ptr() == fv.data_ptr()          # aliasing of hand_net.py:364,373
+    d_tok = _rand(B, 21, 784, seed=9)
+    tok_ref.backward(d_tok.double())
+    x2g, wg, mg = SF.conv_bwd(d_tok.cuda(), torch.from_numpy(x2).cuda(), cw.cuda().view(21, 512), idx_dev)
+    assert rel_max(x2g, xr.grad) < 2e-5
+    assert rel_max(wg, cwr.grad.view(21, 512)) < 2e-5
+    if idx:
+        assert rel_max(mg, mtr.grad.view(-1)) < 2e-5
+        assert torch.all(wg[idx] == 0)                   # masked tokens: exactly zero conv-weight gradient rows
+
+
+@pytest.mark.parametrize("B,it", [(96, 3), (2, 1), (5, 0)])
+def test_regressor_fwd(B, it):
+    from scat_b200 import functional as SF
+    W = synth.make_head_weights(8)
+    _, mf, _ = synth.make_head_inputs(B, 1)
+    feat_out = _rand(B, 63, seed=3, scale=0.05)
+    mean = torch.from_numpy(synth.make_mean_params("hand"))
+    w, b = torch.from_numpy(W["regressor.weight"]), torch.from_numpy(W["regressor.bias"])
+    p0 = mean.double().repeat(B, 1)
+    p0[:, 3:] += feat_out.double()
+    ref = head_oracle.iterative_regressor(torch.from_numpy(mf).double(), p0, w.double(), b.double(), it)
+    j = ref[:, 3:].view(B, 21, 3)
+    ref = torch.cat([ref[:, :3], (j - j[:, 1:2]).reshape(B, 63)], dim=1)
+    pred = SF.regressor_fwd(torch.from_numpy(mf).cuda(), feat_out.cuda(), mean.cuda().view(-1), w.cuda(), b.cuda(), it)
+    assert rel_max(pred, ref) < 1e-5
+    assert torch.all(pred[:, 6:9] == 0)
+
+
+def test_h3dw_encoder_regressor():
+    from scat_b200.hand_net import H3DWEncoder
+    from tests.util import StubBackbone
+    g = np.random.Generator(np.random.PCG64(5))
+    mean = torch.from_numpy((0.1 * g.standard_normal(size=(1, 61))).astype(np.float32))
+    enc = H3DWEncoder(None, mean, backbone=StubBackbone()).cuda()
+    with torch.no_grad():
+        for p in enc.parameters():
+            p.copy_(torch.from_numpy((0.02 * g.standard_normal(size=tuple(p.shape))).astype(np.float32)))
+    _, mf, _ = synth.make_head_inputs(7, 2)
+    fc2, reg = enc.feat_encoder[1], enc.regressor[0]
+    f_ref, p_ref = head_oracle.h3dw_regressor(torch.from_numpy(mf).double(), mean.double(), fc2.weight.detach().double().cpu(),
+                                              fc2.bias.detach().double().cpu(), reg.weight.detach().double().cpu(),
+                                              reg.bias.detach().double().cpu())
+    with torch.no_grad():
+        feat, pred = enc.forward_features(torch.from_numpy(mf).cuda())
+    assert rel_max(feat, f_ref) < 1e-5
+    assert rel_max(pred, p_ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,with_pl", [(96, True), (2, False), (1, True)])
+def test_proj_loss_and_gradient(B, with_pl):
+    from scat_b200 import functional as SF
+    _, _, labels = synth.make_head_inputs(B, 4)
+    pred = _rand(B, 66, seed=2, scale=0.05)
+    pred[:, 0] += 5.0
+    pl = _rand(B, 21, 28, 28, seed=3, scale=0.01) if with_pl else None
+    pr = pred.double().requires_grad_(True)
+    loss_ref, l3, l2, lpl = head_oracle.train_loss(pr, torch.from_numpy(labels).double(), None if pl is None else pl.double())
+    loss_ref.backward()
+    pd = pred.cuda().requires_grad_(True)
+    loss, parts = SF.proj_loss(pd, torch.from_numpy(labels).cuda(), None if pl is None else pl.cuda())
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=2e-5)
+    np.testing.assert_allclose(parts.cpu().numpy(), [loss_ref.item(), l3.item(), l2.item(), lpl.item()], rtol=5e-5, atol=1e-12)
+    assert rel_max(pd.grad, pr.grad) < 2e-5

