@@ -157,10 +157,10 @@ int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float
                        int32_t heads, void* stream);
 
 /* hand_net.py:379-393 (root_relative=1, n_out=66) and hand_net.py:53-57 (root_relative=0, n_out=61).
- * states[B,iteration,n_out] may be NULL when no backward follows. */
+ * states[B,iteration,n_out] may be NULL when no backward follows; scratch: batch*n_out floats. */
 int scat_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* w,
-                       const float* b, float* pred, float* states, int32_t batch, int32_t feat_dim, int32_t n_out,
-                       int32_t iteration, int32_t root_relative, void* stream);
+                       const float* b, float* pred, float* states, float* scratch, int32_t batch, int32_t feat_dim,
+                       int32_t n_out, int32_t iteration, int32_t root_relative, void* stream);
 
 /* MANO linear blend skinning, models/mano.py:280-391 (rot_pose_beta_to_mesh).
  * asset (as in MANO_RIGHT.pkl, row-major fp32): v_template[778,3] shapedirs[778,3,10] posedirs[778,3,135]

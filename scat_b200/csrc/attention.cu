@@ -25,7 +25,8 @@ __device__ __forceinline__ void load_head_tile(const float* __restrict__ src, lo
 }
 
 __global__ void __launch_bounds__(ATT_THREADS)
-attention_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ P, int n, int heads) {
+attention_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ P, int n, int heads,
+                     int round_out) {
     extern __shared__ float sm[];
     float* Qs = sm;
     float* Ks = Qs + n * LDS;
@@ -75,13 +76,13 @@ attention_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float
         const int i = e / DH, d = e % DH;
         float o = 0.f;
         for (int j = 0; j < n; ++j) o = fmaf(Ss[i * lds + j], Vs[j * LDS + d], o);
-        Ob[(long long)i * inner + d] = o;
+        Ob[(long long)i * inner + d] = round_out ? round_tf32(o) : o;
     }
 }
 
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dO,
-                     float* __restrict__ dQKV, int n, int heads) {
+                     float* __restrict__ dQKV, int n, int heads, int round_out) {
     extern __shared__ float sm[];
     float* Qs = sm;
     float* Ks = Qs + n * LDS;
@@ -129,35 +130,45 @@ attention_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ P,
             dv = fmaf(Ps[j * lds + i], Gs[j * LDS + d], dv);   // dV[i] = sum_j P[j,i] dO[j]
         }
         float* o = dbase + (long long)i * rs + d;
-        o[0] = dq;
-        o[inner] = dk;
-        o[2 * inner] = dv;
+        o[0] = round_out ? round_tf32(dq) : dq;
+        o[inner] = round_out ? round_tf32(dk) : dk;
+        o[2 * inner] = round_out ? round_tf32(dv) : dv;
     }
 }
 
 }  // namespace
 
-int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, cudaStream_t stream) {
+// attention_small.cu: warp-per-problem kernels for the n = 21 training path
+bool attention_small_supported(int n);
+int launch_attention_small_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
+                               cudaStream_t stream);
+int launch_attention_small_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+                               int round_out, cudaStream_t stream);
+
+int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
+                         cudaStream_t stream) {
     SCAT_REQUIRE(n >= 1 && n <= 128, kErrUnsupported, "attention: n=%d not in [1,128]", n);
+    if (attention_small_supported(n)) return launch_attention_small_fwd(QKV, O, P, B, n, heads, round_out, stream);
     const size_t smem = sizeof(float) * ((size_t)3 * n * LDS + (size_t)n * (n + 1));
     if (smem > 48 * 1024) {
         SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
     }
-    attention_fwd_kernel<<<B * heads, ATT_THREADS, smem, stream>>>(QKV, O, P, n, heads);
+    attention_fwd_kernel<<<B * heads, ATT_THREADS, smem, stream>>>(QKV, O, P, n, heads, round_out);
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 
 int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
-                         cudaStream_t stream) {
+                         int round_out, cudaStream_t stream) {
     SCAT_REQUIRE(n >= 1 && n <= 64, kErrUnsupported, "attention bwd: n=%d not in [1,64] (training path is n=21)", n);
+    if (attention_small_supported(n)) return launch_attention_small_bwd(QKV, P, dO, dQKV, B, n, heads, round_out, stream);
     const size_t smem = sizeof(float) * ((size_t)4 * n * LDS + (size_t)2 * n * (n + 1));
     if (smem > 48 * 1024) {
         SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
     }
-    attention_bwd_kernel<<<B * heads, ATT_THREADS, smem, stream>>>(QKV, P, dO, dQKV, n, heads);
+    attention_bwd_kernel<<<B * heads, ATT_THREADS, smem, stream>>>(QKV, P, dO, dQKV, n, heads, round_out);
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -160,15 +160,15 @@ __global__ void mask_bwd_copy_kernel(const float* __restrict__ dX0, const int32_
     }
 }
 
-// d mask_token[p] = sum_b sum_{t in idx} dX0[b,t,p]   (deterministic: one thread per p)
+// d mask_token[p] = sum_b sum_{t in idx} dX0[b,t,p]: grid (pixel blocks, sample slices), slices combine with atomics
 __global__ void mask_token_grad_kernel(const float* __restrict__ dX0, const int32_t* __restrict__ mask_idx,
                                        int n_masked, float* __restrict__ d_mask_token, int B, int T, int HW) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
     float s = 0.f;
-    for (int b = 0; b < B; ++b)
+    for (int b = blockIdx.y; b < B; b += gridDim.y)
         for (int i = 0; i < n_masked; ++i) s += dX0[((long long)b * T + mask_idx[i]) * HW + p];
-    d_mask_token[p] = s;
+    atomicAdd(d_mask_token + p, s);
 }
 
 // x2g[b,c,p] = sum_t Wc[t,c] dFv[b,t,p]
@@ -336,8 +336,12 @@ int launch_mask_bwd(const float* dX0, const int32_t* mask_idx, int n_masked, int
         SCAT_CHECK_LAUNCH();
     }
     if (d_mask_token != nullptr) {
-        mask_token_grad_kernel<<<ceil_div(HW, 128), 128, 0, stream>>>(dX0, mask_idx, n_masked, d_mask_token, B, T, HW);
-        SCAT_CHECK_LAUNCH();
+        SCAT_CHECK_CUDA(cudaMemsetAsync(d_mask_token, 0, (size_t)HW * sizeof(float), stream));
+        if (n_masked > 0) {
+            mask_token_grad_kernel<<<dim3(ceil_div(HW, 128), min(B, 32)), 128, 0, stream>>>(dX0, mask_idx, n_masked,
+                                                                                            d_mask_token, B, T, HW);
+            SCAT_CHECK_LAUNCH();
+        }
     }
     return 0;
 }

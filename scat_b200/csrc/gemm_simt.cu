@@ -4,6 +4,8 @@
 // Replaces the cuBLAS calls behind nn.Linear on the reference's path (vision_transformer.py:33-35,53-55)
 // and their autograd backward.  C = epilogue(A * B^T) with A(m,k) and B(n,k) addressed through
 // (row, col) strides so forward / dgrad / wgrad are the same kernel (see kernels.h).
+// Small-output / long-K problems (weight gradients: K = B*21 rows) are split along K over gridDim.z and
+// combined with fp32 atomics so that they still fill the 148 SMs.
 #include "kernels.h"
 
 namespace scat {
@@ -47,7 +49,7 @@ __device__ __forceinline__ void store_tile(float (*S)[BM + PAD], int tid, const 
 }
 
 template <bool A_K, bool B_K>
-__global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_per_split) {
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
     const int tid = threadIdx.x;
@@ -60,15 +62,18 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    const int nk_all = (g.K + BK - 1) / BK;
+    const int kt_beg = blockIdx.z * kt_per_split;
+    const int kt_end = min(nk_all, kt_beg + kt_per_split);
+    if (kt_beg >= kt_end) return;
     Frag fa, fb;
-    load_tile<A_K>(g.A, g.sam, g.sak, m0, 0, g.M, g.K, tid, fa);
-    load_tile<B_K>(g.B, g.sbn, g.sbk, n0, 0, g.N, g.K, tid, fb);
-    const int nk = (g.K + BK - 1) / BK;
-    for (int kt = 0; kt < nk; ++kt) {
+    load_tile<A_K>(g.A, g.sam, g.sak, m0, kt_beg * BK, g.M, g.K, tid, fa);
+    load_tile<B_K>(g.B, g.sbn, g.sbk, n0, kt_beg * BK, g.N, g.K, tid, fb);
+    for (int kt = kt_beg; kt < kt_end; ++kt) {
         store_tile<A_K>(As, tid, fa);
         store_tile<B_K>(Bs, tid, fb);
         __syncthreads();
-        if (kt + 1 < nk) {
+        if (kt + 1 < kt_end) {
             load_tile<A_K>(g.A, g.sam, g.sak, m0, (kt + 1) * BK, g.M, g.K, tid, fa);
             load_tile<B_K>(g.B, g.sbn, g.sbk, n0, (kt + 1) * BK, g.N, g.K, tid, fb);
         }
@@ -86,6 +91,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
         __syncthreads();
     }
 
+    const bool split = gridDim.z > 1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -107,31 +113,48 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
                 case EPI_RESID: v += g.aux_in[(long long)m * g.ld_aux_in + n]; break;
                 default: break;
             }
+            if (g.round_out) v = round_tf32(v);
             float* c = g.C + (long long)m * g.ldc + n;
-            *c = g.accumulate ? (*c + v) : v;
+            if (split) atomicAdd(c, v);                       // C was cleared (or holds the accumulate base)
+            else *c = g.accumulate ? (*c + v) : v;
         }
     }
 }
 
-__global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N, float* __restrict__ out,
-                              int accumulate) {
-    // block = 32 columns x 8 row-lanes; grid.x over column groups; deterministic (no atomics)
+// column sums out[n] (+)= sum_m X[m,n]: grid (column groups, row slices); slices combine with atomics
+__global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N, float* __restrict__ out) {
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
     if (c < N)
-        for (int m = threadIdx.y; m < M; m += 8) s += X[(long long)m * ld + c];
+        for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += 8 * gridDim.y) s += X[(long long)m * ld + c];
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < N) {
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-        out[c] = accumulate ? out[c] + t : t;
+        atomicAdd(out + c, t);
+    }
+}
+
+__global__ void round_copy_kernel(const RoundJobs jobs) {
+    const RoundJob job = jobs.job[blockIdx.y];
+    const long long total = (long long)job.rows * job.ld_dst;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / job.ld_dst), c = (int)(i % job.ld_dst);
+        job.dst[i] = c < job.cols ? round_tf32(__ldg(job.src + (long long)r * job.ld_src + c)) : 0.f;
     }
 }
 
 }  // namespace
+
+int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
+    SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 12, kErrBadArg, "round_copy: %d jobs", jobs.n);
+    round_copy_kernel<<<dim3(74, jobs.n), 256, 0, stream>>>(jobs);
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     SCAT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, kErrBadArg, "gemm: bad shape %d %d %d", g.M, g.N, g.K);
@@ -142,20 +165,34 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
         SCAT_REQUIRE(g.aux_in != nullptr, kErrBadArg, "gemm: epilogue %d needs aux_in", g.epilogue);
     if (g.epilogue == EPI_BIAS_GELU)
         SCAT_REQUIRE(g.aux_out != nullptr, kErrBadArg, "gemm: epilogue %d needs aux_out", g.epilogue);
-    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), 1);
+    const int nk = ceil_div(g.K, BK);
+    int splits = 1;
+    if (g.allow_split_k && g.epilogue == EPI_NONE && (int)(grid.x * grid.y) < 74 && nk >= 16) {
+        splits = min(min(32, nk / 4), ceil_div(296, (int)(grid.x * grid.y)));
+        if (splits < 1) splits = 1;
+    }
+    const int kt_per_split = ceil_div(nk, splits);
+    grid.z = ceil_div(nk, kt_per_split);
+    if (grid.z > 1 && !g.accumulate)
+        SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
     const bool a_k = (g.sak == 1) || (g.sam != 1);
     const bool b_k = (g.sbk == 1) || (g.sbn != 1);
-    if (a_k && b_k) gemm_simt_kernel<true, true><<<grid, THREADS, 0, stream>>>(g);
-    else if (a_k && !b_k) gemm_simt_kernel<true, false><<<grid, THREADS, 0, stream>>>(g);
-    else if (!a_k && b_k) gemm_simt_kernel<false, true><<<grid, THREADS, 0, stream>>>(g);
-    else gemm_simt_kernel<false, false><<<grid, THREADS, 0, stream>>>(g);
+    if (a_k && b_k) gemm_simt_kernel<true, true><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
+    else if (a_k && !b_k) gemm_simt_kernel<true, false><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
+    else if (!a_k && b_k) gemm_simt_kernel<false, true><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
+    else gemm_simt_kernel<false, false><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 
 int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream) {
     SCAT_REQUIRE(X && out && M > 0 && N > 0, kErrBadArg, "colsum: bad args");
-    colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, stream>>>(X, ld, M, N, out, accumulate);
+    if (!accumulate) SCAT_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), stream));
+    const int gx = ceil_div(N, 32);
+    int gy = min(ceil_div(M, 8 * 4), max(1, 592 / gx));       // >= 4 rows per thread, ~4 blocks per SM
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(X, ld, M, N, out);
     SCAT_CHECK_LAUNCH();
     return 0;
 }

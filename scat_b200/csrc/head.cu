@@ -4,6 +4,12 @@
 // Transformer.forward (vision_transformer.py:97-101); the backward is the autograd graph of that code
 // written out by hand.  All activations needed by the backward live in a
 // caller-owned workspace laid out by HeadPlan; nothing here allocates or synchronises.
+//
+// Precision plan (desc.precision != FP32): the large GEMMs run on tcgen05 kind::tf32.  The tensor core
+// truncates fp32 operands, so every tensor that FEEDS a tensor-core GEMM is stored already rounded to
+// TF32-nearest by the kernel that produces it (LayerNorm, attention, GELU / dGELU epilogues, LayerNorm
+// backward) and the GEMM weights get a rounded (and 16-byte-padded) copy once per forward.  The regressor,
+// the last feed-forward (196->147->3) and the conv front end stay fp32.
 #include <stdarg.h>
 
 #include "../../include/scat_b200.h"
@@ -23,7 +29,9 @@ const char* last_error() { return g_err; }
 unsigned long long g_launch_count = 0;
 
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
-    if (precision != PREC_FP32 && gemm_tc_supported(g)) return launch_gemm_tc(g, precision, stream);
+    // tiny problems (regressor / N=3 grads) stay on the FFMA kernel: a 128-row tensor tile would be mostly padding
+    if (precision != PREC_FP32 && (long long)g.M * g.N * g.K >= (1LL << 22) && gemm_tc_supported(g))
+        return launch_gemm_tc(g, precision, stream);
     return launch_gemm_simt(g, stream);
 }
 
@@ -42,10 +50,13 @@ enum ParamIdx {
     P_REG_W = 33, P_REG_B = 34,
 };
 inline int layer_base(int l) { return 2 + 11 * l; }
+inline int pad4(int x) { return (x + 3) / 4 * 4; }
 
 struct LayerPlan {
     int d, hid, out, ldh;
     size_t X, Na, mean_a, rstd_a, QKV, P, O, X1, Nf, mean_f, rstd_f, Z, H;   // float offsets
+    size_t w_qkv, w_out, w_fc1, w_fc2;   // TF32-rounded weight copies (tensor-core layers only)
+    int ld_qkv, ld_out, ld_fc1, ld_fc2;  // their leading dimensions (padded to 4 floats)
     bool last;
     int p_na_w, p_na_b, p_qkv, p_out_w, p_out_b, p_nf_w, p_nf_b, p_fc1_w, p_fc1_b, p_fc2_w, p_fc2_b;
 };
@@ -54,7 +65,7 @@ struct HeadPlan {
     int B, T, C, D, heads, inner, M, it, F, NP;
     LayerPlan L[kDepth];
     size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dX, dFv, conv_scratch, pl_scratch,
-        g_pred, ones, total;
+        g_pred, ones, hreg, total;
 };
 
 size_t take(size_t& cur, size_t n) {
@@ -78,7 +89,7 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     for (int l = 0; l < kDepth; ++l) {
         LayerPlan& L = p.L[l];
         L.last = (l == kDepth - 1);
-        L.d = dim; L.hid = (dim * 3) / 4; L.out = L.last ? 3 : dim / 2; L.ldh = (L.hid + 3) / 4 * 4;
+        L.d = dim; L.hid = (dim * 3) / 4; L.out = L.last ? 3 : dim / 2; L.ldh = pad4(L.hid);
         ldh_max = L.ldh > ldh_max ? L.ldh : ldh_max;
         L.X = take(cur, M * dim);
         L.Na = take(cur, M * dim);
@@ -91,6 +102,15 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
         else { L.Nf = L.X1; L.mean_f = L.rstd_f = 0; }
         L.Z = take(cur, M * L.ldh);
         L.H = take(cur, M * L.ldh);
+        L.ld_qkv = pad4(dim); L.ld_out = p.inner; L.ld_fc1 = pad4(dim); L.ld_fc2 = pad4(L.hid);
+        L.w_qkv = take(cur, (size_t)3 * p.inner * L.ld_qkv);
+        L.w_out = take(cur, (size_t)dim * L.ld_out);
+        if (!L.last) {
+            L.w_fc1 = take(cur, (size_t)L.hid * L.ld_fc1);
+            L.w_fc2 = take(cur, (size_t)L.out * L.ld_fc2);
+        } else {
+            L.w_fc1 = L.w_fc2 = 0;
+        }
         const int base = layer_base(l);
         L.p_na_w = base + L_NA_W; L.p_na_b = base + L_NA_B; L.p_qkv = base + L_QKV_W; L.p_out_w = base + L_OUT_W;
         L.p_out_b = base + L_OUT_B;
@@ -111,6 +131,7 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     p.dfeat = take(cur, M * 3);
     p.ones = take(cur, M * 3);
     p.g_pred = take(cur, (size_t)p.B * NP);
+    p.hreg = take(cur, (size_t)p.B * NP);
     p.dZ = take(cur, M * ldh_max);
     p.dNf = take(cur, M * dmax);
     p.dX1 = take(cur, M * dmax);
@@ -140,40 +161,78 @@ __global__ void token_mean_kernel(const float* __restrict__ X, float* __restrict
     out[b * 3 + c] = s / (float)n;
 }
 
+// Weight views used by the GEMMs of one layer: the caller's fp32 tensors, or the rounded/padded copies.
+struct LayerW {
+    const float *qkv, *out, *fc1, *fc2;
+    int ld_qkv, ld_out, ld_fc1, ld_fc2;
+};
+LayerW layer_weights(const HeadPlan& p, int l, const float* const* W, const float* ws, int prec) {
+    const LayerPlan& L = p.L[l];
+    LayerW w;
+    const bool tc = prec != PREC_FP32;
+    w.qkv = tc ? ws + L.w_qkv : W[L.p_qkv];   w.ld_qkv = tc ? L.ld_qkv : L.d;
+    w.out = tc ? ws + L.w_out : W[L.p_out_w]; w.ld_out = tc ? L.ld_out : p.inner;
+    const bool tc_ff = tc && !L.last;         // last feed-forward stays fp32 on the caller's weights
+    w.fc1 = tc_ff ? ws + L.w_fc1 : W[L.p_fc1_w]; w.ld_fc1 = tc_ff ? L.ld_fc1 : L.d;
+    w.fc2 = tc_ff ? ws + L.w_fc2 : W[L.p_fc2_w]; w.ld_fc2 = tc_ff ? L.ld_fc2 : L.hid;
+    return w;
+}
+
+// one launch: TF32-round (and pad the leading dimension of) every weight a tensor-core GEMM reads
+int round_weights(const HeadPlan& p, const float* const* W, float* ws, cudaStream_t st) {
+    RoundJobs jobs;
+    int n = 0;
+    for (int l = 0; l < kDepth; ++l) {
+        const LayerPlan& L = p.L[l];
+        jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, L.ld_qkv};
+        jobs.job[n++] = RoundJob{W[L.p_out_w], ws + L.w_out, L.d, p.inner, p.inner, L.ld_out};
+        if (!L.last) {
+            jobs.job[n++] = RoundJob{W[L.p_fc1_w], ws + L.w_fc1, L.hid, L.d, L.d, L.ld_fc1};
+            jobs.job[n++] = RoundJob{W[L.p_fc2_w], ws + L.w_fc2, L.out, L.hid, L.hid, L.ld_fc2};
+        }
+    }
+    jobs.n = n;
+    return launch_round_copy(jobs, st);
+}
+
 // ---- forward through the transformer (vision_transformer.py:97-101) --------------------------------
 int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st,
                         float* X0_override) {
     const int M = p.M;
+    const int tc = prec != PREC_FP32;
+    if (tc) SCAT_PROPAGATE(round_weights(p, W, ws, st));
     for (int l = 0; l < kDepth; ++l) {
         const LayerPlan& L = p.L[l];
+        const LayerW w = layer_weights(p, l, W, ws, prec);
         float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         // PreNorm + Attention + Residual (:18,:26,:59-79)
         SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, L.d, ws + L.mean_a,
-                                            ws + L.rstd_a, M, L.d, st));
+                                            ws + L.rstd_a, M, L.d, tc, st));
         GemmArgs g;
-        g.A = ws + L.Na; g.sam = L.d; g.sak = 1; g.B = W[L.p_qkv]; g.sbn = L.d; g.sbk = 1;
-        g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d;
+        g.A = ws + L.Na; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1;
+        g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, st));
+        SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, tc, st));
         g = GemmArgs();
-        g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = W[L.p_out_w]; g.sbn = p.inner; g.sbk = 1;
-        g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner;
+        g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1;
+        g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
         g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // (PreNorm +) FeedForward, no residual (:44,:94 / :89)
         if (!L.last)
             SCAT_PROPAGATE(launch_layernorm_fwd(ws + L.X1, L.d, W[L.p_nf_w], W[L.p_nf_b], ws + L.Nf, L.d,
-                                                ws + L.mean_f, ws + L.rstd_f, M, L.d, st));
+                                                ws + L.mean_f, ws + L.rstd_f, M, L.d, tc, st));
         const int ffprec = L.last ? PREC_FP32 : prec;   // last FF stays fp32
+        const int fftc = ffprec != PREC_FP32;
         g = GemmArgs();
-        g.A = ws + L.Nf; g.sam = L.d; g.sak = 1; g.B = W[L.p_fc1_w]; g.sbn = L.d; g.sbk = 1;
-        g.C = ws + L.H; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.d;
+        g.A = ws + L.Nf; g.sam = L.d; g.sak = 1; g.B = w.fc1; g.sbn = w.ld_fc1; g.sbk = 1;
+        g.C = ws + L.H; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.d; g.prerounded = fftc; g.round_out = fftc;
         g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
         g = GemmArgs();
-        g.A = ws + L.H; g.sam = L.ldh; g.sak = 1; g.B = W[L.p_fc2_w]; g.sbn = L.hid; g.sbk = 1;
-        g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid;
+        g.A = ws + L.H; g.sam = L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1;
+        g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid; g.prerounded = fftc;
         g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
     }
@@ -181,79 +240,84 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 }
 
 // ---- reverse sweep: d/dX0 of <up, feat_out>, optionally with parameter gradients ---------------------
-// up: [M,3] cotangent of the transformer output.  Result lands in ws + p.dX ([M, D]).
+// up: [M,3] cotangent of the transformer output.  Result lands in ws + p.dX ([M, D]).  Uses the rounded weight
+// copies left in the workspace by transformer_forward.
 int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
                          int prec, const float* up, cudaStream_t st, const float* X0_override) {
     const int M = p.M;
+    const int tc = prec != PREC_FP32;
     const float* dY = up;
     for (int l = kDepth - 1; l >= 0; --l) {
         const LayerPlan& L = p.L[l];
+        const LayerW w = layer_weights(p, l, W, ws, prec);
         const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         const int ffprec = L.last ? PREC_FP32 : prec;
+        const int fftc = ffprec != PREC_FP32;
         GemmArgs g;
         if (G) {
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
             g.A = dY; g.sam = 1; g.sak = L.out; g.B = ws + L.H; g.sbn = 1; g.sbk = L.ldh;
-            g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M;
+            g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.prerounded = fftc;
             SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
             SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 0, st));
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
-        g.A = dY; g.sam = L.out; g.sak = 1; g.B = W[L.p_fc2_w]; g.sbn = 1; g.sbk = L.hid;
-        g.C = ws + p.dZ; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.out;
+        g.A = dY; g.sam = L.out; g.sak = 1; g.B = w.fc2; g.sbn = 1; g.sbk = w.ld_fc2;
+        g.C = ws + p.dZ; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.out; g.prerounded = fftc; g.round_out = fftc;
         g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         if (G) {
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             g = GemmArgs();
             g.A = ws + p.dZ; g.sam = 1; g.sak = L.ldh; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.d;
-            g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M;
+            g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.prerounded = fftc;
             SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
             SCAT_PROPAGATE(launch_colsum(ws + p.dZ, L.ldh, M, L.hid, G[L.p_fc1_b], 0, st));
         }
-        // dNf = dZ W1
+        // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs: round it)
         g = GemmArgs();
-        g.A = ws + p.dZ; g.sam = L.ldh; g.sak = 1; g.B = W[L.p_fc1_w]; g.sbn = 1; g.sbk = L.d;
-        g.C = ws + p.dNf; g.ldc = L.d; g.M = M; g.N = L.d; g.K = L.hid;
+        g.A = ws + p.dZ; g.sam = L.ldh; g.sak = 1; g.B = w.fc1; g.sbn = 1; g.sbk = w.ld_fc1;
+        g.C = ws + p.dNf; g.ldc = L.d; g.M = M; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
+        g.round_out = (L.last && tc) ? 1 : 0;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         const float* dX1 = ws + p.dNf;
         if (!L.last) {
             SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
                                                 ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d,
-                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, M, L.d, st));
+                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, M, L.d, tc, st));
             dX1 = ws + p.dX1;
         }
         if (G) {
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1)
             g = GemmArgs();
             g.A = dX1; g.sam = 1; g.sak = L.d; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner;
-            g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M;
+            g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
             SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 0, st));
         }
         // dO = dX1 Wo
         g = GemmArgs();
-        g.A = dX1; g.sam = L.d; g.sak = 1; g.B = W[L.p_out_w]; g.sbn = 1; g.sbk = p.inner;
-        g.C = ws + p.dO; g.ldc = p.inner; g.M = M; g.N = p.inner; g.K = L.d;
+        g.A = dX1; g.sam = L.d; g.sak = 1; g.B = w.out; g.sbn = 1; g.sbk = w.ld_out;
+        g.C = ws + p.dO; g.ldc = p.inner; g.M = M; g.N = p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B, p.T, p.heads, st));
+        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B, p.T, p.heads, tc, st));
         if (G) {
             // dWqkv[3inner,d] = dQKV^T Na
             g = GemmArgs();
             g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = L.d;
-            g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M;
+            g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
         }
         // dNa = dQKV Wqkv
         g = GemmArgs();
-        g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = W[L.p_qkv]; g.sbn = 1; g.sbk = L.d;
-        g.C = ws + p.dNa; g.ldc = L.d; g.M = M; g.N = L.d; g.K = 3 * p.inner;
+        g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv;
+        g.C = ws + p.dNa; g.ldc = L.d; g.M = M; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18)
+        // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs
         SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
                                             L.d, ws + p.dX, L.d, G ? G[L.p_na_w] : nullptr,
-                                            G ? G[L.p_na_b] : nullptr, M, L.d, st));
+                                            G ? G[L.p_na_b] : nullptr, M, L.d, (tc && l > 0) ? 1 : 0, st));
         dY = ws + p.dX;
     }
     return 0;
@@ -285,7 +349,7 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
                                            X0, p.B, p.C, p.D, p.T, st));
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
     SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
-                                        ws + p.states, p.B, p.F, p.NP, p.it, 1, st));
+                                        ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st));
     if (d.pl_reg) {
         // autograd.grad(sum(feat_out), feat_visual) (hand_net.py:396): dgrad-only sweep with a ones cotangent
         fill_kernel<<<64, 256, 0, st>>>(ws + p.ones, 1.0f, (long long)p.M * 3);
@@ -313,12 +377,12 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         const int ldw = p.F + p.NP;
         GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
         g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
-        g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B;
+        g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1;
         SCAT_PROPAGATE(launch_gemm_simt(g, st));
         if (p.it > 0) {   // dWr[:, F:] = sum over samples and steps of g_step (x) state
             g = GemmArgs();
             g.A = ws + p.gsteps; g.sam = 1; g.sak = p.NP; g.B = ws + p.states; g.sbn = 1; g.sbk = p.NP;
-            g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it;
+            g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it; g.allow_split_k = 1;
             SCAT_PROPAGATE(launch_gemm_simt(g, st));
         } else {
             SCAT_CHECK_CUDA(cudaMemset2DAsync(G[P_REG_W] + p.F, ldw * sizeof(float), 0, p.NP * sizeof(float), p.NP, st));
@@ -338,7 +402,6 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, ws + p.dfeat, st, d.pos_embed ? nullptr : fv_alias));
     // through masking / positional encoding into the conv output
     SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st));
-    if (d.n_masked == 0) SCAT_CHECK_CUDA(cudaMemsetAsync(G[P_MASK_TOKEN], 0, p.D * sizeof(float), st));
     if (g_fv != nullptr) {
         add_inplace_kernel<<<148 * 4, 256, 0, st>>>(ws + p.dFv, g_fv, (long long)p.M * p.D);
         SCAT_CHECK_LAUNCH();
@@ -444,7 +507,7 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
     if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
     SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
                  "scat_gemm: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
-    return launch_gemm_tc(g, precision, (cudaStream_t)stream);
+    return launch_gemm_tc(g, precision, (cudaStream_t)stream);   // operands rounded to TF32-nearest inside the kernel
 }
 
 int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
@@ -472,7 +535,7 @@ int scat_conv_bwd(const float* d_tokens, const float* x2, const float* conv_w, c
 
 int scat_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
                        int32_t rows, int32_t dim, void* stream) {
-    return launch_layernorm_fwd(x, dim, gamma, beta, y, dim, mean, rstd, rows, dim, (cudaStream_t)stream);
+    return launch_layernorm_fwd(x, dim, gamma, beta, y, dim, mean, rstd, rows, dim, 0, (cudaStream_t)stream);
 }
 
 int scat_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
@@ -483,23 +546,23 @@ int scat_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
         SCAT_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, dim * sizeof(float), st));
         SCAT_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, dim * sizeof(float), st));
     }
-    return launch_layernorm_bwd(dy, dim, x, dim, gamma, mean, rstd, resid, dim, dx, dim, dgamma, dbeta, rows, dim, st);
+    return launch_layernorm_bwd(dy, dim, x, dim, gamma, mean, rstd, resid, dim, dx, dim, dgamma, dbeta, rows, dim, 0, st);
 }
 
 int scat_attention_fwd(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream) {
-    return launch_attention_fwd(qkv, o, p, batch, n, heads, (cudaStream_t)stream);
+    return launch_attention_fwd(qkv, o, p, batch, n, heads, 0, (cudaStream_t)stream);
 }
 
 int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
                        int32_t heads, void* stream) {
-    return launch_attention_bwd(qkv, p, d_o, d_qkv, batch, n, heads, (cudaStream_t)stream);
+    return launch_attention_bwd(qkv, p, d_o, d_qkv, batch, n, heads, 0, (cudaStream_t)stream);
 }
 
 int scat_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* w,
-                       const float* b, float* pred, float* states, int32_t batch, int32_t feat_dim, int32_t n_out,
-                       int32_t iteration, int32_t root_relative, void* stream) {
-    return launch_regressor_fwd(main_feat, feat_out, mean_params, w, b, pred, states, batch, feat_dim, n_out, iteration,
-                                root_relative, (cudaStream_t)stream);
+                       const float* b, float* pred, float* states, float* scratch, int32_t batch, int32_t feat_dim,
+                       int32_t n_out, int32_t iteration, int32_t root_relative, void* stream) {
+    return launch_regressor_fwd(main_feat, feat_out, mean_params, w, b, pred, states, scratch, batch, feat_dim, n_out,
+                                iteration, root_relative, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -38,7 +38,20 @@ struct GemmArgs {
     const float* aux_in = nullptr; int ld_aux_in = 0;
     float* aux_out = nullptr; int ld_aux_out = 0;
     int accumulate = 0;  // C += epilogue(...)
+    int allow_split_k = 0;   // FFMA kernel may split K over CTAs and combine with atomics (weight gradients)
+    int prerounded = 0;      // tensor-core kernel: operands are already TF32-representable, skip the in-kernel rounding
+    int round_out = 0;       // store C rounded to TF32 (nearest): it feeds a tensor-core GEMM next
 };
+
+#ifdef __CUDACC__
+// fp32 -> nearest TF32-representable fp32 (10-bit mantissa).  The tensor core truncates, so operands are rounded
+// by whoever produces them (or inside the GEMM kernel when they are not).
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+#endif
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // tcgen05 path; returns kErrUnsupported if the operand strides cannot be expressed as TMA tensor maps
@@ -71,19 +84,25 @@ int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mas
 // LayerNorm (vision_transformer.py:23,26; eps 1e-5, affine)
 // ------------------------------------------------------------------------------------------
 int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
-                         float* mean, float* rstd, int M, int D, cudaStream_t stream);
+                         float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream);
 // dX = LN'(dY) (+ resid); dgamma/dbeta accumulated with atomics when non-null (must be pre-zeroed)
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
-                         float* dbeta, int M, int D, cudaStream_t stream);
+                         float* dbeta, int M, int D, int round_out, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
 // softmax attention over n tokens, heads of 64 (vision_transformer.py:61-77)
 //   QKV [B*n, 3*inner] (q | k | v, head g = columns g*64..g*64+63), O [B*n, inner], P [B,h,n,n]
 // ------------------------------------------------------------------------------------------
-int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, cudaStream_t stream);
-int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                          cudaStream_t stream);
+int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+                         int round_out, cudaStream_t stream);
+// dst[r, c] = round_tf32(src[r, c]) (pad columns zero-filled) for a list of weight matrices, one launch;
+// the job table travels by value as a kernel argument (no device-side table, graph-capturable)
+struct RoundJob { const float* src; float* dst; int rows, cols, ld_src, ld_dst; };
+struct RoundJobs { RoundJob job[12]; int n; };
+int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
 // autoregressive regressor (hand_net.py:379-393) and its backward
@@ -91,8 +110,8 @@ int launch_attention_bwd(const float* QKV, const float* P, const float* dO, floa
 // pred0 = mean + [0,0,0,feat_out]; `iteration` x pred += [mf|pred] Wr^T + br; root-relative joints.
 // states [B, iteration, P] keeps pred before each step (for backward).  P = n_out (66), F = feature width.
 int launch_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* Wr,
-                         const float* br, float* pred, float* states, int B, int F, int P, int iteration,
-                         int root_relative, cudaStream_t stream);
+                         const float* br, float* pred, float* states, float* h_scratch /* [B,P] */, int B, int F, int P,
+                         int iteration, int root_relative, cudaStream_t stream);
 // g_pred [B,P] -> d_feat_out [B,P-3], d_main_feat [B,F] (nullable), gsum [B,P], gsteps [B,iteration,P]
 int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out, float* d_main_feat, float* gsum,
                          float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream);

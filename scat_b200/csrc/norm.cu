@@ -12,7 +12,7 @@ template <int NPL>  // elements per lane (row length <= 32*NPL)
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ Y, int ldy, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int M, int D) {
+                     float* __restrict__ rstd_out, int M, int D, int round_out) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -39,7 +39,10 @@ layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restri
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
         const int c = i * 32 + lane;
-        if (c < D) y[c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+        if (c < D) {
+            const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            y[c] = round_out ? round_tf32(o) : o;
+        }
     }
     if (lane == 0) {
         mean_out[row] = mean;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ resid, int ldr, float* __restrict__ dX, int lddx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D, int round_out) {
     __shared__ float red[LN_WARPS][32 * NPL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float gam[NPL], dg[NPL], db[NPL];
@@ -91,7 +94,7 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
             if (c < D) {
                 float o = rs * (g[i] - s1 - xh[i] * s2);
                 if (resid != nullptr) o += resid[(long long)row * ldr + c];
-                dx[c] = o;
+                dx[c] = round_out ? round_tf32(o) : o;
             }
         }
     }
@@ -120,24 +123,24 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
 }  // namespace
 
 int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
-                         float* mean, float* rstd, int M, int D, cudaStream_t stream) {
+                         float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm: D=%d not in [1,1024]", D);
     const int grid = ceil_div(M, LN_WARPS);
-    if (D <= 256) layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D);
-    else if (D <= 512) layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D);
-    else layernorm_fwd_kernel<32><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D);
+    if (D <= 256) layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out);
+    else if (D <= 512) layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out);
+    else layernorm_fwd_kernel<32><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out);
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
-                         float* dbeta, int M, int D, cudaStream_t stream) {
+                         float* dbeta, int M, int D, int round_out, cudaStream_t stream) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm bwd: D=%d not in [1,1024]", D);
     SCAT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), kErrBadArg, "layernorm bwd: dgamma/dbeta must both be set or null");
     const int grid = min(ceil_div(M, LN_WARPS), 148 * 2);
 #define SCAT_LN_BWD(NPL) layernorm_bwd_kernel<NPL><<<grid, LN_WARPS * 32, 0, stream>>>( \
-        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D)
+        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out)
     if (D <= 256) SCAT_LN_BWD(8);
     else if (D <= 512) SCAT_LN_BWD(16);
     else SCAT_LN_BWD(32);

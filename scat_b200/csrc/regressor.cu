@@ -1,49 +1,87 @@
-// Autoregressive offset regressor of the head (hand_net.py:379-393) as one fused kernel, plus backward.
+// Autoregressive offset regressor of the head (hand_net.py:379-393), fused, plus its backward.
 //
 //   pred = mean_params (broadcast);  pred[3:] += feat_out                        :379-383
 //   repeat `iteration` times:  pred += [main_feat | pred] Wr^T + br              :385-387
 //   joints = pred[3:66] as [21,3];  joints -= joints[1]                          :389-393
 //
-// The product with main_feat is iteration-invariant, so it is computed once per sample
-// (h = Wr[:, :F] main_feat + br, warp-level dot products) and the recurrence only applies the
-// P x P block Wr[:, F:] held in shared memory.  Always fp32: the output error of the whole head is
-// dominated by these K=1024 dot products.
+// The product with main_feat is iteration-invariant, so it is hoisted: h = Wr[:, :F] main_feat + br is
+// computed once (kernel 1: warp-level dot products, 8 samples share every weight row from registers), and the
+// recurrence (kernel 2: one CTA per sample) only applies the P x P block Wr[:, F:] held in shared memory.
+// Always fp32: the output error of the whole head is dominated by these K=1024 dot products.
 // Also used with root_relative=0, P=61, F=1024 for the H3DWEncoder regressor (hand_net.py:53-57).
 #include "kernels.h"
 
 namespace scat {
 namespace {
 
-constexpr int REG_THREADS = 256;
 constexpr int MAXP = 96;
+constexpr int HS = 8;              // samples per CTA in the hoist kernel
+constexpr int HJ = 8;              // weight rows per CTA (one per warp)
 
-__global__ void __launch_bounds__(REG_THREADS)
-regressor_fwd_kernel(const float* __restrict__ main_feat, const float* __restrict__ feat_out,
-                     const float* __restrict__ mean_params, const float* __restrict__ Wr, const float* __restrict__ br,
-                     float* __restrict__ pred, float* __restrict__ states, int F, int P, int iteration,
-                     int root_relative) {
+// h[b,j] = br[j] + sum_k Wr[j,k] mf[b,k],  k < F.   grid (ceil(B/HS), ceil(P/HJ)), 256 threads
+__global__ void __launch_bounds__(256)
+regressor_hoist_kernel(const float* __restrict__ main_feat, const float* __restrict__ Wr, const float* __restrict__ br,
+                       float* __restrict__ h, int B, int F, int P) {
+    extern __shared__ __align__(16) float mfs[];   // [HS][F]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = blockIdx.x * HS, j = blockIdx.y * HJ + warp;
+    const int ns = min(HS, B - b0);
+    for (int i = tid; i < HS * (F >> 1); i += 256) {
+        const int s = i / (F >> 1), k2 = i % (F >> 1);
+        reinterpret_cast<float2*>(mfs)[i] = s < ns ? __ldg(reinterpret_cast<const float2*>(main_feat + (long long)(b0 + s) * F) + k2)
+                                                   : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    if (j >= P) return;
+    const int ldw = F + P;
+    float acc[HS];
+#pragma unroll
+    for (int s = 0; s < HS; ++s) acc[s] = 0.f;
+    if ((ldw & 1) == 0) {                   // rows 8-byte aligned (EncoderTransformer: 1090): float2 loads
+        const float2* w = reinterpret_cast<const float2*>(Wr + (long long)j * ldw);
+        for (int k2 = lane; k2 < (F >> 1); k2 += 32) {
+            const float2 wv = __ldg(w + k2);
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                const float2 m = reinterpret_cast<const float2*>(mfs + s * F)[k2];
+                acc[s] = fmaf(wv.x, m.x, acc[s]);
+                acc[s] = fmaf(wv.y, m.y, acc[s]);
+            }
+        }
+    } else {                                // odd leading dimension (H3DWEncoder: 1085): scalar loads
+        const float* w = Wr + (long long)j * ldw;
+        for (int k = lane; k < F; k += 32) {
+            const float wv = __ldg(w + k);
+#pragma unroll
+            for (int s = 0; s < HS; ++s) acc[s] = fmaf(wv, mfs[s * F + k], acc[s]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < HS; ++s) acc[s] = warp_sum(acc[s]);
+    if (lane == 0) {
+        const float bj = br[j];
+        for (int s = 0; s < ns; ++s) h[(long long)(b0 + s) * P + j] = acc[s] + bj;
+    }
+}
+
+// recurrence + root-relative step; one CTA per sample, 128 threads
+__global__ void __launch_bounds__(128)
+regressor_iter_kernel(const float* __restrict__ h_all, const float* __restrict__ feat_out,
+                      const float* __restrict__ mean_params, const float* __restrict__ Wr, float* __restrict__ pred,
+                      float* __restrict__ states, int F, int P, int iteration, int root_relative) {
     extern __shared__ float sm[];
-    float* mf = sm;                    // [F]
-    float* Wp = mf + F;                // [P][P+1]
+    float* Wp = sm;                    // [P][P+1]
     float* h = Wp + P * (P + 1);       // [P]
     float* p = h + P;                  // [P]
     float* pn = p + P;                 // [P]
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int ldw = F + P;
-    for (int k = tid; k < F; k += REG_THREADS) mf[k] = main_feat[(long long)b * F + k];
-    for (int i = tid; i < P * P; i += REG_THREADS) Wp[(i / P) * (P + 1) + (i % P)] = Wr[(long long)(i / P) * ldw + F + (i % P)];
+    for (int i = tid; i < P * P; i += 128) Wp[(i / P) * (P + 1) + (i % P)] = __ldg(Wr + (long long)(i / P) * ldw + F + (i % P));
     if (tid < P) {
         float v = mean_params[tid];
         if (feat_out != nullptr && tid >= 3) v += feat_out[(long long)b * (P - 3) + tid - 3];
         p[tid] = v;
-    }
-    __syncthreads();
-    for (int j = warp; j < P; j += REG_THREADS / 32) {
-        const float* w = Wr + (long long)j * ldw;
-        float s = 0.f;
-        for (int k = lane; k < F; k += 32) s = fmaf(w[k], mf[k], s);
-        s = warp_sum(s);
-        if (lane == 0) h[j] = s + br[j];
+        h[tid] = h_all[(long long)b * P + tid];
     }
     __syncthreads();
     for (int it = 0; it < iteration; ++it) {
@@ -64,23 +102,21 @@ regressor_fwd_kernel(const float* __restrict__ main_feat, const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(REG_THREADS)
-regressor_bwd_kernel(const float* __restrict__ g_pred, const float* __restrict__ Wr, float* __restrict__ d_feat_out,
-                     float* __restrict__ d_main_feat, float* __restrict__ gsum_out, float* __restrict__ gsteps, int F,
-                     int P, int iteration, int root_relative) {
+// reverse recurrence: g_pred -> gsum (sum over steps of the per-step output gradient), gsteps, d feat_out
+__global__ void __launch_bounds__(128)
+regressor_iter_bwd_kernel(const float* __restrict__ g_pred, const float* __restrict__ Wr, float* __restrict__ d_feat_out,
+                          float* __restrict__ gsum_out, float* __restrict__ gsteps, int F, int P, int iteration,
+                          int root_relative) {
     extern __shared__ float sm[];
     float* Wp = sm;                    // [P][P+1]
     float* g = Wp + P * (P + 1);       // [P]
     float* gn = g + P;                 // [P]
-    float* gsum = gn + P;              // [P]
-    float* rootg = gsum + P;           // [3]
+    float* rootg = gn + P;             // [3]
     const int b = blockIdx.x, tid = threadIdx.x;
     const int ldw = F + P;
-    for (int i = tid; i < P * P; i += REG_THREADS) Wp[(i / P) * (P + 1) + (i % P)] = Wr[(long long)(i / P) * ldw + F + (i % P)];
-    if (tid < P) {
-        g[tid] = g_pred[(long long)b * P + tid];
-        gsum[tid] = 0.f;
-    }
+    for (int i = tid; i < P * P; i += 128) Wp[(i / P) * (P + 1) + (i % P)] = __ldg(Wr + (long long)(i / P) * ldw + F + (i % P));
+    float gsum = 0.f;
+    if (tid < P) g[tid] = g_pred[(long long)b * P + tid];
     __syncthreads();
     if (root_relative) {
         if (tid < 3) {
@@ -95,7 +131,7 @@ regressor_bwd_kernel(const float* __restrict__ g_pred, const float* __restrict__
     for (int it = iteration - 1; it >= 0; --it) {
         if (tid < P) {
             gsteps[((long long)b * iteration + it) * P + tid] = g[tid];
-            gsum[tid] += g[tid];
+            gsum += g[tid];
             float s = g[tid];
             for (int j = 0; j < P; ++j) s = fmaf(Wp[j * (P + 1) + tid], g[j], s);   // (I + Wp^T) g
             gn[tid] = s;
@@ -105,30 +141,28 @@ regressor_bwd_kernel(const float* __restrict__ g_pred, const float* __restrict__
         __syncthreads();
     }
     if (tid < P) {
-        gsum_out[(long long)b * P + tid] = gsum[tid];
+        gsum_out[(long long)b * P + tid] = gsum;
         if (d_feat_out != nullptr && tid >= 3) d_feat_out[(long long)b * (P - 3) + tid - 3] = g[tid];
-    }
-    if (d_main_feat != nullptr) {
-        for (int k = tid; k < F; k += REG_THREADS) {
-            float s = 0.f;
-            for (int j = 0; j < P; ++j) s = fmaf(Wr[(long long)j * ldw + k], gsum[j], s);
-            d_main_feat[(long long)b * F + k] = s;
-        }
     }
 }
 
 }  // namespace
 
 int launch_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* Wr,
-                         const float* br, float* pred, float* states, int B, int F, int P, int iteration,
-                         int root_relative, cudaStream_t stream) {
-    SCAT_REQUIRE(P >= 4 && P <= MAXP && F >= 1 && F <= 4096, kErrUnsupported, "regressor: P=%d F=%d out of range", P, F);
+                         const float* br, float* pred, float* states, float* h_scratch, int B, int F, int P,
+                         int iteration, int root_relative, cudaStream_t stream) {
+    SCAT_REQUIRE(P >= 4 && P <= MAXP && F >= 2 && F <= 4096 && (F & 1) == 0, kErrUnsupported,
+                 "regressor: P=%d F=%d out of range (F even, P<=96, F<=4096)", P, F);
     SCAT_REQUIRE(!root_relative || (P - 3) % 3 == 0, kErrBadArg, "regressor: root_relative needs P=3+3k");
-    const size_t smem = sizeof(float) * ((size_t)F + (size_t)P * (P + 1) + 3 * (size_t)P);
-    if (smem > 48 * 1024)
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(regressor_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    regressor_fwd_kernel<<<B, REG_THREADS, smem, stream>>>(main_feat, feat_out, mean_params, Wr, br, pred, states, F, P,
-                                                          iteration, root_relative);
+    SCAT_REQUIRE(h_scratch != nullptr, kErrBadArg, "regressor: h scratch [B,P] required");
+    const size_t smem1 = sizeof(float) * (size_t)HS * F;
+    if (smem1 > 48 * 1024)
+        SCAT_CHECK_CUDA(cudaFuncSetAttribute(regressor_hoist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    regressor_hoist_kernel<<<dim3(ceil_div(B, HS), ceil_div(P, HJ)), 256, smem1, stream>>>(main_feat, Wr, br, h_scratch, B, F, P);
+    SCAT_CHECK_LAUNCH();
+    const size_t smem2 = sizeof(float) * ((size_t)P * (P + 1) + 3 * (size_t)P);
+    regressor_iter_kernel<<<B, 128, smem2, stream>>>(h_scratch, feat_out, mean_params, Wr, pred, states, F, P, iteration,
+                                                    root_relative);
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -137,10 +171,15 @@ int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out
                          float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream) {
     SCAT_REQUIRE(P >= 4 && P <= MAXP, kErrUnsupported, "regressor bwd: P=%d out of range", P);
     SCAT_REQUIRE(gsum && gsteps, kErrBadArg, "regressor bwd: gsum/gsteps scratch required");
-    const size_t smem = sizeof(float) * ((size_t)P * (P + 1) + 3 * (size_t)P + 4);
-    regressor_bwd_kernel<<<B, REG_THREADS, smem, stream>>>(g_pred, Wr, d_feat_out, d_main_feat, gsum, gsteps, F, P,
-                                                          iteration, root_relative);
+    const size_t smem = sizeof(float) * ((size_t)P * (P + 1) + 2 * (size_t)P + 4);
+    regressor_iter_bwd_kernel<<<B, 128, smem, stream>>>(g_pred, Wr, d_feat_out, gsum, gsteps, F, P, iteration, root_relative);
     SCAT_CHECK_LAUNCH();
+    if (d_main_feat != nullptr) {
+        GemmArgs g;   // d main_feat[B,F] = gsum[B,P] Wr[:, :F]
+        g.A = gsum; g.sam = P; g.sak = 1; g.B = Wr; g.sbn = 1; g.sbk = F + P;
+        g.C = d_main_feat; g.ldc = F; g.M = B; g.N = F; g.K = P;
+        SCAT_PROPAGATE(launch_gemm_simt(g, stream));
+    }
     return 0;
 }
 

@@ -258,7 +258,8 @@ def regressor_fwd(main_feat, feat_out, mean_params, w, b, iteration=3, root_rela
     P = w.shape[0]
     pred = torch.empty(B, P, device=main_feat.device)
     states = torch.empty(B, max(iteration, 1), P, device=main_feat.device) if keep_states else None
+    scratch = torch.empty(B, P, device=main_feat.device)
     check(lib.scat_regressor_fwd(ptr(main_feat), ptr(feat_out), ptr(_f32c(mean_params, "mean_params")),
-                                 ptr(_f32c(w, "w")), ptr(_f32c(b, "b")), ptr(pred), ptr(states), B, F, P, iteration,
-                                 int(root_relative), stream_ptr()), "scat_regressor_fwd")
+                                 ptr(_f32c(w, "w")), ptr(_f32c(b, "b")), ptr(pred), ptr(states), ptr(scratch), B, F, P,
+                                 iteration, int(root_relative), stream_ptr()), "scat_regressor_fwd")
     return (pred, states) if keep_states else pred

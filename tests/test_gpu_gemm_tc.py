@@ -1,0 +1,81 @@
+"""GPU: the tcgen05/TMEM/TMA TF32 GEMM against float64, all operand layouts and epilogues.
+
+TF32 keeps 10 mantissa bits (the tensor core truncates the fp32 operands), so a K-long dot product of O(1)
+values carries ~1e-3 relative error w.r.t. the largest output: tolerance 3e-3 of max|ref|, and the result must
+agree with the fp32 FFMA kernel of the same library to the same bound."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-3
+
+
+def _mk(M, N, K, a, b, seed=1):
+    g = np.random.Generator(np.random.PCG64(seed))
+    A = torch.from_numpy(g.standard_normal((M, K)).astype(np.float32))
+    B = torch.from_numpy(g.standard_normal((N, K)).astype(np.float32))
+    Ad = A.cuda() if a == "k" else A.t().contiguous().cuda()
+    Bd = B.cuda() if b == "k" else B.t().contiguous().cuda()
+    return A, B, Ad, Bd, ((K, 1) if a == "k" else (1, M)), ((K, 1) if b == "k" else (1, N))
+
+
+def _err(x, ref):
+    return float((x.double().cpu() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K,a,b", [
+    (128, 64, 32, "k", "k"), (2016, 1536, 784, "k", "k"), (2016, 392, 588, "k", "k"), (2016, 588, 784, "k", "k"),
+    (2016, 784, 512, "k", "mn"), (2016, 392, 1536, "k", "mn"), (2016, 588, 392, "k", "mn"),
+    (1536, 784, 2016, "mn", "mn"), (588, 784, 2016, "mn", "mn"), (196, 294, 2016, "mn", "mn"),
+    (300, 200, 100, "mn", "k"), (1, 8, 8, "k", "k"), (129, 65, 33, "k", "k"), (4032, 1536, 196, "k", "k"),
+])
+def test_tc_gemm_layouts(M, N, K, a, b):
+    from scat_b200 import functional as SF
+    A, B, Ad, Bd, sa, sb = _mk(M, N, K, a, b)
+    if a == "mn" and M % 4 or b == "mn" and N % 4 or a == "k" and K % 4 or b == "k" and K % 4:
+        with pytest.raises(RuntimeError, match="TMA"):          # not expressible as a tensor map: refused, no fallback
+            SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="tf32")
+        return
+    ref = A.double() @ B.double().t()
+    out = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="tf32")
+    assert _err(out, ref) < TOL
+    simt = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="fp32")
+    assert _err(out, simt.double().cpu()) < TOL
+
+
+def test_tc_gemm_epilogues_and_padded_ld():
+    from scat_b200 import functional as SF
+    M, N, K = 2016, 294, 392                       # fc1 of layer 1: hidden 294 lives in a ld=296 buffer
+    A, B, Ad, Bd, sa, sb = _mk(M, N, K, "k", "k", seed=3)
+    g = np.random.Generator(np.random.PCG64(9))
+    bias = torch.from_numpy(g.standard_normal(N).astype(np.float32))
+    res = torch.from_numpy(g.standard_normal((M, 296)).astype(np.float32))
+    ref = A.double() @ B.double().t()
+    out = torch.zeros(M, 296, device="cuda")
+    y, z = SF.gemm(Ad, Bd, epilogue="bias_gelu", bias=bias.cuda(), precision="tf32", out=out[:, :N])
+    assert _err(z[:, :N], ref + bias.double()) < TOL and _err(y[:, :N], F.gelu(ref + bias.double())) < TOL
+    assert torch.all(out[:, N:] == 0)                                            # pad columns untouched
+    r = SF.gemm(Ad, Bd, epilogue="bias_resid", bias=bias.cuda(), aux_in=res.cuda()[:, :N], precision="tf32")
+    assert _err(r, ref + bias.double() + res[:, :N].double()) < TOL
+    zz = res.double()[:, :N].requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    d = SF.gemm(Ad, Bd, epilogue="dgelu", aux_in=res.cuda()[:, :N], precision="tf32")
+    assert _err(d, ref * zz.grad) < TOL
+    acc = torch.ones(M, N, device="cuda")
+    SF.gemm(Ad, Bd, precision="tf32", out=acc, accumulate=True)
+    assert _err(acc, ref + 1.0) < TOL
+
+
+def test_tc_gemm_is_linear_and_exact_on_tf32_representable_inputs():
+    """Size-independent property: with inputs that are exactly representable in TF32 (small integers) the
+    tensor-core result is bit-exact against integer arithmetic."""
+    from scat_b200 import functional as SF
+    g = np.random.Generator(np.random.PCG64(4))
+    M, N, K = 2016, 1536, 784
+    A = torch.from_numpy(g.integers(-8, 9, (M, K)).astype(np.float32))
+    B = torch.from_numpy(g.integers(-8, 9, (N, K)).astype(np.float32))
+    ref = (A.double() @ B.double().t()).float()
+    out = SF.gemm(A.cuda(), B.cuda(), precision="tf32")
+    assert torch.equal(out.cpu(), ref)
