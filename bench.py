@@ -176,6 +176,117 @@ def time_kernel(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
+def graph_time(fn, it=10, reps=5):
+    """Average device time of fn() replayed from a CUDA graph (host launch cost excluded, L2 warm like in-step)."""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(it):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * it) * 1e-3
+
+
+def step_gemm_table(M, heads=8, pl_reg=True):
+    """(M, N, K, layout, launches per step) of every tensor-core GEMM of one train step (csrc/head.cu)."""
+    inner, dims = 64 * heads, synth.layer_dims()
+    sweeps = 2 if pl_reg else 1                      # dgrad chain runs for the path-length VJP and for the backward
+    t = []
+    for l, (d, hid, out) in enumerate(dims):
+        last = l == len(dims) - 1
+        t += [(M, 3 * inner, d, "nt", 1), (M, d, inner, "nt", 1)]
+        t += [(M, inner, d, "nn", sweeps), (M, d, 3 * inner, "nn", sweeps)]
+        t += [(d, inner, M, "tn", 1), (3 * inner, d, M, "tn", 1)]
+        if not last:                                 # last feed-forward stays fp32 FFMA
+            t += [(M, hid, d, "nt", 1), (M, out, hid, "nt", 1)]
+            t += [(M, hid, out, "nn", sweeps), (M, d, hid, "nn", sweeps)]
+            t += [(out, hid, M, "tn", 1), (hid, d, M, "tn", 1)]
+    return t
+
+
+def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
+    from scat_b200 import functional as SF
+    from scat_b200._lib import ptr, check, stream_ptr
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+
+    def dram(name):
+        t = traffic.get(name)
+        return None if not t else t["dram_read"] + t["dram_write"]
+
+    # --- HBM-bound front end: conv kernels, timed live with CUDA events (inputs 154 MB > L2) ---
+    x2d = ts.x2
+    W = net.head_parameters()
+    pe = net.positionalEncoding.pe[0]
+    idx = ts.mask_dev[: ts.n_masked]
+    cw = W[1].data.view(21, 512)
+    dtok = torch.randn(B, 21, 784, device=dev)
+    t_fwd = time_kernel(lambda: SF.conv_pe_mask_fwd(x2d, cw, pe, W[0].data.view(-1), idx, True))
+    scratch = torch.empty(lib.scat_conv_bwd_scratch_floats(B, 512, 784, 21), device=dev)
+    x2g, wg, mg = torch.empty_like(x2d), torch.empty(21, 512, device=dev), torch.empty(784, device=dev)
+
+    def conv_bwd():
+        check(lib.scat_conv_bwd(ptr(dtok), ptr(x2d), ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
+                                ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd")
+    t_bwd = time_kernel(conv_bwd)
+    kernels = [
+        {"kernel": "conv_pe_mask_fwd", "bound": "hbm", "achieved": BYTES_CONV_FWD * B / t_fwd / 1e9,
+         "peak": pk["hbm"], "unit": "GB/s", "us": t_fwd * 1e6, "traffic": dram("conv_pe_mask_fwd")},
+        {"kernel": "conv_bwd (mask_bwd + conv_dgrad + conv_wgrad_partial + reduce)", "bound": "hbm",
+         "achieved": (BYTES_CONV_DGRAD + BYTES_CONV_WGRAD) * B / t_bwd / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+         "us": t_bwd * 1e6,
+         "traffic": None if dram("conv_dgrad") is None else dram("conv_dgrad") + dram("conv_wgrad_partial")},
+    ]
+    # --- dominant kernel by time share: the tcgen05 GEMM, every shape of the step replayed from a CUDA graph ---
+    gemm = None
+    if precision != "fp32":
+        tot_t, tot_f, n_launch = 0.0, 0.0, 0
+        for (M, N, K, lay, cnt) in step_gemm_table(B * 21):
+            M, N, K = ((v + 3) // 4 * 4 for v in (M, N, K))    # hidden 294 lives in 296-wide (16-byte) rows in the step
+            A = torch.randn(M, K, device=dev)
+            Bm = torch.randn(N, K, device=dev)
+            if lay == "nt":
+                a, b, sa, sb = A, Bm, (K, 1), (K, 1)
+            elif lay == "nn":
+                a, b, sa, sb = A, Bm.t().contiguous(), (K, 1), (1, N)
+            else:
+                a, b, sa, sb = A.t().contiguous(), Bm.t().contiguous(), (1, M), (1, N)
+            out = torch.empty(M, N, device=dev)
+            t = graph_time(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision=precision, out=out))
+            tot_t += cnt * t
+            tot_f += cnt * 2.0 * M * N * K
+            n_launch += cnt
+        tf32_peak = pk["bf16"] / 2.0          # TF32 dense = half of BF16 dense; BF16 burst peak is the measured one
+        gemm = {"kernel": f"gemm_tc_kernel (tcgen05 kind::tf32, TMEM accumulators, TMA), {n_launch} launches/step",
+                "bound": "tensor", "achieved": tot_f / tot_t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                "us": tot_t * 1e6, "traffic": dram("gemm_tc_kernel<128> (qkv layer 0)"),
+                "note": "peak = measured cuBLAS bf16 burst / 2 (TF32); standalone launches round operands in-kernel, "
+                        "the in-step launches read pre-rounded operands and are slightly faster"}
+        kernels.insert(0, gemm)
+    for k in kernels:
+        k["frac"] = k["achieved"] / k["peak"]
+    dom = kernels[0]
+    return {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+            "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": pk["src"],
+            "share_of_step": dom["us"] * 1e-6 / step_s, "kernels": kernels,
+            "step": {"algorithmic_bytes": BYTES_STEP * B, "hbm_floor_us": BYTES_STEP * B / (pk["hbm"] * 1e9) * 1e6,
+                     "algorithmic_flops": FLOPS_STEP * B, "us": step_s * 1e6,
+                     "frac_of_hbm_floor": BYTES_STEP * B / (pk["hbm"] * 1e9) / step_s}}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from scat_b200 import _lib, dp
@@ -210,7 +321,7 @@ def run_ours(args):
     dp.broadcast_parameters(net.head_parameters(), 0)
 
     B = B_PER_GPU
-    ts = HeadTrainStep(net, B, 1e5, 10.0, use_graph=not args.no_graph)
+    ts = HeadTrainStep(net, B, 1e5, 10.0, use_graph=not args.no_graph, input_slots=2)
     # two distinct synthetic batches per rank, pinned on the host (e2e) and resident on the device (value)
     host = []
     for s in range(2):
@@ -254,16 +365,24 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(ts.losses[0].item())
 
-    # ---- end to end: pinned host inputs -> device, step, loss back to the host, every step ----
+    # ---- end to end: every step's inputs travel pinned host -> device inside the timed region, the step's
+    # losses travel back.  Two input slots: the copy of batch i+1 (copy stream) overlaps the compute of batch i.
     loss_host = torch.empty(4).pin_memory()
-    for i in range(2):
-        ts.load_inputs(*host[i % 2]); one_step(); loss_host.copy_(ts.losses, non_blocking=True)
+    copy_stream = torch.cuda.Stream(device=dev)
+    for slot in range(2):                       # warm both slots' graphs
+        ts.load_inputs(*host[slot], slot=slot)
+        ts.set_mask()
+        ts.step(slot=slot)
     barrier()
     w0 = time.perf_counter()
     e0.record()
+    copy_stream.wait_event(e0)
+    ts.load_inputs(*host[0], slot=0, stream=copy_stream)
     for i in range(args.steps):
-        ts.load_inputs(*host[i % 2])
-        one_step()
+        if i + 1 < args.steps:
+            ts.load_inputs(*host[(i + 1) % 2], slot=(i + 1) % 2, stream=copy_stream)
+        ts.set_mask()
+        ts.step(slot=i % 2)
         loss_host.copy_(ts.losses, non_blocking=True)
     e1.record()
     barrier()
@@ -278,39 +397,7 @@ def run_ours(args):
         t_dev, t_e2e = tt.tolist()
 
     if rank == 0:
-        # ---- roofline of the HBM-bound front-end kernels, timed live with CUDA events ----
-        x2d = ts.x2
-        W = net.head_parameters()
-        pe = net.positionalEncoding.pe[0]
-        idx = ts.mask_dev[: ts.n_masked]
-        cw = W[1].data.view(21, 512)
-        dtok = torch.randn(B, 21, 784, device=dev)
-        t_fwd = time_kernel(lambda: SF.conv_pe_mask_fwd(x2d, cw, pe, W[0].data.view(-1), idx, True))
-        scratch = torch.empty(lib.scat_conv_bwd_scratch_floats(B, 512, 784, 21), device=dev)
-        x2g, wg, mg = torch.empty_like(x2d), torch.empty(21, 512, device=dev), torch.empty(784, device=dev)
-        from scat_b200._lib import ptr, check, stream_ptr
-
-        def conv_bwd():
-            check(lib.scat_conv_bwd(ptr(dtok), ptr(x2d), ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
-                                    ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd")
-        t_bwd = time_kernel(conv_bwd)
-        kernels = [
-            {"kernel": "conv_pe_mask_fwd", "bound": "hbm", "achieved": BYTES_CONV_FWD * B / t_fwd / 1e9,
-             "peak": pk["hbm"], "unit": "GB/s", "us": t_fwd * 1e6},
-            {"kernel": "conv_bwd (mask_bwd+dgrad+wgrad)", "bound": "hbm",
-             "achieved": (BYTES_CONV_DGRAD + BYTES_CONV_WGRAD) * B / t_bwd / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-             "us": t_bwd * 1e6},
-        ]
-        for k in kernels:
-            k["frac"] = k["achieved"] / k["peak"]
-        dom = kernels[1]
-        step_s = t_dev / args.steps
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": pk["src"],
-                    "kernels": kernels,
-                    "step": {"algorithmic_bytes": BYTES_STEP * B, "hbm_floor_us": BYTES_STEP * B / (pk["hbm"] * 1e9) * 1e6,
-                             "algorithmic_flops": FLOPS_STEP * B, "us": step_s * 1e6,
-                             "frac_of_hbm_floor": BYTES_STEP * B / (pk["hbm"] * 1e9) / step_s}}
+        roofline = measure_roofline(ts, net, lib, pk, dev, B, t_dev / args.steps, args.precision)
         cpu = cpu_reference_run(steps=8, warmup=1, max_seconds=30.0)
         total = B * world * args.steps
         line = {

@@ -140,10 +140,22 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N,
 
 __global__ void round_copy_kernel(const RoundJobs jobs) {
     const RoundJob job = jobs.job[blockIdx.y];
-    const long long total = (long long)job.rows * job.ld_dst;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / job.ld_dst), c = (int)(i % job.ld_dst);
-        job.dst[i] = c < job.cols ? round_tf32(__ldg(job.src + (long long)r * job.ld_src + c)) : 0.f;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (((job.cols | job.ld_src | job.ld_dst) & 3) == 0) {          // float4 path (every weight but fc2 of layer 1)
+        const int c4n = job.ld_dst >> 2, total = job.rows * c4n;
+        for (int i = tid; i < total; i += nthr) {
+            const int r = i / c4n, c4 = i - r * c4n;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 * 4 < job.cols) v = __ldg(reinterpret_cast<const float4*>(job.src + (size_t)r * job.ld_src) + c4);
+            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+            reinterpret_cast<float4*>(job.dst)[i] = v;
+        }
+    } else {
+        const int total = job.rows * job.ld_dst;
+        for (int i = tid; i < total; i += nthr) {
+            const int r = i / job.ld_dst, c = i - r * job.ld_dst;
+            job.dst[i] = c < job.cols ? round_tf32(__ldg(job.src + (size_t)r * job.ld_src + c)) : 0.f;
+        }
     }
 }
 
@@ -151,7 +163,7 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 12, kErrBadArg, "round_copy: %d jobs", jobs.n);
-    round_copy_kernel<<<dim3(74, jobs.n), 256, 0, stream>>>(jobs);
+    round_copy_kernel<<<dim3(60, jobs.n), 256, 0, stream>>>(jobs);
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -121,7 +121,7 @@ struct TcParams {
 
 template <int BN>
 struct SmemLayout {
-    static constexpr int STAGES = BN >= 128 ? 3 : 4;      // 96 KB of ring either way: two CTAs fit one SM
+    static constexpr int STAGES = BN >= 128 ? 6 : 8;      // 192 KB ring, one CTA per SM: the loop is latency x bytes-in-flight bound
     static constexpr int A_BYTES = BM * BK * 4;           // 16 KB
     static constexpr int B_BYTES = BN * BK * 4;           // 8 / 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -130,7 +130,7 @@ struct SmemLayout {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using L = SmemLayout<BN>;
     constexpr int STAGES = L::STAGES;

@@ -138,7 +138,7 @@ int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, con
                          float* dbeta, int M, int D, int round_out, cudaStream_t stream) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm bwd: D=%d not in [1,1024]", D);
     SCAT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), kErrBadArg, "layernorm bwd: dgamma/dbeta must both be set or null");
-    const int grid = min(ceil_div(M, LN_WARPS), 148 * 2);
+    const int grid = min(ceil_div(M, 2 * LN_WARPS), 148);     // >= 2 rows per warp: halves the atomic tail
 #define SCAT_LN_BWD(NPL) layernorm_bwd_kernel<NPL><<<grid, LN_WARPS * 32, 0, stream>>>( \
         dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out)
     if (D <= 256) SCAT_LN_BWD(8);
