@@ -27,6 +27,7 @@ __device__ __forceinline__ void load_head_tile(const float* __restrict__ src, lo
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ P, int n, int heads,
                      int round_out) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* Qs = sm;
     float* Ks = Qs + n * LDS;
@@ -83,6 +84,7 @@ attention_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dO,
                      float* __restrict__ dQKV, int n, int heads, int round_out) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* Qs = sm;
     float* Ks = Qs + n * LDS;
@@ -143,7 +145,7 @@ bool attention_small_supported(int n);
 int launch_attention_small_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                                cudaStream_t stream);
 int launch_attention_small_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
-                               int round_out, cudaStream_t stream);
+                               int round_out, cudaStream_t stream, int act_batch);
 
 int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                          cudaStream_t stream) {
@@ -154,21 +156,22 @@ int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int
         SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
     }
-    attention_fwd_kernel<<<B * heads, ATT_THREADS, smem, stream>>>(QKV, O, P, n, heads, round_out);
+    SCAT_CHECK_CUDA(launch_k(attention_fwd_kernel, dim3(B * heads), dim3(ATT_THREADS), smem, stream, QKV, O, P, n, heads, round_out));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 
 int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
-                         int round_out, cudaStream_t stream) {
+                         int round_out, cudaStream_t stream, int act_batch) {
     SCAT_REQUIRE(n >= 1 && n <= 64, kErrUnsupported, "attention bwd: n=%d not in [1,64] (training path is n=21)", n);
-    if (attention_small_supported(n)) return launch_attention_small_bwd(QKV, P, dO, dQKV, B, n, heads, round_out, stream);
+    if (attention_small_supported(n)) return launch_attention_small_bwd(QKV, P, dO, dQKV, B, n, heads, round_out, stream, act_batch);
+    SCAT_REQUIRE(act_batch == 0, kErrUnsupported, "attention bwd: stacked cotangents only on the n=21 path");
     const size_t smem = sizeof(float) * ((size_t)4 * n * LDS + (size_t)2 * n * (n + 1));
     if (smem > 48 * 1024) {
         SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
     }
-    attention_bwd_kernel<<<B * heads, ATT_THREADS, smem, stream>>>(QKV, P, dO, dQKV, n, heads, round_out);
+    SCAT_CHECK_CUDA(launch_k(attention_bwd_kernel, dim3(B * heads), dim3(ATT_THREADS), smem, stream, QKV, P, dO, dQKV, n, heads, round_out));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

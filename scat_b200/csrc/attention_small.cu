@@ -60,6 +60,7 @@ template <int N>
 __global__ void __launch_bounds__(NW * 32)
 attention_fwd_small_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ P, int heads,
                            int round_out) {
+    pdl_sync();
     constexpr int LS = N + 1;
     __shared__ __align__(16) float Qs[N * DH];
     __shared__ __align__(16) float Vs[N * DH];
@@ -108,7 +109,8 @@ attention_fwd_small_kernel(const float* __restrict__ QKV, float* __restrict__ O,
 template <int N>
 __global__ void __launch_bounds__(NW * 32)
 attention_bwd_small_kernel(const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dO,
-                           float* __restrict__ dQKV, int heads, int round_out) {
+                           float* __restrict__ dQKV, int heads, int round_out, int act_batch) {
+    pdl_sync();
     constexpr int LS = N + 1;
     __shared__ __align__(16) float Qs[N * DH];
     __shared__ __align__(16) float Ks[N * DH];
@@ -120,11 +122,12 @@ attention_bwd_small_kernel(const float* __restrict__ QKV, const float* __restric
     const int prob = blockIdx.x, b = prob / heads, g = prob % heads;
     const int inner = heads * DH;
     const long long rs = 3LL * inner;
-    const float* base = QKV + (long long)b * N * rs + g * DH;
+    const int ba = act_batch > 0 ? b % act_batch : b;        // stacked cotangents share the saved activations
+    const float* base = QKV + (long long)ba * N * rs + g * DH;
     load_rows_to_smem(base, rs, N, Qs);
     load_rows_to_smem(base + inner, rs, N, Ks);
     load_rows_to_smem(dO + (long long)b * N * inner + g * DH, inner, N, Gs);
-    const float* Pg = P + (long long)prob * N * N;
+    const float* Pg = P + ((long long)ba * heads + g) * N * N;
     for (int e = threadIdx.x; e < N * N; e += NW * 32) Ps[(e / N) * LS + (e % N)] = __ldg(Pg + e);
     const bool act = lane < N;
     float vreg[DS];
@@ -170,14 +173,14 @@ bool attention_small_supported(int n) { return n == 21; }
 int launch_attention_small_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                                cudaStream_t stream) {
     SCAT_REQUIRE(n == 21, kErrUnsupported, "attention_small: n=%d", n);
-    attention_fwd_small_kernel<21><<<B * heads, NW * 32, 0, stream>>>(QKV, O, P, heads, round_out);
+    SCAT_CHECK_CUDA(launch_k(attention_fwd_small_kernel<21>, dim3(B * heads), dim3(NW * 32), 0, stream, QKV, O, P, heads, round_out));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 int launch_attention_small_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
-                               int round_out, cudaStream_t stream) {
+                               int round_out, cudaStream_t stream, int act_batch) {
     SCAT_REQUIRE(n == 21, kErrUnsupported, "attention_small: n=%d", n);
-    attention_bwd_small_kernel<21><<<B * heads, NW * 32, 0, stream>>>(QKV, P, dO, dQKV, heads, round_out);
+    SCAT_CHECK_CUDA(launch_k(attention_bwd_small_kernel<21>, dim3(B * heads), dim3(NW * 32), 0, stream, QKV, P, dO, dQKV, heads, round_out, act_batch));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -47,6 +47,32 @@ constexpr int kErrBadArg = -1;
 constexpr int kErrWorkspace = -2;
 constexpr int kErrUnsupported = -3;
 
+// ---- launches: every kernel goes out with the programmatic-dependent-launch attribute (SCAT_PDL=0 disables) so
+// that the next kernel's launch latency and prologue overlap the tail of the current one.  Every kernel calls
+// pdl_sync() before it touches global memory: it waits for the preceding grid to complete (and flush), then lets
+// the following grid start launching.  Without the attribute both instructions are no-ops.
+extern int g_use_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

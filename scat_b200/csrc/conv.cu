@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
 conv_pe_mask_fwd_kernel(const float* __restrict__ x2, const float* __restrict__ Wc, const float* __restrict__ pe,
                         const float* __restrict__ mask_token, const int32_t* __restrict__ mask_idx, int n_masked,
                         int pos_embed, float* __restrict__ Fv, float* __restrict__ X0, int B, int C, int HW) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     __shared__ uint32_t s_bits[4];
     float* Ws = smem;  // [C][TP], later reused as the cross-warp reduction buffer [warps][T][4][32]
@@ -126,6 +127,7 @@ conv_pe_mask_fwd_kernel(const float* __restrict__ x2, const float* __restrict__ 
 __global__ void pe_mask_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ pe,
                                       const float* __restrict__ mask_token, const int32_t* __restrict__ mask_idx,
                                       int n_masked, int pos_embed, float* __restrict__ X0, int B, int T, int D) {
+    pdl_sync();
     __shared__ uint32_t s_bits[4];
     if (threadIdx.x < 4) s_bits[threadIdx.x] = 0;
     __syncthreads();
@@ -145,6 +147,7 @@ __global__ void pe_mask_tokens_kernel(const float* __restrict__ tok, const float
 // dFv = dX0 with masked rows zeroed (float4 per thread)
 __global__ void mask_bwd_copy_kernel(const float* __restrict__ dX0, const int32_t* __restrict__ mask_idx, int n_masked,
                                      int keep_masked, float* __restrict__ dFv, int B, int T, int HW) {
+    pdl_sync();
     __shared__ uint32_t s_bits[4];
     if (threadIdx.x < 4) s_bits[threadIdx.x] = 0;
     __syncthreads();
@@ -163,6 +166,7 @@ __global__ void mask_bwd_copy_kernel(const float* __restrict__ dX0, const int32_
 // d mask_token[p] = sum_b sum_{t in idx} dX0[b,t,p]: grid (pixel blocks, sample slices), slices combine with atomics
 __global__ void mask_token_grad_kernel(const float* __restrict__ dX0, const int32_t* __restrict__ mask_idx,
                                        int n_masked, float* __restrict__ d_mask_token, int B, int T, int HW) {
+    pdl_sync();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
     float s = 0.f;
@@ -176,6 +180,7 @@ template <int T>
 __global__ void __launch_bounds__(CONV_THREADS, 2)
 conv_dgrad_kernel(const float* __restrict__ dFv, const float* __restrict__ Wc, float* __restrict__ x2g, int B, int C,
                   int HW) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;  // [C][TP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,6 +232,7 @@ template <int T, int CPT /* channels per thread */>
 __global__ void __launch_bounds__(CONV_THREADS, 2)
 conv_wgrad_partial_kernel(const float* __restrict__ dFv, const float* __restrict__ x2, float* __restrict__ partial,
                           int B, int C, int HW) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                  // [C][WG_PX]
     float* ds = smem + C * WG_PX;      // [T][WG_PX]
@@ -285,6 +291,7 @@ conv_wgrad_partial_kernel(const float* __restrict__ dFv, const float* __restrict
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int n, float* __restrict__ out) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
@@ -310,8 +317,8 @@ int launch_conv_pe_mask_fwd(const float* x2, const float* Wc, const float* pe, c
     SCAT_REQUIRE(smem <= 96 * 1024, kErrUnsupported, "conv fwd: C too large");
     const long long groups = (long long)B * (HW / 4);
     const int grid = (int)((groups + 31) / 32);
-    conv_pe_mask_fwd_kernel<21><<<grid, CONV_THREADS, smem, stream>>>(x2, Wc, pe, mask_token, mask_idx, n_masked,
-                                                                      pos_embed, feat_visual, X0, B, C, HW);
+    SCAT_CHECK_CUDA(launch_k(conv_pe_mask_fwd_kernel<21>, dim3(grid), dim3(CONV_THREADS), smem, stream, x2, Wc, pe, mask_token, mask_idx, n_masked,
+                                                                      pos_embed, feat_visual, X0, B, C, HW));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -321,7 +328,7 @@ int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mas
     SCAT_REQUIRE(T <= 128, kErrUnsupported, "token front end: at most 128 tokens (got %d)", T);
     const long long total = (long long)B * T * D;
     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    pe_mask_tokens_kernel<<<grid, 256, 0, stream>>>(tokens, pe, mask_token, mask_idx, n_masked, pos_embed, X0, B, T, D);
+    SCAT_CHECK_CUDA(launch_k(pe_mask_tokens_kernel, dim3(grid), dim3(256), 0, stream, tokens, pe, mask_token, mask_idx, n_masked, pos_embed, X0, B, T, D));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -332,14 +339,14 @@ int launch_mask_bwd(const float* dX0, const int32_t* mask_idx, int n_masked, int
     if (dFv != nullptr) {
         const long long total = (long long)B * T * (HW / 4);
         const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        mask_bwd_copy_kernel<<<grid, 256, 0, stream>>>(dX0, mask_idx, n_masked, keep_masked, dFv, B, T, HW);
+        SCAT_CHECK_CUDA(launch_k(mask_bwd_copy_kernel, dim3(grid), dim3(256), 0, stream, dX0, mask_idx, n_masked, keep_masked, dFv, B, T, HW));
         SCAT_CHECK_LAUNCH();
     }
     if (d_mask_token != nullptr) {
         SCAT_CHECK_CUDA(cudaMemsetAsync(d_mask_token, 0, (size_t)HW * sizeof(float), stream));
         if (n_masked > 0) {
-            mask_token_grad_kernel<<<dim3(ceil_div(HW, 128), min(B, 32)), 128, 0, stream>>>(dX0, mask_idx, n_masked,
-                                                                                            d_mask_token, B, T, HW);
+            SCAT_CHECK_CUDA(launch_k(mask_token_grad_kernel, dim3(dim3(ceil_div(HW, 128), min(B, 32))), dim3(128), 0, stream, dX0, mask_idx, n_masked,
+                                                                                            d_mask_token, B, T, HW));
             SCAT_CHECK_LAUNCH();
         }
     }
@@ -358,7 +365,7 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
     }
     SCAT_REQUIRE(smem <= 96 * 1024, kErrUnsupported, "conv dgrad: C too large");
     const long long groups = (long long)B * (HW / 4);
-    conv_dgrad_kernel<21><<<(int)((groups + 31) / 32), CONV_THREADS, smem, stream>>>(dFv, Wc, x2_grad, B, C, HW);
+    SCAT_CHECK_CUDA(launch_k(conv_dgrad_kernel<21>, dim3((int)((groups + 31) / 32)), dim3(CONV_THREADS), smem, stream, dFv, Wc, x2_grad, B, C, HW));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -379,9 +386,9 @@ int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scra
     }
     const int items = B * (HW / WG_PX);
     const int grid = min(items, kConvWgradCtas);
-    conv_wgrad_partial_kernel<21, 2><<<grid, CONV_THREADS, smem, stream>>>(dFv, x2, scratch, B, C, HW);
+    SCAT_CHECK_CUDA(launch_k(conv_wgrad_partial_kernel<21, 2>, dim3(grid), dim3(CONV_THREADS), smem, stream, dFv, x2, scratch, B, C, HW));
     SCAT_CHECK_LAUNCH();
-    reduce_partials_kernel<<<ceil_div(T * C, 256), 256, 0, stream>>>(scratch, grid, T * C, dWc);
+    SCAT_CHECK_CUDA(launch_k(reduce_partials_kernel, dim3(ceil_div(T * C, 256)), dim3(256), 0, stream, scratch, grid, T * C, dWc));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

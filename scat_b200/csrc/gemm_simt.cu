@@ -50,6 +50,7 @@ __device__ __forceinline__ void store_tile(float (*S)[BM + PAD], int tid, const 
 
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_per_split) {
+    pdl_sync();
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
     const int tid = threadIdx.x;
@@ -101,16 +102,17 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
             const int n = n0 + tx * 4 + j;
             if (n >= g.N) continue;
             float v = acc[i][j];
+            const long long ma = g.aux_row_mod > 0 ? m % g.aux_row_mod : m;
             switch (g.epilogue) {
                 case EPI_BIAS: v += g.bias[n]; break;
-                case EPI_BIAS_RESID: v += g.bias[n] + g.aux_in[(long long)m * g.ld_aux_in + n]; break;
+                case EPI_BIAS_RESID: v += g.bias[n] + g.aux_in[ma * g.ld_aux_in + n]; break;
                 case EPI_BIAS_GELU: {
                     v += g.bias[n];
                     g.aux_out[(long long)m * g.ld_aux_out + n] = v;
                     v = gelu_erf(v);
                 } break;
-                case EPI_DGELU: v *= gelu_erf_grad(g.aux_in[(long long)m * g.ld_aux_in + n]); break;
-                case EPI_RESID: v += g.aux_in[(long long)m * g.ld_aux_in + n]; break;
+                case EPI_DGELU: v *= gelu_erf_grad(g.aux_in[ma * g.ld_aux_in + n]); break;
+                case EPI_RESID: v += g.aux_in[ma * g.ld_aux_in + n]; break;
                 default: break;
             }
             if (g.round_out) v = round_tf32(v);
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
 
 // column sums out[n] (+)= sum_m X[m,n]: grid (column groups, row slices); slices combine with atomics
 __global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N, float* __restrict__ out) {
+    pdl_sync();
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
@@ -139,6 +142,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N,
 }
 
 __global__ void round_copy_kernel(const RoundJobs jobs) {
+    pdl_sync();
     const RoundJob job = jobs.job[blockIdx.y];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     if (((job.cols | job.ld_src | job.ld_dst) & 3) == 0) {          // float4 path (every weight but fc2 of layer 1)
@@ -163,7 +167,7 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 12, kErrBadArg, "round_copy: %d jobs", jobs.n);
-    round_copy_kernel<<<dim3(60, jobs.n), 256, 0, stream>>>(jobs);
+    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(dim3(60, jobs.n)), dim3(256), 0, stream, jobs));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -190,10 +194,10 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
         SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
     const bool a_k = (g.sak == 1) || (g.sam != 1);
     const bool b_k = (g.sbk == 1) || (g.sbn != 1);
-    if (a_k && b_k) gemm_simt_kernel<true, true><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
-    else if (a_k && !b_k) gemm_simt_kernel<true, false><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
-    else if (!a_k && b_k) gemm_simt_kernel<false, true><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
-    else gemm_simt_kernel<false, false><<<grid, THREADS, 0, stream>>>(g, kt_per_split);
+    if (a_k && b_k) SCAT_CHECK_CUDA(launch_k(gemm_simt_kernel<true, true>, dim3(grid), dim3(THREADS), 0, stream, g, kt_per_split));
+    else if (a_k && !b_k) SCAT_CHECK_CUDA(launch_k(gemm_simt_kernel<true, false>, dim3(grid), dim3(THREADS), 0, stream, g, kt_per_split));
+    else if (!a_k && b_k) SCAT_CHECK_CUDA(launch_k(gemm_simt_kernel<false, true>, dim3(grid), dim3(THREADS), 0, stream, g, kt_per_split));
+    else SCAT_CHECK_CUDA(launch_k(gemm_simt_kernel<false, false>, dim3(grid), dim3(THREADS), 0, stream, g, kt_per_split));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -204,7 +208,7 @@ int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumula
     const int gx = ceil_div(N, 32);
     int gy = min(ceil_div(M, 8 * 4), max(1, 592 / gx));       // >= 4 rows per thread, ~4 blocks per SM
     if (gy < 1) gy = 1;
-    colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(X, ld, M, N, out);
+    SCAT_CHECK_CUDA(launch_k(colsum_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, stream, X, ld, M, N, out));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

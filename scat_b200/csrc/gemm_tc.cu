@@ -112,7 +112,7 @@ struct TcParams {
     float* C; int ldc;
     int epilogue;
     const float* bias;
-    const float* aux_in; int ld_aux_in;
+    const float* aux_in; int ld_aux_in; int aux_row_mod;
     float* aux_out; int ld_aux_out;
     int accumulate;
     int round_out;                  // 1: store C rounded to TF32-nearest (it feeds another tensor-core GEMM)
@@ -160,6 +160,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation) overlapped the previous kernel's tail; operands and the
+    // output buffer may only be touched once that kernel has completed
+    pdl_sync();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -249,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const bool row_ok = row < p.M;
         float* crow = p.C + (long long)row * p.ldc;
-        const float* arow = p.aux_in ? p.aux_in + (long long)row * p.ld_aux_in : nullptr;
+        const float* arow = p.aux_in ? p.aux_in + (long long)(p.aux_row_mod > 0 ? row % p.aux_row_mod : row) * p.ld_aux_in : nullptr;
         float* zrow = p.aux_out ? p.aux_out + (long long)row * p.ld_aux_out : nullptr;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.aux_in || (((p.ld_aux_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0))) &&
@@ -377,12 +380,12 @@ int launch_bn(const GemmArgs& g, cudaStream_t stream) {
     else SCAT_PROPAGATE(make_map(&tmB, g.B, g.N, g.K, g.sbk, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     TcParams p;
     p.M = g.M; p.N = g.N; p.K = g.K; p.a_mn_major = a_mn; p.b_mn_major = b_mn; p.C = g.C; p.ldc = g.ldc;
-    p.epilogue = g.epilogue; p.bias = g.bias; p.aux_in = g.aux_in; p.ld_aux_in = g.ld_aux_in; p.aux_out = g.aux_out;
+    p.epilogue = g.epilogue; p.bias = g.bias; p.aux_in = g.aux_in; p.ld_aux_in = g.ld_aux_in; p.aux_row_mod = g.aux_row_mod; p.aux_out = g.aux_out;
     p.ld_aux_out = g.ld_aux_out; p.accumulate = g.accumulate;
     p.round_operands = g.prerounded ? 0 : 1;
     p.round_out = g.round_out;
     dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    SCAT_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), L::TOTAL, stream, tmA, tmB, p));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

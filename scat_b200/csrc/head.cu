@@ -11,6 +11,7 @@
 // backward) and the GEMM weights get a rounded (and 16-byte-padded) copy once per forward.  The regressor,
 // the last feed-forward (196->147->3) and the conv front end stay fp32.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/scat_b200.h"
 #include "kernels.h"
@@ -27,6 +28,11 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 unsigned long long g_launch_count = 0;
+static int read_pdl_env() {
+    const char* e = getenv("SCAT_PDL");
+    return (e && e[0] == '0') ? 0 : 1;
+}
+int g_use_pdl = read_pdl_env();
 
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
     // tiny problems (regressor / N=3 grads) stay on the FFMA kernel: a 128-row tensor tile would be mostly padding
@@ -65,7 +71,7 @@ struct HeadPlan {
     int B, T, C, D, heads, inner, M, it, F, NP;
     LayerPlan L[kDepth];
     size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dX, dFv, conv_scratch, pl_scratch,
-        g_pred, ones, hreg, total;
+        g_pred, ones, hreg, up2, total;
 };
 
 size_t take(size_t& cur, size_t n) {
@@ -132,13 +138,17 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     p.ones = take(cur, M * 3);
     p.g_pred = take(cur, (size_t)p.B * NP);
     p.hreg = take(cur, (size_t)p.B * NP);
-    p.dZ = take(cur, M * ldh_max);
-    p.dNf = take(cur, M * dmax);
-    p.dX1 = take(cur, M * dmax);
-    p.dO = take(cur, M * p.inner);
-    p.dQKV = take(cur, M * 3 * p.inner);
-    p.dNa = take(cur, M * dmax);
-    p.dX = take(cur, M * dmax);
+    // gradient scratch: the fused train step sweeps the real cotangent and the path-length (ones) cotangent
+    // through the backward together, stacked along the row dimension (2M rows)
+    const size_t MS = d.pl_reg ? 2 * M : M;
+    p.up2 = take(cur, MS * 3);
+    p.dZ = take(cur, MS * ldh_max);
+    p.dNf = take(cur, MS * dmax);
+    p.dX1 = take(cur, MS * dmax);
+    p.dO = take(cur, MS * p.inner);
+    p.dQKV = take(cur, MS * 3 * p.inner);
+    p.dNa = take(cur, MS * dmax);
+    p.dX = take(cur, MS * dmax);
     p.dFv = take(cur, M * dmax);
     p.conv_scratch = take(cur, p.C > 0 ? conv_wgrad_scratch_floats(p.C, p.T) : 64);
     p.pl_scratch = take(cur, (size_t)p.B);
@@ -147,12 +157,15 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
 }
 
 __global__ void fill_kernel(float* p, float v, long long n) {
+    pdl_sync();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    pdl_sync();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
 }
 __global__ void token_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int n) {
+    pdl_sync();
     // out[b, c] = mean_t X[b, t, c], c < 3  (hand_net.py:203)
     const int b = blockIdx.x, c = threadIdx.x;
     if (c >= 3) return;
@@ -242,9 +255,14 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 // ---- reverse sweep: d/dX0 of <up, feat_out>, optionally with parameter gradients ---------------------
 // up: [M,3] cotangent of the transformer output.  Result lands in ws + p.dX ([M, D]).  Uses the rounded weight
 // copies left in the workspace by transformer_forward.
+// sweeps = 2: `up` holds two stacked cotangents [2M,3] (rows < M: the real one, rows >= M: the path-length ones);
+// every dgrad-type kernel then runs once over 2M rows against the same saved activations, parameter gradients
+// only see the first M rows.
 int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
-                         int prec, const float* up, cudaStream_t st, const float* X0_override) {
+                         int prec, const float* up, cudaStream_t st, const float* X0_override, int sweeps = 1) {
     const int M = p.M;
+    const int MR = M * sweeps;                       // rows of every cotangent tensor
+    const int amod = sweeps > 1 ? M : 0;             // activation row = cotangent row % M
     const int tc = prec != PREC_FP32;
     const float* dY = up;
     for (int l = kDepth - 1; l >= 0; --l) {
@@ -264,8 +282,8 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
         g.A = dY; g.sam = L.out; g.sak = 1; g.B = w.fc2; g.sbn = 1; g.sbk = w.ld_fc2;
-        g.C = ws + p.dZ; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.out; g.prerounded = fftc; g.round_out = fftc;
-        g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh;
+        g.C = ws + p.dZ; g.ldc = L.ldh; g.M = MR; g.N = L.hid; g.K = L.out; g.prerounded = fftc; g.round_out = fftc;
+        g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         if (G) {
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
@@ -278,14 +296,14 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs: round it)
         g = GemmArgs();
         g.A = ws + p.dZ; g.sam = L.ldh; g.sak = 1; g.B = w.fc1; g.sbn = 1; g.sbk = w.ld_fc1;
-        g.C = ws + p.dNf; g.ldc = L.d; g.M = M; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
+        g.C = ws + p.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
         g.round_out = (L.last && tc) ? 1 : 0;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         const float* dX1 = ws + p.dNf;
         if (!L.last) {
             SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
                                                 ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d,
-                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, M, L.d, tc, st));
+                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, MR, L.d, tc, st, amod));
             dX1 = ws + p.dX1;
         }
         if (G) {
@@ -299,9 +317,10 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         // dO = dX1 Wo
         g = GemmArgs();
         g.A = dX1; g.sam = L.d; g.sak = 1; g.B = w.out; g.sbn = 1; g.sbk = w.ld_out;
-        g.C = ws + p.dO; g.ldc = p.inner; g.M = M; g.N = p.inner; g.K = L.d; g.prerounded = tc;
+        g.C = ws + p.dO; g.ldc = p.inner; g.M = MR; g.N = p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B, p.T, p.heads, tc, st));
+        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B * sweeps, p.T, p.heads, tc,
+                                            st, sweeps > 1 ? p.B : 0));
         if (G) {
             // dWqkv[3inner,d] = dQKV^T Na
             g = GemmArgs();
@@ -312,12 +331,12 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         // dNa = dQKV Wqkv
         g = GemmArgs();
         g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv;
-        g.C = ws + p.dNa; g.ldc = L.d; g.M = M; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
+        g.C = ws + p.dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs
         SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
                                             L.d, ws + p.dX, L.d, G ? G[L.p_na_w] : nullptr,
-                                            G ? G[L.p_na_b] : nullptr, M, L.d, (tc && l > 0) ? 1 : 0, st));
+                                            G ? G[L.p_na_b] : nullptr, MR, L.d, (tc && l > 0) ? 1 : 0, st, amod));
         dY = ws + p.dX;
     }
     return 0;
@@ -333,7 +352,7 @@ int check_ws(const HeadPlan& p, void* ws, size_t bytes) {
 
 int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, const float* mean_params,
                  const int32_t* mask_idx, const float* x2, const float* main_feat, float* pred, float* fv, float* pl,
-                 void* workspace, size_t ws_bytes, cudaStream_t st) {
+                 void* workspace, size_t ws_bytes, cudaStream_t st, bool defer_pl = false) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
     SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
@@ -350,9 +369,9 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
     SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
                                         ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st));
-    if (d.pl_reg) {
+    if (d.pl_reg && !defer_pl) {
         // autograd.grad(sum(feat_out), feat_visual) (hand_net.py:396): dgrad-only sweep with a ones cotangent
-        fill_kernel<<<64, 256, 0, st>>>(ws + p.ones, 1.0f, (long long)p.M * 3);
+        SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, ws + p.ones, 1.0f, (long long)p.M * 3));
         SCAT_CHECK_LAUNCH();
         SCAT_PROPAGATE(transformer_backward(p, W, nullptr, ws, d.precision, ws + p.ones, st, d.pos_embed ? nullptr : fv));
         // masked tokens do not depend on feat_visual (zero rows) unless the overwrite aliased feat_visual itself
@@ -363,7 +382,8 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
 
 int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* mask_idx, const float* x2,
                   const float* main_feat, const float* g_pred, const float* g_fv, float* const* G, float* x2_grad,
-                  float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias) {
+                  float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias,
+                  float* pl_out = nullptr /* non-null: also sweep the path-length cotangent (stacked) into pl_out */) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
     SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
@@ -371,8 +391,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_REQUIRE(d.pos_embed || fv_alias, kErrBadArg, "head_backward: pos_embed==0 needs the forward's feat_visual");
     float* ws = (float*)workspace;
     // regressor + root-relative backward
-    SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], ws + p.dfeat, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
+    const int sweeps = pl_out ? 2 : 1;
+    float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
+    SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], up, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
                                         p.NP, p.it, 1, st));
+    if (pl_out) {
+        SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, up + (size_t)p.M * 3, 1.0f, (long long)p.M * 3));
+        SCAT_CHECK_LAUNCH();
+    }
     {
         const int ldw = p.F + p.NP;
         GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
@@ -399,11 +425,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
             SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_nf_b], 0, L.d * sizeof(float), st));
         }
     }
-    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, ws + p.dfeat, st, d.pos_embed ? nullptr : fv_alias));
+    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps));
     // through masking / positional encoding into the conv output
     SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st));
+    if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
+        SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX + (size_t)p.M * p.D, mask_idx, d.n_masked, d.pos_embed ? 0 : 1, pl_out,
+                                       nullptr, p.B, p.T, p.D, st));
     if (g_fv != nullptr) {
-        add_inplace_kernel<<<148 * 4, 256, 0, st>>>(ws + p.dFv, g_fv, (long long)p.M * p.D);
+        SCAT_CHECK_CUDA(launch_k(add_inplace_kernel, dim3(148 * 4), dim3(256), 0, st, ws + p.dFv, g_fv, (long long)p.M * p.D));
         SCAT_CHECK_LAUNCH();
     }
     if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], x2_grad, p.B, p.C, p.D, p.T, st));
@@ -463,16 +492,21 @@ int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, c
                          float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream) {
     SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
     cudaStream_t st = (cudaStream_t)stream;
+    // The path-length VJP is a dgrad-only sweep of the same graph as the backward and its result carries no
+    // gradient (hand_net.py:396, train.py:201), so it rides along with the real cotangent: one stacked sweep.
+    const bool pl = desc->pl_reg != 0;
     SCAT_PROPAGATE(head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual,
-                                pl_term, workspace, workspace_bytes, st));
+                                pl_term, workspace, workspace_bytes, st, /*defer_pl=*/true));
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(*desc, p));
     float* ws = (float*)workspace;
-    SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, desc->pl_reg ? pl_term : nullptr, p.T * p.D, p.T,
-                                    l_weight_3d, l_weight_2d, grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch,
-                                    p.B, st));
-    return head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
-                         main_feat_grad, workspace, workspace_bytes, st, feat_visual);
+    SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, nullptr, p.T * p.D, p.T, l_weight_3d, l_weight_2d,
+                                    grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch, p.B, st));
+    SCAT_PROPAGATE(head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
+                                 main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr));
+    if (pl)       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
+        SCAT_PROPAGATE(launch_pl_loss_add(pl_term, p.T * p.D, p.T, losses, ws + p.pl_scratch, p.B, st));
+    return 0;
 }
 
 int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const int32_t* mask_idx,
@@ -489,7 +523,7 @@ int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, co
     SCAT_PROPAGATE(transformer_forward(p, params, ws, desc->precision, st, nullptr));
     SCAT_CHECK_CUDA(cudaMemcpyAsync(out, ws + p.feat_out, (size_t)p.M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (mean != nullptr) {
-        token_mean_kernel<<<p.B, 32, 0, st>>>(ws + p.feat_out, mean, p.T);
+        SCAT_CHECK_CUDA(launch_k(token_mean_kernel, dim3(p.B), dim3(32), 0, st, ws + p.feat_out, mean, p.T));
         SCAT_CHECK_LAUNCH();
     }
     return 0;

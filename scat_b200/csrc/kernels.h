@@ -36,6 +36,7 @@ struct GemmArgs {
     int epilogue = EPI_NONE;
     const float* bias = nullptr;
     const float* aux_in = nullptr; int ld_aux_in = 0;
+    int aux_row_mod = 0;     // > 0: aux_in row = m % aux_row_mod (stacked cotangents share one saved activation)
     float* aux_out = nullptr; int ld_aux_out = 0;
     int accumulate = 0;  // C += epilogue(...)
     int allow_split_k = 0;   // FFMA kernel may split K over CTAs and combine with atomics (weight gradients)
@@ -88,7 +89,9 @@ int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const floa
 // dX = LN'(dY) (+ resid); dgamma/dbeta accumulated with atomics when non-null (must be pre-zeroed)
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
-                         float* dbeta, int M, int D, int round_out, cudaStream_t stream);
+                         float* dbeta, int M, int D, int round_out, cudaStream_t stream, int act_rows = 0);
+// act_rows > 0: dY/dX/resid have M rows, the saved activations (X, mean, rstd) have act_rows rows and row m uses
+// activation row m % act_rows; dgamma/dbeta only accumulate rows m < act_rows (the real cotangent)
 
 // ------------------------------------------------------------------------------------------
 // softmax attention over n tokens, heads of 64 (vision_transformer.py:61-77)
@@ -97,7 +100,8 @@ int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, con
 int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                          cudaStream_t stream);
 int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
-                         int round_out, cudaStream_t stream);
+                         int round_out, cudaStream_t stream, int act_batch = 0);
+// act_batch > 0: dO/dQKV have B samples, QKV/P have act_batch samples and sample b uses activations of b % act_batch
 // dst[r, c] = round_tf32(src[r, c]) (pad columns zero-filled) for a list of weight matrices, one launch;
 // the job table travels by value as a kernel argument (no device-side table, graph-capturable)
 struct RoundJob { const float* src; float* dst; int rows, cols, ld_src, ld_dst; };
@@ -123,6 +127,9 @@ int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out
 int launch_proj_loss(const float* pred, const float* labels, int ld_labels, const float* pl_term, int pl_row_elems,
                      int n_tokens, float w3d, float w2d, float grad_scale, float* losses, float* g_pred,
                      float* pl_scratch, int B, cudaStream_t stream);
+// losses[3] = l_pl; losses[0] += 10 * l_pl   (the path-length term alone, train.py:178-183,201)
+int launch_pl_loss_add(const float* pl_term, int pl_row_elems, int n_tokens, float* losses, float* pl_scratch, int B,
+                       cudaStream_t stream);
 
 // MANO linear blend skinning (mano.py:280-391) lives in lbs.cu with its own C-ABI wrappers.
 

@@ -43,6 +43,7 @@ __device__ void rodrigues(float rx, float ry, float rz, float* R) {
 __global__ void lbs_prepare_kernel(const float* __restrict__ v_template, const float* __restrict__ shapedirs,
                                    const float* __restrict__ posedirs, const float* __restrict__ J_reg,
                                    const float* __restrict__ weights, float* __restrict__ derived) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = DERIVED_FLOATS;
     if (i >= total) return;
@@ -81,6 +82,7 @@ struct SampleSetup {
 __global__ void __launch_bounds__(LBS_THREADS)
 lbs_fwd_kernel(const float* __restrict__ derived, const float* __restrict__ hands_mean, const float* __restrict__ rots,
                const float* __restrict__ poses, const float* __restrict__ betas, float* __restrict__ out, int B) {
+    pdl_sync();
     __shared__ SampleSetup S[LBS_S];
     __shared__ float Rl[LBS_S][NJ][9];
     __shared__ float Jp[LBS_S][NJ][3];
@@ -253,8 +255,8 @@ size_t lbs_derived_floats() { return DERIVED_FLOATS; }
 int launch_lbs_prepare_all(const float* v_template, const float* shapedirs, const float* posedirs, const float* J_reg,
                            const float* weights, float* derived, cudaStream_t stream) {
     SCAT_REQUIRE(v_template && shapedirs && posedirs && J_reg && weights && derived, kErrBadArg, "lbs_prepare: null");
-    lbs_prepare_kernel<<<ceil_div(DERIVED_FLOATS, 256), 256, 0, stream>>>(v_template, shapedirs, posedirs, J_reg, weights,
-                                                                          derived);
+    SCAT_CHECK_CUDA(launch_k(lbs_prepare_kernel, dim3(ceil_div(DERIVED_FLOATS, 256)), dim3(256), 0, stream, v_template, shapedirs, posedirs, J_reg, weights,
+                                                                          derived));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -262,7 +264,7 @@ int launch_lbs_prepare_all(const float* v_template, const float* shapedirs, cons
 int launch_lbs_fwd_derived(const float* derived, const float* hands_mean, const float* rots, const float* poses,
                            const float* betas, float* out, int B, cudaStream_t stream) {
     SCAT_REQUIRE(derived && hands_mean && rots && poses && betas && out && B > 0, kErrBadArg, "lbs_fwd: bad args");
-    lbs_fwd_kernel<<<ceil_div(B, LBS_S), LBS_THREADS, 0, stream>>>(derived, hands_mean, rots, poses, betas, out, B);
+    SCAT_CHECK_CUDA(launch_k(lbs_fwd_kernel, dim3(ceil_div(B, LBS_S)), dim3(LBS_THREADS), 0, stream, derived, hands_mean, rots, poses, betas, out, B));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -16,6 +16,7 @@ constexpr int LOSS_THREADS = 256;
 
 __global__ void __launch_bounds__(LOSS_THREADS)
 rowsumsq_kernel(const float* __restrict__ X, int row_elems, float* __restrict__ out) {
+    pdl_sync();
     __shared__ float part[LOSS_THREADS / 32];
     const float* x = X + (long long)blockIdx.x * row_elems;
     float s = 0.f;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 proj_loss_kernel(const float* __restrict__ pred, const float* __restrict__ labels, int ld_labels,
                  const float* __restrict__ pl_sumsq, int n_tokens, float w3d, float w2d, float grad_scale,
                  float* __restrict__ losses, float* __restrict__ g_pred, int B) {
+    pdl_sync();
     __shared__ float scratch[LOSS_THREADS / 32];
     const int tid = threadIdx.x;
     const float inv3 = 1.0f / (63.0f * (float)B), inv2 = 1.0f / (42.0f * (float)B);
@@ -114,7 +116,37 @@ proj_loss_kernel(const float* __restrict__ pred, const float* __restrict__ label
     }
 }
 
+__global__ void __launch_bounds__(LOSS_THREADS)
+pl_loss_add_kernel(const float* __restrict__ pl_sumsq, int n_tokens, float* __restrict__ losses, int B) {
+    pdl_sync();
+    __shared__ float scratch[LOSS_THREADS / 32];
+    const int tid = threadIdx.x;
+    float a = 0.f;
+    for (int b = tid; b < B; b += LOSS_THREADS) a += sqrtf(pl_sumsq[b] / (float)n_tokens);
+    const float pl_mean = 0.01f * (block_sum(a, scratch) / (float)B);
+    float q = 0.f;
+    for (int b = tid; b < B; b += LOSS_THREADS) {
+        const float d = sqrtf(pl_sumsq[b] / (float)n_tokens) - pl_mean;
+        q += d * d;
+    }
+    const float lpl = block_sum(q, scratch) / (float)B;
+    if (tid == 0) {
+        losses[3] = lpl;
+        losses[0] += 10.0f * lpl;
+    }
+}
+
 }  // namespace
+
+int launch_pl_loss_add(const float* pl_term, int pl_row_elems, int n_tokens, float* losses, float* pl_scratch, int B,
+                       cudaStream_t stream) {
+    SCAT_REQUIRE(pl_term && losses && pl_scratch && B > 0, kErrBadArg, "pl_loss_add: bad args");
+    SCAT_CHECK_CUDA(launch_k(rowsumsq_kernel, dim3(B), dim3(LOSS_THREADS), 0, stream, pl_term, pl_row_elems, pl_scratch));
+    SCAT_CHECK_LAUNCH();
+    SCAT_CHECK_CUDA(launch_k(pl_loss_add_kernel, dim3(1), dim3(LOSS_THREADS), 0, stream, (const float*)pl_scratch, n_tokens, losses, B));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
 
 int launch_proj_loss(const float* pred, const float* labels, int ld_labels, const float* pl_term, int pl_row_elems,
                      int n_tokens, float w3d, float w2d, float grad_scale, float* losses, float* g_pred,
@@ -123,11 +155,11 @@ int launch_proj_loss(const float* pred, const float* labels, int ld_labels, cons
     SCAT_REQUIRE(ld_labels >= 105, kErrBadArg, "proj_loss: labels need >= 105 columns (63 3D + 42 2D), got %d", ld_labels);
     if (pl_term != nullptr) {
         SCAT_REQUIRE(pl_scratch != nullptr, kErrBadArg, "proj_loss: pl_scratch[B] required with pl_term");
-        rowsumsq_kernel<<<B, LOSS_THREADS, 0, stream>>>(pl_term, pl_row_elems, pl_scratch);
+        SCAT_CHECK_CUDA(launch_k(rowsumsq_kernel, dim3(B), dim3(LOSS_THREADS), 0, stream, pl_term, pl_row_elems, pl_scratch));
         SCAT_CHECK_LAUNCH();
     }
-    proj_loss_kernel<<<1, LOSS_THREADS, 0, stream>>>(pred, labels, ld_labels, pl_term ? pl_scratch : nullptr, n_tokens,
-                                                     w3d, w2d, grad_scale, losses, g_pred, B);
+    SCAT_CHECK_CUDA(launch_k(proj_loss_kernel, dim3(1), dim3(LOSS_THREADS), 0, stream, pred, labels, ld_labels, pl_term ? pl_scratch : nullptr, n_tokens,
+                                                     w3d, w2d, grad_scale, losses, g_pred, B));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ Y, int ldy, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int D, int round_out) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ resid, int ldr, float* __restrict__ dX, int lddx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D, int round_out) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D, int round_out, int act_rows) {
+    pdl_sync();
     __shared__ float red[LN_WARPS][32 * NPL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float gam[NPL], dg[NPL], db[NPL];
@@ -68,8 +70,10 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
     }
     const float invD = 1.0f / (float)D;
     for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
-        const float mu = mean[row], rs = rstd[row];
-        const float* x = X + (long long)row * ldx;
+        const int arow = act_rows > 0 ? row % act_rows : row;
+        const bool real = act_rows <= 0 || row < act_rows;     // stacked ones-cotangent rows carry no parameter gradient
+        const float mu = mean[arow], rs = rstd[arow];
+        const float* x = X + (long long)arow * ldx;
         const float* dy = dY + (long long)row * lddy;
         float xh[NPL], g[NPL];
         float s1 = 0.f, s2 = 0.f;
@@ -82,8 +86,10 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
             g[i] = dv * gam[i];
             s1 += g[i];
             s2 = fmaf(g[i], xh[i], s2);
-            dg[i] = fmaf(dv, xh[i], dg[i]);
-            db[i] += dv;
+            if (real) {
+                dg[i] = fmaf(dv, xh[i], dg[i]);
+                db[i] += dv;
+            }
         }
         s1 = warp_sum(s1) * invD;
         s2 = warp_sum(s2) * invD;
@@ -126,21 +132,21 @@ int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const floa
                          float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm: D=%d not in [1,1024]", D);
     const int grid = ceil_div(M, LN_WARPS);
-    if (D <= 256) layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out);
-    else if (D <= 512) layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out);
-    else layernorm_fwd_kernel<32><<<grid, LN_WARPS * 32, 0, stream>>>(X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out);
+    if (D <= 256) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out));
+    else if (D <= 512) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out));
+    else SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<32>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
-                         float* dbeta, int M, int D, int round_out, cudaStream_t stream) {
+                         float* dbeta, int M, int D, int round_out, cudaStream_t stream, int act_rows) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm bwd: D=%d not in [1,1024]", D);
     SCAT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), kErrBadArg, "layernorm bwd: dgamma/dbeta must both be set or null");
     const int grid = min(ceil_div(M, 2 * LN_WARPS), 148);     // >= 2 rows per warp: halves the atomic tail
-#define SCAT_LN_BWD(NPL) layernorm_bwd_kernel<NPL><<<grid, LN_WARPS * 32, 0, stream>>>( \
-        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out)
+#define SCAT_LN_BWD(NPL) SCAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<NPL>, dim3(grid), dim3(LN_WARPS * 32), 0, stream,  \
+        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out, act_rows))
     if (D <= 256) SCAT_LN_BWD(8);
     else if (D <= 512) SCAT_LN_BWD(16);
     else SCAT_LN_BWD(32);

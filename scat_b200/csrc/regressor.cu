@@ -22,6 +22,7 @@ constexpr int HJ = 8;              // weight rows per CTA (one per warp)
 __global__ void __launch_bounds__(256)
 regressor_hoist_kernel(const float* __restrict__ main_feat, const float* __restrict__ Wr, const float* __restrict__ br,
                        float* __restrict__ h, int B, int F, int P) {
+    pdl_sync();
     extern __shared__ __align__(16) float mfs[];   // [HS][F]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * HS, j = blockIdx.y * HJ + warp;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(128)
 regressor_iter_kernel(const float* __restrict__ h_all, const float* __restrict__ feat_out,
                       const float* __restrict__ mean_params, const float* __restrict__ Wr, float* __restrict__ pred,
                       float* __restrict__ states, int F, int P, int iteration, int root_relative) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* Wp = sm;                    // [P][P+1]
     float* h = Wp + P * (P + 1);       // [P]
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(128)
 regressor_iter_bwd_kernel(const float* __restrict__ g_pred, const float* __restrict__ Wr, float* __restrict__ d_feat_out,
                           float* __restrict__ gsum_out, float* __restrict__ gsteps, int F, int P, int iteration,
                           int root_relative) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* Wp = sm;                    // [P][P+1]
     float* g = Wp + P * (P + 1);       // [P]
@@ -158,11 +161,11 @@ int launch_regressor_fwd(const float* main_feat, const float* feat_out, const fl
     const size_t smem1 = sizeof(float) * (size_t)HS * F;
     if (smem1 > 48 * 1024)
         SCAT_CHECK_CUDA(cudaFuncSetAttribute(regressor_hoist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    regressor_hoist_kernel<<<dim3(ceil_div(B, HS), ceil_div(P, HJ)), 256, smem1, stream>>>(main_feat, Wr, br, h_scratch, B, F, P);
+    SCAT_CHECK_CUDA(launch_k(regressor_hoist_kernel, dim3(dim3(ceil_div(B, HS), ceil_div(P, HJ))), dim3(256), smem1, stream, main_feat, Wr, br, h_scratch, B, F, P));
     SCAT_CHECK_LAUNCH();
     const size_t smem2 = sizeof(float) * ((size_t)P * (P + 1) + 3 * (size_t)P);
-    regressor_iter_kernel<<<B, 128, smem2, stream>>>(h_scratch, feat_out, mean_params, Wr, pred, states, F, P, iteration,
-                                                    root_relative);
+    SCAT_CHECK_CUDA(launch_k(regressor_iter_kernel, dim3(B), dim3(128), smem2, stream, h_scratch, feat_out, mean_params, Wr, pred, states, F, P, iteration,
+                                                    root_relative));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -172,7 +175,7 @@ int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out
     SCAT_REQUIRE(P >= 4 && P <= MAXP, kErrUnsupported, "regressor bwd: P=%d out of range", P);
     SCAT_REQUIRE(gsum && gsteps, kErrBadArg, "regressor bwd: gsum/gsteps scratch required");
     const size_t smem = sizeof(float) * ((size_t)P * (P + 1) + 2 * (size_t)P + 4);
-    regressor_iter_bwd_kernel<<<B, 128, smem, stream>>>(g_pred, Wr, d_feat_out, gsum, gsteps, F, P, iteration, root_relative);
+    SCAT_CHECK_CUDA(launch_k(regressor_iter_bwd_kernel, dim3(B), dim3(128), smem, stream, g_pred, Wr, d_feat_out, gsum, gsteps, F, P, iteration, root_relative));
     SCAT_CHECK_LAUNCH();
     if (d_main_feat != nullptr) {
         GemmArgs g;   // d main_feat[B,F] = gsum[B,P] Wr[:, :F]
