@@ -5,6 +5,8 @@
 // n = 21 for the hand head (one token per joint), up to 128 for the HRNet-token variant.  At these
 // sizes a (b,h) problem is far below one UMMA tile, so each CTA keeps Q,K,V in shared memory and
 // uses FFMA; the kernel is latency/launch bound, not tensor bound.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace scat {
@@ -140,7 +142,7 @@ attention_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ P,
 
 }  // namespace
 
-// attention_small.cu: warp-per-problem kernels for the n = 21 training path
+// attention_small.cu: fp32 FFMA kernels for the n = 21 training path
 bool attention_small_supported(int n);
 int launch_attention_small_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                                cudaStream_t stream);

@@ -16,10 +16,25 @@ constexpr int DH = 64;
 constexpr int NW = 4;            // warps per CTA, each owns DS = 16 of the 64 head dims
 constexpr int DS = DH / NW;
 
-__device__ __forceinline__ void load_rows_to_smem(const float* __restrict__ src, long long row_stride, int n, float* dst) {
-    for (int e = threadIdx.x; e < n * (DH / 4); e += NW * 32) {
-        const int r = e >> 4, c4 = e & 15;
-        reinterpret_cast<float4*>(dst)[e] = __ldg(reinterpret_cast<const float4*>(src + (long long)r * row_stride) + c4);
+// [N][64] global rows -> registers (load phase) -> shared (store phase); compile-time trip count so that every
+// global load of every tile is in flight before the first is consumed
+template <int N>
+struct RowRegs { float4 v[(N * (DH / 4) + NW * 32 - 1) / (NW * 32)]; };
+template <int N>
+__device__ __forceinline__ void rows_load(const float* __restrict__ src, long long row_stride, RowRegs<N>& t) {
+#pragma unroll
+    for (int i = 0; i < (N * (DH / 4) + NW * 32 - 1) / (NW * 32); ++i) {
+        const int e = threadIdx.x + i * NW * 32, r = e >> 4, c4 = e & 15;
+        t.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < N) t.v[i] = __ldg(reinterpret_cast<const float4*>(src + (long long)r * row_stride) + c4);
+    }
+}
+template <int N>
+__device__ __forceinline__ void rows_store(float* dst, const RowRegs<N>& t) {
+#pragma unroll
+    for (int i = 0; i < (N * (DH / 4) + NW * 32 - 1) / (NW * 32); ++i) {
+        const int e = threadIdx.x + i * NW * 32;
+        if (e < N * (DH / 4)) reinterpret_cast<float4*>(dst)[e] = t.v[i];
     }
 }
 __device__ __forceinline__ void load_slice(const float* __restrict__ src, float* reg) {
@@ -71,11 +86,16 @@ attention_fwd_small_kernel(const float* __restrict__ QKV, float* __restrict__ O,
     const int inner = heads * DH;
     const long long rs = 3LL * inner;
     const float* base = QKV + (long long)b * N * rs + g * DH;
-    load_rows_to_smem(base, rs, N, Qs);
-    load_rows_to_smem(base + 2 * inner, rs, N, Vs);
     const bool act = lane < N;
     float kreg[DS];
-    if (act) load_slice(base + inner + (long long)lane * rs + warp * DS, kreg);
+    {
+        RowRegs<N> tq, tv;
+        rows_load<N>(base, rs, tq);
+        rows_load<N>(base + 2 * inner, rs, tv);
+        if (act) load_slice(base + inner + (long long)lane * rs + warp * DS, kreg);
+        rows_store<N>(Qs, tq);
+        rows_store<N>(Vs, tv);
+    }
     __syncthreads();
     if (act) {
 #pragma unroll
@@ -124,14 +144,30 @@ attention_bwd_small_kernel(const float* __restrict__ QKV, const float* __restric
     const long long rs = 3LL * inner;
     const int ba = act_batch > 0 ? b % act_batch : b;        // stacked cotangents share the saved activations
     const float* base = QKV + (long long)ba * N * rs + g * DH;
-    load_rows_to_smem(base, rs, N, Qs);
-    load_rows_to_smem(base + inner, rs, N, Ks);
-    load_rows_to_smem(dO + (long long)b * N * inner + g * DH, inner, N, Gs);
     const float* Pg = P + ((long long)ba * heads + g) * N * N;
-    for (int e = threadIdx.x; e < N * N; e += NW * 32) Ps[(e / N) * LS + (e % N)] = __ldg(Pg + e);
     const bool act = lane < N;
     float vreg[DS];
-    if (act) load_slice(base + 2 * inner + (long long)lane * rs + warp * DS, vreg);
+    {
+        RowRegs<N> tq, tk, tg;
+        float pr[(N * N + NW * 32 - 1) / (NW * 32)];
+        rows_load<N>(base, rs, tq);
+        rows_load<N>(base + inner, rs, tk);
+        rows_load<N>(dO + (long long)b * N * inner + g * DH, inner, tg);
+#pragma unroll
+        for (int i = 0; i < (N * N + NW * 32 - 1) / (NW * 32); ++i) {
+            const int e = threadIdx.x + i * NW * 32;
+            pr[i] = e < N * N ? __ldg(Pg + e) : 0.f;
+        }
+        if (act) load_slice(base + 2 * inner + (long long)lane * rs + warp * DS, vreg);
+        rows_store<N>(Qs, tq);
+        rows_store<N>(Ks, tk);
+        rows_store<N>(Gs, tg);
+#pragma unroll
+        for (int i = 0; i < (N * N + NW * 32 - 1) / (NW * 32); ++i) {
+            const int e = threadIdx.x + i * NW * 32;
+            if (e < N * N) Ps[(e / N) * LS + (e % N)] = pr[i];
+        }
+    }
     __syncthreads();
     if (act) {
 #pragma unroll

@@ -27,6 +27,14 @@ __device__ __forceinline__ uint32_t build_mask_bits(const int32_t* __restrict__ 
     return 0;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int T>
 __global__ void __launch_bounds__(CONV_THREADS, 2)
 conv_pe_mask_fwd_kernel(const float* __restrict__ x2, const float* __restrict__ Wc, const float* __restrict__ pe,
@@ -248,16 +256,17 @@ conv_wgrad_partial_kernel(const float* __restrict__ dFv, const float* __restrict
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / chunks, p0 = (item % chunks) * WG_PX;
         __syncthreads();
+        // stage the [C][28] slab of x2 and the [T][28] slab of dFv with cp.async: every 16-byte copy is in flight
+        // at once and none of them holds a register (a load->store loop would serialise one round trip per pass)
         for (int i = tid; i < C * px4; i += CONV_THREADS) {
             const int c = i / px4, q = i % px4;
-            reinterpret_cast<float4*>(xs)[i] =
-                __ldg(reinterpret_cast<const float4*>(x2 + ((long long)b * C + c) * HW + p0) + q);
+            cp_async16(reinterpret_cast<float4*>(xs) + i, reinterpret_cast<const float4*>(x2 + ((long long)b * C + c) * HW + p0) + q);
         }
         for (int i = tid; i < T * px4; i += CONV_THREADS) {
             const int t = i / px4, q = i % px4;
-            reinterpret_cast<float4*>(ds)[i] =
-                __ldg(reinterpret_cast<const float4*>(dFv + ((long long)b * T + t) * HW + p0) + q);
+            cp_async16(reinterpret_cast<float4*>(ds) + i, reinterpret_cast<const float4*>(dFv + ((long long)b * T + t) * HW + p0) + q);
         }
+        cp_async_wait_all();
         __syncthreads();
 #pragma unroll 1
         for (int q = 0; q < px4; ++q) {
