@@ -132,6 +132,21 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
               const float* aux_in, int32_t ld_aux_in, float* aux_out, int32_t ld_aux_out,
               int32_t accumulate, int32_t precision, void* stream);
 
+/* Same contraction with bf16 operands already in HBM (tcgen05 kind::f16, fp32 accumulation in TMEM): the GEMM the
+ * head runs in SCAT_PREC_BF16 mode, where every producer kernel stores the bf16 copy its consumer GEMM reads.
+ * A, B: bf16 (uint16 storage), strides in elements, unit stride in one direction, 16-byte aligned rows.
+ * C (fp32, NULL to skip) and/or C16 (bf16 copy, NULL to skip) receive epilogue(A B^T).  split_k != 0 lets the
+ * kernel slice K over CTAs and combine with reductions in L2 (C must then be zero on entry, epilogue NONE). */
+int scat_gemm_bf16(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sbn, int64_t sbk, float* C,
+                   int32_t ldc, void* C16, int32_t ldc16, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                   const float* bias, const float* aux_in, int32_t ld_aux_in, float* aux_out, int32_t ld_aux_out,
+                   int32_t split_k, void* stream);
+
+/* Profiling hook: when set to a device buffer of 8 int64, CTA (0,0,0) of every tensor-core GEMM launch records
+ * clock64() at entry / setup done / dependency wait done / first stage landed / epilogue waiting / accumulator
+ * ready / stores issued / teardown.  NULL (default) disables it.  See tools/gemm_timeline.py. */
+void scat_debug_gemm_timeline(void* dev_int64x8);
+
 /* hand_net.py:363-373 */
 int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
                           const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,

@@ -44,6 +44,9 @@ SIGNATURES = {
     "scat_tokens_forward": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _sz, _f]),
     "scat_gemm": (_i32, [_f, _i64, _i64, _f, _i64, _i64, _f, _i32, _i32, _i32, _i32, _i32, _f, _f, _i32, _f, _i32,
                          _i32, _i32, _f]),
+    "scat_gemm_bf16": (_i32, [_f, _i64, _i64, _f, _i64, _i64, _f, _i32, _f, _i32, _i32, _i32, _i32, _i32, _f, _f, _i32,
+                              _f, _i32, _i32, _f]),
+    "scat_debug_gemm_timeline": (None, [_f]),
     "scat_conv_pe_mask_fwd": (_i32, [_f, _f, _f, _f, _f, _i32, _i32, _f, _f, _i32, _i32, _i32, _i32, _f]),
     "scat_conv_bwd_scratch_floats": (_sz, [_i32, _i32, _i32, _i32]),
     "scat_conv_bwd": (_i32, [_f, _f, _f, _f, _i32, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),

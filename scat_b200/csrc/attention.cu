@@ -74,12 +74,12 @@ attention_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float
         }
     }
     __syncthreads();
-    float* Ob = O + (long long)b * n * inner + g * DH;
+    const long long ob = (long long)b * n * inner + g * DH;
     for (int e = threadIdx.x; e < n * DH; e += blockDim.x) {
         const int i = e / DH, d = e % DH;
         float o = 0.f;
         for (int j = 0; j < n; ++j) o = fmaf(Ss[i * lds + j], Vs[j * LDS + d], o);
-        Ob[(long long)i * inner + d] = round_out ? round_tf32(o) : o;
+        store_out(O, ob + (long long)i * inner + d, o, round_out);
     }
 }
 
@@ -124,7 +124,7 @@ attention_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ P,
         for (int j = lane; j < n; j += 32) Ds[i * lds + j] = Ps[i * lds + j] * (Ds[i * lds + j] - r) * 0.125f;
     }
     __syncthreads();
-    float* dbase = dQKV + (long long)b * n * rs + g * DH;
+    const long long dbase = (long long)b * n * rs + g * DH;
     for (int e = threadIdx.x; e < n * DH; e += blockDim.x) {
         const int i = e / DH, d = e % DH;
         float dq = 0.f, dk = 0.f, dv = 0.f;
@@ -133,10 +133,10 @@ attention_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ P,
             dk = fmaf(Ds[j * lds + i], Qs[j * LDS + d], dk);   // dK[i] = sum_j dS[j,i] Q[j]
             dv = fmaf(Ps[j * lds + i], Gs[j * LDS + d], dv);   // dV[i] = sum_j P[j,i] dO[j]
         }
-        float* o = dbase + (long long)i * rs + d;
-        o[0] = round_out ? round_tf32(dq) : dq;
-        o[inner] = round_out ? round_tf32(dk) : dk;
-        o[2 * inner] = round_out ? round_tf32(dv) : dv;
+        const long long o = dbase + (long long)i * rs + d;
+        store_out(dQKV, o, dq, round_out);
+        store_out(dQKV, o + inner, dk, round_out);
+        store_out(dQKV, o + 2 * inner, dv, round_out);
     }
 }
 

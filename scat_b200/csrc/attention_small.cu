@@ -62,13 +62,11 @@ __device__ __forceinline__ void axpy_slice(float w, const float* srow, float* ac
         acc[4 * c4 + 2] = fmaf(w, v.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(w, v.w, acc[4 * c4 + 3]);
     }
 }
-__device__ __forceinline__ void store_slice(float* dst, const float* acc, int round_out) {
+// DS consecutive outputs starting at element `off` of a tensor stored in `out_mode` (fp32 / TF32-rounded / bf16)
+__device__ __forceinline__ void store_slice(float* base, long long off, const float* acc, int out_mode) {
 #pragma unroll
-    for (int c4 = 0; c4 < DS / 4; ++c4) {
-        float4 v = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-        if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-        reinterpret_cast<float4*>(dst)[c4] = v;
-    }
+    for (int c4 = 0; c4 < DS / 4; ++c4)
+        store_out4(base, off + 4 * c4, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]), out_mode);
 }
 
 template <int N>
@@ -122,7 +120,7 @@ attention_fwd_small_kernel(const float* __restrict__ QKV, float* __restrict__ O,
         for (int d = 0; d < DS; ++d) acc[d] = 0.f;
 #pragma unroll 7
         for (int j = 0; j < N; ++j) axpy_slice(Ps[lane * LS + j], Vs + j * DH + warp * DS, acc);
-        store_slice(O + ((long long)b * N + lane) * inner + g * DH + warp * DS, acc, round_out);
+        store_slice(O, ((long long)b * N + lane) * inner + g * DH + warp * DS, acc, round_out);
     }
 }
 
@@ -182,23 +180,23 @@ attention_bwd_small_kernel(const float* __restrict__ QKV, const float* __restric
     }
     __syncthreads();
     if (act) {
-        float* drow = dQKV + ((long long)b * N + lane) * rs + g * DH + warp * DS;
+        const long long drow = ((long long)b * N + lane) * rs + g * DH + warp * DS;
         float acc[DS];
 #pragma unroll
         for (int d = 0; d < DS; ++d) acc[d] = 0.f;
 #pragma unroll 7
         for (int i = 0; i < N; ++i) axpy_slice(Ps[i * LS + lane], Gs + i * DH + warp * DS, acc);    // dV[j] = sum_i P[i,j] dO[i]
-        store_slice(drow + 2 * inner, acc, round_out);
+        store_slice(dQKV, drow + 2 * inner, acc, round_out);
 #pragma unroll
         for (int d = 0; d < DS; ++d) acc[d] = 0.f;
 #pragma unroll 7
         for (int i = 0; i < N; ++i) axpy_slice(Ds[i * LS + lane], Qs + i * DH + warp * DS, acc);    // dK[j] = sum_i dS[i,j] Q[i]
-        store_slice(drow + inner, acc, round_out);
+        store_slice(dQKV, drow + inner, acc, round_out);
 #pragma unroll
         for (int d = 0; d < DS; ++d) acc[d] = 0.f;
 #pragma unroll 7
         for (int j = 0; j < N; ++j) axpy_slice(Ds[lane * LS + j], Ks + j * DH + warp * DS, acc);    // dQ[i] = sum_j dS[i,j] K[j]
-        store_slice(drow, acc, round_out);
+        store_slice(dQKV, drow, acc, round_out);
     }
 }
 

@@ -1,5 +1,6 @@
 // Shared device/host helpers for the scat_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -73,6 +74,12 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 }
 #endif
 
+// How a producer kernel stores a tensor that feeds a tensor-core GEMM (`out_mode` arguments):
+//   OUT_F32  plain fp32;  OUT_TF32  fp32 rounded to the nearest TF32 value (the tensor core would truncate);
+//   OUT_BF16 bf16 written through the same pointer (the buffer is then a bf16 array with the given leading
+//   dimension in ELEMENTS; it occupies the first half of its fp32-sized workspace slot).
+enum OutMode : int { OUT_F32 = 0, OUT_TF32 = 1, OUT_BF16 = 2 };
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
@@ -86,6 +93,29 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+__device__ __forceinline__ float round_tf32_dev(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+// element `idx` of an output tensor stored in `mode`
+__device__ __forceinline__ void store_out(float* base, long long idx, float v, int mode) {
+    if (mode == OUT_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+    else base[idx] = mode == OUT_TF32 ? round_tf32_dev(v) : v;
+}
+// four consecutive elements starting at `idx` (idx % 4 == 0, base 16-byte aligned)
+__device__ __forceinline__ void store_out4(float* base, long long idx, float4 v, int mode) {
+    if (mode == OUT_BF16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = pk;
+    } else {
+        if (mode == OUT_TF32) { v.x = round_tf32_dev(v.x); v.y = round_tf32_dev(v.y); v.z = round_tf32_dev(v.z); v.w = round_tf32_dev(v.w); }
+        *reinterpret_cast<float4*>(base + idx) = v;
+    }
 }
 // exact (erf) GELU, the nn.GELU() default used by vision_transformer.py:33
 __device__ __forceinline__ float gelu_erf(float x) {

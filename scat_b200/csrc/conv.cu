@@ -343,7 +343,7 @@ int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mas
 }
 
 int launch_mask_bwd(const float* dX0, const int32_t* mask_idx, int n_masked, int keep_masked, float* dFv,
-                    float* d_mask_token, int B, int T, int HW, cudaStream_t stream) {
+                    float* d_mask_token, int B, int T, int HW, cudaStream_t stream, int token_grad_zeroed) {
     SCAT_REQUIRE(HW % 4 == 0 && T <= 128, kErrUnsupported, "mask bwd: HW%%4, T<=128");
     if (dFv != nullptr) {
         const long long total = (long long)B * T * (HW / 4);
@@ -352,7 +352,7 @@ int launch_mask_bwd(const float* dX0, const int32_t* mask_idx, int n_masked, int
         SCAT_CHECK_LAUNCH();
     }
     if (d_mask_token != nullptr) {
-        SCAT_CHECK_CUDA(cudaMemsetAsync(d_mask_token, 0, (size_t)HW * sizeof(float), stream));
+        if (!token_grad_zeroed) SCAT_CHECK_CUDA(cudaMemsetAsync(d_mask_token, 0, (size_t)HW * sizeof(float), stream));
         if (n_masked > 0) {
             SCAT_CHECK_CUDA(launch_k(mask_token_grad_kernel, dim3(dim3(ceil_div(HW, 128), min(B, 32))), dim3(128), 0, stream, dX0, mask_idx, n_masked,
                                                                                             d_mask_token, B, T, HW));

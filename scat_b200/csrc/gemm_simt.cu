@@ -68,15 +68,15 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
     const int kt_end = min(nk_all, kt_beg + kt_per_split);
     if (kt_beg >= kt_end) return;
     Frag fa, fb;
-    load_tile<A_K>(g.A, g.sam, g.sak, m0, kt_beg * BK, g.M, g.K, tid, fa);
-    load_tile<B_K>(g.B, g.sbn, g.sbk, n0, kt_beg * BK, g.N, g.K, tid, fb);
+    load_tile<A_K>(static_cast<const float*>(g.A), g.sam, g.sak, m0, kt_beg * BK, g.M, g.K, tid, fa);
+    load_tile<B_K>(static_cast<const float*>(g.B), g.sbn, g.sbk, n0, kt_beg * BK, g.N, g.K, tid, fb);
     for (int kt = kt_beg; kt < kt_end; ++kt) {
         store_tile<A_K>(As, tid, fa);
         store_tile<B_K>(Bs, tid, fb);
         __syncthreads();
         if (kt + 1 < kt_end) {
-            load_tile<A_K>(g.A, g.sam, g.sak, m0, (kt + 1) * BK, g.M, g.K, tid, fa);
-            load_tile<B_K>(g.B, g.sbn, g.sbk, n0, (kt + 1) * BK, g.N, g.K, tid, fb);
+            load_tile<A_K>(static_cast<const float*>(g.A), g.sam, g.sak, m0, (kt + 1) * BK, g.M, g.K, tid, fa);
+            load_tile<B_K>(static_cast<const float*>(g.B), g.sbn, g.sbk, n0, (kt + 1) * BK, g.N, g.K, tid, fb);
         }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
@@ -175,6 +175,7 @@ int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     SCAT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, kErrBadArg, "gemm: bad shape %d %d %d", g.M, g.N, g.K);
     SCAT_REQUIRE(g.A && g.B && g.C, kErrBadArg, "gemm: null operand");
+    SCAT_REQUIRE(!g.operand_bf16 && !g.C16, kErrUnsupported, "gemm: the FFMA kernel takes fp32 operands only");
     if (g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_BIAS_GELU)
         SCAT_REQUIRE(g.bias != nullptr, kErrBadArg, "gemm: epilogue %d needs bias", g.epilogue);
     if (g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_DGELU || g.epilogue == EPI_RESID)
@@ -190,7 +191,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     }
     const int kt_per_split = ceil_div(nk, splits);
     grid.z = ceil_div(nk, kt_per_split);
-    if (grid.z > 1 && !g.accumulate)
+    if (grid.z > 1 && !g.accumulate && !g.c_zeroed)
         SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
     const bool a_k = (g.sak == 1) || (g.sam != 1);
     const bool b_k = (g.sbk == 1) || (g.sbn != 1);

@@ -1,18 +1,28 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a: C[M,N] = epilogue(A * B^T), fp32 in HBM, TF32 tensor-core math,
-// fp32 accumulation in tensor memory.
+// tcgen05 / TMEM / TMA GEMM for sm_100a: C[M,N] = epilogue(A * B^T), fp32 accumulation in tensor memory.
+//   operands fp32 in HBM  -> tcgen05.mma kind::tf32 (K = 8 per instruction, 32 k per 128-byte swizzle row)
+//   operands bf16 in HBM  -> tcgen05.mma kind::f16  (K = 16 per instruction, 64 k per 128-byte swizzle row)
 //
 // Replaces the cuBLAS calls behind the reference's nn.Linear layers (vision_transformer.py:33-35,53-55) and
 // their autograd backward (dgrad / wgrad).  One kernel covers all three because both operands may be
 // K-major (row stride, unit k stride) or MN-major (unit row stride, k stride): the majorness only changes the
-// TMA box issue pattern, the UMMA shared-memory descriptors and two bits of the instruction descriptor.
+// TMA box issue pattern, the UMMA shared-memory descriptors and two bits of the instruction descriptor, all
+// of them compile-time here.
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.kind::tf32, K = 8 per MMA)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> bias / GELU / residual -> global)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, 4 per stage)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> bias / GELU / residual -> global fp32 and/or bf16)
 //
-// Tile: BM = 128 rows (TMEM lanes) x BN in {64,128} columns x BK = 32 fp32 (one 128-byte swizzle row),
-// 4-stage shared-memory ring.  Out-of-range rows / columns / k are zero-filled by TMA, stores are bounds-checked.
+// Tile: BM = 128 rows (TMEM lanes) x BN in {64,128} columns x one 128-byte swizzle row of k per stage.  Two CTAs
+// are resident per SM (<= 97 KB of shared memory and <= 128 TMEM columns each) so that one CTA's epilogue and
+// prologue overlap the other's main loop; the head's GEMMs are small (M = 2016) and one tile per CTA.
+// Out-of-range rows / columns / k are zero-filled by TMA, stores are bounds-checked.
+//
+// The producer and MMA loops are executed by whole warps with elect.sync around the issuing instructions and
+// incremental stage / phase / descriptor arithmetic: a single-lane `if (lane == 0)` loop makes the compiler wrap
+// every uniform-datapath instruction (UTMALDG, UTCHMMA, UTCBAR) in an election loop, ~150 dependent instructions
+// per k-block, which bounded the first version of this kernel at ~0.45 us per k-block.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "kernels.h"
 
@@ -20,7 +30,6 @@ namespace scat {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements per 128-byte swizzle row
 constexpr int TC_THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
@@ -29,35 +38,45 @@ constexpr uint32_t SPIN_LIMIT = 1u << 28;
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // bounded wait: a protocol bug must fault the kernel, never hang the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > SPIN_LIMIT) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
@@ -68,15 +87,27 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                     uint32_t acc) {
+    if (BF16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
+    }
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -91,25 +122,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout type [61,64): SWIZZLE_128B = 2 (K-major), SWIZZLE_128B_BASE32B = 1 (MN-major tf32:
-// "for mn-major tf32 operands, SW128_32B is the only available smem layout", 32-byte swizzle atoms, 4 k-rows deep)
-constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout << 61;
-    return d;
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic transaction per 4 floats
+__device__ __forceinline__ void red_add_v4(float* dst, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ---------------------------------------------------------------------------------------------
+// element traits.  UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) |
+// SBO>>4 [32,46) | version=1 [46,48) | layout type [61,64).
+//   K-major, 128B swizzle (layout 2): 8-row groups 1024 B apart (SBO); a k-slice of one MMA is +32 B inside the row
+//   MN-major fp32 (layout 1 = SWIZZLE_128B_BASE32B, "the only smem layout for mn-major tf32"): TMA mode
+//     SWIZZLE_128B_ATOM_32B, boxes of 32 mn x 32 k; 32-wide mn groups one box apart (LBO), 4-k-row atoms 512 B apart
+//     (SBO), a k-slice of 8 = +1024 B
+//   MN-major bf16 (layout 2): boxes of 64 mn x 64 k; 64-wide mn groups one box apart (LBO), 8-k-row atoms 1024 B
+//     apart (SBO), a k-slice of 16 = +2048 B
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+struct Elem {
+    static constexpr int BYTES = BF16 ? 2 : 4;
+    static constexpr int BK = 128 / BYTES;            // k per stage (one swizzle row)
+    static constexpr int UK = 32 / BYTES;             // k per MMA
+    static constexpr int MN_BOX = 128 / BYTES;        // mn elements per 128-byte row of an MN-major box
+    static constexpr uint32_t FMT = BF16 ? 1u : 2u;   // instruction-descriptor operand format: BF16 = 1, TF32 = 2
+    static constexpr uint32_t MN_LAYOUT = BF16 ? 2u : 1u;
+    static constexpr uint32_t MN_SBO = BF16 ? 1024u : 512u;
+    static constexpr uint32_t MN_KSTEP = BF16 ? 2048u : 1024u;
+    static constexpr uint32_t MN_LBO = BK * 128;      // one box
+};
 
 struct TcParams {
     int M, N, K;
-    int a_mn_major, b_mn_major;     // 0: K-major (unit k stride), 1: MN-major (unit row stride)
-    float* C; int ldc;
+    float* C; int ldc;                  // fp32 output (may be null when only the bf16 copy is wanted)
+    __nv_bfloat16* C16; int ldc16;      // bf16 copy of the output (null = none): it feeds another bf16 GEMM
     int epilogue;
     const float* bias;
     const float* aux_in; int ld_aux_in; int aux_row_mod;
@@ -117,40 +161,214 @@ struct TcParams {
     int accumulate;
     int round_out;                  // 1: store C rounded to TF32-nearest (it feeds another tensor-core GEMM)
     int round_operands;             // 1: round fp32 operands to TF32 (nearest) in shared memory before the MMA
+    int kb_per_split;               // k-blocks per gridDim.z slice (split-K: weight gradients, K = B*21 rows)
+    int atomic_out;                 // 1: C += tile with red.global.add (split-K slices combine in L2; C pre-zeroed)
+    int vec_ok;                     // every pointer / leading dimension the epilogue touches allows 16-byte accesses
+    long long* dbg;                 // optional: CTA (0,0,0) records clock64() at 8 milestones (tools/gemm_timeline.py)
 };
+__device__ __forceinline__ void dbg_mark(const TcParams& p, int slot) {
+    if (p.dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) p.dbg[slot] = clock64();
+}
 
 template <int BN>
 struct SmemLayout {
-    static constexpr int STAGES = BN >= 128 ? 6 : 8;      // 192 KB ring, one CTA per SM: the loop is latency x bytes-in-flight bound
-    static constexpr int A_BYTES = BM * BK * 4;           // 16 KB
-    static constexpr int B_BYTES = BN * BK * 4;           // 8 / 16 KB
+    static constexpr int STAGES = BN >= 128 ? 3 : 4;      // 96 KB ring per CTA, two CTAs per SM
+    static constexpr int A_BYTES = BM * 128;              // 16 KB
+    static constexpr int B_BYTES = BN * 128;              // 8 / 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;    // barriers + tmem slot + slack for 1024-byte alignment
+    static constexpr int TOTAL = BAR_OFF + 128 + 1024;    // barriers + tmem slot + slack for 1024-byte alignment
 };
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BN tile, executed by the four epilogue warps (warp q owns TMEM lanes / tile rows 32q..32q+31).
+//
+// tcgen05.ld hands lane l the accumulator ROW l of the warp's quadrant; stored from there every global access would
+// touch 32 different rows (32 L1 wavefronts per instruction, half-used sectors).  Each warp therefore bounces its
+// 32x32 chunk through a private padded scratch in the (now idle) operand ring and continues in a coalesced mapping:
+// 8 lanes x float4 cover 128 contiguous bytes of one row, 4 rows per instruction.  Each epilogue warp sits alone on
+// its SM sub-partition, so instruction latency is fully exposed: addresses are carried incrementally, flags are
+// tested once per chunk (not per element), and all global reads of a chunk (bias, residual / saved pre-activation
+// or old C) are issued before the TMEM load so that they overlap it and each other.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_lane_base, float* scratch, int row_base,
+                                              int n0, int lane, int BN) {
+    constexpr int PITCH = 36;                    // floats per scratch row: float4 accesses stay conflict-free
+    const int rsub = lane >> 3, csub = (lane & 7) * 4;
+    const int epi = p.epilogue;
+    const bool has_aux = epi == EPI_BIAS_RESID || epi == EPI_RESID || epi == EPI_DGELU;
+    const bool has_bias = epi == EPI_BIAS || epi == EPI_BIAS_RESID || epi == EPI_BIAS_GELU;
+    const bool rmw = p.accumulate && !p.atomic_out && p.C != nullptr && !has_aux;
+    // rows this lane touches: row_base + rsub + 4i, i < 8
+    const int row0 = row_base + rsub;
+    uint32_t valid = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) valid |= (row0 + 4 * i < p.M ? 1u : 0u) << i;
+    const long long c_step = 4LL * p.ldc, h_step = 4LL * p.ldc16, z_step = 4LL * p.ld_aux_out;
+    float* cptr = p.C ? p.C + (long long)row0 * p.ldc + n0 + csub : nullptr;
+    __nv_bfloat16* hptr = p.C16 ? p.C16 + (long long)row0 * p.ldc16 + n0 + csub : nullptr;
+    float* zptr = p.aux_out ? p.aux_out + (long long)row0 * p.ld_aux_out + n0 + csub : nullptr;
+    float* srow = scratch + lane * PITCH;                       // TMEM-row mapping: this lane's row of the chunk
+    const float* scol = scratch + rsub * PITCH + csub;          // coalesced mapping: + 4i rows
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+        const int n = n0 + c + csub;                 // this lane's 4 columns
+        if (n0 + c >= p.N) break;                    // warp-uniform: nothing left in this tile row
+        const bool vec = p.vec_ok && n + 4 <= p.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ext[8];                               // residual / saved pre-activation, or old C (accumulate)
+        if (vec) {
+            if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            if (has_aux) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = row0 + 4 * i;
+                    const long long ar = p.aux_row_mod > 0 ? row % p.aux_row_mod : row;
+                    if ((valid >> i) & 1) ext[i] = __ldg(reinterpret_cast<const float4*>(p.aux_in + ar * p.ld_aux_in + n));
+                }
+            } else if (rmw) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((valid >> i) & 1) ext[i] = *reinterpret_cast<const float4*>(cptr + i * c_step);
+            }
+        }
+        float v[32];
+        __syncwarp();                                // tcgen05.ld is warp-collective; scratch reads of the last chunk done
+        tmem_ld32(tmem_lane_base + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (vec) {
+            float4 acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = *reinterpret_cast<const float4*>(scol + i * 4 * PITCH);
+            // ---- math phase (registers only, except the saved pre-activation of BIAS_GELU) ----
+            if (has_bias) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { acc[i].x += b4.x; acc[i].y += b4.y; acc[i].z += b4.z; acc[i].w += b4.w; }
+            }
+            if (epi == EPI_BIAS_RESID || epi == EPI_RESID || rmw) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((valid >> i) & 1) { acc[i].x += ext[i].x; acc[i].y += ext[i].y; acc[i].z += ext[i].z; acc[i].w += ext[i].w; }
+            } else if (epi == EPI_DGELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((valid >> i) & 1) {
+                        acc[i].x *= gelu_erf_grad(ext[i].x); acc[i].y *= gelu_erf_grad(ext[i].y);
+                        acc[i].z *= gelu_erf_grad(ext[i].z); acc[i].w *= gelu_erf_grad(ext[i].w);
+                    }
+            } else if (epi == EPI_BIAS_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if ((valid >> i) & 1) *reinterpret_cast<float4*>(zptr + i * z_step) = acc[i];
+                    acc[i].x = gelu_erf(acc[i].x); acc[i].y = gelu_erf(acc[i].y);
+                    acc[i].z = gelu_erf(acc[i].z); acc[i].w = gelu_erf(acc[i].w);
+                }
+            }
+            if (p.round_out) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[i].x = round_tf32(acc[i].x); acc[i].y = round_tf32(acc[i].y);
+                    acc[i].z = round_tf32(acc[i].z); acc[i].w = round_tf32(acc[i].w);
+                }
+            }
+            // ---- store phase ----
+            if (hptr != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[i].x, acc[i].y), hi = __floats2bfloat162_rn(acc[i].z, acc[i].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    if ((valid >> i) & 1) *reinterpret_cast<uint2*>(hptr + i * h_step) = pk;
+                }
+            }
+            if (cptr != nullptr) {
+                if (p.atomic_out) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if ((valid >> i) & 1) red_add_v4(cptr + i * c_step, acc[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if ((valid >> i) & 1) *reinterpret_cast<float4*>(cptr + i * c_step) = acc[i];
+                }
+            }
+        } else if (n < p.N) {
+            // ragged / unaligned edge: scalar, rolled (rare: N tails and odd leading dimensions)
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int row = row0 + 4 * i;
+                if (row >= p.M) break;
+                const float4 o = *reinterpret_cast<const float4*>(scol + i * 4 * PITCH);
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+                const long long ar = p.aux_row_mod > 0 ? row % p.aux_row_mod : row;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ne = n + e;
+                    if (ne >= p.N) break;
+                    float t = ov[e];
+                    switch (epi) {
+                        case EPI_BIAS: t += p.bias[ne]; break;
+                        case EPI_BIAS_RESID: t += p.bias[ne] + p.aux_in[ar * p.ld_aux_in + ne]; break;
+                        case EPI_BIAS_GELU: t += p.bias[ne]; p.aux_out[(long long)row * p.ld_aux_out + ne] = t; t = gelu_erf(t); break;
+                        case EPI_DGELU: t *= gelu_erf_grad(p.aux_in[ar * p.ld_aux_in + ne]); break;
+                        case EPI_RESID: t += p.aux_in[ar * p.ld_aux_in + ne]; break;
+                        default: break;
+                    }
+                    if (p.round_out) t = round_tf32(t);
+                    if (p.C16) p.C16[(long long)row * p.ldc16 + ne] = __float2bfloat16_rn(t);
+                    if (p.C) {
+                        float* cp = p.C + (long long)row * p.ldc + ne;
+                        if (p.atomic_out) atomicAdd(cp, t);
+                        else *cp = (p.accumulate && !has_aux) ? *cp + t : t;
+                    }
+                }
+            }
+        }
+        if (cptr != nullptr) cptr += 32;
+        if (hptr != nullptr) hptr += 32;
+        if (zptr != nullptr) zptr += 32;
+    }
+}
+
+template <bool BF16, int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using L = SmemLayout<BN>;
+    using E = Elem<BF16>;
     constexpr int STAGES = L::STAGES;
+    constexpr int BK = E::BK;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* conv_bar = empty_bar + STAGES;
-    uint64_t* accum_bar = conv_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    // 1024-byte alignment (128B swizzle atoms) by an integer offset into the extern array: pointer arithmetic on
+    // smem_raw keeps the shared address space known to the compiler (LDS/STS instead of generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_bar = smem_base + L::BAR_OFF;          // STAGES x 8 B each
+    const uint32_t empty_bar = full_bar + 8 * STAGES;
+    const uint32_t conv_bar = empty_bar + 8 * STAGES;
+    const uint32_t accum_bar = conv_bar + 8 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (3 * STAGES + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) dbg_mark(p, 0);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int kb_all = (p.K + BK - 1) / BK;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int num_kb = min(kb_all, kb_begin + p.kb_per_split) - kb_begin;      // host guarantees >= 1
 
     if (warp == 0 && lane == 0) {
+        // fetch the two TMA descriptors while the barriers are set up (they are kernel parameters, not data of
+        // the preceding kernel): the first bulk load otherwise pays the descriptor miss on top of the L2 latency
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+#pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-            mbar_init(&conv_bar[s], TC_THREADS - 64);     // every epilogue/converter thread arrives
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+            mbar_init(conv_bar + 8 * s, TC_THREADS - 64);     // every epilogue/converter thread arrives
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -163,74 +381,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // everything above (barrier init, TMEM allocation) overlapped the previous kernel's tail; operands and the
     // output buffer may only be touched once that kernel has completed
     pdl_sync();
+    if (threadIdx.x == 0) dbg_mark(p, 1);
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-                uint8_t* sa = smem + s * L::STAGE_BYTES;
-                uint8_t* sb = sa + L::A_BYTES;
-                const int k0 = kb * BK;
-                if (!p.a_mn_major) {
-                    tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);                                 // box {32 k, 128 rows}
+        int s = 0;
+        uint32_t ph = 0;
+        int k0 = kb_begin * BK;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar + 8 * s, ph ^ 1);
+            if (elect_one()) {
+                const uint32_t fb = full_bar + 8 * s;
+                mbar_expect_tx(fb, L::STAGE_BYTES);
+                const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+                const uint32_t sb = sa + L::A_BYTES;
+                if (!A_MN) {
+                    tma_load_2d(&tmA, fb, sa, k0, m0);                                        // box {BK k, 128 rows}
                 } else {
 #pragma unroll
-                    for (int i = 0; i < BM / 32; ++i)
-                        tma_load_2d(&tmA, &full_bar[s], sa + i * 4096, m0 + 32 * i, k0);         // box {32 rows, 32 k}
+                    for (int i = 0; i < BM / E::MN_BOX; ++i)
+                        tma_load_2d(&tmA, fb, sa + i * E::MN_LBO, m0 + E::MN_BOX * i, k0);    // box {MN_BOX rows, BK k}
                 }
-                if (!p.b_mn_major) {
-                    tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);                                 // box {32 k, BN rows}
+                if (!B_MN) {
+                    tma_load_2d(&tmB, fb, sb, k0, n0);                                        // box {BK k, BN rows}
                 } else {
 #pragma unroll
-                    for (int i = 0; i < BN / 32; ++i)
-                        tma_load_2d(&tmB, &full_bar[s], sb + i * 4096, n0 + 32 * i, k0);
+                    for (int i = 0; i < BN / E::MN_BOX; ++i)
+                        tma_load_2d(&tmB, fb, sb + i * E::MN_LBO, n0 + E::MN_BOX * i, k0);
                 }
             }
+            __syncwarp();
+            k0 += BK;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), a/b major bits 15/16,
-            // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
-                                   ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(p.round_operands ? &conv_bar[s] : &full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-                const uint32_t sb = sa + L::A_BYTES;
+        // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format at [7,10)/[10,13), a/b major bits 15/16,
+        // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+        constexpr uint32_t idesc = (1u << 4) | (E::FMT << 7) | (E::FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        constexpr uint32_t a_lbo = A_MN ? E::MN_LBO : 16u, a_sbo = A_MN ? E::MN_SBO : 1024u, a_lay = A_MN ? E::MN_LAYOUT : 2u;
+        constexpr uint32_t b_lbo = B_MN ? E::MN_LBO : 16u, b_sbo = B_MN ? E::MN_SBO : 1024u, b_lay = B_MN ? E::MN_LAYOUT : 2u;
+        constexpr uint32_t a_hi = (a_sbo >> 4) | (1u << 14) | (a_lay << 29);
+        constexpr uint32_t b_hi = (b_sbo >> 4) | (1u << 14) | (b_lay << 29);
+        constexpr uint32_t a_kstep = (A_MN ? E::MN_KSTEP : 32u) >> 4, b_kstep = (B_MN ? E::MN_KSTEP : 32u) >> 4;
+        const uint32_t a_lo0 = (smem_base >> 4) | ((a_lbo >> 4) << 16);
+        const uint32_t b_lo0 = ((smem_base + L::A_BYTES) >> 4) | ((b_lbo >> 4) << 16);
+        const uint32_t ready_bar = p.round_operands ? conv_bar : full_bar;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(ready_bar + 8 * s, ph);
+            tc_fence_after();
+            if (kb == 0 && lane == 0) dbg_mark(p, 2);
+            if (elect_one()) {
+                const uint32_t a_lo = a_lo0 + s * (L::STAGE_BYTES >> 4);
+                const uint32_t b_lo = b_lo0 + s * (L::STAGE_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    // K-major : 8-row groups 1024 B apart (SBO), k-slice = +32 B inside the 128 B swizzle row
-                    // MN-major: 32-wide MN groups 4096 B apart (LBO), 4-k-row swizzle atoms 512 B apart (SBO),
-                    //           k-slice of 8 = +1024 B
-                    const uint64_t ad = p.a_mn_major ? make_smem_desc(sa + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
-                                                     : make_smem_desc(sa + k * 32, 16, 1024, LAYOUT_SW128);
-                    const uint64_t bd = p.b_mn_major ? make_smem_desc(sb + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
-                                                     : make_smem_desc(sb + k * 32, 16, 1024, LAYOUT_SW128);
-                    umma_tf32(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty_bar[s]);          // smem slot is free once these MMAs have read it
+                for (int k = 0; k < BK / E::UK; ++k)
+                    umma<BF16>(tmem_base, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(empty_bar + 8 * s);              // smem slot is free once these MMAs have read it
+                if (kb == num_kb - 1) umma_commit(accum_bar);   // accumulator complete
             }
-            umma_commit(accum_bar);                  // accumulator complete
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else {
-        // ===== operand conditioning during the main loop, then the epilogue =====
+        // ===== operand conditioning during the main loop (fp32 operands only), then the epilogue =====
         // The tensor core TRUNCATES fp32 operands to TF32 (measured: -6.6e-4 mean bias on positive data, 2.6x the
         // error of round-to-nearest).  These four otherwise idle warps round every landed stage to TF32-nearest
         // in place (cvt.rna.tf32.f32) and hand it to the MMA warp through conv_bar.
-        if (p.round_operands) {
+        if (!BF16 && p.round_operands) {
             const int ctid = threadIdx.x - 64;
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(full_bar + 8 * s, ph);
                 uint4* st = reinterpret_cast<uint4*>(smem + s * L::STAGE_BYTES);
 #pragma unroll 4
                 for (int i = ctid; i < L::STAGE_BYTES / 16; i += TC_THREADS - 64) {
@@ -242,74 +468,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     st[i] = v;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (UMMA) reads
-                mbar_arrive(&conv_bar[s]);
+                mbar_arrive(conv_bar + 8 * s);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> shared (transpose) -> registers -> global =====
         const int q = warp & 3;                      // a warp may only touch TMEM lanes [32*(warp%4), +32)
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(accum_bar, 0);
+        mbar_wait(accum_bar, 0);                     // every MMA has completed: the ring is free for generic writes
         tc_fence_after();
-        const bool row_ok = row < p.M;
-        float* crow = p.C + (long long)row * p.ldc;
-        const float* arow = p.aux_in ? p.aux_in + (long long)(p.aux_row_mod > 0 ? row % p.aux_row_mod : row) * p.ld_aux_in : nullptr;
-        float* zrow = p.aux_out ? p.aux_out + (long long)row * p.ld_aux_out : nullptr;
-        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                            (!p.aux_in || (((p.ld_aux_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0))) &&
-                            (!p.aux_out || (((p.ld_aux_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)));
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            __syncwarp();                                                         // tcgen05.ld is warp-collective
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            const int nbase = n0 + c;
-            if (!row_ok || nbase >= p.N) {
-                // nothing to store for this lane / column block
-            } else if (vec_ok && nbase + 32 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    const int n = nbase + j;
-                    if (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_RESID || p.epilogue == EPI_BIAS_GELU) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                    }
-                    if (p.epilogue == EPI_BIAS_RESID || p.epilogue == EPI_RESID) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(arow + n);
-                        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                    } else if (p.epilogue == EPI_DGELU) {
-                        const float4 z4 = *reinterpret_cast<const float4*>(arow + n);
-                        o.x *= gelu_erf_grad(z4.x); o.y *= gelu_erf_grad(z4.y); o.z *= gelu_erf_grad(z4.z); o.w *= gelu_erf_grad(z4.w);
-                    } else if (p.epilogue == EPI_BIAS_GELU) {
-                        *reinterpret_cast<float4*>(zrow + n) = o;
-                        o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
-                    }
-                    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                    float4* dst = reinterpret_cast<float4*>(crow + n);
-                    if (p.accumulate) { const float4 c4 = *dst; o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w; }
-                    *dst = o;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = nbase + j;
-                    if (n < p.N) {
-                        float o = v[j];
-                        switch (p.epilogue) {
-                            case EPI_BIAS: o += p.bias[n]; break;
-                            case EPI_BIAS_RESID: o += p.bias[n] + arow[n]; break;
-                            case EPI_BIAS_GELU: o += p.bias[n]; zrow[n] = o; o = gelu_erf(o); break;
-                            case EPI_DGELU: o *= gelu_erf_grad(arow[n]); break;
-                            case EPI_RESID: o += arow[n]; break;
-                            default: break;
-                        }
-                        if (p.round_out) o = round_tf32(o);
-                        crow[n] = p.accumulate ? crow[n] + o : o;
-                    }
-                }
-            }
-        }
+        if (threadIdx.x == 64) dbg_mark(p, 3);
+        epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16), reinterpret_cast<float*>(smem) + q * 32 * 36, m0 + q * 32,
+                      n0, lane, BN);
     }
+    if (threadIdx.x == 64) dbg_mark(p, 7);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -317,6 +488,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_dealloc(tmem_base, BN);
     }
 }
+
+long long* g_gemm_dbg = nullptr;
 
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps
@@ -339,78 +512,113 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows `outer_stride` floats apart, 128B swizzle
-int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long outer_stride, int box_inner,
-             int box_outer, CUtensorMapSwizzle swizzle) {
+// 2-D tensor map: inner (contiguous) extent `inner`, `outer` rows `outer_stride` elements apart
+int make_map(CUtensorMap* map, const void* base, int elem_bytes, long long inner, long long outer, long long outer_stride,
+             int box_inner, int box_outer, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = get_encode_fn();
     SCAT_REQUIRE(fn != nullptr, kErrUnsupported, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)outer_stride * sizeof(float)};
+    cuuint64_t strides[1] = {(cuuint64_t)outer_stride * elem_bytes};
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SCAT_REQUIRE(r == CUDA_SUCCESS, kErrUnsupported, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld stride=%lld",
                  (int)r, inner, outer, outer_stride);
     return 0;
 }
 
-bool operand_ok(const float* p, long long s_row, long long s_k, int rows) {
+// unit stride in one direction, 16-byte aligned base and leading stride
+bool operand_ok(const void* p, long long s_row, long long s_k, int elem_bytes) {
+    const long long q = 16 / elem_bytes;
     if (reinterpret_cast<uintptr_t>(p) & 15) return false;
-    if (s_k == 1) return (s_row % 4 == 0) && s_row >= 1;                  // K-major
-    if (s_row == 1) return (s_k % 4 == 0) && rows >= 1;                   // MN-major
+    if (s_k == 1) return (s_row % q == 0) && s_row >= 1;                  // K-major
+    if (s_row == 1) return (s_k % q == 0) && s_k >= 1;                    // MN-major
     return false;
 }
 
-template <int BN>
-int launch_bn(const GemmArgs& g, cudaStream_t stream) {
+template <bool BF16, int BN, bool A_MN, bool B_MN>
+int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     using L = SmemLayout<BN>;
+    using E = Elem<BF16>;
+    auto kern = gemm_tc_kernel<BF16, BN, A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SCAT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_done = true;
     }
-    const int a_mn = (g.sak == 1) ? 0 : 1, b_mn = (g.sbk == 1) ? 0 : 1;
     CUtensorMap tmA, tmB;
-    // K-major tiles use the plain 128B swizzle, MN-major tf32 tiles the 128B swizzle with 32-byte atoms
-    if (!a_mn) SCAT_PROPAGATE(make_map(&tmA, g.A, g.K, g.M, g.sam, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B));
-    else SCAT_PROPAGATE(make_map(&tmA, g.A, g.M, g.K, g.sak, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    if (!b_mn) SCAT_PROPAGATE(make_map(&tmB, g.B, g.K, g.N, g.sbn, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B));
-    else SCAT_PROPAGATE(make_map(&tmB, g.B, g.N, g.K, g.sbk, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    const CUtensorMapSwizzle mn_sw = BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!A_MN) SCAT_PROPAGATE(make_map(&tmA, g.A, E::BYTES, g.K, g.M, g.sam, E::BK, BM, CU_TENSOR_MAP_SWIZZLE_128B));
+    else SCAT_PROPAGATE(make_map(&tmA, g.A, E::BYTES, g.M, g.K, g.sak, E::MN_BOX, E::BK, mn_sw));
+    if (!B_MN) SCAT_PROPAGATE(make_map(&tmB, g.B, E::BYTES, g.K, g.N, g.sbn, E::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B));
+    else SCAT_PROPAGATE(make_map(&tmB, g.B, E::BYTES, g.N, g.K, g.sbk, E::MN_BOX, E::BK, mn_sw));
     TcParams p;
-    p.M = g.M; p.N = g.N; p.K = g.K; p.a_mn_major = a_mn; p.b_mn_major = b_mn; p.C = g.C; p.ldc = g.ldc;
+    p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc;
+    p.C16 = reinterpret_cast<__nv_bfloat16*>(g.C16); p.ldc16 = g.ldc16;
     p.epilogue = g.epilogue; p.bias = g.bias; p.aux_in = g.aux_in; p.ld_aux_in = g.ld_aux_in; p.aux_row_mod = g.aux_row_mod; p.aux_out = g.aux_out;
     p.ld_aux_out = g.ld_aux_out; p.accumulate = g.accumulate;
-    p.round_operands = g.prerounded ? 0 : 1;
+    p.round_operands = (BF16 || g.prerounded) ? 0 : 1;
     p.round_out = g.round_out;
-    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
-    SCAT_CHECK_CUDA(launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), L::TOTAL, stream, tmA, tmB, p));
+    p.dbg = g_gemm_dbg;
+    auto al16 = [](const void* q, long long ld) { return q == nullptr || (((uintptr_t)q & 15) == 0 && (ld & 3) == 0); };
+    p.vec_ok = al16(g.C, g.ldc) && (g.C16 == nullptr || (((uintptr_t)g.C16 & 7) == 0 && (g.ldc16 & 3) == 0)) &&
+               al16(g.aux_in, g.ld_aux_in) && al16(g.aux_out, g.ld_aux_out) && al16(g.bias, 0);
+    SCAT_REQUIRE(!(g.accumulate && (g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_RESID || g.epilogue == EPI_DGELU)),
+                 kErrUnsupported, "gemm_tc: accumulate cannot be combined with an epilogue that reads aux_in");
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), 1);
+    // split-K (weight gradients: few output tiles, K = B*21 rows): slice the k-blocks over gridDim.z so that the
+    // launch covers the 148 SMs twice; slices combine with vector reductions in L2 (C is pre-zeroed by the caller)
+    const int kb_all = ceil_div(g.K, E::BK);
+    int splits = 1;
+    const int tiles = (int)(grid.x * grid.y);
+    if (g.allow_split_k && g.epilogue == EPI_NONE && !g.round_out && !g.C16 && tiles <= 148 && kb_all >= 8)
+        splits = max(1, min(kb_all / 4, 296 / tiles));
+    p.kb_per_split = ceil_div(kb_all, splits);
+    grid.z = ceil_div(kb_all, p.kb_per_split);
+    p.atomic_out = grid.z > 1 ? 1 : 0;
+    if (p.atomic_out && !g.accumulate && !g.c_zeroed)
+        SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
+    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(TC_THREADS), L::TOTAL, stream, tmA, tmB, p));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
 
+template <bool BF16, int BN>
+int launch_major(const GemmArgs& g, cudaStream_t stream) {
+    const bool a_mn = g.sak != 1, b_mn = g.sbk != 1;
+    if (!a_mn && !b_mn) return launch_variant<BF16, BN, false, false>(g, stream);
+    if (!a_mn && b_mn) return launch_variant<BF16, BN, false, true>(g, stream);
+    if (a_mn && !b_mn) return launch_variant<BF16, BN, true, false>(g, stream);
+    return launch_variant<BF16, BN, true, true>(g, stream);
+}
+
 }  // namespace
 
+void gemm_tc_set_debug_buffer(long long* dev8) { g_gemm_dbg = dev8; }
+
 bool gemm_tc_supported(const GemmArgs& g) {
+    const int eb = g.operand_bf16 ? 2 : 4;
     if (g.M < 1 || g.N < 8 || g.K < 8) return false;
-    if (!operand_ok(g.A, g.sam, g.sak, g.M) || !operand_ok(g.B, g.sbn, g.sbk, g.N)) return false;
+    if (!operand_ok(g.A, g.sam, g.sak, eb) || !operand_ok(g.B, g.sbn, g.sbk, eb)) return false;
     return get_encode_fn() != nullptr;
 }
 
 int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
     SCAT_REQUIRE(precision == PREC_TF32 || precision == PREC_BF16, kErrBadArg, "gemm_tc: precision %d", precision);
-    SCAT_REQUIRE(operand_ok(g.A, g.sam, g.sak, g.M) && operand_ok(g.B, g.sbn, g.sbk, g.N), kErrUnsupported,
+    const int eb = g.operand_bf16 ? 2 : 4;
+    SCAT_REQUIRE(operand_ok(g.A, g.sam, g.sak, eb) && operand_ok(g.B, g.sbn, g.sbk, eb), kErrUnsupported,
                  "gemm_tc: operands need a unit stride, 16-byte aligned base and 16-byte multiple leading stride");
-    // fp32 storage is kept in both reduced-precision modes; BF16 operand storage is a later round's change,
-    // so PREC_BF16 currently runs the TF32 instruction (strictly more mantissa than requested).
-    // The mainloop is bound by the per-SM shared-memory fill rate (fp32 operands: 4 bytes per TF32 value), so
-    // pick the tile width that minimises bytes staged per SM: waves x (BM + BN) rows of K.
+    SCAT_REQUIRE(g.C != nullptr || g.C16 != nullptr, kErrBadArg, "gemm_tc: no output");
+    // The main loop is bound by the shared-memory fill (L2 -> SMEM), so pick the tile width that minimises the
+    // bytes staged per SM: waves x (BM + BN) rows of K.
     const int tm = ceil_div(g.M, BM);
     const long long cost64 = (long long)ceil_div(tm * ceil_div(g.N, 64), 148) * (BM + 64);
     const long long cost128 = (long long)ceil_div(tm * ceil_div(g.N, 128), 148) * (BM + 128);
-    if (g.N > 64 && cost128 <= cost64) return launch_bn<128>(g, stream);
-    return launch_bn<64>(g, stream);
+    const bool wide = g.N > 64 && cost128 <= cost64;
+    if (g.operand_bf16) return wide ? launch_major<true, 128>(g, stream) : launch_major<true, 64>(g, stream);
+    return wide ? launch_major<false, 128>(g, stream) : launch_major<false, 64>(g, stream);
 }
 
 }  // namespace scat

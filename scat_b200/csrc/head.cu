@@ -164,6 +164,22 @@ __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restric
     pdl_sync();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
 }
+// one launch clears every parameter-gradient tensor: split-K GEMMs, column sums and LayerNorm affine gradients
+// all combine partial results with reductions in L2, and a memset node per tensor would serialise the graph
+struct ZeroJobs { float* ptr[40]; unsigned n[40]; int count; };
+__global__ void zero_many_kernel(const ZeroJobs jobs) {
+    pdl_sync();
+    float* p = jobs.ptr[blockIdx.y];
+    const unsigned n = jobs.n[blockIdx.y];
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        for (unsigned i = tid; i < (n >> 2); i += nthr) reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned i = (n & ~3u) + tid; i < n; i += nthr) p[i] = 0.f;
+    } else {
+        for (unsigned i = tid; i < n; i += nthr) p[i] = 0.f;
+    }
+}
+
 __global__ void token_mean_kernel(const float* __restrict__ X, float* __restrict__ out, int n) {
     pdl_sync();
     // out[b, c] = mean_t X[b, t, c], c < 3  (hand_net.py:203)
@@ -275,9 +291,9 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (G) {
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
             g.A = dY; g.sam = 1; g.sak = L.out; g.B = ws + L.H; g.sbn = 1; g.sbk = L.ldh;
-            g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.prerounded = fftc;
+            g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
-            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 0, st));
+            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, st));
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
@@ -289,9 +305,9 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             g = GemmArgs();
             g.A = ws + p.dZ; g.sam = 1; g.sak = L.ldh; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.d;
-            g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.prerounded = fftc;
+            g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
-            SCAT_PROPAGATE(launch_colsum(ws + p.dZ, L.ldh, M, L.hid, G[L.p_fc1_b], 0, st));
+            SCAT_PROPAGATE(launch_colsum(ws + p.dZ, L.ldh, M, L.hid, G[L.p_fc1_b], 1, st));
         }
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs: round it)
         g = GemmArgs();
@@ -310,9 +326,9 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1)
             g = GemmArgs();
             g.A = dX1; g.sam = 1; g.sak = L.d; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner;
-            g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.prerounded = tc;
+            g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
-            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 0, st));
+            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, st));
         }
         // dO = dX1 Wo
         g = GemmArgs();
@@ -325,7 +341,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dWqkv[3inner,d] = dQKV^T Na
             g = GemmArgs();
             g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = L.d;
-            g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.prerounded = tc;
+            g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
         }
         // dNa = dQKV Wqkv
@@ -339,6 +355,28 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
                                             G ? G[L.p_na_b] : nullptr, MR, L.d, (tc && l > 0) ? 1 : 0, st, amod));
         dY = ws + p.dX;
     }
+    return 0;
+}
+
+int zero_param_grads(const HeadPlan& p, float* const* G, cudaStream_t st) {
+    ZeroJobs z;
+    int n = 0;
+    auto add = [&](int idx, size_t numel) { z.ptr[n] = G[idx]; z.n[n] = (unsigned)numel; ++n; };
+    add(P_MASK_TOKEN, p.D);
+    add(P_CONV_W, (size_t)p.T * p.C);
+    for (int l = 0; l < kDepth; ++l) {
+        const LayerPlan& L = p.L[l];
+        add(L.p_na_w, L.d); add(L.p_na_b, L.d);
+        add(L.p_qkv, (size_t)3 * p.inner * L.d);
+        add(L.p_out_w, (size_t)L.d * p.inner); add(L.p_out_b, L.d);
+        if (!L.last) { add(L.p_nf_w, L.d); add(L.p_nf_b, L.d); }
+        add(L.p_fc1_w, (size_t)L.hid * L.d); add(L.p_fc1_b, L.hid);
+        add(L.p_fc2_w, (size_t)L.out * L.hid); add(L.p_fc2_b, L.out);
+    }
+    add(P_REG_W, (size_t)p.NP * (p.F + p.NP)); add(P_REG_B, p.NP);
+    z.count = n;
+    SCAT_CHECK_CUDA(launch_k(zero_many_kernel, dim3(16, n), dim3(256), 0, st, z));
+    SCAT_CHECK_LAUNCH();
     return 0;
 }
 
@@ -390,6 +428,8 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_REQUIRE(W && G && x2 && main_feat && g_pred, kErrBadArg, "head_backward: null tensor");
     SCAT_REQUIRE(d.pos_embed || fv_alias, kErrBadArg, "head_backward: pos_embed==0 needs the forward's feat_visual");
     float* ws = (float*)workspace;
+    // every parameter gradient is accumulated into (split-K / column-sum / LayerNorm reductions): clear them once
+    SCAT_PROPAGATE(zero_param_grads(p, G, st));
     // regressor + root-relative backward
     const int sweeps = pl_out ? 2 : 1;
     float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
@@ -403,31 +443,19 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         const int ldw = p.F + p.NP;
         GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
         g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
-        g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1;
+        g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1; g.c_zeroed = 1;
         SCAT_PROPAGATE(launch_gemm_simt(g, st));
         if (p.it > 0) {   // dWr[:, F:] = sum over samples and steps of g_step (x) state
             g = GemmArgs();
             g.A = ws + p.gsteps; g.sam = 1; g.sak = p.NP; g.B = ws + p.states; g.sbn = 1; g.sbk = p.NP;
-            g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it; g.allow_split_k = 1;
+            g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it; g.allow_split_k = 1; g.c_zeroed = 1;
             SCAT_PROPAGATE(launch_gemm_simt(g, st));
-        } else {
-            SCAT_CHECK_CUDA(cudaMemset2DAsync(G[P_REG_W] + p.F, ldw * sizeof(float), 0, p.NP * sizeof(float), p.NP, st));
         }
-        SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 0, st));
-    }
-    // LayerNorm affine grads are accumulated with atomics: clear them first
-    for (int l = 0; l < kDepth; ++l) {
-        const LayerPlan& L = p.L[l];
-        SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_na_w], 0, L.d * sizeof(float), st));
-        SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_na_b], 0, L.d * sizeof(float), st));
-        if (!L.last) {
-            SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_nf_w], 0, L.d * sizeof(float), st));
-            SCAT_CHECK_CUDA(cudaMemsetAsync(G[L.p_nf_b], 0, L.d * sizeof(float), st));
-        }
+        SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 1, st));
     }
     SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps));
     // through masking / positional encoding into the conv output
-    SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st));
+    SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st, 1));
     if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
         SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX + (size_t)p.M * p.D, mask_idx, d.n_masked, d.pos_embed ? 0 : 1, pl_out,
                                        nullptr, p.B, p.T, p.D, st));
@@ -538,10 +566,29 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
     g.A = A; g.sam = sam; g.sak = sak; g.B = B; g.sbn = sbn; g.sbk = sbk; g.C = C; g.ldc = ldc;
     g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
     g.aux_out = aux_out; g.ld_aux_out = ld_aux_out; g.accumulate = accumulate;
+    static const int probe_prerounded = getenv("SCAT_GEMM_ASSUME_ROUNDED") != nullptr;   // microbenchmarks only
+    g.prerounded = probe_prerounded;
     if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
     SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
                  "scat_gemm: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
     return launch_gemm_tc(g, precision, (cudaStream_t)stream);   // operands rounded to TF32-nearest inside the kernel
+}
+
+void scat_debug_gemm_timeline(void* dev_int64x8) { gemm_tc_set_debug_buffer((long long*)dev_int64x8); }
+
+int scat_gemm_bf16(const void* A, int64_t sam, int64_t sak, const void* B, int64_t sbn, int64_t sbk, float* C,
+                   int32_t ldc, void* C16, int32_t ldc16, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                   const float* bias, const float* aux_in, int32_t ld_aux_in, float* aux_out, int32_t ld_aux_out,
+                   int32_t split_k, void* stream) {
+    GemmArgs g;
+    g.A = A; g.sam = sam; g.sak = sak; g.B = B; g.sbn = sbn; g.sbk = sbk; g.operand_bf16 = 1;
+    g.C = C; g.ldc = ldc; g.C16 = C16; g.ldc16 = ldc16;
+    g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
+    g.aux_out = aux_out; g.ld_aux_out = ld_aux_out;
+    g.allow_split_k = split_k ? 1 : 0; g.c_zeroed = split_k ? 1 : 0;
+    SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
+                 "scat_gemm_bf16: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
+    return launch_gemm_tc(g, PREC_BF16, (cudaStream_t)stream);
 }
 
 int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe, const float* mask_token,

@@ -29,9 +29,11 @@ enum Precision : int {
 };
 
 struct GemmArgs {
-    const float* A = nullptr; long long sam = 0, sak = 0;
-    const float* B = nullptr; long long sbn = 0, sbk = 0;
-    float* C = nullptr; int ldc = 0;
+    const void* A = nullptr; long long sam = 0, sak = 0;     // fp32, or bf16 when operand_bf16 (strides in elements)
+    const void* B = nullptr; long long sbn = 0, sbk = 0;
+    int operand_bf16 = 0;    // tensor-core kernel only: A and B hold bf16 (tcgen05 kind::f16), else fp32 (kind::tf32)
+    float* C = nullptr; int ldc = 0;                         // fp32 output (tensor-core kernel: may be null if C16 is set)
+    void* C16 = nullptr; int ldc16 = 0;                      // tensor-core kernel only: bf16 copy of the output
     int M = 0, N = 0, K = 0;
     int epilogue = EPI_NONE;
     const float* bias = nullptr;
@@ -39,6 +41,7 @@ struct GemmArgs {
     int aux_row_mod = 0;     // > 0: aux_in row = m % aux_row_mod (stacked cotangents share one saved activation)
     float* aux_out = nullptr; int ld_aux_out = 0;
     int accumulate = 0;  // C += epilogue(...)
+    int c_zeroed = 0;        // C is known to be zero: split-K slices may reduce into it without a memset
     int allow_split_k = 0;   // FFMA kernel may split K over CTAs and combine with atomics (weight gradients)
     int prerounded = 0;      // tensor-core kernel: operands are already TF32-representable, skip the in-kernel rounding
     int round_out = 0;       // store C rounded to TF32 (nearest): it feeds a tensor-core GEMM next
@@ -58,6 +61,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // tcgen05 path; returns kErrUnsupported if the operand strides cannot be expressed as TMA tensor maps
 int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream);
 bool gemm_tc_supported(const GemmArgs& g);
+void gemm_tc_set_debug_buffer(long long* dev8);   // 8 x int64 device buffer, or null (profiling hook)
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream);  // dispatch on precision/shape
 
 // column sums: out[n] (+)= sum_m X[m*ld + n]
@@ -71,7 +75,7 @@ int launch_conv_pe_mask_fwd(const float* x2, const float* Wc, const float* pe, c
                             int B, int C, int HW, int T, cudaStream_t stream);
 // dFv = dX0 with masked token rows zeroed (unless keep_masked); d mask_token = sum over b, masked t of dX0
 int launch_mask_bwd(const float* dX0, const int32_t* mask_idx, int n_masked, int keep_masked, float* dFv,
-                    float* d_mask_token, int B, int T, int HW, cudaStream_t stream);
+                    float* d_mask_token, int B, int T, int HW, cudaStream_t stream, int token_grad_zeroed = 0);
 int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, int C, int HW, int T,
                       cudaStream_t stream);
 size_t conv_wgrad_scratch_floats(int C, int T);
@@ -89,7 +93,8 @@ int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const floa
 // dX = LN'(dY) (+ resid); dgamma/dbeta accumulated with atomics when non-null (must be pre-zeroed)
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
-                         float* dbeta, int M, int D, int round_out, cudaStream_t stream, int act_rows = 0);
+                         float* dbeta, int M, int D, int round_out, cudaStream_t stream, int act_rows = 0,
+                         void* dX16 = nullptr, int lddx16 = 0);   // dX16: optional bf16 shadow copy of dX
 // act_rows > 0: dY/dX/resid have M rows, the saved activations (X, mean, rstd) have act_rows rows and row m uses
 // activation row m % act_rows; dgamma/dbeta only accumulate rows m < act_rows (the real cotangent)
 

@@ -36,13 +36,12 @@ layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restri
     }
     const float var = warp_sum(q) / (float)D;
     const float rstd = 1.0f / sqrtf(var + kEps);
-    float* y = Y + (long long)row * ldy;
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
         const int c = i * 32 + lane;
         if (c < D) {
             const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
-            y[c] = round_out ? round_tf32(o) : o;
+            store_out(Y, (long long)row * ldy + c, o, round_out);
         }
     }
     if (lane == 0) {
@@ -56,15 +55,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ resid, int ldr, float* __restrict__ dX, int lddx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D, int round_out, int act_rows) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D, int round_out, int act_rows,
+                     __nv_bfloat16* __restrict__ dX16, int lddx16) {
     pdl_sync();
     __shared__ float red[LN_WARPS][32 * NPL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float gam[NPL], dg[NPL], db[NPL];
+    float dg[NPL], db[NPL];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
-        const int c = i * 32 + lane;
-        gam[i] = c < D ? gamma[c] : 0.f;
         dg[i] = 0.f;
         db[i] = 0.f;
     }
@@ -75,15 +73,24 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
         const float mu = mean[arow], rs = rstd[arow];
         const float* x = X + (long long)arow * ldx;
         const float* dy = dY + (long long)row * lddy;
-        float xh[NPL], g[NPL];
+        const float* rr = resid != nullptr ? resid + (long long)row * ldr : nullptr;
+        // every global read of the row (x, dy, residual) is issued before the first store: dX may alias any of them
+        // as far as the compiler knows, and a load placed after a store waits for one L2 round trip per element
+        float xh[NPL], g[NPL], rv[NPL];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int c = i * 32 + lane;
+            xh[i] = c < D ? __ldg(x + c) : mu;
+            g[i] = c < D ? __ldg(dy + c) : 0.f;
+            rv[i] = (rr != nullptr && c < D) ? __ldg(rr + c) : 0.f;
+        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
             const int c = i * 32 + lane;
-            const float xv = c < D ? x[c] : mu;
-            const float dv = c < D ? dy[c] : 0.f;
-            xh[i] = (xv - mu) * rs;
-            g[i] = dv * gam[i];
+            const float dv = g[i];
+            xh[i] = (xh[i] - mu) * rs;
+            g[i] = dv * (c < D ? __ldg(gamma + c) : 0.f);
             s1 += g[i];
             s2 = fmaf(g[i], xh[i], s2);
             if (real) {
@@ -98,9 +105,9 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
         for (int i = 0; i < NPL; ++i) {
             const int c = i * 32 + lane;
             if (c < D) {
-                float o = rs * (g[i] - s1 - xh[i] * s2);
-                if (resid != nullptr) o += resid[(long long)row * ldr + c];
-                dx[c] = round_out ? round_tf32(o) : o;
+                const float o = rs * (g[i] - s1 - xh[i] * s2) + rv[i];
+                dx[c] = round_out == OUT_TF32 ? round_tf32(o) : o;
+                if (dX16 != nullptr) dX16[(long long)row * lddx16 + c] = __float2bfloat16_rn(o);   // shadow for the bf16 GEMMs
             }
         }
     }
@@ -141,12 +148,14 @@ int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const floa
 
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,
-                         float* dbeta, int M, int D, int round_out, cudaStream_t stream, int act_rows) {
+                         float* dbeta, int M, int D, int round_out, cudaStream_t stream, int act_rows, void* dX16,
+                         int lddx16) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm bwd: D=%d not in [1,1024]", D);
     SCAT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), kErrBadArg, "layernorm bwd: dgamma/dbeta must both be set or null");
     const int grid = min(ceil_div(M, 2 * LN_WARPS), 148);     // >= 2 rows per warp: halves the atomic tail
 #define SCAT_LN_BWD(NPL) SCAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<NPL>, dim3(grid), dim3(LN_WARPS * 32), 0, stream,  \
-        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out, act_rows))
+        dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out, act_rows,  \
+        reinterpret_cast<__nv_bfloat16*>(dX16), lddx16))
     if (D <= 256) SCAT_LN_BWD(8);
     else if (D <= 512) SCAT_LN_BWD(16);
     else SCAT_LN_BWD(32);

@@ -181,6 +181,40 @@ def gemm(a, b, *, a_strides=None, b_strides=None, m=None, n=None, k=None, epilog
     return (c, z) if z is not None else c
 
 
+def gemm_bf16(a, b, *, a_strides=None, b_strides=None, m=None, n=None, k=None, epilogue="none", bias=None,
+              aux_in=None, out=None, out16=None, want16=False, split_k=False):
+    """bf16-operand tensor-core GEMM (tcgen05 kind::f16): a, b are torch.bfloat16 CUDA tensors; returns the fp32
+    result (and the bf16 copy when want16 / out16).  Same stride conventions as gemm()."""
+    lib = _lib.load()
+    for t, name in ((a, "a"), (b, "b")):
+        if not t.is_cuda or t.dtype != torch.bfloat16:
+            raise RuntimeError(f"scat_b200: {name} must be a CUDA bfloat16 tensor")
+    a, b = a.contiguous(), b.contiguous()
+    if a_strides is None:
+        m, k = a.shape
+        a_strides = (a.stride(0), a.stride(1))
+    if b_strides is None:
+        n = b.shape[0]
+        b_strides = (b.stride(0), b.stride(1))
+    if out is None:
+        c = torch.zeros(m, n, device=a.device, dtype=torch.float32) if split_k else torch.empty(m, n, device=a.device, dtype=torch.float32)
+    else:
+        c = out
+    if out16 is None and want16:
+        out16 = torch.empty(m, (n + 7) // 8 * 8, device=a.device, dtype=torch.bfloat16)
+    z = torch.empty_like(c) if epilogue == "bias_gelu" else None
+    check(lib.scat_gemm_bf16(ptr(a), a_strides[0], a_strides[1], ptr(b), b_strides[0], b_strides[1], ptr(c), c.stride(0),
+                             ptr(out16), 0 if out16 is None else out16.stride(0), m, n, k, EPI[epilogue], ptr(bias),
+                             ptr(aux_in), 0 if aux_in is None else aux_in.stride(0), ptr(z),
+                             0 if z is None else z.stride(0), int(split_k), stream_ptr()), "scat_gemm_bf16")
+    res = [c]
+    if z is not None:
+        res.append(z)
+    if out16 is not None:
+        res.append(out16)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
 def layernorm_fwd(x, gamma, beta):
     lib = _lib.load()
     x = _f32c(x, "x")

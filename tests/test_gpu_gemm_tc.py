@@ -79,3 +79,78 @@ def test_tc_gemm_is_linear_and_exact_on_tf32_representable_inputs():
     ref = (A.double() @ B.double().t()).float()
     out = SF.gemm(A.cuda(), B.cuda(), precision="tf32")
     assert torch.equal(out.cpu(), ref)
+
+
+# ---- bf16 operands (tcgen05 kind::f16) -------------------------------------------------------------------------
+def _mk16(M, N, K, a, b, seed=1):
+    """bf16 operands with 16-byte aligned leading dimensions (the head pads 588 -> 592, 196 -> 200, ...)."""
+    g = np.random.Generator(np.random.PCG64(seed))
+    A = torch.from_numpy(g.standard_normal((M, K)).astype(np.float32)).bfloat16()
+    B = torch.from_numpy(g.standard_normal((N, K)).astype(np.float32)).bfloat16()
+    pad = lambda v: (v + 7) // 8 * 8
+
+    def place(X, major):                      # [rows, K] logical -> device buffer + (row stride, k stride)
+        rows = X.shape[0]
+        if major == "k":
+            buf = torch.zeros(rows, pad(K), dtype=torch.bfloat16)
+            buf[:, :K] = X
+            return buf.cuda(), (pad(K), 1)
+        buf = torch.zeros(K, pad(rows), dtype=torch.bfloat16)
+        buf[:, :rows] = X.t()
+        return buf.cuda(), (1, pad(rows))
+    Ad, sa = place(A, a)
+    Bd, sb = place(B, b)
+    return A, B, Ad, Bd, sa, sb
+
+
+@pytest.mark.parametrize("M,N,K,a,b", [
+    (128, 64, 64, "k", "k"), (2016, 1536, 784, "k", "k"), (2016, 392, 588, "k", "k"), (2016, 196, 294, "k", "k"),
+    (2016, 784, 512, "k", "mn"), (4032, 392, 1536, "k", "mn"), (2016, 588, 392, "k", "mn"), (2016, 294, 196, "k", "mn"),
+    (1536, 784, 2016, "mn", "mn"), (588, 784, 2016, "mn", "mn"), (196, 294, 2016, "mn", "mn"), (392, 512, 2016, "mn", "mn"),
+    (300, 200, 100, "mn", "k"), (1, 8, 8, "k", "k"), (129, 65, 33, "k", "k"),
+])
+def test_bf16_gemm_layouts(M, N, K, a, b):
+    """bf16 x bf16 products are exact in fp32, so the only error is fp32 accumulation order: tight tolerance."""
+    from scat_b200 import functional as SF
+    A, B, Ad, Bd, sa, sb = _mk16(M, N, K, a, b)
+    ref = A.double() @ B.double().t()
+    out, out16 = SF.gemm_bf16(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, want16=True)
+    assert _err(out, ref) < 2e-5
+    assert _err(out16[:, :N].float(), ref) < 6e-3                         # bf16 copy of the output: 8 mantissa bits
+    if a == "mn" and b == "mn":                                           # weight-gradient shape: split-K path
+        sk = SF.gemm_bf16(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, split_k=True)
+        assert _err(sk, ref) < 2e-5
+
+
+def test_bf16_gemm_epilogues():
+    from scat_b200 import functional as SF
+    M, N, K = 2016, 294, 392
+    A, B, Ad, Bd, sa, sb = _mk16(M, N, K, "k", "k", seed=3)
+    g = np.random.Generator(np.random.PCG64(9))
+    bias = torch.from_numpy(g.standard_normal(N).astype(np.float32))
+    res = torch.from_numpy(g.standard_normal((M, 296)).astype(np.float32))
+    ref = A.double() @ B.double().t()
+    out = torch.zeros(M, 296, device="cuda")
+    y, z, y16 = SF.gemm_bf16(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, epilogue="bias_gelu", bias=bias.cuda(),
+                             out=out[:, :N], want16=True)
+    assert _err(z[:, :N], ref + bias.double()) < 2e-5 and _err(y[:, :N], F.gelu(ref + bias.double())) < 2e-5
+    assert _err(y16[:, :N].float(), F.gelu(ref + bias.double())) < 6e-3
+    assert torch.all(out[:, N:] == 0)
+    r = SF.gemm_bf16(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, epilogue="bias_resid", bias=bias.cuda(),
+                     aux_in=res.cuda()[:, :N])
+    assert _err(r, ref + bias.double() + res[:, :N].double()) < 2e-5
+    zz = res.double()[:, :N].requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    d = SF.gemm_bf16(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, epilogue="dgelu", aux_in=res.cuda()[:, :N])
+    assert _err(d, ref * zz.grad) < 2e-5
+
+
+def test_bf16_gemm_exact_on_small_integers():
+    from scat_b200 import functional as SF
+    g = np.random.Generator(np.random.PCG64(4))
+    M, N, K = 2016, 1536, 784
+    A = torch.from_numpy(g.integers(-8, 9, (M, K)).astype(np.float32))
+    B = torch.from_numpy(g.integers(-8, 9, (N, K)).astype(np.float32))
+    ref = (A.double() @ B.double().t()).float()
+    out = SF.gemm_bf16(A.bfloat16().cuda(), B.bfloat16().cuda())
+    assert torch.equal(out.cpu(), ref)

@@ -32,12 +32,18 @@ shapes = [  # (M, N, K, layout)
 prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 tot = 0.0
 for M, N, K, lay in shapes:
-    A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
+    if prec == "bf16":
+        M, N, K = ((v + 7) // 8 * 8 for v in (M, N, K))
+    dt = torch.bfloat16 if prec == "bf16" else torch.float32
+    A = torch.randn(M, K, device="cuda").to(dt); B = torch.randn(N, K, device="cuda").to(dt)
     if lay == "nt": a, b, sa, sb = A, B, (K, 1), (K, 1)
     elif lay == "nn": a, b, sa, sb = A, B.t().contiguous(), (K, 1), (1, N)
     else: a, b, sa, sb = A.t().contiguous(), B.t().contiguous(), (1, M), (1, N)
     out = torch.empty(M, N, device="cuda")
-    us = t_us(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision=prec, out=out))
+    if prec == "bf16":
+        us = t_us(lambda: SF.gemm_bf16(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, out=out))
+    else:
+        us = t_us(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision=prec, out=out))
     tot += us
-    print(f"{prec} {lay} M={M:5d} N={N:5d} K={K:5d}: {us:7.1f} us  {2*M*N*K/us/1e6:7.1f} TFLOP/s  {(M*K+N*K+M*N)*4/us/1e3:7.1f} GB/s(min traffic)")
+    print(f"{prec} {lay} M={M:5d} N={N:5d} K={K:5d}: {us:7.1f} us  {2*M*N*K/us/1e6:7.1f} TFLOP/s  {(M*K+N*K)*A.element_size()/us/1e3+M*N*4/us/1e3:7.1f} GB/s(min traffic)")
 print("total", tot)
