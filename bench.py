@@ -234,47 +234,62 @@ def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
     idx = ts.mask_dev[: ts.n_masked]
     cw = W[1].data.view(21, 512)
     dtok = torch.randn(B, 21, 784, device=dev)
-    t_fwd = time_kernel(lambda: SF.conv_pe_mask_fwd(x2d, cw, pe, W[0].data.view(-1), idx, True))
-    scratch = torch.empty(lib.scat_conv_bwd_scratch_floats(B, 512, 784, 21), device=dev)
+    tc = precision != "fp32"        # TF32 / BF16 modes run the conv passes on the tensor cores (batched tcgen05 GEMM)
+    t_fwd = time_kernel(lambda: SF.conv_pe_mask_fwd(x2d, cw, pe, W[0].data.view(-1), idx, True, tc=tc))
+    nsc = lib.scat_conv_tc_scratch_floats(B, 512, 784, 21) if tc else lib.scat_conv_bwd_scratch_floats(B, 512, 784, 21)
+    scratch = torch.empty(nsc, device=dev)
     x2g, wg, mg = torch.empty_like(x2d), torch.empty(21, 512, device=dev), torch.empty(784, device=dev)
+    bwd_fn = lib.scat_conv_bwd_tc if tc else lib.scat_conv_bwd
 
     def conv_bwd():
-        check(lib.scat_conv_bwd(ptr(dtok), ptr(x2d), ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
-                                ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd")
+        check(bwd_fn(ptr(dtok), ptr(x2d), ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
+                     ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd")
     t_bwd = time_kernel(conv_bwd)
+    how = "tcgen05 kind::tf32 batched GEMM" if tc else "fp32 FFMA"
     kernels = [
-        {"kernel": "conv_pe_mask_fwd", "bound": "hbm", "achieved": BYTES_CONV_FWD * B / t_fwd / 1e9,
+        {"kernel": f"conv_pe_mask_fwd ({how})", "bound": "hbm", "achieved": BYTES_CONV_FWD * B / t_fwd / 1e9,
          "peak": pk["hbm"], "unit": "GB/s", "us": t_fwd * 1e6, "traffic": dram("conv_pe_mask_fwd")},
-        {"kernel": "conv_bwd (mask_bwd + conv_dgrad + conv_wgrad_partial + reduce)", "bound": "hbm",
+        {"kernel": f"conv_bwd (mask_bwd + dgrad + wgrad, {how})", "bound": "hbm",
          "achieved": (BYTES_CONV_DGRAD + BYTES_CONV_WGRAD) * B / t_bwd / 1e9, "peak": pk["hbm"], "unit": "GB/s",
          "us": t_bwd * 1e6,
          "traffic": None if dram("conv_dgrad") is None else dram("conv_dgrad") + dram("conv_wgrad_partial")},
     ]
     # --- dominant kernel by time share: the tcgen05 GEMM, every shape of the step replayed from a CUDA graph ---
+    # operands as the step holds them: TF32 path = fp32 already rounded by the producer, BF16 path = bf16 in HBM
     gemm = None
     if precision != "fp32":
+        bf = precision == "bf16"
         tot_t, tot_f, n_launch = 0.0, 0.0, 0
+        pad = 8 if bf else 4
         for (M, N, K, lay, cnt) in step_gemm_table(B * 21):
-            M, N, K = ((v + 3) // 4 * 4 for v in (M, N, K))    # hidden 294 lives in 296-wide (16-byte) rows in the step
-            A = torch.randn(M, K, device=dev)
-            Bm = torch.randn(N, K, device=dev)
+            M, N, K = ((v + pad - 1) // pad * pad for v in (M, N, K))   # hidden 294 lives in padded (16-byte) rows in the step
+            dt = torch.bfloat16 if bf else torch.float32
+            A = torch.randn(M, K, device=dev).to(dt)
+            Bm = torch.randn(N, K, device=dev).to(dt)
             if lay == "nt":
                 a, b, sa, sb = A, Bm, (K, 1), (K, 1)
             elif lay == "nn":
                 a, b, sa, sb = A, Bm.t().contiguous(), (K, 1), (1, N)
             else:
                 a, b, sa, sb = A.t().contiguous(), Bm.t().contiguous(), (1, M), (1, N)
-            out = torch.empty(M, N, device=dev)
-            t = graph_time(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision=precision, out=out))
+            out = torch.zeros(M, N, device=dev)
+            wg = lay == "tn"                                             # weight gradients run split-K in the step
+            if bf:
+                t = graph_time(lambda: SF.gemm_bf16(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, out=out, split_k=wg))
+            else:
+                t = graph_time(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="tf32", out=out,
+                                               prerounded=True))
             tot_t += cnt * t
             tot_f += cnt * 2.0 * M * N * K
             n_launch += cnt
-        tf32_peak = pk["bf16"] / 2.0          # TF32 dense = half of BF16 dense; BF16 burst peak is the measured one
-        gemm = {"kernel": f"gemm_tc_kernel (tcgen05 kind::tf32, TMEM accumulators, TMA), {n_launch} launches/step",
-                "bound": "tensor", "achieved": tot_f / tot_t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+        peak = pk["bf16"] if bf else pk["bf16"] / 2.0    # TF32 dense = half of BF16 dense; BF16 burst peak is the measured one
+        kind = "kind::f16 (bf16 operands)" if bf else "kind::tf32"
+        gemm = {"kernel": f"gemm_tc_kernel (tcgen05 {kind}, TMEM accumulators, TMA), {n_launch} launches/step",
+                "bound": "tensor", "achieved": tot_f / tot_t / 1e12, "peak": peak, "unit": "TFLOP/s",
                 "us": tot_t * 1e6, "traffic": dram("gemm_tc_kernel<128> (qkv layer 0)"),
-                "note": "peak = measured cuBLAS bf16 burst / 2 (TF32); standalone launches round operands in-kernel, "
-                        "the in-step launches read pre-rounded operands and are slightly faster"}
+                "note": ("peak = measured cuBLAS bf16 burst" if bf else "peak = measured cuBLAS bf16 burst / 2 (TF32)") +
+                        "; every GEMM shape of the step timed alone from a CUDA graph with the operand storage the step uses"
+                        + ("" if bf else "; the TF32 weight-gradient GEMMs run split-K inside the step, not in this table")}
         kernels.insert(0, gemm)
     for k in kernels:
         k["frac"] = k["achieved"] / k["peak"]
@@ -396,6 +411,28 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = tt.tolist()
 
+    # the other tensor-core path of BASELINE config 2 ("bf16 and TF32 paths"), device-resident, same run
+    other = None
+    other_prec = {"tf32": "bf16", "bf16": "tf32"}.get(args.precision)
+    if other_prec is not None and world == 1:
+        net2 = EncoderTransformer(opt, mean, precision=other_prec, backbone=Seam())
+        net2.load_state_dict(sd, strict=True)
+        net2 = net2.to(dev)
+        ts2 = HeadTrainStep(net2, B, 1e5, 10.0, use_graph=not args.no_graph)
+        ts2.load_inputs(*[t.to(dev) for t in host[0]])
+        for _ in range(3):
+            ts2.set_mask(); ts2.step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            ts2.set_mask(); ts2.step()
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = e0.elapsed_time(e1) * 1e-3
+        other = {"precision": other_prec, "value": B * args.steps / t2, "unit": "samples/s",
+                 "ms_per_step": t2 / args.steps * 1e3, "loss": float(ts2.losses[0].item())}
+        del ts2, net2
+
     if rank == 0:
         roofline = measure_roofline(ts, net, lib, pk, dev, B, t_dev / args.steps, args.precision)
         cpu = cpu_reference_run(steps=8, warmup=1, max_seconds=30.0)
@@ -410,7 +447,7 @@ def run_ours(args):
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "loss": loss_val,
-            "clocks": clocks, "roofline": roofline,
+            "clocks": clocks, "roofline": roofline, "other_precision": other,
             "cpu_baseline": {"value": cpu["samples_per_s"], "unit": "samples/s", "cores": cpu["cores"], "kind": "port",
                              "sample": f"{cpu['steps']} steps of B={cpu['batch']} on {cpu_model()} (oracle port, fp32)"},
         }

@@ -35,6 +35,9 @@ extern "C" {
 #define SCAT_PREC_FP32 0   /* CUDA-core FFMA everywhere ("parity mode")                         */
 #define SCAT_PREC_TF32 1   /* tcgen05 kind::tf32, operands stay fp32 in HBM, fp32 accumulate    */
 #define SCAT_PREC_BF16 2   /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate             */
+/* scat_gemm only, OR-ed into SCAT_PREC_TF32: the fp32 operands are already TF32-representable (their producer
+ * rounded them), so the kernel skips its in-shared-memory rounding pass -- how the head itself runs its GEMMs */
+#define SCAT_PREC_FLAG_PREROUNDED 0x100
 
 /* GEMM epilogues (scat_gemm) */
 #define SCAT_EPI_NONE       0
@@ -152,6 +155,19 @@ int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe,
                           const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
                           float* tokens_out, int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens,
                           void* stream);
+/* The same front end on the tensor cores (tcgen05 kind::tf32 through the batched GEMM kernel, one problem per
+ * sample): what the head runs in SCAT_PREC_TF32 / SCAT_PREC_BF16.  x2 and d_tokens are read as fp32 and truncated
+ * to TF32 by the tensor core (compensated, see csrc/conv.cu); results are TF32-grade (~3e-4 relative), masked
+ * rows stay bit-exact copies of the mask token.  scratch: scat_conv_tc_scratch_floats() floats. */
+size_t scat_conv_tc_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens);
+int scat_conv_pe_mask_fwd_tc(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
+                             const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
+                             float* tokens_out, float* scratch, int32_t batch, int32_t channels, int32_t hw,
+                             int32_t n_tokens, void* stream);
+int scat_conv_bwd_tc(const float* d_tokens, const float* x2, const float* conv_w, const int32_t* mask_idx,
+                     int32_t n_masked, float* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
+                     int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens, void* stream);
+
 /* backward of the conv: d_tokens[B,T,hw] -> x2_grad (NULL to skip), conv_w_grad[T,C], mask_token_grad[hw];
  * scratch: scat_conv_bwd_scratch_floats() floats */
 size_t scat_conv_bwd_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens);

@@ -48,6 +48,9 @@ SIGNATURES = {
                               _f, _i32, _i32, _f]),
     "scat_debug_gemm_timeline": (None, [_f]),
     "scat_conv_pe_mask_fwd": (_i32, [_f, _f, _f, _f, _f, _i32, _i32, _f, _f, _i32, _i32, _i32, _i32, _f]),
+    "scat_conv_tc_scratch_floats": (_sz, [_i32, _i32, _i32, _i32]),
+    "scat_conv_pe_mask_fwd_tc": (_i32, [_f, _f, _f, _f, _f, _i32, _i32, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
+    "scat_conv_bwd_tc": (_i32, [_f, _f, _f, _f, _i32, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
     "scat_conv_bwd_scratch_floats": (_sz, [_i32, _i32, _i32, _i32]),
     "scat_conv_bwd": (_i32, [_f, _f, _f, _f, _i32, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
     "scat_layernorm_fwd": (_i32, [_f, _f, _f, _f, _f, _f, _i32, _i32, _f]),

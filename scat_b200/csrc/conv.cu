@@ -379,6 +379,99 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core front end: the three conv passes are GEMMs with one tiny dimension (T = 21 tokens), so they ride
+// the tcgen05 GEMM kernel in batched mode, one problem per sample, and become pure HBM streams of x2 / x2.grad:
+//   fwd    Fv[b]  [T x HW]  = Wc [T x C]       . x2[b] [C x HW]       A = Wc K-major,   B = x2[b] MN-major (px contiguous)
+//   dgrad  dx2[b] [C x HW]  = Wc^T [C x T]     . dFv[b] [T x HW]      A = Wc MN-major,  B = dFv[b] MN-major
+//   wgrad  dWc    [T x C]  += dFv[b] [T x HW]  . x2[b]^T [HW x C]     A = dFv[b] K-major, B = x2[b] K-major, reduced over b
+// The seam tensors arrive in fp32 and are not ours to round: tcgen05 kind::tf32 truncates them (drops 13 mantissa
+// bits, always toward zero), which shrinks every product by E[tail/mantissa] = 3.3e-4 per truncated operand
+// (measured on B200, tools/tf32_rounding_probe.py).  out_scale multiplies that back; what is left is zero-mean
+// TF32 rounding noise.  The fp32 "parity" precision keeps the FFMA kernels above.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float kTruncShrink = 3.3e-4f;
+
+// dFv [B,T,HW] -> dFv3 [B,3T,HW]: rows 0..T-1 hi = the TF32-nearest part, rows T..2T-1 lo = the (TF32-rounded)
+// remainder, rows 2T..3T-1 hi again.  Every value is exactly representable on the tensor core, so against the
+// stacked weight [Wh; Wh; Wl] the conv dgrad computes Wh hi + Wh lo + Wl hi: fp32-grade (the d tokens are small:
+// 66 KB per sample against 1.6 MB of x2.grad).  hi alone feeds the weight gradient.
+__global__ void split_tf32_kernel(const float* __restrict__ dFv, float* __restrict__ dFv2, int B, int T, int HW) {
+    pdl_sync();
+    const long long n4 = (long long)B * T * (HW >> 2);
+    const int row4 = HW >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long bt = i / row4;
+        const int q = (int)(i - bt * row4);
+        const long long b = bt / T;
+        const int t = (int)(bt - b * T);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dFv) + i);
+        float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+        float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+        float4* dst = reinterpret_cast<float4*>(dFv2 + ((b * 3 * T + t) * (long long)HW)) + q;
+        dst[0] = hi;
+        dst[(long long)T * row4] = lo;
+        dst[(long long)2 * T * row4] = hi;
+    }
+}
+
+int launch_split_tf32(const float* dFv, float* dFv2, int B, int T, int HW, cudaStream_t stream) {
+    SCAT_REQUIRE(HW % 4 == 0, kErrUnsupported, "split: HW%%4");
+    const long long n4 = (long long)B * T * (HW / 4);
+    const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    SCAT_CHECK_CUDA(launch_k(split_tf32_kernel, dim3(grid), dim3(256), 0, stream, dFv, dFv2, B, T, HW));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_conv_pe_mask_fwd_tc(const float* x2, const float* Wc_tf32, const float* pe, const float* mask_token,
+                               const int32_t* mask_idx, int n_masked, int pos_embed, float* feat_visual, float* X0,
+                               int B, int C, int HW, int T, cudaStream_t stream) {
+    SCAT_REQUIRE(HW % 4 == 0 && C % 4 == 0 && T <= 128, kErrUnsupported, "conv fwd (tc): HW%%4, C%%4, T<=128");
+    GemmArgs g;
+    g.A = Wc_tf32; g.sam = C; g.sak = 1;                       // [T, C] K-major
+    g.B = x2; g.sbn = 1; g.sbk = HW;                            // x2[b] as B(n = px, k = c): MN-major
+    g.M = T; g.N = HW; g.K = C;
+    g.batch = B; g.b_k_z = C;                                   // sample b: k rows b*C .. b*C + C of the [B*C, HW] matrix
+    g.C = feat_visual; g.ldc = HW; g.c_z = (long long)T * HW;
+    g.epilogue = EPI_PE_MASK; g.bias = mask_token; g.mask_idx = mask_idx; g.n_masked = n_masked;
+    if (pos_embed) { g.aux_in = pe; g.ld_aux_in = HW; }
+    if (X0 != feat_visual) { g.aux_out = X0; g.ld_aux_out = HW; g.aux_out_z = (long long)T * HW; }
+    g.prerounded = 1;                                           // no in-kernel rounding pass: memory-bound stream
+    g.out_scale = 1.0f + kTruncShrink;
+    g.force_bn = 128;
+    return launch_gemm_tc(g, PREC_TF32, stream);
+}
+
+int launch_conv_dgrad_tc(const float* dFv2, const float* Wc2_tf32, float* x2_grad, int B, int C, int HW, int T,
+                         cudaStream_t stream) {
+    SCAT_REQUIRE(HW % 4 == 0 && C % 4 == 0, kErrUnsupported, "conv dgrad (tc): HW%%4, C%%4");
+    GemmArgs g;
+    g.A = Wc2_tf32; g.sam = 1; g.sak = C;                       // A(m = c, k = j) = [Wh; Wh; Wl][j, c]: MN-major
+    g.B = dFv2; g.sbn = 1; g.sbk = HW;                          // B(n = px, k = j) = [hi; lo; hi][j, px] of sample b: MN-major
+    g.M = C; g.N = HW; g.K = 3 * T;
+    g.batch = B; g.b_k_z = 3 * T;                               // rows b*3T .. of the [B*3T, HW] matrix; the k tail of a box
+                                                                // reaches into sample b+1 but meets A's zero-filled k rows
+    g.C = x2_grad; g.ldc = HW; g.c_z = (long long)C * HW;
+    g.prerounded = 1;                                           // every operand value is TF32-representable: exact products
+    g.force_bn = 128;
+    return launch_gemm_tc(g, PREC_TF32, stream);
+}
+
+int launch_conv_wgrad_tc(const float* dFv2, const float* x2, float* dWc, int B, int C, int HW, int T, cudaStream_t stream) {
+    SCAT_REQUIRE(HW % 4 == 0 && C % 4 == 0 && T <= 64, kErrUnsupported, "conv wgrad (tc): HW%%4, C%%4, T<=64");
+    GemmArgs g;
+    g.A = dFv2; g.sam = HW; g.sak = 1;                          // A(m = t, k = px): the hi rows of sample b, K-major; the rows
+    g.B = x2; g.sbn = HW; g.sbk = 1;                            // behind them (lo, next sample) land in accumulator rows >= T
+    g.M = T; g.N = C; g.K = HW;                                 // that are never stored
+    g.batch = B; g.a_row_z = 3 * T; g.b_row_z = C; g.batch_accumulate = 1;
+    g.C = dWc; g.ldc = C;
+    g.prerounded = 1;
+    g.out_scale = 1.0f + kTruncShrink;                          // x2 is truncated by the tensor core, hi is exact
+    g.force_bn = 128;
+    return launch_gemm_tc(g, PREC_TF32, stream);
+}
+
 size_t conv_wgrad_scratch_floats(int C, int T) { return (size_t)kConvWgradCtas * T * C; }
 
 int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scratch, int B, int C, int HW, int T,

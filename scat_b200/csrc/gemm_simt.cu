@@ -14,48 +14,61 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, THREADS = 256, PAD = 4;
 
-struct Frag { float v[4]; };
+constexpr int STAGES = 4;     // cp.async ring: the K loop of these small GEMMs is latency bound, not FMA bound
 
-// Load a [64 x 16] (rows x k) operand tile into registers.  Two thread->element maps so that the
-// unit-stride direction is the fastest-varying one across a warp (coalesced either way).
-template <bool ROW_CONTIG_K>
-__device__ __forceinline__ void load_tile(const float* __restrict__ P, long long s_row, long long s_k, int row0,
-                                          int k0, int rows, int K, int tid, Frag& f) {
-    if (ROW_CONTIG_K) {
-        const int r = row0 + (tid >> 2);
-        const int k = k0 + (tid & 3) * 4;
-        const float* p = P + (long long)r * s_row + (long long)k * s_k;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) f.v[i] = (r < rows && k + i < K) ? __ldg(p + i * s_k) : 0.f;
-    } else {
-        const int k = k0 + (tid >> 4);
-        const int r = row0 + (tid & 15) * 4;
-        const float* p = P + (long long)r * s_row + (long long)k * s_k;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) f.v[i] = (k < K && r + i < rows) ? __ldg(p + i * s_row) : 0.f;
-    }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned bytes = valid ? 4u : 0u;       // 0 source bytes = zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned bytes = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Stage a [64 rows x 16 k] operand tile into S[k][row] with asynchronous copies.  Two thread->element maps so that
+// the unit-stride direction is the fastest-varying one across a warp (coalesced either way); the K-contiguous map
+// transposes on the fly (4-byte copies), the row-contiguous one moves 16 bytes when the operand allows it.
 template <bool ROW_CONTIG_K>
-__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], int tid, const Frag& f) {
+__device__ __forceinline__ void stage_tile(const float* __restrict__ P, long long s_row, long long s_k, int row0, int k0,
+                                           int rows, int K, int tid, float (*S)[BM + PAD], bool vec16) {
     if (ROW_CONTIG_K) {
-        const int r = tid >> 2, k = (tid & 3) * 4;
+        const int r = tid >> 2, kk = (tid & 3) * 4;
+        const int gr = row0 + r, gk = k0 + kk;
+        const float* p = P + (long long)gr * s_row + (long long)gk * s_k;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) S[k + i][r] = f.v[i];
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = gr < rows && gk + i < K;
+            cp_async4(&S[kk + i][r], ok ? p + i * s_k : P, ok);
+        }
     } else {
-        const int k = tid >> 4, r = (tid & 15) * 4;
-        *reinterpret_cast<float4*>(&S[k][r]) = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+        const int kk = tid >> 4, r = (tid & 15) * 4;
+        const int gk = k0 + kk, gr = row0 + r;
+        const float* p = P + (long long)gr * s_row + (long long)gk * s_k;
+        if (vec16 && gk < K && gr + 3 < rows) {
+            cp_async16(&S[kk][r], p, true);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = gk < K && gr + i < rows;
+                cp_async4(&S[kk][r + i], ok ? p + i * s_row : P, ok);
+            }
+        }
     }
 }
 
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_per_split) {
     pdl_sync();
-    __shared__ __align__(16) float As[BK][BM + PAD];
-    __shared__ __align__(16) float Bs[BK][BN + PAD];
+    __shared__ __align__(16) float As[STAGES][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[STAGES][BK][BN + PAD];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int ty = tid >> 4, tx = tid & 15;
+    const float* A = static_cast<const float*>(g.A);
+    const float* B = static_cast<const float*>(g.B);
 
     float acc[4][4];
 #pragma unroll
@@ -67,21 +80,32 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
     const int kt_beg = blockIdx.z * kt_per_split;
     const int kt_end = min(nk_all, kt_beg + kt_per_split);
     if (kt_beg >= kt_end) return;
-    Frag fa, fb;
-    load_tile<A_K>(static_cast<const float*>(g.A), g.sam, g.sak, m0, kt_beg * BK, g.M, g.K, tid, fa);
-    load_tile<B_K>(static_cast<const float*>(g.B), g.sbn, g.sbk, n0, kt_beg * BK, g.N, g.K, tid, fb);
-    for (int kt = kt_beg; kt < kt_end; ++kt) {
-        store_tile<A_K>(As, tid, fa);
-        store_tile<B_K>(Bs, tid, fb);
-        __syncthreads();
-        if (kt + 1 < kt_end) {
-            load_tile<A_K>(static_cast<const float*>(g.A), g.sam, g.sak, m0, (kt + 1) * BK, g.M, g.K, tid, fa);
-            load_tile<B_K>(static_cast<const float*>(g.B), g.sbn, g.sbk, n0, (kt + 1) * BK, g.N, g.K, tid, fb);
+    const int nkt = kt_end - kt_beg;
+    // 16-byte copies need a unit row stride, 16-byte aligned k-rows and base
+    const bool a16 = !A_K && g.sam == 1 && (g.sak & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (m0 & 3) == 0;
+    const bool b16 = !B_K && g.sbn == 1 && (g.sbk & 3) == 0 && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (n0 & 3) == 0;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nkt) {
+            stage_tile<A_K>(A, g.sam, g.sak, m0, (kt_beg + s) * BK, g.M, g.K, tid, As[s], a16);
+            stage_tile<B_K>(B, g.sbn, g.sbk, n0, (kt_beg + s) * BK, g.N, g.K, tid, Bs[s], b16);
         }
+        cp_async_commit();
+    }
+    for (int it = 0; it < nkt; ++it) {
+        cp_async_wait<STAGES - 2>();          // the group that filled stage it % STAGES has landed (for this thread)
+        __syncthreads();                      // ... and for every thread; everyone is also done computing on stage it-1
+        const int nxt = it + STAGES - 1;
+        if (nxt < nkt) {
+            stage_tile<A_K>(A, g.sam, g.sak, m0, (kt_beg + nxt) * BK, g.M, g.K, tid, As[nxt % STAGES], a16);
+            stage_tile<B_K>(B, g.sbn, g.sbk, n0, (kt_beg + nxt) * BK, g.N, g.K, tid, Bs[nxt % STAGES], b16);
+        }
+        cp_async_commit();
+        const int st = it % STAGES;
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float4 a = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[st][k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w};
             const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -89,7 +113,6 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        __syncthreads();
     }
 
     const bool split = gridDim.z > 1;
@@ -119,6 +142,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
             float* c = g.C + (long long)m * g.ldc + n;
             if (split) atomicAdd(c, v);                       // C was cleared (or holds the accumulate base)
             else *c = g.accumulate ? (*c + v) : v;
+            if (g.C16 != nullptr) reinterpret_cast<__nv_bfloat16*>(g.C16)[(long long)m * g.ldc16 + n] = __float2bfloat16_rn(v);
         }
     }
 }
@@ -141,10 +165,45 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ld, int M, int N,
     }
 }
 
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ld, int M, int N, float* __restrict__ out) {
+    pdl_sync();
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < N)
+        for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += 8 * gridDim.y) s += __bfloat162float(X[(long long)m * ld + c]);
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
 __global__ void round_copy_kernel(const RoundJobs jobs) {
     pdl_sync();
     const RoundJob job = jobs.job[blockIdx.y];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (job.to_bf16 == 2) {                                          // TF32 remainder: src - round(src), itself rounded
+        const int total = job.rows * job.ld_dst;
+        for (int i = tid; i < total; i += nthr) {
+            const int r = i / job.ld_dst, c = i - r * job.ld_dst;
+            const float v = c < job.cols ? __ldg(job.src + (size_t)r * job.ld_src + c) : 0.f;
+            job.dst[i] = round_tf32(v - round_tf32(v));
+        }
+        return;
+    }
+    if (job.to_bf16 == 1) {                                          // bf16 copy, pad columns zero-filled
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(job.dst);
+        const int total = job.rows * job.ld_dst;
+        for (int i = tid; i < total; i += nthr) {
+            const int r = i / job.ld_dst, c = i - r * job.ld_dst;
+            dst[i] = __float2bfloat16_rn(c < job.cols ? __ldg(job.src + (size_t)r * job.ld_src + c) : 0.f);
+        }
+        return;
+    }
     if (((job.cols | job.ld_src | job.ld_dst) & 3) == 0) {          // float4 path (every weight but fc2 of layer 1)
         const int c4n = job.ld_dst >> 2, total = job.rows * c4n;
         for (int i = tid; i < total; i += nthr) {
@@ -166,7 +225,7 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
 }  // namespace
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
-    SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 12, kErrBadArg, "round_copy: %d jobs", jobs.n);
+    SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 16, kErrBadArg, "round_copy: %d jobs", jobs.n);
     SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(dim3(60, jobs.n)), dim3(256), 0, stream, jobs));
     SCAT_CHECK_LAUNCH();
     return 0;
@@ -175,7 +234,7 @@ int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     SCAT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, kErrBadArg, "gemm: bad shape %d %d %d", g.M, g.N, g.K);
     SCAT_REQUIRE(g.A && g.B && g.C, kErrBadArg, "gemm: null operand");
-    SCAT_REQUIRE(!g.operand_bf16 && !g.C16, kErrUnsupported, "gemm: the FFMA kernel takes fp32 operands only");
+    SCAT_REQUIRE(!g.operand_bf16, kErrUnsupported, "gemm: the FFMA kernel takes fp32 operands only");
     if (g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_BIAS_GELU)
         SCAT_REQUIRE(g.bias != nullptr, kErrBadArg, "gemm: epilogue %d needs bias", g.epilogue);
     if (g.epilogue == EPI_BIAS_RESID || g.epilogue == EPI_DGELU || g.epilogue == EPI_RESID)
@@ -185,7 +244,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), 1);
     const int nk = ceil_div(g.K, BK);
     int splits = 1;
-    if (g.allow_split_k && g.epilogue == EPI_NONE && (int)(grid.x * grid.y) < 74 && nk >= 16) {
+    if (g.allow_split_k && g.epilogue == EPI_NONE && !g.C16 && (int)(grid.x * grid.y) < 74 && nk >= 16) {
         splits = min(min(32, nk / 4), ceil_div(296, (int)(grid.x * grid.y)));
         if (splits < 1) splits = 1;
     }
@@ -203,13 +262,17 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     return 0;
 }
 
-int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream) {
+int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream, int x_bf16) {
     SCAT_REQUIRE(X && out && M > 0 && N > 0, kErrBadArg, "colsum: bad args");
     if (!accumulate) SCAT_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), stream));
     const int gx = ceil_div(N, 32);
     int gy = min(ceil_div(M, 8 * 4), max(1, 592 / gx));       // >= 4 rows per thread, ~4 blocks per SM
     if (gy < 1) gy = 1;
-    SCAT_CHECK_CUDA(launch_k(colsum_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, stream, X, ld, M, N, out));
+    if (x_bf16)
+        SCAT_CHECK_CUDA(launch_k(colsum_bf16_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, stream,
+                                 reinterpret_cast<const __nv_bfloat16*>(X), ld, M, N, out));
+    else
+        SCAT_CHECK_CUDA(launch_k(colsum_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, stream, X, ld, M, N, out));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -163,6 +163,15 @@ struct TcParams {
     int round_operands;             // 1: round fp32 operands to TF32 (nearest) in shared memory before the MMA
     int kb_per_split;               // k-blocks per gridDim.z slice (split-K: weight gradients, K = B*21 rows)
     int atomic_out;                 // 1: C += tile with red.global.add (split-K slices combine in L2; C pre-zeroed)
+    // batched launches (blockIdx.z = batch index instead of a split-K slice): per-batch TMA coordinate offsets of the
+    // operands (rows / k, in elements of the respective tensor-map dimension) and element offsets of the outputs
+    int batched;
+    int a_row_z, a_k_z, b_row_z, b_k_z;
+    long long c_z, aux_out_z;
+    float out_scale;                // accumulator scale applied first (1 = none): operand-truncation bias correction
+    const int32_t* mask_idx; int n_masked;   // EPI_PE_MASK: rows (tokens) replaced by bias[n] (the mask token)
+    int tiles_m, tiles_n, tiles_z;  // tile space walked by the CTAs (n fastest); z = split-K slice or batch index
+    int persistent;                 // a CTA may own several tiles: double-buffered accumulators, dedicated scratch
     int vec_ok;                     // every pointer / leading dimension the epilogue touches allows 16-byte accesses
     long long* dbg;                 // optional: CTA (0,0,0) records clock64() at 8 milestones (tools/gemm_timeline.py)
 };
@@ -177,7 +186,9 @@ struct SmemLayout {
     static constexpr int B_BYTES = BN * 128;              // 8 / 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 128 + 1024;    // barriers + tmem slot + slack for 1024-byte alignment
+    static constexpr int SCRATCH_OFF = BAR_OFF + 256;     // persistent CTAs: 4 warps x 32x32 floats of epilogue scratch
+    static constexpr int TOTAL = BAR_OFF + 256;           // barriers + tmem slot
+    static constexpr int TOTAL_PERSISTENT = SCRATCH_OFF + 4 * 32 * 32 * 4;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -191,25 +202,45 @@ struct SmemLayout {
 // tested once per chunk (not per element), and all global reads of a chunk (bias, residual / saved pre-activation
 // or old C) are issued before the TMEM load so that they overlap it and each other.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_lane_base, float* scratch, int row_base,
-                                              int n0, int lane, int BN) {
-    constexpr int PITCH = 36;                    // floats per scratch row: float4 accesses stay conflict-free
+__device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t tmem_lane_base, float* scratch, int row_base,
+                                                   int n0, int lane, int BN, int zb, bool mark) {
+    // scratch: 32 rows x 32 floats per warp; the float4 chunk c of row r lives at chunk c ^ (r & 7), which keeps both
+    // the row-wise writes and the 4-rows-per-instruction reads free of bank conflicts without padding
     const int rsub = lane >> 3, csub = (lane & 7) * 4;
     const int epi = p.epilogue;
-    const bool has_aux = epi == EPI_BIAS_RESID || epi == EPI_RESID || epi == EPI_DGELU;
-    const bool has_bias = epi == EPI_BIAS || epi == EPI_BIAS_RESID || epi == EPI_BIAS_GELU;
+    const bool has_aux = epi == EPI_BIAS_RESID || epi == EPI_RESID || epi == EPI_DGELU || (epi == EPI_PE_MASK && p.aux_in != nullptr);
+    const bool has_bias = epi == EPI_BIAS || epi == EPI_BIAS_RESID || epi == EPI_BIAS_GELU || (epi == EPI_PE_MASK && p.n_masked > 0);
     const bool rmw = p.accumulate && !p.atomic_out && p.C != nullptr && !has_aux;
     // rows this lane touches: row_base + rsub + 4i, i < 8
     const int row0 = row_base + rsub;
     uint32_t valid = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) valid |= (row0 + 4 * i < p.M ? 1u : 0u) << i;
-    const long long c_step = 4LL * p.ldc, h_step = 4LL * p.ldc16, z_step = 4LL * p.ld_aux_out;
-    float* cptr = p.C ? p.C + (long long)row0 * p.ldc + n0 + csub : nullptr;
+#define SCAT_ROW_OK(i) ((valid >> (i)) & 1u)
+    // the common case gets out early below: plain fp32 store of the accumulator, nothing else to do
+    const bool plain = epi == EPI_NONE && p.out_scale == 1.0f && !p.round_out && p.C16 == nullptr && !p.atomic_out &&
+                       !p.accumulate && p.C != nullptr;
+    const long long c_step = 4LL * p.ldc, h_step = 4LL * p.ldc16, z_step = 4LL * p.ld_aux_out, a_step = 4LL * p.ld_aux_in;
+    float* cptr = p.C ? p.C + zb * p.c_z + (long long)row0 * p.ldc + n0 + csub : nullptr;
     __nv_bfloat16* hptr = p.C16 ? p.C16 + (long long)row0 * p.ldc16 + n0 + csub : nullptr;
-    float* zptr = p.aux_out ? p.aux_out + (long long)row0 * p.ld_aux_out + n0 + csub : nullptr;
-    float* srow = scratch + lane * PITCH;                       // TMEM-row mapping: this lane's row of the chunk
-    const float* scol = scratch + rsub * PITCH + csub;          // coalesced mapping: + 4i rows
+    float* zptr = p.aux_out ? p.aux_out + zb * p.aux_out_z + (long long)row0 * p.ld_aux_out + n0 + csub : nullptr;
+    // residual / saved pre-activation rows; with stacked cotangents (aux_row_mod) row m reads activation row m % mod
+    const bool aux_linear = p.aux_row_mod <= 0 || row_base + 32 <= p.aux_row_mod;
+    const float* aptr = p.aux_in ? p.aux_in + (long long)row0 * p.ld_aux_in + n0 + csub : nullptr;
+    // EPI_PE_MASK (conv front end, hand_net.py:366-373): rows are tokens; bit i = this lane's row row0 + 4i is masked
+    uint32_t masked = 0;
+    if (epi == EPI_PE_MASK) {
+        for (int k = 0; k < p.n_masked; ++k) {
+            const int t = __ldg(p.mask_idx + k);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) masked |= (t == row0 + 4 * i ? 1u : 0u) << i;
+        }
+    }
+    const bool has_pe = epi == EPI_PE_MASK && p.aux_in != nullptr;
+    float* srow = scratch + lane * 32;                          // TMEM-row mapping: this lane's row of the chunk
+    const int cc = lane & 7;                                    // coalesced mapping: chunk cc of rows rsub + 4i
+    const float* sread0 = scratch + rsub * 32 + 4 * (cc ^ rsub);            // rows rsub + 8j     ((row & 7) = rsub)
+    const float* sread1 = scratch + (rsub + 4) * 32 + 4 * (cc ^ (rsub + 4)); // rows rsub + 4 + 8j ((row & 7) = rsub + 4)
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
         const int n = n0 + c + csub;                 // this lane's 4 columns
@@ -220,16 +251,22 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_l
         if (vec) {
             if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             if (has_aux) {
+                if (aux_linear) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = row0 + 4 * i;
-                    const long long ar = p.aux_row_mod > 0 ? row % p.aux_row_mod : row;
-                    if ((valid >> i) & 1) ext[i] = __ldg(reinterpret_cast<const float4*>(p.aux_in + ar * p.ld_aux_in + n));
+                    for (int i = 0; i < 8; ++i)
+                        if (SCAT_ROW_OK(i)) ext[i] = __ldg(reinterpret_cast<const float4*>(aptr + i * a_step));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row0 + 4 * i;
+                        if (SCAT_ROW_OK(i))
+                            ext[i] = __ldg(reinterpret_cast<const float4*>(p.aux_in + (long long)(row % p.aux_row_mod) * p.ld_aux_in + n));
+                    }
                 }
             } else if (rmw) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if ((valid >> i) & 1) ext[i] = *reinterpret_cast<const float4*>(cptr + i * c_step);
+                    if (SCAT_ROW_OK(i)) ext[i] = *reinterpret_cast<const float4*>(cptr + i * c_step);
             }
         }
         float v[32];
@@ -237,32 +274,59 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_l
         tmem_ld32(tmem_lane_base + (uint32_t)c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(srow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(srow + 4 * (j ^ (lane & 7))) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         if (vec) {
             float4 acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = *reinterpret_cast<const float4*>(scol + i * 4 * PITCH);
+            for (int j = 0; j < 4; ++j) {
+                acc[2 * j] = *reinterpret_cast<const float4*>(sread0 + j * 8 * 32);
+                acc[2 * j + 1] = *reinterpret_cast<const float4*>(sread1 + j * 8 * 32);
+            }
+            if (plain) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (SCAT_ROW_OK(i)) *reinterpret_cast<float4*>(cptr + i * c_step) = acc[i];
+                cptr += 32;
+                continue;
+            }
             // ---- math phase (registers only, except the saved pre-activation of BIAS_GELU) ----
-            if (has_bias) {
+            if (p.out_scale != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { acc[i].x *= p.out_scale; acc[i].y *= p.out_scale; acc[i].z *= p.out_scale; acc[i].w *= p.out_scale; }
+            }
+            if (epi == EPI_PE_MASK) {
+                // C <- conv output (masked rows overwritten only when the token matrix aliases it: no aux_out);
+                // aux_out <- token matrix: mask token on masked rows, else conv output (+ positional encoding)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (!SCAT_ROW_OK(i)) continue;
+                    const bool mk = (masked >> i) & 1;
+                    float4 tok = acc[i];
+                    if (mk) tok = b4;
+                    else if (has_pe) { tok.x += ext[i].x; tok.y += ext[i].y; tok.z += ext[i].z; tok.w += ext[i].w; }
+                    if (zptr != nullptr) *reinterpret_cast<float4*>(zptr + i * z_step) = tok;
+                    else acc[i] = tok;
+                }
+            } else if (has_bias) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { acc[i].x += b4.x; acc[i].y += b4.y; acc[i].z += b4.z; acc[i].w += b4.w; }
             }
             if (epi == EPI_BIAS_RESID || epi == EPI_RESID || rmw) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if ((valid >> i) & 1) { acc[i].x += ext[i].x; acc[i].y += ext[i].y; acc[i].z += ext[i].z; acc[i].w += ext[i].w; }
+                    if (SCAT_ROW_OK(i)) { acc[i].x += ext[i].x; acc[i].y += ext[i].y; acc[i].z += ext[i].z; acc[i].w += ext[i].w; }
             } else if (epi == EPI_DGELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if ((valid >> i) & 1) {
+                    if (SCAT_ROW_OK(i)) {
                         acc[i].x *= gelu_erf_grad(ext[i].x); acc[i].y *= gelu_erf_grad(ext[i].y);
                         acc[i].z *= gelu_erf_grad(ext[i].z); acc[i].w *= gelu_erf_grad(ext[i].w);
                     }
             } else if (epi == EPI_BIAS_GELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if ((valid >> i) & 1) *reinterpret_cast<float4*>(zptr + i * z_step) = acc[i];
+                    if (SCAT_ROW_OK(i)) *reinterpret_cast<float4*>(zptr + i * z_step) = acc[i];
                     acc[i].x = gelu_erf(acc[i].x); acc[i].y = gelu_erf(acc[i].y);
                     acc[i].z = gelu_erf(acc[i].z); acc[i].w = gelu_erf(acc[i].w);
                 }
@@ -282,18 +346,18 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_l
                     uint2 pk;
                     pk.x = *reinterpret_cast<const uint32_t*>(&lo);
                     pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                    if ((valid >> i) & 1) *reinterpret_cast<uint2*>(hptr + i * h_step) = pk;
+                    if (SCAT_ROW_OK(i)) *reinterpret_cast<uint2*>(hptr + i * h_step) = pk;
                 }
             }
             if (cptr != nullptr) {
                 if (p.atomic_out) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if ((valid >> i) & 1) red_add_v4(cptr + i * c_step, acc[i]);
+                        if (SCAT_ROW_OK(i)) red_add_v4(cptr + i * c_step, acc[i]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if ((valid >> i) & 1) *reinterpret_cast<float4*>(cptr + i * c_step) = acc[i];
+                        if (SCAT_ROW_OK(i)) *reinterpret_cast<float4*>(cptr + i * c_step) = acc[i];
                 }
             }
         } else if (n < p.N) {
@@ -302,14 +366,21 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_l
             for (int i = 0; i < 8; ++i) {
                 const int row = row0 + 4 * i;
                 if (row >= p.M) break;
-                const float4 o = *reinterpret_cast<const float4*>(scol + i * 4 * PITCH);
+                const float4 o = *reinterpret_cast<const float4*>(scratch + (4 * i + rsub) * 32 + 4 * (cc ^ ((4 * i + rsub) & 7)));
                 const float ov[4] = {o.x, o.y, o.z, o.w};
                 const long long ar = p.aux_row_mod > 0 ? row % p.aux_row_mod : row;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int ne = n + e;
                     if (ne >= p.N) break;
-                    float t = ov[e];
+                    float t = ov[e] * p.out_scale;
+                    if (epi == EPI_PE_MASK) {
+                        bool mk = false;
+                        for (int k = 0; k < p.n_masked; ++k) mk |= (p.mask_idx[k] == row);
+                        const float tok = mk ? p.bias[ne] : (p.aux_in ? t + p.aux_in[ar * p.ld_aux_in + ne] : t);
+                        if (p.aux_out) p.aux_out[zb * p.aux_out_z + (long long)row * p.ld_aux_out + ne] = tok;
+                        else t = tok;
+                    }
                     switch (epi) {
                         case EPI_BIAS: t += p.bias[ne]; break;
                         case EPI_BIAS_RESID: t += p.bias[ne] + p.aux_in[ar * p.ld_aux_in + ne]; break;
@@ -321,7 +392,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_l
                     if (p.round_out) t = round_tf32(t);
                     if (p.C16) p.C16[(long long)row * p.ldc16 + ne] = __float2bfloat16_rn(t);
                     if (p.C) {
-                        float* cp = p.C + (long long)row * p.ldc + ne;
+                        float* cp = p.C + zb * p.c_z + (long long)row * p.ldc + ne;
                         if (p.atomic_out) atomicAdd(cp, t);
                         else *cp = (p.accumulate && !has_aux) ? *cp + t : t;
                     }
@@ -331,7 +402,18 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_l
         if (cptr != nullptr) cptr += 32;
         if (hptr != nullptr) hptr += 32;
         if (zptr != nullptr) zptr += 32;
+        if (aptr != nullptr) aptr += 32;
     }
+#undef SCAT_ROW_OK
+}
+
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_lane_base, float* scratch, int row_base,
+                                              int n0, int lane, int BN, int zb, bool mark) {
+    // (Compile-time specialisation of this function per (epilogue, output mode) was tried and measured: as inlined
+    // code it spills at the 168-register cap of two CTAs per SM, as out-of-line functions the by-reference parameter
+    // block costs every thread a 688-byte local copy, +1.2 us per launch.  The runtime-flag version stays.)
+    if (row_base >= p.M) return;     // this warp's 32 rows are all outside M (the conv front end uses 21 of 128 rows)
+    epilogue_tile_impl(p, tmem_lane_base, scratch, row_base, n0, lane, BN, zb, mark);
 }
 
 template <bool BF16, int BN, bool A_MN, bool B_MN>
@@ -341,23 +423,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     using E = Elem<BF16>;
     constexpr int STAGES = L::STAGES;
     constexpr int BK = E::BK;
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment (128B swizzle atoms) by an integer offset into the extern array: pointer arithmetic on
-    // smem_raw keeps the shared address space known to the compiler (LDS/STS instead of generic LD/ST)
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // no static shared memory in this kernel: the dynamic window starts at the CTA's shared base, which is 1024-byte
+    // aligned (128B swizzle atoms need it); checked below rather than paid for with a kilobyte of slack
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_base + L::BAR_OFF;          // STAGES x 8 B each
     const uint32_t empty_bar = full_bar + 8 * STAGES;
     const uint32_t conv_bar = empty_bar + 8 * STAGES;
-    const uint32_t accum_bar = conv_bar + 8 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (3 * STAGES + 1));
+    const uint32_t tfull_bar = conv_bar + 8 * STAGES;          // 2: accumulator buffer complete (MMA -> epilogue)
+    const uint32_t tempty_bar = tfull_bar + 16;                // 2: accumulator buffer drained (epilogue -> MMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) dbg_mark(p, 0);
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (threadIdx.x == 0 && (smem_base & 1023u) != 0) __trap();
     const int kb_all = (p.K + BK - 1) / BK;
-    const int kb_begin = blockIdx.z * p.kb_per_split;
-    const int num_kb = min(kb_all, kb_begin + p.kb_per_split) - kb_begin;      // host guarantees >= 1
+    // tile space, n fastest: [z][m tile][n tile]; a CTA walks it with stride gridDim.x (one tile each unless persistent)
+    // One tile per CTA (the usual case): a 3-D grid, the tile is the block index and nothing is divided.  Persistent:
+    // a 1-D grid of resident CTAs strides through the linear tile index.
+    const int tiles_n = p.tiles_n, tiles_mn = p.tiles_n * p.tiles_m;
+    const bool persistent = p.persistent != 0;
+    const int total_tiles = persistent ? tiles_mn * p.tiles_z : 1;
+    const int tile_first = persistent ? (int)blockIdx.x : 0, tile_stride = persistent ? (int)gridDim.x : 1;
+    auto decode_tile = [&](int tile, int& z, int& m0, int& n0) {
+        if (persistent) {
+            z = tile / tiles_mn;
+            const int mn = tile - z * tiles_mn, mt = mn / tiles_n;
+            m0 = mt * BM; n0 = (mn - mt * tiles_n) * BN;
+        } else {
+            z = blockIdx.z; m0 = blockIdx.y * BM; n0 = blockIdx.x * BN;
+        }
+    };
+    const uint32_t tmem_cols = persistent ? 2 * BN : BN;
 
     if (warp == 0 && lane == 0) {
         // fetch the two TMA descriptors while the barriers are set up (they are kernel parameters, not data of
@@ -370,10 +467,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(empty_bar + 8 * s, 1);
             mbar_init(conv_bar + 8 * s, TC_THREADS - 64);     // every epilogue/converter thread arrives
         }
-        mbar_init(accum_bar, 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar + 8 * i, 1);
+            mbar_init(tempty_bar + 8 * i, 4);                 // one elected lane of each epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -384,35 +485,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) dbg_mark(p, 1);
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: runs ahead of the MMA warp across tile boundaries =====
         int s = 0;
         uint32_t ph = 0;
-        int k0 = kb_begin * BK;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(empty_bar + 8 * s, ph ^ 1);
-            if (elect_one()) {
-                const uint32_t fb = full_bar + 8 * s;
-                mbar_expect_tx(fb, L::STAGE_BYTES);
-                const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-                const uint32_t sb = sa + L::A_BYTES;
-                if (!A_MN) {
-                    tma_load_2d(&tmA, fb, sa, k0, m0);                                        // box {BK k, 128 rows}
-                } else {
+        for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
+            int z, m0, n0;
+            decode_tile(tile, z, m0, n0);
+            const int zb = p.batched ? z : 0;
+            const int kb_begin = p.batched ? 0 : z * p.kb_per_split;
+            const int num_kb = min(kb_all, kb_begin + p.kb_per_split) - kb_begin;      // host guarantees >= 1
+            int k0 = kb_begin * BK;
+            const int am0 = m0 + zb * p.a_row_z, ak_off = zb * p.a_k_z, bn0 = n0 + zb * p.b_row_z, bk_off = zb * p.b_k_z;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar + 8 * s, ph ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = full_bar + 8 * s;
+                    mbar_expect_tx(fb, L::STAGE_BYTES);
+                    const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+                    const uint32_t sb = sa + L::A_BYTES;
+                    if (!A_MN) {
+                        tma_load_2d(&tmA, fb, sa, k0 + ak_off, am0);                              // box {BK k, 128 rows}
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < BM / E::MN_BOX; ++i)
-                        tma_load_2d(&tmA, fb, sa + i * E::MN_LBO, m0 + E::MN_BOX * i, k0);    // box {MN_BOX rows, BK k}
-                }
-                if (!B_MN) {
-                    tma_load_2d(&tmB, fb, sb, k0, n0);                                        // box {BK k, BN rows}
-                } else {
+                        for (int i = 0; i < BM / E::MN_BOX; ++i)
+                            tma_load_2d(&tmA, fb, sa + i * E::MN_LBO, am0 + E::MN_BOX * i, k0 + ak_off);    // box {MN_BOX rows, BK k}
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(&tmB, fb, sb, k0 + bk_off, bn0);                              // box {BK k, BN rows}
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < BN / E::MN_BOX; ++i)
-                        tma_load_2d(&tmB, fb, sb + i * E::MN_LBO, n0 + E::MN_BOX * i, k0);
+                        for (int i = 0; i < BN / E::MN_BOX; ++i)
+                            tma_load_2d(&tmB, fb, sb + i * E::MN_LBO, bn0 + E::MN_BOX * i, k0 + bk_off);
+                    }
                 }
+                __syncwarp();
+                k0 += BK;
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
-            k0 += BK;
-            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -430,62 +539,89 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ready_bar = p.round_operands ? conv_bar : full_bar;
         int s = 0;
         uint32_t ph = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(ready_bar + 8 * s, ph);
+        int it = 0;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_stride, ++it) {
+            int z, m0_unused, n0_unused;
+            decode_tile(tile, z, m0_unused, n0_unused);
+            const int kb_begin = p.batched ? 0 : z * p.kb_per_split;
+            const int num_kb = min(kb_all, kb_begin + p.kb_per_split) - kb_begin;
+            const int as = it & 1;                                   // accumulator buffer
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tempty_bar + 8 * as, aph ^ 1);                 // the epilogue has drained this buffer (2 tiles ago)
             tc_fence_after();
-            if (kb == 0 && lane == 0) dbg_mark(p, 2);
-            if (elect_one()) {
-                const uint32_t a_lo = a_lo0 + s * (L::STAGE_BYTES >> 4);
-                const uint32_t b_lo = b_lo0 + s * (L::STAGE_BYTES >> 4);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(ready_bar + 8 * s, ph);
+                tc_fence_after();
+                if (it == 0 && kb == 0 && lane == 0) dbg_mark(p, 2);
+                if (elect_one()) {
+                    const uint32_t a_lo = a_lo0 + s * (L::STAGE_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + s * (L::STAGE_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < BK / E::UK; ++k)
-                    umma<BF16>(tmem_base, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                umma_commit(empty_bar + 8 * s);              // smem slot is free once these MMAs have read it
-                if (kb == num_kb - 1) umma_commit(accum_bar);   // accumulator complete
+                    for (int k = 0; k < BK / E::UK; ++k)
+                        umma<BF16>(tmem_d, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar + 8 * s);                  // smem slot is free once these MMAs have read it
+                    if (kb == num_kb - 1) umma_commit(tfull_bar + 8 * as);   // accumulator complete
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
-            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else {
         // ===== operand conditioning during the main loop (fp32 operands only), then the epilogue =====
         // The tensor core TRUNCATES fp32 operands to TF32 (measured: -6.6e-4 mean bias on positive data, 2.6x the
         // error of round-to-nearest).  These four otherwise idle warps round every landed stage to TF32-nearest
         // in place (cvt.rna.tf32.f32) and hand it to the MMA warp through conv_bar.
-        if (!BF16 && p.round_operands) {
-            const int ctid = threadIdx.x - 64;
-            int s = 0;
-            uint32_t ph = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(full_bar + 8 * s, ph);
-                uint4* st = reinterpret_cast<uint4*>(smem + s * L::STAGE_BYTES);
-#pragma unroll 4
-                for (int i = ctid; i < L::STAGE_BYTES / 16; i += TC_THREADS - 64) {
-                    uint4 v = st[i];
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.x) : "f"(__uint_as_float(v.x)));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.y) : "f"(__uint_as_float(v.y)));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.z) : "f"(__uint_as_float(v.z)));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.w) : "f"(__uint_as_float(v.w)));
-                    st[i] = v;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (UMMA) reads
-                mbar_arrive(conv_bar + 8 * s);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
-            }
-        }
-        // ===== epilogue: TMEM -> registers -> shared (transpose) -> registers -> global =====
         const int q = warp & 3;                      // a warp may only touch TMEM lanes [32*(warp%4), +32)
-        mbar_wait(accum_bar, 0);                     // every MMA has completed: the ring is free for generic writes
-        tc_fence_after();
-        if (threadIdx.x == 64) dbg_mark(p, 3);
-        epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16), reinterpret_cast<float*>(smem) + q * 32 * 36, m0 + q * 32,
-                      n0, lane, BN);
+        // transposition scratch of the epilogue: the idle operand ring when this CTA owns a single tile, a dedicated
+        // region behind the barriers when it is persistent (the ring is then busy with the next tile)
+        float* scratch = reinterpret_cast<float*>(smem + (persistent ? L::SCRATCH_OFF : 0)) + q * 32 * 32;
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_stride, ++it) {
+            int z, m0, n0;
+            decode_tile(tile, z, m0, n0);
+            const int zb = p.batched ? z : 0;
+            if (!BF16 && p.round_operands) {
+                const int kb_begin = p.batched ? 0 : z * p.kb_per_split;
+                const int num_kb = min(kb_all, kb_begin + p.kb_per_split) - kb_begin;
+                const int ctid = threadIdx.x - 64;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar + 8 * s, ph);
+                    uint4* st = reinterpret_cast<uint4*>(smem + s * L::STAGE_BYTES);
+#pragma unroll 4
+                    for (int i = ctid; i < L::STAGE_BYTES / 16; i += TC_THREADS - 64) {
+                        uint4 v = st[i];
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.x) : "f"(__uint_as_float(v.x)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.y) : "f"(__uint_as_float(v.y)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.z) : "f"(__uint_as_float(v.z)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.w) : "f"(__uint_as_float(v.w)));
+                        st[i] = v;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (UMMA) reads
+                    mbar_arrive(conv_bar + 8 * s);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+            // ===== epilogue: TMEM -> registers -> shared (transpose) -> registers -> global =====
+            const int as = it & 1;
+            mbar_wait(tfull_bar + 8 * as, (it >> 1) & 1);          // every MMA of this tile has completed
+            tc_fence_after();
+            if (it == 0 && threadIdx.x == 64) dbg_mark(p, 3);
+            epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), scratch, m0 + q * 32, n0, lane, BN, zb,
+                          it == 0 && threadIdx.x == 64);
+            tc_fence_before();                                       // TMEM reads ordered before the hand-back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+        }
     }
     if (threadIdx.x == 64) dbg_mark(p, 7);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -545,15 +681,19 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     auto kern = gemm_tc_kernel<BF16, BN, A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SCAT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL_PERSISTENT));
         attr_done = true;
     }
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle mn_sw = BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (!A_MN) SCAT_PROPAGATE(make_map(&tmA, g.A, E::BYTES, g.K, g.M, g.sam, E::BK, BM, CU_TENSOR_MAP_SWIZZLE_128B));
-    else SCAT_PROPAGATE(make_map(&tmA, g.A, E::BYTES, g.M, g.K, g.sak, E::MN_BOX, E::BK, mn_sw));
-    if (!B_MN) SCAT_PROPAGATE(make_map(&tmB, g.B, E::BYTES, g.K, g.N, g.sbn, E::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B));
-    else SCAT_PROPAGATE(make_map(&tmB, g.B, E::BYTES, g.N, g.K, g.sbk, E::MN_BOX, E::BK, mn_sw));
+    // extents of the tensor maps: one problem, or (batched) the whole stack of problems along rows / k
+    const int nb1 = g.batch > 1 ? g.batch - 1 : 0;
+    const long long a_rows = g.M + (long long)nb1 * g.a_row_z, a_k = g.K + (long long)nb1 * g.a_k_z;
+    const long long b_rows = g.N + (long long)nb1 * g.b_row_z, b_k = g.K + (long long)nb1 * g.b_k_z;
+    if (!A_MN) SCAT_PROPAGATE(make_map(&tmA, g.A, E::BYTES, a_k, a_rows, g.sam, E::BK, BM, CU_TENSOR_MAP_SWIZZLE_128B));
+    else SCAT_PROPAGATE(make_map(&tmA, g.A, E::BYTES, a_rows, a_k, g.sak, E::MN_BOX, E::BK, mn_sw));
+    if (!B_MN) SCAT_PROPAGATE(make_map(&tmB, g.B, E::BYTES, b_k, b_rows, g.sbn, E::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B));
+    else SCAT_PROPAGATE(make_map(&tmB, g.B, E::BYTES, b_rows, b_k, g.sbk, E::MN_BOX, E::BK, mn_sw));
     TcParams p;
     p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc;
     p.C16 = reinterpret_cast<__nv_bfloat16*>(g.C16); p.ldc16 = g.ldc16;
@@ -561,6 +701,9 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     p.ld_aux_out = g.ld_aux_out; p.accumulate = g.accumulate;
     p.round_operands = (BF16 || g.prerounded) ? 0 : 1;
     p.round_out = g.round_out;
+    p.batched = g.batch > 1 ? 1 : 0;
+    p.a_row_z = g.a_row_z; p.a_k_z = g.a_k_z; p.b_row_z = g.b_row_z; p.b_k_z = g.b_k_z; p.c_z = g.c_z; p.aux_out_z = g.aux_out_z;
+    p.out_scale = g.out_scale; p.mask_idx = g.mask_idx; p.n_masked = g.n_masked;
     p.dbg = g_gemm_dbg;
     auto al16 = [](const void* q, long long ld) { return q == nullptr || (((uintptr_t)q & 15) == 0 && (ld & 3) == 0); };
     p.vec_ok = al16(g.C, g.ldc) && (g.C16 == nullptr || (((uintptr_t)g.C16 & 7) == 0 && (g.ldc16 & 3) == 0)) &&
@@ -575,12 +718,20 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     const int tiles = (int)(grid.x * grid.y);
     if (g.allow_split_k && g.epilogue == EPI_NONE && !g.round_out && !g.C16 && tiles <= 148 && kb_all >= 8)
         splits = max(1, min(kb_all / 4, 296 / tiles));
+    if (g.batch > 1) splits = 1;
     p.kb_per_split = ceil_div(kb_all, splits);
-    grid.z = ceil_div(kb_all, p.kb_per_split);
-    p.atomic_out = grid.z > 1 ? 1 : 0;
+    grid.z = g.batch > 1 ? g.batch : ceil_div(kb_all, p.kb_per_split);
+    p.atomic_out = (g.batch > 1 ? g.batch_accumulate : grid.z > 1) ? 1 : 0;
+    // 1-D grid over the tile space; more tiles than resident CTA slots (2 per SM): persistent CTAs with
+    // double-buffered accumulators stride through it, so that loads and epilogues of successive tiles overlap
+    p.tiles_n = (int)grid.x; p.tiles_m = (int)grid.y; p.tiles_z = (int)grid.z;
+    const int total_tiles = p.tiles_n * p.tiles_m * p.tiles_z;
+    constexpr int kSlots = 2 * 148;
+    p.persistent = total_tiles > kSlots ? 1 : 0;
+    if (p.persistent) grid = dim3(kSlots, 1, 1);
     if (p.atomic_out && !g.accumulate && !g.c_zeroed)
         SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
-    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(TC_THREADS), L::TOTAL, stream, tmA, tmB, p));
+    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(TC_THREADS), p.persistent ? L::TOTAL_PERSISTENT : L::TOTAL, stream, tmA, tmB, p));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -616,7 +767,7 @@ int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
     const int tm = ceil_div(g.M, BM);
     const long long cost64 = (long long)ceil_div(tm * ceil_div(g.N, 64), 148) * (BM + 64);
     const long long cost128 = (long long)ceil_div(tm * ceil_div(g.N, 128), 148) * (BM + 128);
-    const bool wide = g.N > 64 && cost128 <= cost64;
+    const bool wide = g.force_bn ? g.force_bn == 128 : (g.N > 64 && cost128 <= cost64);
     if (g.operand_bf16) return wide ? launch_major<true, 128>(g, stream) : launch_major<true, 64>(g, stream);
     return wide ? launch_major<false, 128>(g, stream) : launch_major<false, 64>(g, stream);
 }

@@ -36,6 +36,7 @@ int g_use_pdl = read_pdl_env();
 
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
     // tiny problems (regressor / N=3 grads) stay on the FFMA kernel: a 128-row tensor tile would be mostly padding
+    if (g.operand_bf16) return launch_gemm_tc(g, precision, stream);     // bf16 operands only exist for the tensor core
     if (precision != PREC_FP32 && (long long)g.M * g.N * g.K >= (1LL << 22) && gemm_tc_supported(g))
         return launch_gemm_tc(g, precision, stream);
     return launch_gemm_simt(g, stream);
@@ -57,6 +58,7 @@ enum ParamIdx {
 };
 inline int layer_base(int l) { return 2 + 11 * l; }
 inline int pad4(int x) { return (x + 3) / 4 * 4; }
+inline int pad8(int x) { return (x + 7) / 8 * 8; }
 
 struct LayerPlan {
     int d, hid, out, ldh;
@@ -71,7 +73,7 @@ struct HeadPlan {
     int B, T, C, D, heads, inner, M, it, F, NP;
     LayerPlan L[kDepth];
     size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dX, dFv, conv_scratch, pl_scratch,
-        g_pred, ones, hreg, up2, total;
+        g_pred, ones, hreg, up2, dX16, dX1_16, w_conv, dFv2, total;   // w_conv: [2T,C] TF32-rounded conv weight, twice; dFv2: hi/lo split of dFv   // dX16 / dX1_16: bf16 shadows of dX / dX1 (PREC_BF16 only)
 };
 
 size_t take(size_t& cur, size_t n) {
@@ -149,6 +151,13 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     p.dQKV = take(cur, MS * 3 * p.inner);
     p.dNa = take(cur, MS * dmax);
     p.dX = take(cur, MS * dmax);
+    p.dX16 = p.dX1_16 = 0;
+    p.w_conv = take(cur, p.C > 0 ? (size_t)3 * p.T * p.C : 64);
+    p.dFv2 = take(cur, (p.C > 0 && d.precision != PREC_FP32) ? 3 * M * dmax : 64);
+    if (d.precision == PREC_BF16) {
+        p.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+        p.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+    }
     p.dFv = take(cur, M * dmax);
     p.conv_scratch = take(cur, p.C > 0 ? conv_wgrad_scratch_floats(p.C, p.T) : 64);
     p.pl_scratch = take(cur, (size_t)p.B);
@@ -198,69 +207,86 @@ struct LayerW {
 LayerW layer_weights(const HeadPlan& p, int l, const float* const* W, const float* ws, int prec) {
     const LayerPlan& L = p.L[l];
     LayerW w;
-    const bool tc = prec != PREC_FP32;
-    w.qkv = tc ? ws + L.w_qkv : W[L.p_qkv];   w.ld_qkv = tc ? L.ld_qkv : L.d;
-    w.out = tc ? ws + L.w_out : W[L.p_out_w]; w.ld_out = tc ? L.ld_out : p.inner;
+    const bool tc = prec != PREC_FP32, bf = prec == PREC_BF16;
+    // tensor-core modes read the per-forward copies in the workspace: TF32-rounded fp32 (leading dimension padded to
+    // 4) or bf16 (padded to 8, stored in the first half of the same slot)
+    w.qkv = tc ? ws + L.w_qkv : W[L.p_qkv];   w.ld_qkv = bf ? pad8(L.d) : tc ? L.ld_qkv : L.d;
+    w.out = tc ? ws + L.w_out : W[L.p_out_w]; w.ld_out = p.inner;
     const bool tc_ff = tc && !L.last;         // last feed-forward stays fp32 on the caller's weights
-    w.fc1 = tc_ff ? ws + L.w_fc1 : W[L.p_fc1_w]; w.ld_fc1 = tc_ff ? L.ld_fc1 : L.d;
-    w.fc2 = tc_ff ? ws + L.w_fc2 : W[L.p_fc2_w]; w.ld_fc2 = tc_ff ? L.ld_fc2 : L.hid;
+    w.fc1 = tc_ff ? ws + L.w_fc1 : W[L.p_fc1_w]; w.ld_fc1 = !tc_ff ? L.d : bf ? pad8(L.d) : L.ld_fc1;
+    w.fc2 = tc_ff ? ws + L.w_fc2 : W[L.p_fc2_w]; w.ld_fc2 = !tc_ff ? L.hid : bf ? pad8(L.hid) : L.ld_fc2;
     return w;
 }
 
 // one launch: TF32-round (and pad the leading dimension of) every weight a tensor-core GEMM reads
-int round_weights(const HeadPlan& p, const float* const* W, float* ws, cudaStream_t st) {
+int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st) {
     RoundJobs jobs;
     int n = 0;
+    const bool bf = prec == PREC_BF16;
     for (int l = 0; l < kDepth; ++l) {
         const LayerPlan& L = p.L[l];
-        jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, L.ld_qkv};
-        jobs.job[n++] = RoundJob{W[L.p_out_w], ws + L.w_out, L.d, p.inner, p.inner, L.ld_out};
+        jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, bf ? pad8(L.d) : L.ld_qkv};
+        jobs.job[n++] = RoundJob{W[L.p_out_w], ws + L.w_out, L.d, p.inner, p.inner, p.inner};
         if (!L.last) {
-            jobs.job[n++] = RoundJob{W[L.p_fc1_w], ws + L.w_fc1, L.hid, L.d, L.d, L.ld_fc1};
-            jobs.job[n++] = RoundJob{W[L.p_fc2_w], ws + L.w_fc2, L.out, L.hid, L.hid, L.ld_fc2};
+            jobs.job[n++] = RoundJob{W[L.p_fc1_w], ws + L.w_fc1, L.hid, L.d, L.d, bf ? pad8(L.d) : L.ld_fc1};
+            jobs.job[n++] = RoundJob{W[L.p_fc2_w], ws + L.w_fc2, L.out, L.hid, L.hid, bf ? pad8(L.hid) : L.ld_fc2};
         }
+    }
+    for (int i = 0; i < n; ++i) jobs.job[i].to_bf16 = bf ? 1 : 0;
+    if (p.C > 0) {                                                   // conv stays kind::tf32; stacked twice for its dgrad
+        jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv, p.T, p.C, p.C, p.C, 0};
+        jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv + (size_t)p.T * p.C, p.T, p.C, p.C, p.C, 0};
+        jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv + (size_t)2 * p.T * p.C, p.T, p.C, p.C, p.C, 2};
     }
     jobs.n = n;
     return launch_round_copy(jobs, st);
 }
 
 // ---- forward through the transformer (vision_transformer.py:97-101) --------------------------------
+// Storage of the tensors that feed tensor-core GEMMs (Na, O, Nf, H; backward: dY, dZ, dX1, dQKV):
+//   PREC_TF32: fp32, rounded to TF32-nearest by the producing kernel
+//   PREC_BF16: bf16 in the same workspace slot (leading dimension padded to 8 elements); tensors that a
+//              non-GEMM kernel also reads in fp32 (dX, dX1) get a separate bf16 shadow
 int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st,
                         float* X0_override) {
     const int M = p.M;
-    const int tc = prec != PREC_FP32;
-    if (tc) SCAT_PROPAGATE(round_weights(p, W, ws, st));
+    const bool tc = prec != PREC_FP32, bf = prec == PREC_BF16;
+    const int omode = bf ? OUT_BF16 : tc ? OUT_TF32 : OUT_F32;
     for (int l = 0; l < kDepth; ++l) {
         const LayerPlan& L = p.L[l];
         const LayerW w = layer_weights(p, l, W, ws, prec);
         float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
+        const int ld_n = bf ? pad8(L.d) : L.d;             // leading dimension of Na / Nf
+        const int ld_h = bf ? pad8(L.hid) : L.ldh;         // leading dimension of H as a GEMM operand
         // PreNorm + Attention + Residual (:18,:26,:59-79)
-        SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, L.d, ws + L.mean_a,
-                                            ws + L.rstd_a, M, L.d, tc, st));
+        SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, ld_n, ws + L.mean_a,
+                                            ws + L.rstd_a, M, L.d, omode, st));
         GemmArgs g;
-        g.A = ws + L.Na; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1;
+        g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
         g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, tc, st));
+        SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
         g = GemmArgs();
-        g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1;
+        g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
         g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
         g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // (PreNorm +) FeedForward, no residual (:44,:94 / :89)
         if (!L.last)
-            SCAT_PROPAGATE(launch_layernorm_fwd(ws + L.X1, L.d, W[L.p_nf_w], W[L.p_nf_b], ws + L.Nf, L.d,
-                                                ws + L.mean_f, ws + L.rstd_f, M, L.d, tc, st));
+            SCAT_PROPAGATE(launch_layernorm_fwd(ws + L.X1, L.d, W[L.p_nf_w], W[L.p_nf_b], ws + L.Nf, ld_n,
+                                                ws + L.mean_f, ws + L.rstd_f, M, L.d, omode, st));
         const int ffprec = L.last ? PREC_FP32 : prec;   // last FF stays fp32
-        const int fftc = ffprec != PREC_FP32;
+        const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
         g = GemmArgs();
-        g.A = ws + L.Nf; g.sam = L.d; g.sak = 1; g.B = w.fc1; g.sbn = w.ld_fc1; g.sbk = 1;
-        g.C = ws + L.H; g.ldc = L.ldh; g.M = M; g.N = L.hid; g.K = L.d; g.prerounded = fftc; g.round_out = fftc;
+        g.A = ws + L.Nf; g.sam = ffbf ? ld_n : L.d; g.sak = 1; g.B = w.fc1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
+        g.M = M; g.N = L.hid; g.K = L.d; g.prerounded = fftc;
+        if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
+        else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
         g = GemmArgs();
-        g.A = ws + L.H; g.sam = L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1;
+        g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
         g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid; g.prerounded = fftc;
         g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
@@ -269,8 +295,8 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 }
 
 // ---- reverse sweep: d/dX0 of <up, feat_out>, optionally with parameter gradients ---------------------
-// up: [M,3] cotangent of the transformer output.  Result lands in ws + p.dX ([M, D]).  Uses the rounded weight
-// copies left in the workspace by transformer_forward.
+// up: [M,3] cotangent of the transformer output.  Result lands in ws + p.dX ([M, D]).  Uses the weight copies
+// left in the workspace by transformer_forward.
 // sweeps = 2: `up` holds two stacked cotangents [2M,3] (rows < M: the real one, rows >= M: the path-length ones);
 // every dgrad-type kernel then runs once over 2M rows against the same saved activations, parameter gradients
 // only see the first M rows.
@@ -279,81 +305,96 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
     const int M = p.M;
     const int MR = M * sweeps;                       // rows of every cotangent tensor
     const int amod = sweeps > 1 ? M : 0;             // activation row = cotangent row % M
-    const int tc = prec != PREC_FP32;
-    const float* dY = up;
+    const bool tc = prec != PREC_FP32, bf = prec == PREC_BF16;
+    const int omode = bf ? OUT_BF16 : tc ? OUT_TF32 : OUT_F32;
+    const float* dY = up;                            // fp32 cotangent of the layer output
+    const float* dYg = up;                           // the copy GEMMs read: same tensor, or its bf16 shadow
+    int ld_dYg = 3;
     for (int l = kDepth - 1; l >= 0; --l) {
         const LayerPlan& L = p.L[l];
         const LayerW w = layer_weights(p, l, W, ws, prec);
         const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         const int ffprec = L.last ? PREC_FP32 : prec;
-        const int fftc = ffprec != PREC_FP32;
+        const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
+        const int ld_n = bf ? pad8(L.d) : L.d;                 // Na / Nf / dX1 as GEMM operands
+        const int ld_h = ffbf ? pad8(L.hid) : L.ldh;           // H / dZ as GEMM operands
+        float* dZ = ws + p.dZ;
         GemmArgs g;
         if (G) {
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
-            g.A = dY; g.sam = 1; g.sak = L.out; g.B = ws + L.H; g.sbn = 1; g.sbk = L.ldh;
+            g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
             SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, st));
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
-        g.A = dY; g.sam = L.out; g.sak = 1; g.B = w.fc2; g.sbn = 1; g.sbk = w.ld_fc2;
-        g.C = ws + p.dZ; g.ldc = L.ldh; g.M = MR; g.N = L.hid; g.K = L.out; g.prerounded = fftc; g.round_out = fftc;
+        g.A = dYg; g.sam = ld_dYg; g.sak = 1; g.B = w.fc2; g.sbn = 1; g.sbk = w.ld_fc2; g.operand_bf16 = ffbf;
+        g.M = MR; g.N = L.hid; g.K = L.out; g.prerounded = fftc;
+        if (ffbf) { g.C16 = dZ; g.ldc16 = ld_h; }
+        else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         if (G) {
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             g = GemmArgs();
-            g.A = ws + p.dZ; g.sam = 1; g.sak = L.ldh; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.d;
+            g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = ffbf ? ld_n : L.d; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
-            SCAT_PROPAGATE(launch_colsum(ws + p.dZ, L.ldh, M, L.hid, G[L.p_fc1_b], 1, st));
+            SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, st, ffbf));
         }
-        // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs: round it)
+        // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs)
         g = GemmArgs();
-        g.A = ws + p.dZ; g.sam = L.ldh; g.sak = 1; g.B = w.fc1; g.sbn = 1; g.sbk = w.ld_fc1;
+        g.A = dZ; g.sam = ld_h; g.sak = 1; g.B = w.fc1; g.sbn = 1; g.sbk = w.ld_fc1; g.operand_bf16 = ffbf;
         g.C = ws + p.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
-        g.round_out = (L.last && tc) ? 1 : 0;
+        if (L.last && bf) { g.C16 = ws + p.dX1_16; g.ldc16 = ld_n; }
+        else g.round_out = (L.last && tc) ? 1 : 0;
         SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
         const float* dX1 = ws + p.dNf;
         if (!L.last) {
             SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
                                                 ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d,
-                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, MR, L.d, tc, st, amod));
+                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, MR, L.d,
+                                                bf ? OUT_F32 : omode, st, amod, bf ? ws + p.dX1_16 : nullptr, ld_n));
             dX1 = ws + p.dX1;
         }
+        const float* dX1g = bf ? ws + p.dX1_16 : dX1;           // what the GEMMs read
         if (G) {
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1)
             g = GemmArgs();
-            g.A = dX1; g.sam = 1; g.sak = L.d; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner;
+            g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
             SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, st));
         }
         // dO = dX1 Wo
         g = GemmArgs();
-        g.A = dX1; g.sam = L.d; g.sak = 1; g.B = w.out; g.sbn = 1; g.sbk = w.ld_out;
+        g.A = dX1g; g.sam = ld_n; g.sak = 1; g.B = w.out; g.sbn = 1; g.sbk = w.ld_out; g.operand_bf16 = bf;
         g.C = ws + p.dO; g.ldc = p.inner; g.M = MR; g.N = p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B * sweeps, p.T, p.heads, tc,
+        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B * sweeps, p.T, p.heads, omode,
                                             st, sweeps > 1 ? p.B : 0));
         if (G) {
             // dWqkv[3inner,d] = dQKV^T Na
             g = GemmArgs();
-            g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = L.d;
+            g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_n; g.operand_bf16 = bf;
             g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
         }
         // dNa = dQKV Wqkv
         g = GemmArgs();
-        g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv;
+        g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
         g.C = ws + p.dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs
+        const bool feeds_gemm = tc && l > 0;
         SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
                                             L.d, ws + p.dX, L.d, G ? G[L.p_na_w] : nullptr,
-                                            G ? G[L.p_na_b] : nullptr, MR, L.d, (tc && l > 0) ? 1 : 0, st, amod));
+                                            G ? G[L.p_na_b] : nullptr, MR, L.d, (feeds_gemm && !bf) ? OUT_TF32 : OUT_F32, st,
+                                            amod, (feeds_gemm && bf) ? ws + p.dX16 : nullptr, ld_n));
         dY = ws + p.dX;
+        dYg = bf ? ws + p.dX16 : dY;
+        ld_dYg = bf ? ld_n : L.d;
     }
     return 0;
 }
@@ -402,8 +443,16 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     float* ws = (float*)workspace;
     // with pos_embed == 0 the reference's token matrix is a view of feat_visual (hand_net.py:364): alias it
     float* X0 = d.pos_embed ? ws + p.L[0].X : fv;
-    SCAT_PROPAGATE(launch_conv_pe_mask_fwd(x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed, fv,
-                                           X0, p.B, p.C, p.D, p.T, st));
+    const bool tc = d.precision != PREC_FP32;
+    if (tc) {
+        // per-forward weight copies for the tensor cores (TF32-rounded fp32 or bf16), then the conv as a batched GEMM
+        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, st));
+        SCAT_PROPAGATE(launch_conv_pe_mask_fwd_tc(x2, ws + p.w_conv, pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed,
+                                                  fv, X0, p.B, p.C, p.D, p.T, st));
+    } else {
+        SCAT_PROPAGATE(launch_conv_pe_mask_fwd(x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed, fv,
+                                               X0, p.B, p.C, p.D, p.T, st));
+    }
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
     SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
                                         ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st));
@@ -463,8 +512,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         SCAT_CHECK_CUDA(launch_k(add_inplace_kernel, dim3(148 * 4), dim3(256), 0, st, ws + p.dFv, g_fv, (long long)p.M * p.D));
         SCAT_CHECK_LAUNCH();
     }
-    if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], x2_grad, p.B, p.C, p.D, p.T, st));
-    SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
+    if (d.precision != PREC_FP32) {
+        SCAT_PROPAGATE(launch_split_tf32(ws + p.dFv, ws + p.dFv2, p.B, p.T, p.D, st));
+        if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad_tc(ws + p.dFv2, ws + p.w_conv, x2_grad, p.B, p.C, p.D, p.T, st));
+        SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, G[P_CONV_W], p.B, p.C, p.D, p.T, st));   // G was zeroed above
+    } else {
+        if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], x2_grad, p.B, p.C, p.D, p.T, st));
+        SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
+    }
     return 0;
 }
 
@@ -546,6 +601,7 @@ int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, co
     SCAT_PROPAGATE(make_plan(*desc, p));
     SCAT_PROPAGATE(check_ws(p, workspace, workspace_bytes));
     float* ws = (float*)workspace;
+    if (desc->precision != PREC_FP32) SCAT_PROPAGATE(round_weights(p, params, ws, desc->precision, st));
     SCAT_PROPAGATE(launch_pe_mask_tokens(tokens, pe, params[P_MASK_TOKEN], mask_idx, desc->n_masked, desc->pos_embed,
                                          ws + p.L[0].X, p.B, p.T, p.D, st));
     SCAT_PROPAGATE(transformer_forward(p, params, ws, desc->precision, st, nullptr));
@@ -566,8 +622,8 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
     g.A = A; g.sam = sam; g.sak = sak; g.B = B; g.sbn = sbn; g.sbk = sbk; g.C = C; g.ldc = ldc;
     g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
     g.aux_out = aux_out; g.ld_aux_out = ld_aux_out; g.accumulate = accumulate;
-    static const int probe_prerounded = getenv("SCAT_GEMM_ASSUME_ROUNDED") != nullptr;   // microbenchmarks only
-    g.prerounded = probe_prerounded;
+    g.prerounded = (precision & SCAT_PREC_FLAG_PREROUNDED) ? 1 : 0;
+    precision &= ~SCAT_PREC_FLAG_PREROUNDED;
     if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
     SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
                  "scat_gemm: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
@@ -597,6 +653,47 @@ int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe,
                           void* stream) {
     return launch_conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, n_masked, pos_embed, feat_visual, tokens_out,
                                    batch, channels, hw, n_tokens, (cudaStream_t)stream);
+}
+
+// ---- tensor-core (tcgen05 kind::tf32) front end as single operators: what the head runs in TF32 / BF16 mode ----
+size_t scat_conv_tc_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens) {
+    return round_up((size_t)3 * n_tokens * channels, 64) + (size_t)4 * batch * n_tokens * hw;
+}
+
+static int round_conv_weight(const float* conv_w, float* dst, int T, int C, cudaStream_t st) {
+    RoundJobs jobs;                          // [Wh; Wh; Wl]: TF32-nearest twice, then its TF32 remainder
+    jobs.job[0] = RoundJob{conv_w, dst, T, C, C, C, 0};
+    jobs.job[1] = RoundJob{conv_w, dst + (size_t)T * C, T, C, C, C, 0};
+    jobs.job[2] = RoundJob{conv_w, dst + (size_t)2 * T * C, T, C, C, C, 2};
+    jobs.n = 3;
+    return launch_round_copy(jobs, st);
+}
+
+int scat_conv_pe_mask_fwd_tc(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
+                             const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
+                             float* tokens_out, float* scratch, int32_t batch, int32_t channels, int32_t hw,
+                             int32_t n_tokens, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SCAT_REQUIRE(scratch, kErrBadArg, "conv_fwd_tc: scratch is null");
+    SCAT_PROPAGATE(round_conv_weight(conv_w, scratch, n_tokens, channels, st));
+    return launch_conv_pe_mask_fwd_tc(x2, scratch, pe, mask_token, mask_idx, n_masked, pos_embed, feat_visual, tokens_out,
+                                      batch, channels, hw, n_tokens, st);
+}
+
+int scat_conv_bwd_tc(const float* d_tokens, const float* x2, const float* conv_w, const int32_t* mask_idx,
+                     int32_t n_masked, float* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
+                     int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SCAT_REQUIRE(scratch, kErrBadArg, "conv_bwd_tc: scratch is null");
+    float* w_tf32 = scratch;
+    float* dFv = scratch + round_up((size_t)3 * n_tokens * channels, 64);
+    float* dFv2 = dFv + (size_t)batch * n_tokens * hw;
+    SCAT_PROPAGATE(round_conv_weight(conv_w, w_tf32, n_tokens, channels, st));
+    SCAT_PROPAGATE(launch_mask_bwd(d_tokens, mask_idx, n_masked, 0, dFv, mask_token_grad, batch, n_tokens, hw, st));
+    SCAT_PROPAGATE(launch_split_tf32(dFv, dFv2, batch, n_tokens, hw, st));
+    if (x2_grad) SCAT_PROPAGATE(launch_conv_dgrad_tc(dFv2, w_tf32, x2_grad, batch, channels, hw, n_tokens, st));
+    SCAT_CHECK_CUDA(cudaMemsetAsync(conv_w_grad, 0, (size_t)n_tokens * channels * sizeof(float), st));
+    return launch_conv_wgrad_tc(dFv2, x2, conv_w_grad, batch, channels, hw, n_tokens, st);
 }
 
 size_t scat_conv_bwd_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens) {

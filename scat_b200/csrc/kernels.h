@@ -20,6 +20,9 @@ enum Epilogue : int {
     EPI_BIAS_GELU = 3,   // z = acc + bias[n]; aux_out[m,n] = z; C = gelu(z)
     EPI_DGELU = 4,       // C = acc * gelu'(aux_in[m,n])
     EPI_RESID = 5,       // C = acc + aux_in[m,n]
+    EPI_PE_MASK = 6,     // tensor-core kernel only, rows = tokens (conv front end, hand_net.py:363-373):
+                         //   tok = row in mask_idx ? bias[n] (mask token) : acc (+ aux_in[m,n] = positional encoding);
+                         //   aux_out set: C = acc, aux_out = tok;   aux_out null (token matrix aliases C): C = tok
 };
 
 enum Precision : int {
@@ -45,6 +48,14 @@ struct GemmArgs {
     int allow_split_k = 0;   // FFMA kernel may split K over CTAs and combine with atomics (weight gradients)
     int prerounded = 0;      // tensor-core kernel: operands are already TF32-representable, skip the in-kernel rounding
     int round_out = 0;       // store C rounded to TF32 (nearest): it feeds a tensor-core GEMM next
+    // ---- tensor-core kernel only: a stack of `batch` problems in one launch (blockIdx.z) ----
+    int batch = 1;
+    int a_row_z = 0, a_k_z = 0, b_row_z = 0, b_k_z = 0;   // per-problem offsets of the operands along rows / k (elements)
+    long long c_z = 0, aux_out_z = 0;                    // per-problem element offsets of C / aux_out
+    int batch_accumulate = 0;    // every problem reduces into the same C (red.global.add; C pre-zeroed): K split over the batch
+    float out_scale = 1.0f;      // accumulator scale (compensates the tensor core truncating fp32 operands, see conv_tc)
+    const int32_t* mask_idx = nullptr; int n_masked = 0;   // EPI_PE_MASK
+    int force_bn = 0;            // 64 / 128: tile width override
 };
 
 #ifdef __CUDACC__
@@ -65,7 +76,8 @@ void gemm_tc_set_debug_buffer(long long* dev8);   // 8 x int64 device buffer, or
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream);  // dispatch on precision/shape
 
 // column sums: out[n] (+)= sum_m X[m*ld + n]
-int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream);
+int launch_colsum(const float* X, int ld, int M, int N, float* out, int accumulate, cudaStream_t stream,
+                  int x_bf16 = 0);   // x_bf16: X holds bf16 (ld in elements)
 
 // ------------------------------------------------------------------------------------------
 // 1x1 conv + positional encoding + token masking (hand_net.py:363-373)
@@ -81,6 +93,18 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
 size_t conv_wgrad_scratch_floats(int C, int T);
 int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scratch, int B, int C, int HW, int T,
                       cudaStream_t stream);
+// Tensor-core versions (tcgen05 kind::tf32 through the batched GEMM kernel, one problem per sample, HBM bound).
+// Wc_tf32: the conv weight rounded to TF32-nearest.  x2 / d tokens are read as they are: the tensor core truncates
+// them to TF32, a ~3.3e-4 relative shrink per truncated operand that `out_scale` undoes (see conv.cu).
+int launch_conv_pe_mask_fwd_tc(const float* x2, const float* Wc_tf32, const float* pe, const float* mask_token,
+                               const int32_t* mask_idx, int n_masked, int pos_embed, float* feat_visual, float* X0,
+                               int B, int C, int HW, int T, cudaStream_t stream);
+// backward: dFv2 [B,3T,HW] = launch_split_tf32(dFv) (TF32 hi / lo / hi), Wc2_tf32 [3T,C] = [Wh; Wh; Wl] (TF32 hi, hi, lo)
+int launch_split_tf32(const float* dFv, float* dFv2, int B, int T, int HW, cudaStream_t stream);
+int launch_conv_dgrad_tc(const float* dFv2, const float* Wc2_tf32, float* x2_grad, int B, int C, int HW, int T,
+                         cudaStream_t stream);
+int launch_conv_wgrad_tc(const float* dFv2, const float* x2, float* dWc /* pre-zeroed */, int B, int C, int HW, int T,
+                         cudaStream_t stream);
 // token-only front end (config 4): X0 = tokens (+pe) with masked rows replaced
 int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mask_token, const int32_t* mask_idx,
                           int n_masked, int pos_embed, float* X0, int B, int T, int D, cudaStream_t stream);
@@ -109,8 +133,9 @@ int launch_attention_bwd(const float* QKV, const float* P, const float* dO, floa
 // act_batch > 0: dO/dQKV have B samples, QKV/P have act_batch samples and sample b uses activations of b % act_batch
 // dst[r, c] = round_tf32(src[r, c]) (pad columns zero-filled) for a list of weight matrices, one launch;
 // the job table travels by value as a kernel argument (no device-side table, graph-capturable)
-struct RoundJob { const float* src; float* dst; int rows, cols, ld_src, ld_dst; };
-struct RoundJobs { RoundJob job[12]; int n; };
+// mode 0: dst = TF32-nearest(src) as fp32; 1: dst = bf16(src) (dst is a bf16 array); 2: dst = TF32-nearest(src - TF32-nearest(src))
+struct RoundJob { const float* src; float* dst; int rows, cols, ld_src, ld_dst; int to_bf16 = 0; };
+struct RoundJobs { RoundJob job[16]; int n; };
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------

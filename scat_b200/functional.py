@@ -161,7 +161,7 @@ def token_transformer(transformer, x, mask_token=None, pe=None, mask_idx=None, p
 # single operators (unit tests, micro-benchmarks)
 # ---------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_strides=None, b_strides=None, m=None, n=None, k=None, epilogue="none", bias=None, aux_in=None,
-         precision="fp32", out=None, accumulate=False):
+         precision="fp32", out=None, accumulate=False, prerounded=False):
     """C[M,N] = epilogue(sum_k A(m,k) B(n,k)).  Defaults: a[M,K] row-major, b[N,K] row-major (y = x W^T).
     Returns C, or (C, Z) for the bias_gelu epilogue."""
     lib = _lib.load()
@@ -176,8 +176,8 @@ def gemm(a, b, *, a_strides=None, b_strides=None, m=None, n=None, k=None, epilog
     z = torch.empty_like(c) if epilogue == "bias_gelu" else None
     check(lib.scat_gemm(ptr(a), a_strides[0], a_strides[1], ptr(b), b_strides[0], b_strides[1], ptr(c), c.stride(0),
                         m, n, k, EPI[epilogue], ptr(bias), ptr(aux_in), 0 if aux_in is None else aux_in.stride(0),
-                        ptr(z), 0 if z is None else z.stride(0), int(accumulate), PREC[precision], stream_ptr()),
-          "scat_gemm")
+                        ptr(z), 0 if z is None else z.stride(0), int(accumulate),
+                        PREC[precision] | (0x100 if prerounded else 0), stream_ptr()), "scat_gemm")
     return (c, z) if z is not None else c
 
 
@@ -255,7 +255,8 @@ def attention_bwd(qkv, p, d_o, batch, n, heads):
     return dqkv
 
 
-def conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, pos_embed=True):
+def conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, pos_embed=True, tc=False):
+    """hand_net.py:363-373.  tc=False: fp32 FFMA kernel (parity mode); tc=True: tcgen05 kind::tf32 batched GEMM."""
     lib = _lib.load()
     x2 = _f32c(x2, "x2")
     B, Cc, H, W = x2.shape
@@ -263,21 +264,33 @@ def conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, pos_embed=True):
     fv = torch.empty(B, T, H, W, device=x2.device)
     tok = torch.empty(B, T, H * W, device=x2.device) if pos_embed else fv
     n_masked = 0 if mask_idx is None else int(mask_idx.numel())
+    if tc:
+        scratch = torch.empty(lib.scat_conv_tc_scratch_floats(B, Cc, H * W, T), device=x2.device)
+        check(lib.scat_conv_pe_mask_fwd_tc(ptr(x2), ptr(_f32c(conv_w, "conv_w")), ptr(pe), ptr(mask_token), ptr(mask_idx),
+                                           n_masked, int(pos_embed), ptr(fv), ptr(tok), ptr(scratch), B, Cc, H * W, T,
+                                           stream_ptr()), "scat_conv_pe_mask_fwd_tc")
+        return fv, tok.view(B, T, H * W)
     check(lib.scat_conv_pe_mask_fwd(ptr(x2), ptr(_f32c(conv_w, "conv_w")), ptr(pe), ptr(mask_token), ptr(mask_idx),
                                     n_masked, int(pos_embed), ptr(fv), ptr(tok), B, Cc, H * W, T, stream_ptr()),
           "scat_conv_pe_mask_fwd")
     return fv, tok.view(B, T, H * W)
 
 
-def conv_bwd(d_tokens, x2, conv_w, mask_idx, need_x2_grad=True):
+def conv_bwd(d_tokens, x2, conv_w, mask_idx, need_x2_grad=True, tc=False):
     lib = _lib.load()
     B, Cc, H, W = x2.shape
     T = conv_w.shape[0]
     n_masked = 0 if mask_idx is None else int(mask_idx.numel())
-    scratch = torch.empty(lib.scat_conv_bwd_scratch_floats(B, Cc, H * W, T), device=x2.device)
     x2g = torch.empty_like(x2) if need_x2_grad else None
     wg = torch.empty(T, Cc, device=x2.device)
     mg = torch.zeros(H * W, device=x2.device)
+    if tc:
+        scratch = torch.empty(lib.scat_conv_tc_scratch_floats(B, Cc, H * W, T), device=x2.device)
+        check(lib.scat_conv_bwd_tc(ptr(_f32c(d_tokens, "d_tokens")), ptr(x2), ptr(_f32c(conv_w, "conv_w")), ptr(mask_idx),
+                                   n_masked, ptr(x2g), ptr(wg), ptr(mg) if n_masked else None, ptr(scratch), B, Cc, H * W,
+                                   T, stream_ptr()), "scat_conv_bwd_tc")
+        return x2g, wg, mg
+    scratch = torch.empty(lib.scat_conv_bwd_scratch_floats(B, Cc, H * W, T), device=x2.device)
     check(lib.scat_conv_bwd(ptr(_f32c(d_tokens, "d_tokens")), ptr(x2), ptr(_f32c(conv_w, "conv_w")), ptr(mask_idx),
                             n_masked, ptr(x2g), ptr(wg), ptr(mg) if n_masked else None, ptr(scratch), B, Cc, H * W, T,
                             stream_ptr()), "scat_conv_bwd")

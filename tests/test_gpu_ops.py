@@ -141,6 +141,50 @@ def test_conv_pe_mask_fwd_bwd(B, mask_rate, pos_embed):
         assert torch.all(wg[idx] == 0)                   # masked tokens: exactly zero conv-weight gradient rows
 
 
+@pytest.mark.parametrize("B,mask_rate,pos_embed", [(3, 0.2, True), (2, 0.9, True), (2, 0.0, True), (2, 0.2, False),
+                                                   (96, 0.2, True)])
+def test_conv_tensor_core_fwd_bwd(B, mask_rate, pos_embed):
+    """The conv front end on tcgen05 kind::tf32 (batched GEMM, what the head runs in TF32 / BF16 mode): TF32-grade
+    values, and the masking / indexing still bit-exact.  x2 >= 0 is truncated (not rounded) by the tensor core; the
+    compensation must leave no systematic shrink: the mean signed relative error stays far below 3.3e-4."""
+    from scat_b200 import functional as SF
+    x2, _, _ = synth.make_head_inputs(B, 3)
+    W = synth.make_head_weights(8)
+    cw, mt = torch.from_numpy(W["conv1x1_channel_reduction.weight"]), torch.from_numpy(W["mask_token"])
+    pe = head_oracle.positional_encoding(21, 784)
+    random.seed(5)
+    idx = synth.mask_indices(mask_rate)
+    keep = [t for t in range(21) if t not in idx]
+    xr = torch.from_numpy(x2).double().requires_grad_(True)
+    cwr, mtr = cw.double().requires_grad_(True), mt.double().requires_grad_(True)
+    fv_ref = F.conv2d(xr, cwr)
+    tok_ref = fv_ref.view(B, 21, -1) + pe.double() if pos_embed else fv_ref.view(B, 21, -1).clone()
+    if idx:
+        tok_ref[:, idx, :] = mtr
+    idx_dev = torch.tensor(idx, dtype=torch.int32, device="cuda") if idx else None
+    fv, tok = SF.conv_pe_mask_fwd(torch.from_numpy(x2).cuda(), cw.cuda().view(21, 512), pe[0].cuda(),
+                                  mt.cuda().view(-1), idx_dev, pos_embed, tc=True)
+    got, ref = fv.view(B, 21, -1)[:, keep].double().cpu(), fv_ref.detach().view(B, 21, -1)[:, keep]
+    assert rel_max(got, ref) < 2e-3
+    big = ref.abs() > 0.5 * ref.abs().max()
+    shrink = float(((got - ref) / ref)[big].mean())
+    assert abs(shrink) < 1e-4, shrink                                  # no systematic shrink left (uncorrected: -3.3e-4)
+    if idx:
+        assert torch.equal(tok[:, idx, :].cpu(), mt.view(1, 1, -1).expand(B, len(idx), -1))
+    if pos_embed:
+        assert torch.equal(tok[:, keep].cpu(), (fv.view(B, 21, -1)[:, keep] + pe[0, keep].cuda()).cpu())
+    else:
+        assert tok.data_ptr() == fv.data_ptr()
+    d_tok = _rand(B, 21, 784, seed=9)
+    tok_ref.backward(d_tok.double())
+    x2g, wg, mg = SF.conv_bwd(d_tok.cuda(), torch.from_numpy(x2).cuda(), cw.cuda().view(21, 512), idx_dev, tc=True)
+    assert rel_max(x2g, xr.grad) < 2e-3
+    assert rel_max(wg, cwr.grad.view(21, 512)) < 1e-3
+    if idx:
+        assert rel_max(mg, mtr.grad.view(-1)) < 2e-5
+        assert torch.all(wg[idx] == 0)
+
+
 @pytest.mark.parametrize("B,it", [(96, 3), (2, 1), (5, 0)])
 def test_regressor_fwd(B, it):
     from scat_b200 import functional as SF

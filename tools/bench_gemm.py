@@ -43,7 +43,7 @@ for M, N, K, lay in shapes:
     if prec == "bf16":
         us = t_us(lambda: SF.gemm_bf16(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, out=out))
     else:
-        us = t_us(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision=prec, out=out))
+        us = t_us(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision=prec, out=out, prerounded=True))
     tot += us
     print(f"{prec} {lay} M={M:5d} N={N:5d} K={K:5d}: {us:7.1f} us  {2*M*N*K/us/1e6:7.1f} TFLOP/s  {(M*K+N*K)*A.element_size()/us/1e3+M*N*4/us/1e3:7.1f} GB/s(min traffic)")
 print("total", tot)
