@@ -186,6 +186,11 @@ int scat_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
 int scat_attention_fwd(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream);
 int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
                        int32_t heads, void* stream);
+/* The same for n = 21 tokens on the tensor cores (mma.sync m16n8k8 TF32, one warp per (batch, head) problem, operands
+ * rounded to TF32-nearest): what the head runs in SCAT_PREC_TF32 / SCAT_PREC_BF16.  TF32-grade results. */
+int scat_attention_fwd_tc(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream);
+int scat_attention_bwd_tc(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
+                          int32_t heads, void* stream);
 
 /* hand_net.py:379-393 (root_relative=1, n_out=66) and hand_net.py:53-57 (root_relative=0, n_out=61).
  * states[B,iteration,n_out] may be NULL when no backward follows; scratch: batch*n_out floats. */

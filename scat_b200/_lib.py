@@ -57,6 +57,8 @@ SIGNATURES = {
     "scat_layernorm_bwd": (_i32, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _f]),
     "scat_attention_fwd": (_i32, [_f, _f, _f, _i32, _i32, _i32, _f]),
     "scat_attention_bwd": (_i32, [_f, _f, _f, _f, _i32, _i32, _i32, _f]),
+    "scat_attention_fwd_tc": (_i32, [_f, _f, _f, _i32, _i32, _i32, _f]),
+    "scat_attention_bwd_tc": (_i32, [_f, _f, _f, _f, _i32, _i32, _i32, _f]),
     "scat_regressor_fwd": (_i32, [_f, _f, _f, _f, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _i32, _f]),
     "scat_lbs_derived_floats": (_sz, []),
     "scat_lbs_prepare": (_i32, [_f, _f, _f, _f, _f, _f, _f]),

@@ -149,9 +149,15 @@ int launch_attention_small_fwd(const float* QKV, float* O, float* P, int B, int 
 int launch_attention_small_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
                                int round_out, cudaStream_t stream, int act_batch);
 
+// attention_mma.cu: mma.sync TF32 kernels for n = 21 (TF32 / BF16 precisions)
+int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int out_mode, cudaStream_t stream);
+int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+                             int out_mode, cudaStream_t stream, int act_batch);
+
 int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                          cudaStream_t stream) {
     SCAT_REQUIRE(n >= 1 && n <= 128, kErrUnsupported, "attention: n=%d not in [1,128]", n);
+    if (n == 21 && round_out != OUT_F32) return launch_attention_mma_fwd(QKV, O, P, B, n, heads, round_out, stream);
     if (attention_small_supported(n)) return launch_attention_small_fwd(QKV, O, P, B, n, heads, round_out, stream);
     const size_t smem = sizeof(float) * ((size_t)3 * n * LDS + (size_t)n * (n + 1));
     if (smem > 48 * 1024) {
@@ -166,6 +172,7 @@ int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int
 int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
                          int round_out, cudaStream_t stream, int act_batch) {
     SCAT_REQUIRE(n >= 1 && n <= 64, kErrUnsupported, "attention bwd: n=%d not in [1,64] (training path is n=21)", n);
+    if (n == 21 && round_out != OUT_F32) return launch_attention_mma_bwd(QKV, P, dO, dQKV, B, n, heads, round_out, stream, act_batch);
     if (attention_small_supported(n)) return launch_attention_small_bwd(QKV, P, dO, dQKV, B, n, heads, round_out, stream, act_batch);
     SCAT_REQUIRE(act_batch == 0, kErrUnsupported, "attention bwd: stacked cotangents only on the n=21 path");
     const size_t smem = sizeof(float) * ((size_t)4 * n * LDS + (size_t)2 * n * (n + 1));

@@ -1,0 +1,351 @@
+// Softmax attention for n = 21 tokens x 64-wide heads on the tensor cores (vision_transformer.py:61-77 and its
+// autograd backward), used by the TF32 / BF16 precisions of the head; the fp32 "parity" precision keeps the FFMA
+// kernels of attention_small.cu.
+//
+// A (batch, head) problem is 21x21x64: far below one tcgen05 tile (128 x N, operands through shared memory and
+// TMA), so these kernels use the warp-level mma.sync.m16n8k8 TF32 instruction with every operand fragment loaded
+// straight from global memory (each 21x64 tile is 5.4 KB and stays in L1): one warp owns one problem, there is no
+// block-level synchronisation at all, and the FFMA count of the CUDA-core version (113k per backward problem)
+// becomes 192 tensor instructions.  Operands are rounded to TF32-nearest (cvt.rna) as they are loaded; mma.sync
+// would otherwise truncate them.  Rows / columns 21..31 of the padded 32x24 score tile are zero-filled operands
+// and masked scores.
+#include "kernels.h"
+
+namespace scat {
+namespace {
+
+constexpr int N = 21;            // tokens (hand_net.py:328: one per joint)
+constexpr int DH = 64;           // head width
+constexpr int WARPS = 4;         // problems per CTA
+constexpr int SP = 25;           // pitch of the per-warp dS scratch [32][SP]
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// fragment element with bounds: X[r*ld + c] if r < nr && c < nc else 0
+__device__ __forceinline__ uint32_t ld_tf32(const float* __restrict__ X, long long ld, int r, int c, int nr, int nc) {
+    return (r < nr && c < nc) ? to_tf32(__ldg(X + (long long)r * ld + c)) : 0u;
+}
+// A fragment (16 x 8, rows m0.., cols k0..) of A(m,k) = X[m*ld + k]
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const float* __restrict__ X, long long ld, int m0, int k0, int nm,
+                                       int nk, int g, int t) {
+    a[0] = ld_tf32(X, ld, m0 + g, k0 + t, nm, nk);
+    a[1] = ld_tf32(X, ld, m0 + g + 8, k0 + t, nm, nk);
+    a[2] = ld_tf32(X, ld, m0 + g, k0 + t + 4, nm, nk);
+    a[3] = ld_tf32(X, ld, m0 + g + 8, k0 + t + 4, nm, nk);
+}
+// A fragment of A(m,k) = X[k*ld + m] (a transposed operand, e.g. P^T)
+__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const float* __restrict__ X, long long ld, int m0, int k0, int nm,
+                                         int nk, int g, int t) {
+    a[0] = ld_tf32(X, ld, k0 + t, m0 + g, nk, nm);
+    a[1] = ld_tf32(X, ld, k0 + t, m0 + g + 8, nk, nm);
+    a[2] = ld_tf32(X, ld, k0 + t + 4, m0 + g, nk, nm);
+    a[3] = ld_tf32(X, ld, k0 + t + 4, m0 + g + 8, nk, nm);
+}
+// B fragment (8 x 8, k0.., n0..) of B(k,n) = Y[n*ld + k]  ("n-major": e.g. K^T read from K[j][d])
+__device__ __forceinline__ void frag_b_n(uint32_t (&b)[2], const float* __restrict__ Y, long long ld, int k0, int n0, int nk,
+                                         int nn, int g, int t) {
+    b[0] = ld_tf32(Y, ld, n0 + g, k0 + t, nn, nk);
+    b[1] = ld_tf32(Y, ld, n0 + g, k0 + t + 4, nn, nk);
+}
+// B fragment of B(k,n) = Y[k*ld + n]  ("k-major": e.g. V[j][d] as B(k = j, n = d))
+__device__ __forceinline__ void frag_b_k(uint32_t (&b)[2], const float* __restrict__ Y, long long ld, int k0, int n0, int nk,
+                                         int nn, int g, int t) {
+    b[0] = ld_tf32(Y, ld, k0 + t, n0 + g, nk, nn);
+    b[1] = ld_tf32(Y, ld, k0 + t + 4, n0 + g, nk, nn);
+}
+// two consecutive outputs (idx even) of a tensor stored in out_mode
+__device__ __forceinline__ void store_out2(float* base, long long idx, float v0, float v1, int mode) {
+    if (mode == OUT_BF16) {
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = pk;
+    } else {
+        if (mode == OUT_TF32) { v0 = round_tf32_dev(v0); v1 = round_tf32_dev(v1); }
+        *reinterpret_cast<float2*>(base + idx) = make_float2(v0, v1);
+    }
+}
+// [32 x 64] accumulator tile (2 x 8 fragments) -> rows < N of a row-major tensor
+__device__ __forceinline__ void store_tile(float* base, long long off, long long ld, const float (&acc)[2][8][4], int g, int t,
+                                           int mode) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int r0 = mt * 16 + g, c = nt * 8 + 2 * t;
+            if (r0 < N) store_out2(base, off + (long long)r0 * ld + c, acc[mt][nt][0], acc[mt][nt][1], mode);
+            if (r0 + 8 < N) store_out2(base, off + (long long)(r0 + 8) * ld + c, acc[mt][nt][2], acc[mt][nt][3], mode);
+        }
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 3)
+attention_fwd_mma_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ P, int nprob, int heads,
+                         int out_mode) {
+    pdl_sync();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int prob = blockIdx.x * WARPS + warp;
+    if (prob >= nprob) return;
+    const int b = prob / heads, h = prob % heads;
+    const int inner = heads * DH;
+    const long long rs = 3LL * inner;
+    const float* Qb = QKV + (long long)b * N * rs + h * DH;
+    const float* Kb = Qb + inner;
+    const float* Vb = Qb + 2 * inner;
+
+    // S = Q K^T   [32 x 24], k = 64
+    float s[2][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        uint32_t a[2][4], bf[3][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) frag_a(a[mt], Qb, rs, mt * 16, ks * 8, N, DH, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) frag_b_n(bf[nt], Kb, rs, ks * 8, nt * 8, DH, N, g, t);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) mma_tf32(s[mt][nt], a[mt], bf[nt]);
+    }
+    // softmax over j of S * 64^-0.5 (vision_transformer.py:51,64,74); a row lives in the 4 lanes of a quad
+    float* Pg = P + (long long)prob * N * N;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = nt * 8 + 2 * t + e;
+                    float v = s[mt][nt][hf * 2 + e] * 0.125f;
+                    v = j < N ? v : -INFINITY;
+                    s[mt][nt][hf * 2 + e] = v;
+                    m = fmaxf(m, v);
+                }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float ev = expf(s[mt][nt][hf * 2 + e] - m);       // exp(-inf) = 0 on masked columns
+                    s[mt][nt][hf * 2 + e] = ev;
+                    sum += ev;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.0f / sum;
+            const int i = mt * 16 + hf * 8 + g;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float pv = s[mt][nt][hf * 2 + e] * inv;
+                    s[mt][nt][hf * 2 + e] = pv;
+                    const int j = nt * 8 + 2 * t + e;
+                    if (i < N && j < N) Pg[i * N + j] = pv;                  // saved for the backward
+                }
+        }
+    // O = P V   [32 x 64], k = 24: P from the accumulator layout (cols 2t, 2t+1) to the A layout (cols t, t+4)
+    float o[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+    const int src_lo = (lane & ~3) | (t >> 1), src_hi = src_lo + 2;
+    const bool odd = t & 1;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float l0 = __shfl_sync(0xffffffffu, s[mt][ks][0], src_lo), l1 = __shfl_sync(0xffffffffu, s[mt][ks][1], src_lo);
+            const float l2 = __shfl_sync(0xffffffffu, s[mt][ks][2], src_lo), l3 = __shfl_sync(0xffffffffu, s[mt][ks][3], src_lo);
+            const float h0 = __shfl_sync(0xffffffffu, s[mt][ks][0], src_hi), h1 = __shfl_sync(0xffffffffu, s[mt][ks][1], src_hi);
+            const float h2 = __shfl_sync(0xffffffffu, s[mt][ks][2], src_hi), h3 = __shfl_sync(0xffffffffu, s[mt][ks][3], src_hi);
+            a[mt][0] = to_tf32(odd ? l1 : l0);        // P[g      ][8ks + t]
+            a[mt][1] = to_tf32(odd ? l3 : l2);        // P[g + 8  ][8ks + t]
+            a[mt][2] = to_tf32(odd ? h1 : h0);        // P[g      ][8ks + t + 4]
+            a[mt][3] = to_tf32(odd ? h3 : h2);        // P[g + 8  ][8ks + t + 4]
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t bf[2];
+            frag_b_k(bf, Vb, rs, ks * 8, nt * 8, N, DH, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][nt], a[mt], bf);
+        }
+    }
+    store_tile(O, (long long)b * N * inner + h * DH, inner, o, g, t, out_mode);
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 3)
+attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dO,
+                         float* __restrict__ dQKV, int nprob, int heads, int out_mode, int act_batch) {
+    pdl_sync();
+    __shared__ float scratch[WARPS][32 * SP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int prob = blockIdx.x * WARPS + warp;
+    if (prob >= nprob) return;
+    const int b = prob / heads, h = prob % heads;
+    const int ba = act_batch > 0 ? b % act_batch : b;          // stacked cotangents share the saved activations
+    const int inner = heads * DH;
+    const long long rs = 3LL * inner;
+    const float* Qb = QKV + (long long)ba * N * rs + h * DH;
+    const float* Kb = Qb + inner;
+    const float* Vb = Qb + 2 * inner;
+    const float* Pg = P + ((long long)ba * heads + h) * N * N;
+    const float* Gb = dO + (long long)b * N * inner + h * DH;  // dO rows, stride inner
+    float* sc = scratch[warp];
+
+    // dP = dO V^T   [32 x 24], k = 64
+    float dp[2][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) dp[mt][nt][0] = dp[mt][nt][1] = dp[mt][nt][2] = dp[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        uint32_t a[2][4], bf[3][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) frag_a(a[mt], Gb, inner, mt * 16, ks * 8, N, DH, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) frag_b_n(bf[nt], Vb, rs, ks * 8, nt * 8, DH, N, g, t);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) mma_tf32(dp[mt][nt], a[mt], bf[nt]);
+    }
+    // dS = P * (dP - rowsum(dP * P)) * 64^-0.5, in the accumulator layout; written to this warp's scratch so that the
+    // two products below can read it in either operand orientation
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int i = mt * 16 + hf * 8 + g;
+            float pv[3][2], r = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = nt * 8 + 2 * t + e;
+                    pv[nt][e] = (i < N && j < N) ? __ldg(Pg + i * N + j) : 0.f;
+                    r = fmaf(dp[mt][nt][hf * 2 + e], pv[nt][e], r);
+                }
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    sc[i * SP + nt * 8 + 2 * t + e] = pv[nt][e] * (dp[mt][nt][hf * 2 + e] - r) * 0.125f;
+        }
+    __syncwarp();
+    const long long drow = (long long)b * N * rs + h * DH;
+    float acc[2][8][4];
+    // dV[j] = sum_i P[i,j] dO[i]     A(m = j, k = i) = P[i][j],  B(k = i, n = d) = dO[i][d]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) frag_a_t(a[mt], Pg, N, mt * 16, ks * 8, N, N, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t bf[2];
+            frag_b_k(bf, Gb, inner, ks * 8, nt * 8, N, DH, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], a[mt], bf);
+        }
+    }
+    store_tile(dQKV, drow + 2 * inner, rs, acc, g, t, out_mode);
+    // dK[j] = sum_i dS[i,j] Q[i]     A(m = j, k = i) = dS[i][j] (scratch, transposed read),  B(k = i, n = d) = Q[i][d]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int m = mt * 16 + g, k = ks * 8 + t;             // scratch rows / cols up to 31 / 23 are all written
+            a[mt][0] = to_tf32(sc[k * SP + m]);
+            a[mt][1] = to_tf32(m + 8 < 24 ? sc[k * SP + m + 8] : 0.f);
+            a[mt][2] = to_tf32(sc[(k + 4) * SP + m]);
+            a[mt][3] = to_tf32(m + 8 < 24 ? sc[(k + 4) * SP + m + 8] : 0.f);
+            if (m >= 24) a[mt][0] = a[mt][2] = 0u;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t bf[2];
+            frag_b_k(bf, Qb, rs, ks * 8, nt * 8, N, DH, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], a[mt], bf);
+        }
+    }
+    store_tile(dQKV, drow + inner, rs, acc, g, t, out_mode);
+    // dQ[i] = sum_j dS[i,j] K[j]     A(m = i, k = j) = dS[i][j],  B(k = j, n = d) = K[j][d]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int m = mt * 16 + g, k = ks * 8 + t;
+            a[mt][0] = to_tf32(sc[m * SP + k]);
+            a[mt][1] = to_tf32(sc[(m + 8) * SP + k]);
+            a[mt][2] = to_tf32(sc[m * SP + k + 4]);
+            a[mt][3] = to_tf32(sc[(m + 8) * SP + k + 4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t bf[2];
+            frag_b_k(bf, Kb, rs, ks * 8, nt * 8, N, DH, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], a[mt], bf);
+        }
+    }
+    store_tile(dQKV, drow, rs, acc, g, t, out_mode);
+}
+
+}  // namespace
+
+int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int out_mode, cudaStream_t stream) {
+    SCAT_REQUIRE(n == N, kErrUnsupported, "attention_mma: n=%d", n);
+    const int nprob = B * heads;
+    SCAT_CHECK_CUDA(launch_k(attention_fwd_mma_kernel, dim3(ceil_div(nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, O, P, nprob,
+                             heads, out_mode));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+                             int out_mode, cudaStream_t stream, int act_batch) {
+    SCAT_REQUIRE(n == N, kErrUnsupported, "attention_mma: n=%d", n);
+    const int nprob = B * heads;
+    SCAT_CHECK_CUDA(launch_k(attention_bwd_mma_kernel, dim3(ceil_div(nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, P, dO, dQKV,
+                             nprob, heads, out_mode, act_batch));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace scat

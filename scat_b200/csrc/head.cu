@@ -736,6 +736,15 @@ int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float
     return launch_attention_bwd(qkv, p, d_o, d_qkv, batch, n, heads, 0, (cudaStream_t)stream);
 }
 
+int scat_attention_fwd_tc(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream) {
+    return launch_attention_mma_fwd(qkv, o, p, batch, n, heads, OUT_F32, (cudaStream_t)stream);
+}
+
+int scat_attention_bwd_tc(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
+                          int32_t heads, void* stream) {
+    return launch_attention_mma_bwd(qkv, p, d_o, d_qkv, batch, n, heads, OUT_F32, (cudaStream_t)stream);
+}
+
 int scat_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* w,
                        const float* b, float* pred, float* states, float* scratch, int32_t batch, int32_t feat_dim,
                        int32_t n_out, int32_t iteration, int32_t root_relative, void* stream) {

@@ -131,6 +131,10 @@ int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int
 int launch_attention_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
                          int round_out, cudaStream_t stream, int act_batch = 0);
 // act_batch > 0: dO/dQKV have B samples, QKV/P have act_batch samples and sample b uses activations of b % act_batch
+// the n = 21 tensor-core kernels (mma.sync TF32) directly, any out_mode (attention_mma.cu)
+int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int out_mode, cudaStream_t stream);
+int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
+                             int out_mode, cudaStream_t stream, int act_batch = 0);
 // dst[r, c] = round_tf32(src[r, c]) (pad columns zero-filled) for a list of weight matrices, one launch;
 // the job table travels by value as a kernel argument (no device-side table, graph-capturable)
 // mode 0: dst = TF32-nearest(src) as fp32; 1: dst = bf16(src) (dst is a bf16 array); 2: dst = TF32-nearest(src - TF32-nearest(src))

@@ -238,20 +238,22 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, resid=None, param_grads=True):
     return dx, dg, db
 
 
-def attention_fwd(qkv, batch, n, heads):
+def attention_fwd(qkv, batch, n, heads, tc=False):
+    """vision_transformer.py:61-77.  tc=True (n = 21 only): the mma.sync TF32 kernel of the TF32 / BF16 precisions."""
     lib = _lib.load()
     qkv = _f32c(qkv, "qkv")
     o = torch.empty(batch * n, heads * 64, device=qkv.device)
     p = torch.empty(batch, heads, n, n, device=qkv.device)
-    check(lib.scat_attention_fwd(ptr(qkv), ptr(o), ptr(p), batch, n, heads, stream_ptr()), "scat_attention_fwd")
+    fn = lib.scat_attention_fwd_tc if tc else lib.scat_attention_fwd
+    check(fn(ptr(qkv), ptr(o), ptr(p), batch, n, heads, stream_ptr()), "scat_attention_fwd")
     return o, p
 
 
-def attention_bwd(qkv, p, d_o, batch, n, heads):
+def attention_bwd(qkv, p, d_o, batch, n, heads, tc=False):
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
-    check(lib.scat_attention_bwd(ptr(qkv), ptr(p), ptr(_f32c(d_o, "d_o")), ptr(dqkv), batch, n, heads, stream_ptr()),
-          "scat_attention_bwd")
+    fn = lib.scat_attention_bwd_tc if tc else lib.scat_attention_bwd
+    check(fn(ptr(qkv), ptr(p), ptr(_f32c(d_o, "d_o")), ptr(dqkv), batch, n, heads, stream_ptr()), "scat_attention_bwd")
     return dqkv
 
 

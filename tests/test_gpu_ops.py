@@ -98,6 +98,31 @@ def test_attention_fwd_bwd(B, n, heads):
         assert rel_max(dqkv, q.grad) < 2e-5
 
 
+@pytest.mark.parametrize("B,heads", [(96, 8), (192, 8), (3, 4), (1, 1), (5, 3)])
+def test_attention_tensor_core_fwd_bwd(B, heads):
+    """n = 21 attention on mma.sync TF32 (one warp per (batch, head) problem): TF32-grade against float64."""
+    from scat_b200 import functional as SF
+    n, inner = 21, 64 * heads
+    qkv = _rand(B * n, 3 * inner, seed=11)
+    d_o = _rand(B * n, inner, seed=12)
+    q = qkv.double().requires_grad_(True)
+    qq, kk, vv = q.view(B, n, 3 * inner).chunk(3, dim=-1)
+    sp = lambda t: t.reshape(B, n, heads, 64).permute(0, 2, 1, 3)
+    p_ref = (torch.matmul(sp(qq), sp(kk).transpose(-1, -2)) * 0.125).softmax(-1)
+    o_ref = torch.matmul(p_ref, sp(vv)).permute(0, 2, 1, 3).reshape(B * n, inner)
+    o, p = SF.attention_fwd(qkv.cuda(), B, n, heads, tc=True)
+    assert rel_max(p, p_ref.detach()) < 3e-3
+    assert rel_max(o, o_ref.detach()) < 3e-3
+    assert float((p.sum(-1) - 1).abs().max()) < 1e-5                  # rows of P are normalised in fp32
+    o_ref.backward(d_o.double())
+    dqkv = SF.attention_bwd(qkv.cuda(), p_ref.detach().float().cuda(), d_o.cuda(), B, n, heads, tc=True)
+    assert rel_max(dqkv, q.grad) < 3e-3
+    # against the fp32 FFMA kernels of the same library
+    o32, p32 = SF.attention_fwd(qkv.cuda(), B, n, heads)
+    d32 = SF.attention_bwd(qkv.cuda(), p32, d_o.cuda(), B, n, heads)
+    assert rel_max(o, o32) < 3e-3 and rel_max(dqkv, d32) < 3e-3
+
+
 @pytest.mark.parametrize("B,mask_rate,pos_embed", [(3, 0.2, True), (2, 0.9, True), (2, 0.0, True), (2, 0.2, False),
                                                    (5, 0.5, True)])
 def test_conv_pe_mask_fwd_bwd(B, mask_rate, pos_embed):
