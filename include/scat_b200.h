@@ -35,6 +35,10 @@ extern "C" {
 #define SCAT_PREC_FP32 0   /* CUDA-core FFMA everywhere ("parity mode")                         */
 #define SCAT_PREC_TF32 1   /* tcgen05 kind::tf32, operands stay fp32 in HBM, fp32 accumulate    */
 #define SCAT_PREC_BF16 2   /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate             */
+/* scat_gemm only: fp32-grade result from the warp-level tensor instruction (mma.sync TF32) with the 3xTF32 operand
+ * split; any strides, no alignment requirement.  Measured slower than the fp32 FFMA kernel on B200 (the legacy
+ * mma.sync path has FFMA-class throughput there), so the head does not use it */
+#define SCAT_PREC_TF32X3 3
 /* scat_gemm only, OR-ed into SCAT_PREC_TF32: the fp32 operands are already TF32-representable (their producer
  * rounded them), so the kernel skips its in-shared-memory rounding pass -- how the head itself runs its GEMMs */
 #define SCAT_PREC_FLAG_PREROUNDED 0x100

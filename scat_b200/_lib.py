@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libscat_b200.so")
 
-PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2, "tf32x3": 3}
 EPI = {"none": 0, "bias": 1, "bias_resid": 2, "bias_gelu": 3, "dgelu": 4, "resid": 5}
 NUM_PARAMS = 35
 

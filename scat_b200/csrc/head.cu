@@ -42,6 +42,16 @@ int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
     return launch_gemm_simt(g, stream);
 }
 
+// The contractions that stay fp32-accurate in every precision (last feed-forward, regressor gradients) run on the
+// fp32 FFMA kernel.  The 3xTF32 mma.sync kernel (gemm_mma3.cu, scat_gemm precision SCAT_PREC_TF32X3) computes the same
+// thing to the same accuracy but was measured SLOWER on B200 (44 us vs 25 us for the 2016x147x196 layer): the legacy
+// mma.sync path issues one m16n8k8 TF32 instruction per ~55 cycles per SM sub-partition, i.e. FFMA-class throughput,
+// and the split needs three of them.
+int launch_gemm_exact(const GemmArgs& g, int head_precision, cudaStream_t stream) {
+    (void)head_precision;
+    return launch_gemm_simt(g, stream);
+}
+
 namespace {
 
 constexpr int kDepth = 3;   // hand_net.py:331 depth=3 (opt.vit_depth is ignored by the reference)
@@ -283,13 +293,13 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
         else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh;
-        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        SCAT_PROPAGATE(L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st));
         float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
         g = GemmArgs();
         g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
         g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid; g.prerounded = fftc;
         g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
-        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        SCAT_PROPAGATE(L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st));
     }
     return 0;
 }
@@ -324,7 +334,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
             g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
-            SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
             SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, st));
         }
         // dZ = (dY W2) * gelu'(Z)
@@ -334,13 +344,13 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (ffbf) { g.C16 = dZ; g.ldc16 = ld_h; }
         else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod;
-        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         if (G) {
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             g = GemmArgs();
             g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = ffbf ? ld_n : L.d; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
-            SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
             SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, st, ffbf));
         }
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs)
@@ -349,7 +359,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         g.C = ws + p.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
         if (L.last && bf) { g.C16 = ws + p.dX1_16; g.ldc16 = ld_n; }
         else g.round_out = (L.last && tc) ? 1 : 0;
-        SCAT_PROPAGATE(launch_gemm(g, ffprec, st));
+        SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         const float* dX1 = ws + p.dNf;
         if (!L.last) {
             SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
@@ -493,12 +503,12 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
         g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
         g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1; g.c_zeroed = 1;
-        SCAT_PROPAGATE(launch_gemm_simt(g, st));
+        SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, st));
         if (p.it > 0) {   // dWr[:, F:] = sum over samples and steps of g_step (x) state
             g = GemmArgs();
             g.A = ws + p.gsteps; g.sam = 1; g.sak = p.NP; g.B = ws + p.states; g.sbn = 1; g.sbk = p.NP;
             g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it; g.allow_split_k = 1; g.c_zeroed = 1;
-            SCAT_PROPAGATE(launch_gemm_simt(g, st));
+            SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, st));
         }
         SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 1, st));
     }
@@ -625,6 +635,7 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
     g.prerounded = (precision & SCAT_PREC_FLAG_PREROUNDED) ? 1 : 0;
     precision &= ~SCAT_PREC_FLAG_PREROUNDED;
     if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
+    if (precision == SCAT_PREC_TF32X3) return launch_gemm_mma3(g, (cudaStream_t)stream);
     SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
                  "scat_gemm: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
     return launch_gemm_tc(g, precision, (cudaStream_t)stream);   // operands rounded to TF32-nearest inside the kernel

@@ -69,6 +69,8 @@ __device__ __forceinline__ float round_tf32(float x) {
 #endif
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// fp32-grade small GEMM on mma.sync TF32 with the 3xTF32 split (gemm_mma3.cu): any strides, epilogues NONE..RESID
+int launch_gemm_mma3(const GemmArgs& g, cudaStream_t stream);
 // tcgen05 path; returns kErrUnsupported if the operand strides cannot be expressed as TMA tensor maps
 int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream);
 bool gemm_tc_supported(const GemmArgs& g);

@@ -154,3 +154,42 @@ def test_bf16_gemm_exact_on_small_integers():
     ref = (A.double() @ B.double().t()).float()
     out = SF.gemm_bf16(A.bfloat16().cuda(), B.bfloat16().cuda())
     assert torch.equal(out.cpu(), ref)
+
+
+# ---- 3xTF32 on mma.sync: the fp32-grade small-GEMM kernel ------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,a,b", [
+    (2016, 147, 196, "k", "k"), (2016, 3, 147, "k", "k"), (4032, 147, 3, "k", "mn"), (4032, 196, 147, "k", "mn"),
+    (147, 196, 2016, "mn", "mn"), (3, 147, 2016, "mn", "mn"), (66, 1024, 96, "mn", "mn"), (66, 66, 288, "mn", "mn"),
+    (1, 1, 1, "k", "k"), (33, 65, 9, "k", "k"), (129, 31, 1000, "mn", "k"),
+])
+def test_tf32x3_gemm_is_fp32_grade(M, N, K, a, b):
+    from scat_b200 import functional as SF
+    A, B, Ad, Bd, sa, sb = _mk(M, N, K, a, b)
+    ref = A.double() @ B.double().t()
+    out = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="tf32x3")
+    assert _err(out, ref) < 2e-6
+    simt = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="fp32")
+    assert _err(out, simt.double().cpu()) < 2e-6
+
+
+def test_tf32x3_gemm_epilogues():
+    from scat_b200 import functional as SF
+    M, N, K = 2016, 147, 196
+    A, B, Ad, Bd, sa, sb = _mk(M, N, K, "k", "k", seed=3)
+    g = np.random.Generator(np.random.PCG64(9))
+    bias = torch.from_numpy(g.standard_normal(N).astype(np.float32))
+    res = torch.from_numpy(g.standard_normal((M, 148)).astype(np.float32))
+    ref = A.double() @ B.double().t()
+    out = torch.zeros(M, 148, device="cuda")
+    y, z = SF.gemm(Ad, Bd, epilogue="bias_gelu", bias=bias.cuda(), precision="tf32x3", out=out[:, :N])
+    assert _err(z[:, :N], ref + bias.double()) < 2e-6 and _err(y[:, :N], F.gelu(ref + bias.double())) < 2e-6
+    assert torch.all(out[:, N:] == 0)
+    r = SF.gemm(Ad, Bd, epilogue="bias_resid", bias=bias.cuda(), aux_in=res.cuda()[:, :N], precision="tf32x3")
+    assert _err(r, ref + bias.double() + res[:, :N].double()) < 2e-6
+    zz = res.double()[:, :N].requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    d = SF.gemm(Ad, Bd, epilogue="dgelu", aux_in=res.cuda()[:, :N], precision="tf32x3")
+    assert _err(d, ref * zz.grad) < 2e-6
+    acc = torch.ones(M, N, device="cuda")
+    SF.gemm(Ad, Bd, precision="tf32x3", out=acc, accumulate=True)
+    assert _err(acc, ref + 1.0) < 2e-6
