@@ -278,7 +278,7 @@ def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
                 t = graph_time(lambda: SF.gemm_bf16(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, out=out, split_k=wg))
             else:
                 t = graph_time(lambda: SF.gemm(a, b, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="tf32", out=out,
-                                               prerounded=True))
+                                               prerounded=True, split_k=wg))
             tot_t += cnt * t
             tot_f += cnt * 2.0 * M * N * K
             n_launch += cnt
@@ -289,7 +289,7 @@ def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
                 "us": tot_t * 1e6, "traffic": dram("gemm_tc_kernel<128> (qkv layer 0)"),
                 "note": ("peak = measured cuBLAS bf16 burst" if bf else "peak = measured cuBLAS bf16 burst / 2 (TF32)") +
                         "; every GEMM shape of the step timed alone from a CUDA graph with the operand storage the step uses"
-                        + ("" if bf else "; the TF32 weight-gradient GEMMs run split-K inside the step, not in this table")}
+                        + "; weight gradients split-K with reductions in L2, as in the step"}
         kernels.insert(0, gemm)
     for k in kernels:
         k["frac"] = k["achieved"] / k["peak"]

@@ -42,6 +42,9 @@ extern "C" {
 /* scat_gemm only, OR-ed into SCAT_PREC_TF32: the fp32 operands are already TF32-representable (their producer
  * rounded them), so the kernel skips its in-shared-memory rounding pass -- how the head itself runs its GEMMs */
 #define SCAT_PREC_FLAG_PREROUNDED 0x100
+/* scat_gemm only, OR-ed into the precision: the kernel may slice K over CTAs and combine the slices with reductions
+ * in L2 (how the head runs its weight-gradient GEMMs); C must be zero on entry, epilogue NONE */
+#define SCAT_PREC_FLAG_SPLIT_K 0x200
 
 /* GEMM epilogues (scat_gemm) */
 #define SCAT_EPI_NONE       0

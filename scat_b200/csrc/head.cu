@@ -633,7 +633,8 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
     g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
     g.aux_out = aux_out; g.ld_aux_out = ld_aux_out; g.accumulate = accumulate;
     g.prerounded = (precision & SCAT_PREC_FLAG_PREROUNDED) ? 1 : 0;
-    precision &= ~SCAT_PREC_FLAG_PREROUNDED;
+    if (precision & SCAT_PREC_FLAG_SPLIT_K) { g.allow_split_k = 1; g.c_zeroed = 1; }
+    precision &= ~(SCAT_PREC_FLAG_PREROUNDED | SCAT_PREC_FLAG_SPLIT_K);
     if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
     if (precision == SCAT_PREC_TF32X3) return launch_gemm_mma3(g, (cudaStream_t)stream);
     SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,

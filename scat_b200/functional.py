@@ -161,7 +161,7 @@ def token_transformer(transformer, x, mask_token=None, pe=None, mask_idx=None, p
 # single operators (unit tests, micro-benchmarks)
 # ---------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_strides=None, b_strides=None, m=None, n=None, k=None, epilogue="none", bias=None, aux_in=None,
-         precision="fp32", out=None, accumulate=False, prerounded=False):
+         precision="fp32", out=None, accumulate=False, prerounded=False, split_k=False):
     """C[M,N] = epilogue(sum_k A(m,k) B(n,k)).  Defaults: a[M,K] row-major, b[N,K] row-major (y = x W^T).
     Returns C, or (C, Z) for the bias_gelu epilogue."""
     lib = _lib.load()
@@ -172,12 +172,16 @@ def gemm(a, b, *, a_strides=None, b_strides=None, m=None, n=None, k=None, epilog
     if b_strides is None:
         n = b.shape[0]
         b_strides = (b.stride(0), b.stride(1))
-    c = torch.empty(m, n, device=a.device, dtype=torch.float32) if out is None else out
+    if out is None:
+        c = (torch.zeros if split_k else torch.empty)(m, n, device=a.device, dtype=torch.float32)
+    else:
+        c = out
     z = torch.empty_like(c) if epilogue == "bias_gelu" else None
     check(lib.scat_gemm(ptr(a), a_strides[0], a_strides[1], ptr(b), b_strides[0], b_strides[1], ptr(c), c.stride(0),
                         m, n, k, EPI[epilogue], ptr(bias), ptr(aux_in), 0 if aux_in is None else aux_in.stride(0),
                         ptr(z), 0 if z is None else z.stride(0), int(accumulate),
-                        PREC[precision] | (0x100 if prerounded else 0), stream_ptr()), "scat_gemm")
+                        PREC[precision] | (0x100 if prerounded else 0) | (0x200 if split_k else 0), stream_ptr()),
+          "scat_gemm")
     return (c, z) if z is not None else c
 
 

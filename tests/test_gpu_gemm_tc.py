@@ -43,6 +43,9 @@ def test_tc_gemm_layouts(M, N, K, a, b):
     assert _err(out, ref) < TOL
     simt = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="fp32")
     assert _err(out, simt.double().cpu()) < TOL
+    if a == "mn" and b == "mn":                                           # weight-gradient shape: split-K path
+        sk = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, precision="tf32", split_k=True)
+        assert _err(sk, ref) < TOL
 
 
 def test_tc_gemm_epilogues_and_padded_ld():
