@@ -52,6 +52,64 @@ int launch_gemm_exact(const GemmArgs& g, int head_precision, cudaStream_t stream
     return launch_gemm_simt(g, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second stream for work that is off the critical path (weight gradients, bias column sums, gradient zeroing, the
+// conv weight gradient): the step is a chain of short, latency-bound kernels that each fill a fraction of the 148
+// SMs, so independent launches overlap almost for free.  Fork / join are event record + wait pairs, which is also
+// exactly how a side stream joins a CUDA-graph capture of the caller's stream.  One side stream and a small ring
+// of events per device, created on first use (the only state this library keeps besides the launch counter);
+// SCAT_SIDE_STREAM=0 keeps everything on the caller's stream.
+// ---------------------------------------------------------------------------------------------
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[32];
+    int next = 0;
+    bool ready = false;
+};
+static SideStream g_side[16];
+static int side_enabled() {
+    static const int on = [] { const char* e = getenv("SCAT_SIDE_STREAM"); return (e && e[0] == '0') ? 0 : 1; }();
+    return on;
+}
+static SideStream* get_side() {
+    if (!side_enabled()) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStream& sd = g_side[dev];
+    if (!sd.ready) {
+        if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 32; ++i)
+            if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sd.ready = true;
+    }
+    return &sd;
+}
+// everything enqueued on `from` so far happens before anything enqueued on `to` from now on
+static int order_after(SideStream* sd, cudaStream_t from, cudaStream_t to) {
+    if (sd == nullptr || from == to) return 0;
+    cudaEvent_t e = sd->ev[sd->next];
+    sd->next = (sd->next + 1) % 32;
+    SCAT_CHECK_CUDA(cudaEventRecord(e, from));
+    SCAT_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+}
+
+// split form: mark a point on `from` now, make `to` wait for it later
+static int side_mark(SideStream* sd, cudaStream_t from, cudaEvent_t* out) {
+    *out = nullptr;
+    if (sd == nullptr) return 0;
+    cudaEvent_t e = sd->ev[sd->next];
+    sd->next = (sd->next + 1) % 32;
+    SCAT_CHECK_CUDA(cudaEventRecord(e, from));
+    *out = e;
+    return 0;
+}
+static int side_wait(cudaStream_t to, cudaEvent_t e) {
+    if (e == nullptr) return 0;
+    SCAT_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+}
+
 namespace {
 
 constexpr int kDepth = 3;   // hand_net.py:331 depth=3 (opt.vit_depth is ignored by the reference)
@@ -311,7 +369,11 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 // every dgrad-type kernel then runs once over 2M rows against the same saved activations, parameter gradients
 // only see the first M rows.
 int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
-                         int prec, const float* up, cudaStream_t st, const float* X0_override, int sweeps = 1) {
+                         int prec, const float* up, cudaStream_t st, const float* X0_override, int sweeps = 1,
+                         SideStream* sd = nullptr) {
+    // parameter gradients run on the side stream `sg` (== st without one): each group is forked once its inputs exist
+    // and all groups of a layer are joined before that layer's last kernel overwrites the cotangent buffers they read
+    const cudaStream_t sg = (sd != nullptr && G != nullptr) ? sd->s : st;
     const int M = p.M;
     const int MR = M * sweeps;                       // rows of every cotangent tensor
     const int amod = sweeps > 1 ? M : 0;             // activation row = cotangent row % M
@@ -332,10 +394,11 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         GemmArgs g;
         if (G) {
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
+            SCAT_PROPAGATE(order_after(sd, st, sg));
             g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
-            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
-            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, st));
+            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
+            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, sg));
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
@@ -347,11 +410,12 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         if (G) {
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
+            SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
             g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = ffbf ? ld_n : L.d; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
-            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
-            SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, st, ffbf));
+            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
+            SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, sg, ffbf));
         }
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs)
         g = GemmArgs();
@@ -371,11 +435,12 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         const float* dX1g = bf ? ws + p.dX1_16 : dX1;           // what the GEMMs read
         if (G) {
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1)
+            SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
             g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
-            SCAT_PROPAGATE(launch_gemm(g, prec, st));
-            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, st));
+            SCAT_PROPAGATE(launch_gemm(g, prec, sg));
+            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, sg));
         }
         // dO = dX1 Wo
         g = GemmArgs();
@@ -386,16 +451,20 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
                                             st, sweeps > 1 ? p.B : 0));
         if (G) {
             // dWqkv[3inner,d] = dQKV^T Na
+            SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
             g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_n; g.operand_bf16 = bf;
             g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
-            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+            SCAT_PROPAGATE(launch_gemm(g, prec, sg));
         }
         // dNa = dQKV Wqkv
         g = GemmArgs();
         g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
         g.C = ws + p.dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        // the next kernel overwrites dX (this layer's dY), and the next layer every other cotangent buffer the side-stream
+        // parameter-gradient kernels of this layer read: join them here
+        if (G) SCAT_PROPAGATE(order_after(sd, sg, st));
         // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs
         const bool feeds_gemm = tc && l > 0;
         SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
@@ -487,8 +556,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_REQUIRE(W && G && x2 && main_feat && g_pred, kErrBadArg, "head_backward: null tensor");
     SCAT_REQUIRE(d.pos_embed || fv_alias, kErrBadArg, "head_backward: pos_embed==0 needs the forward's feat_visual");
     float* ws = (float*)workspace;
-    // every parameter gradient is accumulated into (split-K / column-sum / LayerNorm reductions): clear them once
-    SCAT_PROPAGATE(zero_param_grads(p, G, st));
+    SideStream* sd = get_side();
+    const cudaStream_t sg = sd ? sd->s : st;
+    // every parameter gradient is accumulated into (split-K / column-sum / LayerNorm reductions): clear them once,
+    // on the side stream, which then also carries the regressor weight gradients
+    SCAT_PROPAGATE(order_after(sd, st, sg));
+    SCAT_PROPAGATE(zero_param_grads(p, G, sg));
+    cudaEvent_t zeroed = nullptr;
+    SCAT_PROPAGATE(side_mark(sd, sg, &zeroed));
     // regressor + root-relative backward
     const int sweeps = pl_out ? 2 : 1;
     float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
@@ -499,20 +574,22 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         SCAT_CHECK_LAUNCH();
     }
     {
+        SCAT_PROPAGATE(order_after(sd, st, sg));      // gsum / gsteps are ready
         const int ldw = p.F + p.NP;
         GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
         g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
         g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1; g.c_zeroed = 1;
-        SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, st));
+        SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, sg));
         if (p.it > 0) {   // dWr[:, F:] = sum over samples and steps of g_step (x) state
             g = GemmArgs();
             g.A = ws + p.gsteps; g.sam = 1; g.sak = p.NP; g.B = ws + p.states; g.sbn = 1; g.sbk = p.NP;
             g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it; g.allow_split_k = 1; g.c_zeroed = 1;
-            SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, st));
+            SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, sg));
         }
-        SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 1, st));
+        SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 1, sg));
+        SCAT_PROPAGATE(side_wait(st, zeroed));        // the main stream reduces into the gradients from here on
     }
-    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps));
+    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps, sd));
     // through masking / positional encoding into the conv output
     SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st, 1));
     if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
@@ -524,8 +601,11 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     }
     if (d.precision != PREC_FP32) {
         SCAT_PROPAGATE(launch_split_tf32(ws + p.dFv, ws + p.dFv2, p.B, p.T, p.D, st));
+        // the two HBM streams (x2.grad out, x2 in) are latency bound per CTA: run them side by side
+        SCAT_PROPAGATE(order_after(sd, st, sg));
+        SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, G[P_CONV_W], p.B, p.C, p.D, p.T, sg));   // G was zeroed above
         if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad_tc(ws + p.dFv2, ws + p.w_conv, x2_grad, p.B, p.C, p.D, p.T, st));
-        SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, G[P_CONV_W], p.B, p.C, p.D, p.T, st));   // G was zeroed above
+        SCAT_PROPAGATE(order_after(sd, sg, st));
     } else {
         if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], x2_grad, p.B, p.C, p.D, p.T, st));
         SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
