@@ -287,11 +287,12 @@ LayerW layer_weights(const HeadPlan& p, int l, const float* const* W, const floa
 }
 
 // one launch: TF32-round (and pad the leading dimension of) every weight a tensor-core GEMM reads
-int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st) {
+// which: -1 all, 0 the transformer weights only, 1 the conv weight only
+int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st, int which = -1) {
     RoundJobs jobs;
     int n = 0;
     const bool bf = prec == PREC_BF16;
-    for (int l = 0; l < kDepth; ++l) {
+    for (int l = 0; l < kDepth && which != 1; ++l) {
         const LayerPlan& L = p.L[l];
         jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, bf ? pad8(L.d) : L.ld_qkv};
         jobs.job[n++] = RoundJob{W[L.p_out_w], ws + L.w_out, L.d, p.inner, p.inner, p.inner};
@@ -301,12 +302,13 @@ int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec,
         }
     }
     for (int i = 0; i < n; ++i) jobs.job[i].to_bf16 = bf ? 1 : 0;
-    if (p.C > 0) {                                                   // conv stays kind::tf32; stacked twice for its dgrad
+    if (p.C > 0 && which != 0) {                                     // conv stays kind::tf32; stacked [Wh; Wh; Wl] for its dgrad
         jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv, p.T, p.C, p.C, p.C, 0};
         jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv + (size_t)p.T * p.C, p.T, p.C, p.C, p.C, 0};
         jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv + (size_t)2 * p.T * p.C, p.T, p.C, p.C, p.C, 2};
     }
     jobs.n = n;
+    if (n == 0) return 0;
     return launch_round_copy(jobs, st);
 }
 
@@ -523,18 +525,26 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     // with pos_embed == 0 the reference's token matrix is a view of feat_visual (hand_net.py:364): alias it
     float* X0 = d.pos_embed ? ws + p.L[0].X : fv;
     const bool tc = d.precision != PREC_FP32;
+    SideStream* sd = get_side();
+    const cudaStream_t sg = sd ? sd->s : st;
+    // side stream: the iteration-invariant half of the regressor (needs only main_feat) and, below, the weight copies
+    SCAT_PROPAGATE(order_after(sd, st, sg));
+    SCAT_PROPAGATE(launch_regressor_hoist(main_feat, W[P_REG_W], W[P_REG_B], ws + p.hreg, p.B, p.F, p.NP, sg));
     if (tc) {
-        // per-forward weight copies for the tensor cores (TF32-rounded fp32 or bf16), then the conv as a batched GEMM
-        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, st));
+        // per-forward weight copies for the tensor cores (TF32-rounded fp32 or bf16): the conv weight first, on the
+        // main stream; the transformer's copies overlap the conv (a batched tcgen05 GEMM) on the side stream
+        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, st, /*conv=*/1));
+        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, sg, /*conv=*/0));
         SCAT_PROPAGATE(launch_conv_pe_mask_fwd_tc(x2, ws + p.w_conv, pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed,
                                                   fv, X0, p.B, p.C, p.D, p.T, st));
     } else {
         SCAT_PROPAGATE(launch_conv_pe_mask_fwd(x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed, fv,
                                                X0, p.B, p.C, p.D, p.T, st));
     }
+    SCAT_PROPAGATE(order_after(sd, sg, st));       // weight copies (and the hoisted regressor product) are in place
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
     SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
-                                        ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st));
+                                        ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st, /*hoisted=*/1));
     if (d.pl_reg && !defer_pl) {
         // autograd.grad(sum(feat_out), feat_visual) (hand_net.py:396): dgrad-only sweep with a ones cotangent
         SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, ws + p.ones, 1.0f, (long long)p.M * 3));
@@ -568,7 +578,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     const int sweeps = pl_out ? 2 : 1;
     float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
     SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], up, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
-                                        p.NP, p.it, 1, st));
+                                        p.NP, p.it, 1, st, /*skip_main_feat_gemm=*/1));
     if (pl_out) {
         SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, up + (size_t)p.M * 3, 1.0f, (long long)p.M * 3));
         SCAT_CHECK_LAUNCH();
@@ -576,7 +586,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     {
         SCAT_PROPAGATE(order_after(sd, st, sg));      // gsum / gsteps are ready
         const int ldw = p.F + p.NP;
-        GemmArgs g;   // dWr[:, :F] = gsum^T main_feat
+        GemmArgs g;
+        if (mf_grad != nullptr) {   // d main_feat[B,F] = gsum[B,P] Wr[:, :F]: nothing downstream reads it
+            g.A = ws + p.gsum; g.sam = p.NP; g.sak = 1; g.B = W[P_REG_W]; g.sbn = 1; g.sbk = ldw;
+            g.C = mf_grad; g.ldc = p.F; g.M = p.B; g.N = p.F; g.K = p.NP;
+            SCAT_PROPAGATE(launch_gemm_simt(g, sg));
+            g = GemmArgs();
+        }
+        // dWr[:, :F] = gsum^T main_feat
         g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
         g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1; g.c_zeroed = 1;
         SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, sg));

@@ -151,10 +151,14 @@ int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream);
 // states [B, iteration, P] keeps pred before each step (for backward).  P = n_out (66), F = feature width.
 int launch_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* Wr,
                          const float* br, float* pred, float* states, float* h_scratch /* [B,P] */, int B, int F, int P,
-                         int iteration, int root_relative, cudaStream_t stream);
+                         int iteration, int root_relative, cudaStream_t stream, int hoisted = 0);
+// h_scratch = main_feat Wr[:, :F]^T + br (iteration invariant); pass hoisted = 1 to launch_regressor_fwd afterwards
+int launch_regressor_hoist(const float* main_feat, const float* Wr, const float* br, float* h_scratch, int B, int F, int P,
+                           cudaStream_t stream);
 // g_pred [B,P] -> d_feat_out [B,P-3], d_main_feat [B,F] (nullable), gsum [B,P], gsteps [B,iteration,P]
 int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out, float* d_main_feat, float* gsum,
-                         float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream);
+                         float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream,
+                         int skip_main_feat_gemm = 0);   // 1: the caller computes d_main_feat = gsum Wr[:, :F] itself
 
 // ------------------------------------------------------------------------------------------
 // projection + losses (train.py:112-120,165-203) with closed-form gradient w.r.t. pred_params

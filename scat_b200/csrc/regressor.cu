@@ -151,18 +151,29 @@ regressor_iter_bwd_kernel(const float* __restrict__ g_pred, const float* __restr
 
 }  // namespace
 
-int launch_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* Wr,
-                         const float* br, float* pred, float* states, float* h_scratch, int B, int F, int P,
-                         int iteration, int root_relative, cudaStream_t stream) {
+// the iteration-invariant part h = main_feat Wr[:, :F]^T + br: depends on the backbone feature only, so a caller may
+// run it on another stream while the transformer computes feat_out
+int launch_regressor_hoist(const float* main_feat, const float* Wr, const float* br, float* h_scratch, int B, int F, int P,
+                           cudaStream_t stream) {
     SCAT_REQUIRE(P >= 4 && P <= MAXP && F >= 2 && F <= 4096 && (F & 1) == 0, kErrUnsupported,
                  "regressor: P=%d F=%d out of range (F even, P<=96, F<=4096)", P, F);
-    SCAT_REQUIRE(!root_relative || (P - 3) % 3 == 0, kErrBadArg, "regressor: root_relative needs P=3+3k");
     SCAT_REQUIRE(h_scratch != nullptr, kErrBadArg, "regressor: h scratch [B,P] required");
     const size_t smem1 = sizeof(float) * (size_t)HS * F;
     if (smem1 > 48 * 1024)
         SCAT_CHECK_CUDA(cudaFuncSetAttribute(regressor_hoist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     SCAT_CHECK_CUDA(launch_k(regressor_hoist_kernel, dim3(dim3(ceil_div(B, HS), ceil_div(P, HJ))), dim3(256), smem1, stream, main_feat, Wr, br, h_scratch, B, F, P));
     SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_regressor_fwd(const float* main_feat, const float* feat_out, const float* mean_params, const float* Wr,
+                         const float* br, float* pred, float* states, float* h_scratch, int B, int F, int P,
+                         int iteration, int root_relative, cudaStream_t stream, int hoisted) {
+    SCAT_REQUIRE(P >= 4 && P <= MAXP && F >= 2 && F <= 4096 && (F & 1) == 0, kErrUnsupported,
+                 "regressor: P=%d F=%d out of range (F even, P<=96, F<=4096)", P, F);
+    SCAT_REQUIRE(!root_relative || (P - 3) % 3 == 0, kErrBadArg, "regressor: root_relative needs P=3+3k");
+    SCAT_REQUIRE(h_scratch != nullptr, kErrBadArg, "regressor: h scratch [B,P] required");
+    if (!hoisted) SCAT_PROPAGATE(launch_regressor_hoist(main_feat, Wr, br, h_scratch, B, F, P, stream));
     const size_t smem2 = sizeof(float) * ((size_t)P * (P + 1) + 3 * (size_t)P);
     SCAT_CHECK_CUDA(launch_k(regressor_iter_kernel, dim3(B), dim3(128), smem2, stream, h_scratch, feat_out, mean_params, Wr, pred, states, F, P, iteration,
                                                     root_relative));
@@ -171,13 +182,14 @@ int launch_regressor_fwd(const float* main_feat, const float* feat_out, const fl
 }
 
 int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out, float* d_main_feat, float* gsum,
-                         float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream) {
+                         float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream,
+                         int skip_main_feat_gemm) {
     SCAT_REQUIRE(P >= 4 && P <= MAXP, kErrUnsupported, "regressor bwd: P=%d out of range", P);
     SCAT_REQUIRE(gsum && gsteps, kErrBadArg, "regressor bwd: gsum/gsteps scratch required");
     const size_t smem = sizeof(float) * ((size_t)P * (P + 1) + 2 * (size_t)P + 4);
     SCAT_CHECK_CUDA(launch_k(regressor_iter_bwd_kernel, dim3(B), dim3(128), smem, stream, g_pred, Wr, d_feat_out, gsum, gsteps, F, P, iteration, root_relative));
     SCAT_CHECK_LAUNCH();
-    if (d_main_feat != nullptr) {
+    if (d_main_feat != nullptr && !skip_main_feat_gemm) {
         GemmArgs g;   // d main_feat[B,F] = gsum[B,P] Wr[:, :F]
         g.A = gsum; g.sam = P; g.sak = 1; g.B = Wr; g.sbn = 1; g.sbk = F + P;
         g.C = d_main_feat; g.ldc = F; g.M = B; g.N = F; g.K = P;
