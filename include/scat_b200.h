@@ -194,7 +194,9 @@ int scat_attention_fwd(const float* qkv, float* o, float* p, int32_t batch, int3
 int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
                        int32_t heads, void* stream);
 /* The same for n = 21 tokens on the tensor cores (mma.sync m16n8k8 TF32, one warp per (batch, head) problem, operands
- * rounded to TF32-nearest): what the head runs in SCAT_PREC_TF32 / SCAT_PREC_BF16.  TF32-grade results. */
+ * rounded to TF32-nearest): what the head runs in SCAT_PREC_TF32 / SCAT_PREC_BF16.  TF32-grade results.
+ * scat_attention_fwd_tc also takes n = 128 (the HRNet-token variant, inference): one tcgen05 tile per (batch, head)
+ * problem, S and O accumulated in tensor memory; p is then left untouched. */
 int scat_attention_fwd_tc(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream);
 int scat_attention_bwd_tc(const float* qkv, const float* p, const float* d_o, float* d_qkv, int32_t batch, int32_t n,
                           int32_t heads, void* stream);

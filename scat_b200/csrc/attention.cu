@@ -154,10 +154,16 @@ int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n,
 int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
                              int out_mode, cudaStream_t stream, int act_batch);
 
+// attention_tc128.cu: tcgen05 kernel for n = 128 (config 4, inference: P is not written)
+bool attention_tc128_supported(int n, int heads, const float* QKV);
+int launch_attention_tc128_fwd(const float* QKV, float* O, int B, int n, int heads, int out_mode, cudaStream_t stream);
+
 int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int round_out,
                          cudaStream_t stream) {
     SCAT_REQUIRE(n >= 1 && n <= 128, kErrUnsupported, "attention: n=%d not in [1,128]", n);
     if (n == 21 && round_out != OUT_F32) return launch_attention_mma_fwd(QKV, O, P, B, n, heads, round_out, stream);
+    // n = 128 only occurs on the inference-only token path (hand_net.py:193-203): no backward, so P is not needed
+    if (round_out != OUT_F32 && attention_tc128_supported(n, heads, QKV)) return launch_attention_tc128_fwd(QKV, O, B, n, heads, round_out, stream);
     if (attention_small_supported(n)) return launch_attention_small_fwd(QKV, O, P, B, n, heads, round_out, stream);
     const size_t smem = sizeof(float) * ((size_t)3 * n * LDS + (size_t)n * (n + 1));
     if (smem > 48 * 1024) {

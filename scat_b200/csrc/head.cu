@@ -168,13 +168,13 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
         L.d = dim; L.hid = (dim * 3) / 4; L.out = L.last ? 3 : dim / 2; L.ldh = pad4(L.hid);
         ldh_max = L.ldh > ldh_max ? L.ldh : ldh_max;
         L.X = take(cur, M * dim);
-        L.Na = take(cur, M * dim);
+        L.Na = take(cur, M * pad4(dim));     // GEMM operand: rows padded to 16 bytes (TMA), e.g. dim 98 of the token variant
         L.mean_a = take(cur, M); L.rstd_a = take(cur, M);
         L.QKV = take(cur, M * 3 * p.inner);
         L.P = take(cur, (size_t)p.B * p.heads * p.T * p.T);
         L.O = take(cur, M * p.inner);
         L.X1 = take(cur, M * dim);
-        if (!L.last) { L.Nf = take(cur, M * dim); L.mean_f = take(cur, M); L.rstd_f = take(cur, M); }
+        if (!L.last) { L.Nf = take(cur, M * pad4(dim)); L.mean_f = take(cur, M); L.rstd_f = take(cur, M); }
         else { L.Nf = L.X1; L.mean_f = L.rstd_f = 0; }
         L.Z = take(cur, M * L.ldh);
         L.H = take(cur, M * L.ldh);
@@ -326,7 +326,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         const LayerPlan& L = p.L[l];
         const LayerW w = layer_weights(p, l, W, ws, prec);
         float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
-        const int ld_n = bf ? pad8(L.d) : L.d;             // leading dimension of Na / Nf
+        const int ld_n = bf ? pad8(L.d) : pad4(L.d);       // leading dimension of Na / Nf (16-byte rows for TMA)
         const int ld_h = bf ? pad8(L.hid) : L.ldh;         // leading dimension of H as a GEMM operand
         // PreNorm + Attention + Residual (:18,:26,:59-79)
         SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, ld_n, ws + L.mean_a,
@@ -348,7 +348,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         const int ffprec = L.last ? PREC_FP32 : prec;   // last FF stays fp32
         const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
         g = GemmArgs();
-        g.A = ws + L.Nf; g.sam = ffbf ? ld_n : L.d; g.sak = 1; g.B = w.fc1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
+        g.A = ws + L.Nf; g.sam = L.last ? L.d : ld_n; g.sak = 1; g.B = w.fc1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
         g.M = M; g.N = L.hid; g.K = L.d; g.prerounded = fftc;
         if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
         else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
@@ -390,7 +390,8 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         const int ffprec = L.last ? PREC_FP32 : prec;
         const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
-        const int ld_n = bf ? pad8(L.d) : L.d;                 // Na / Nf / dX1 as GEMM operands
+        const int ld_n = bf ? pad8(L.d) : L.d;                 // dX1 / dX as GEMM operands
+        const int ld_na = bf ? pad8(L.d) : pad4(L.d);          // saved Na / Nf (as the forward stored them)
         const int ld_h = ffbf ? pad8(L.hid) : L.ldh;           // H / dZ as GEMM operands
         float* dZ = ws + p.dZ;
         GemmArgs g;
@@ -414,7 +415,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
-            g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = ffbf ? ld_n : L.d; g.operand_bf16 = ffbf;
+            g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.last ? L.d : ld_na; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
             SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, sg, ffbf));
@@ -455,7 +456,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dWqkv[3inner,d] = dQKV^T Na
             SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
-            g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_n; g.operand_bf16 = bf;
+            g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_na; g.operand_bf16 = bf;
             g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, sg));
         }
@@ -846,6 +847,8 @@ int scat_attention_bwd(const float* qkv, const float* p, const float* d_o, float
 }
 
 int scat_attention_fwd_tc(const float* qkv, float* o, float* p, int32_t batch, int32_t n, int32_t heads, void* stream) {
+    if (n == 128)      // tcgen05 kernel of the token variant (inference: p is left untouched); OUT_TF32 = its in-head output mode
+        return launch_attention_tc128_fwd(qkv, o, batch, n, heads, OUT_F32, (cudaStream_t)stream);
     return launch_attention_mma_fwd(qkv, o, p, batch, n, heads, OUT_F32, (cudaStream_t)stream);
 }
 

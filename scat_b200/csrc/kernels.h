@@ -137,6 +137,8 @@ int launch_attention_bwd(const float* QKV, const float* P, const float* dO, floa
 int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int out_mode, cudaStream_t stream);
 int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, float* dQKV, int B, int n, int heads,
                              int out_mode, cudaStream_t stream, int act_batch = 0);
+// n = 128 on tcgen05 (attention_tc128.cu), forward only, P not written
+int launch_attention_tc128_fwd(const float* QKV, float* O, int B, int n, int heads, int out_mode, cudaStream_t stream);
 // dst[r, c] = round_tf32(src[r, c]) (pad columns zero-filled) for a list of weight matrices, one launch;
 // the job table travels by value as a kernel argument (no device-side table, graph-capturable)
 // mode 0: dst = TF32-nearest(src) as fp32; 1: dst = bf16(src) (dst is a bf16 array); 2: dst = TF32-nearest(src - TF32-nearest(src))

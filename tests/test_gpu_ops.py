@@ -123,6 +123,24 @@ def test_attention_tensor_core_fwd_bwd(B, heads):
     assert rel_max(o, o32) < 3e-3 and rel_max(dqkv, d32) < 3e-3
 
 
+@pytest.mark.parametrize("B,heads", [(256, 8), (3, 2), (1, 1)])
+def test_attention_tcgen05_n128_fwd(B, heads):
+    """n = 128 attention (config 4) as one tcgen05 tile per (batch, head) problem: TF32-grade against float64 and
+    against the fp32 FFMA kernel of the same library."""
+    from scat_b200 import functional as SF
+    n, inner = 128, 64 * heads
+    qkv = _rand(B * n, 3 * inner, seed=21)
+    q = qkv.double()
+    qq, kk, vv = q.view(B, n, 3 * inner).chunk(3, dim=-1)
+    sp = lambda t: t.reshape(B, n, heads, 64).permute(0, 2, 1, 3)
+    p_ref = (torch.matmul(sp(qq), sp(kk).transpose(-1, -2)) * 0.125).softmax(-1)
+    o_ref = torch.matmul(p_ref, sp(vv)).permute(0, 2, 1, 3).reshape(B * n, inner)
+    o, _ = SF.attention_fwd(qkv.cuda(), B, n, heads, tc=True)
+    assert rel_max(o, o_ref) < 3e-3
+    o32, _ = SF.attention_fwd(qkv.cuda(), B, n, heads)
+    assert rel_max(o, o32) < 3e-3
+
+
 @pytest.mark.parametrize("B,mask_rate,pos_embed", [(3, 0.2, True), (2, 0.9, True), (2, 0.0, True), (2, 0.2, False),
                                                    (5, 0.5, True)])
 def test_conv_pe_mask_fwd_bwd(B, mask_rate, pos_embed):
