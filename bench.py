@@ -336,7 +336,8 @@ def run_ours(args):
     dp.broadcast_parameters(net.head_parameters(), 0)
 
     B = B_PER_GPU
-    ts = HeadTrainStep(net, B, 1e5, 10.0, use_graph=not args.no_graph, input_slots=2)
+    ts = HeadTrainStep(net, B, 1e5, 10.0, use_graph=not args.no_graph, input_slots=2, comm=args.comm,
+                       phased=args.phased)
     # two distinct synthetic batches per rank, pinned on the host (e2e) and resident on the device (value)
     host = []
     for s in range(2):
@@ -447,6 +448,9 @@ def run_ours(args):
                     "ms_per_step": t_e2e / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall / args.steps * 1e3},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "loss": loss_val,
+            "allreduce": {"none": "none", "peer": "one NVLink peer-memory kernel inside the step's CUDA graph",
+                          "nccl": "NCCL, three phases overlapped with the backward" if ts.phased else
+                                  "NCCL after the step"}[ts.comm],
             "clocks": clocks, "roofline": roofline, "other_precision": other,
             "cpu_baseline": {"value": cpu["samples_per_s"], "unit": "samples/s", "cores": cpu["cores"], "kind": "port",
                              "sample": f"{cpu['steps']} steps of B={cpu['batch']} on {cpu_model()} (oracle port, fp32)"},
@@ -465,6 +469,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SCAT_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--comm", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1 gradient all-reduce: this library's NVLink peer-memory kernel (auto) or NCCL")
+    ap.add_argument("--phased", action="store_true", help="--comm nccl: overlap the all-reduce in three phases")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

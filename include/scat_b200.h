@@ -127,6 +127,36 @@ int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, c
                          float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* The same step in three launches for data-parallel callers, so the gradient all-reduce overlaps the backward:
+ * phase 0 = forward, losses and the backward down to transformer layer 1 (the gradients of layers 1, 2 and of the
+ * regressor -- parameters 13..34 of the gradient list -- are final when it returns); phase 1 = layer 0 and the token
+ * masking (parameters 0 and 2..12 and the losses are final); phase 2 = conv backward (parameter 1, x2_grad).
+ * phase -1 = scat_head_train_step. */
+int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                               const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                               const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d,
+                               float grad_scale, float* pred_params, float* feat_visual, float* pl_term, float* losses,
+                               float* const* grads, float* x2_grad, float* main_feat_grad, void* workspace,
+                               size_t workspace_bytes, void* stream, int32_t phase);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory (the reference imports
+ * DistributedDataParallel at train.py:18 and never uses it, so this has no reference counterpart to replace) ----
+ * One process per GPU.  Each rank allocates its gradient bucket and a signal area with scat_peer_alloc, exports both
+ * (64-byte CUDA IPC handles, exchanged by the host through any channel), and maps every peer's with scat_peer_open.
+ * scat_peer_allreduce then sums elements [lo, hi) (multiples of 4) of all buckets in place, in rank order, in ONE
+ * kernel on `stream` (capturable): buckets[p] / signals[p] are rank p's bucket and signal area as mapped in this
+ * process (own entries = the local allocations).  Every rank must issue the same sequence of calls.
+ * A peer that never arrives does not hang the GPU: after 20 s the kernel gives up and scat_peer_error reports 1. */
+size_t scat_peer_signal_bytes(void);
+int scat_peer_alloc(size_t bytes, void** out);                 /* zero-filled device memory, IPC-exportable */
+int scat_peer_free(void* ptr);
+int scat_peer_export(void* ptr, uint8_t* handle64);
+int scat_peer_open(const uint8_t* handle64, void** out);
+int scat_peer_close(void* ptr);
+int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
+                        long long hi, void* stream);
+int scat_peer_error(const uint32_t* signal, int32_t* out);     /* synchronous read of the time-out flag */
+
 /* Token-only transformer (HRNet-variant path up to feat.mean(dim=1), hand_net.py:193-203):
  *   tokens[B,n,dim] -> out[B,n,3], mean[B,3].  desc.channels = 0, desc.iteration = 0. */
 int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe,

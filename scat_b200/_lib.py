@@ -41,6 +41,16 @@ SIGNATURES = {
     "scat_proj_loss": (_i32, [_i32, _i32, _i32, _f, _f, _i32, _f, _fl, _fl, _fl, _f, _f, _f, _f]),
     "scat_head_train_step": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _i32, _fl, _fl, _fl, _f, _f, _f, _f, _pp,
                                     _f, _f, _f, _sz, _f]),
+    "scat_head_train_step_phase": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _i32, _fl, _fl, _fl, _f, _f, _f, _f, _pp,
+                                          _f, _f, _f, _sz, _f, _i32]),
+    "scat_peer_signal_bytes": (_sz, []),
+    "scat_peer_alloc": (_i32, [_sz, _pp]),
+    "scat_peer_free": (_i32, [_f]),
+    "scat_peer_export": (_i32, [_f, _f]),
+    "scat_peer_open": (_i32, [_f, _pp]),
+    "scat_peer_close": (_i32, [_f]),
+    "scat_peer_allreduce": (_i32, [_pp, _pp, _i32, _i32, C.c_longlong, C.c_longlong, _f]),
+    "scat_peer_error": (_i32, [_f, C.POINTER(C.c_int32)]),
     "scat_tokens_forward": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _sz, _f]),
     "scat_gemm": (_i32, [_f, _i64, _i64, _f, _i64, _i64, _f, _i32, _i32, _i32, _i32, _i32, _f, _f, _i32, _f, _i32,
                          _i32, _i32, _f]),

@@ -372,7 +372,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 // only see the first M rows.
 int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
                          int prec, const float* up, cudaStream_t st, const float* X0_override, int sweeps = 1,
-                         SideStream* sd = nullptr) {
+                         SideStream* sd = nullptr, int l_first = kDepth - 1, int l_last = 0) {
     // parameter gradients run on the side stream `sg` (== st without one): each group is forked once its inputs exist
     // and all groups of a layer are joined before that layer's last kernel overwrites the cotangent buffers they read
     const cudaStream_t sg = (sd != nullptr && G != nullptr) ? sd->s : st;
@@ -384,7 +384,13 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
     const float* dY = up;                            // fp32 cotangent of the layer output
     const float* dYg = up;                           // the copy GEMMs read: same tensor, or its bf16 shadow
     int ld_dYg = 3;
-    for (int l = kDepth - 1; l >= 0; --l) {
+    if (l_first < kDepth - 1) {                      // resuming below the top layer: the cotangent is layer l_first+1's dX
+        const int dn = p.L[l_first + 1].d;
+        dY = ws + p.dX;
+        dYg = bf ? ws + p.dX16 : dY;
+        ld_dYg = bf ? pad8(dn) : dn;
+    }
+    for (int l = l_first; l >= l_last; --l) {
         const LayerPlan& L = p.L[l];
         const LayerW w = layer_weights(p, l, W, ws, prec);
         const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
@@ -560,7 +566,8 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
 int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* mask_idx, const float* x2,
                   const float* main_feat, const float* g_pred, const float* g_fv, float* const* G, float* x2_grad,
                   float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias,
-                  float* pl_out = nullptr /* non-null: also sweep the path-length cotangent (stacked) into pl_out */) {
+                  float* pl_out = nullptr /* non-null: also sweep the path-length cotangent (stacked) into pl_out */,
+                  int phase = -1 /* -1: everything; 0: down to transformer layer 1; 1: layer 0 and masking; 2: conv */) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
     SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
@@ -569,6 +576,9 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     float* ws = (float*)workspace;
     SideStream* sd = get_side();
     const cudaStream_t sg = sd ? sd->s : st;
+    const int sweeps = pl_out ? 2 : 1;
+    float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
+    if (phase <= 0) {
     // every parameter gradient is accumulated into (split-K / column-sum / LayerNorm reductions): clear them once,
     // on the side stream, which then also carries the regressor weight gradients
     SCAT_PROPAGATE(order_after(sd, st, sg));
@@ -576,8 +586,6 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     cudaEvent_t zeroed = nullptr;
     SCAT_PROPAGATE(side_mark(sd, sg, &zeroed));
     // regressor + root-relative backward
-    const int sweeps = pl_out ? 2 : 1;
-    float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
     SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], up, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
                                         p.NP, p.it, 1, st, /*skip_main_feat_gemm=*/1));
     if (pl_out) {
@@ -607,7 +615,15 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 1, sg));
         SCAT_PROPAGATE(side_wait(st, zeroed));        // the main stream reduces into the gradients from here on
     }
-    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps, sd));
+    }
+    // the gradients of layers 2, 1 and of the regressor are final after phase 0: a data-parallel caller can start
+    // reducing that part of the bucket while phase 1 runs; layer 0 (the bulk of the bucket) is final after phase 1 and
+    // its reduction overlaps the conv backward of phase 2
+    if (phase != 2) {
+    const int l_first = phase == 1 ? 0 : kDepth - 1, l_last = phase == 0 ? 1 : 0;
+    SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps, sd,
+                                        l_first, l_last));
+    if (phase == 0) return 0;
     // through masking / positional encoding into the conv output
     SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st, 1));
     if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
@@ -616,6 +632,8 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     if (g_fv != nullptr) {
         SCAT_CHECK_CUDA(launch_k(add_inplace_kernel, dim3(148 * 4), dim3(256), 0, st, ws + p.dFv, g_fv, (long long)p.M * p.D));
         SCAT_CHECK_LAUNCH();
+    }
+    if (phase == 1) return 0;
     }
     if (d.precision != PREC_FP32) {
         SCAT_PROPAGATE(launch_split_tf32(ws + p.dFv, ws + p.dFv2, p.B, p.T, p.D, st));
@@ -676,28 +694,53 @@ int scat_proj_loss(int32_t batch, int32_t n_tokens, int32_t token_dim, const flo
                             l_weight_2d, grad_scale, losses, grad_pred, scratch, batch, (cudaStream_t)stream);
 }
 
+static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                                const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                                const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d, float grad_scale,
+                                float* pred_params, float* feat_visual, float* pl_term, float* losses, float* const* grads,
+                                float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream,
+                                int phase) {
+    SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
+    SCAT_REQUIRE(phase >= -1 && phase <= 2, kErrBadArg, "train_step: phase %d", phase);
+    cudaStream_t st = (cudaStream_t)stream;
+    // The path-length VJP is a dgrad-only sweep of the same graph as the backward and its result carries no
+    // gradient (hand_net.py:396, train.py:201), so it rides along with the real cotangent: one stacked sweep.
+    const bool pl = desc->pl_reg != 0;
+    HeadPlan p;
+    SCAT_PROPAGATE(make_plan(*desc, p));
+    float* ws = (float*)workspace;
+    if (phase <= 0) {
+        SCAT_PROPAGATE(head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual,
+                                    pl_term, workspace, workspace_bytes, st, /*defer_pl=*/true));
+        SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, nullptr, p.T * p.D, p.T, l_weight_3d, l_weight_2d,
+                                        grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch, p.B, st));
+    }
+    SCAT_PROPAGATE(head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
+                                 main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr, phase));
+    if (pl && (phase == -1 || phase == 1))       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
+        SCAT_PROPAGATE(launch_pl_loss_add(pl_term, p.T * p.D, p.T, losses, ws + p.pl_scratch, p.B, st));
+    return 0;
+}
+
 int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, const float* pe,
                          const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
                          const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d, float grad_scale,
                          float* pred_params, float* feat_visual, float* pl_term, float* losses, float* const* grads,
                          float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream) {
-    SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
-    cudaStream_t st = (cudaStream_t)stream;
-    // The path-length VJP is a dgrad-only sweep of the same graph as the backward and its result carries no
-    // gradient (hand_net.py:396, train.py:201), so it rides along with the real cotangent: one stacked sweep.
-    const bool pl = desc->pl_reg != 0;
-    SCAT_PROPAGATE(head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual,
-                                pl_term, workspace, workspace_bytes, st, /*defer_pl=*/true));
-    HeadPlan p;
-    SCAT_PROPAGATE(make_plan(*desc, p));
-    float* ws = (float*)workspace;
-    SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, nullptr, p.T * p.D, p.T, l_weight_3d, l_weight_2d,
-                                    grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch, p.B, st));
-    SCAT_PROPAGATE(head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
-                                 main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr));
-    if (pl)       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
-        SCAT_PROPAGATE(launch_pl_loss_add(pl_term, p.T * p.D, p.T, losses, ws + p.pl_scratch, p.B, st));
-    return 0;
+    return head_train_step_impl(desc, params, pe, mean_params, mask_idx, x2, main_feat, labels, ld_labels, l_weight_3d,
+                                l_weight_2d, grad_scale, pred_params, feat_visual, pl_term, losses, grads, x2_grad,
+                                main_feat_grad, workspace, workspace_bytes, stream, -1);
+}
+
+int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                               const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                               const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d,
+                               float grad_scale, float* pred_params, float* feat_visual, float* pl_term, float* losses,
+                               float* const* grads, float* x2_grad, float* main_feat_grad, void* workspace,
+                               size_t workspace_bytes, void* stream, int32_t phase) {
+    return head_train_step_impl(desc, params, pe, mean_params, mask_idx, x2, main_feat, labels, ld_labels, l_weight_3d,
+                                l_weight_2d, grad_scale, pred_params, feat_visual, pl_term, losses, grads, x2_grad,
+                                main_feat_grad, workspace, workspace_bytes, stream, phase);
 }
 
 int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const int32_t* mask_idx,

@@ -14,15 +14,20 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    """One contiguous fp32 buffer whose slices are the ``.grad`` of the given parameters."""
+    """One contiguous fp32 buffer whose slices are the ``.grad`` of the given parameters.  ``flat`` lets the caller
+    supply the storage (peer-mapped memory for the NVLink all-reduce, see ``PeerMemory``)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], flat: torch.Tensor = None):
         self.params: List[torch.nn.Parameter] = list(params)
         if not self.params:
             raise ValueError("FlatGradBucket needs at least one parameter")
         dev, dt = self.params[0].device, self.params[0].dtype
         sizes = [p.numel() for p in self.params]
-        self.flat = torch.zeros(sum(sizes), device=dev, dtype=dt)
+        if flat is None:
+            flat = torch.zeros(sum(sizes), device=dev, dtype=dt)
+        elif flat.numel() != sum(sizes) or flat.dtype != dt or flat.device != dev or not flat.is_contiguous():
+            raise ValueError("FlatGradBucket: supplied storage does not match the parameters")
+        self.flat = flat
         self.views: List[torch.Tensor] = []
         off = 0
         for p, n in zip(self.params, sizes):
@@ -34,11 +39,111 @@ class FlatGradBucket:
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
 
-    def all_reduce(self, group=None, async_op: bool = False):
-        """Sum the bucket over the process group (no-op for a single process)."""
+    def all_reduce(self, group=None, async_op: bool = False, lo: int = 0, hi: int = None):
+        """Sum the bucket (or its slice [lo, hi)) over the process group (no-op for a single process)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        part = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
+        return dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class _DevicePtr:
+    """A raw device allocation seen by torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, address: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (address, False), "version": 2}
+
+
+class PeerMemory:
+    """The gradient bucket of every rank of this node, mapped into this process, and the one-kernel all-reduce over
+    it (csrc/dp_allreduce.cu, include/scat_b200.h scat_peer_*).
+
+    Each rank allocates ``n_floats`` (rounded up to 4) of device memory plus a signal area through the library
+    (plain cudaMalloc, so the CUDA IPC handle covers exactly the allocation), the 64-byte handles travel through
+    one ``all_gather`` of the process group, and every rank opens its peers'.  ``flat`` is the local bucket as a
+    torch tensor; ``enqueue(stream)`` launches the all-reduce of ``[lo, hi)`` (capturable into a CUDA graph).
+    All ranks must sit on one node with peer access (NVLink / NVSwitch) and issue the same sequence of calls.
+    """
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._check = C, _lib.check
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world not in (1, 2, 4, 8):
+            raise ValueError(f"PeerMemory: world size {self.world} (1, 2, 4 or 8 GPUs of one node)")
+        self.device = torch.device(device)
+        self.n = int(n_floats)
+        self.n_pad = (self.n + 3) // 4 * 4
+        self._opened: List[int] = []
+        with torch.cuda.device(self.device):
+            self._bucket = self._alloc(self.n_pad * 4)
+            self._signal = self._alloc(int(self.lib.scat_peer_signal_bytes()))
+            handles = torch.empty(128, dtype=torch.uint8)
+            buf = (C.c_uint8 * 64)()
+            for i, p in enumerate((self._bucket, self._signal)):
+                self._check(self.lib.scat_peer_export(p, C.cast(buf, C.c_void_p)), "scat_peer_export")
+                handles[64 * i: 64 * i + 64] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+            if self.world > 1:
+                mine = handles.to(self.device)
+                every = torch.empty(self.world * 128, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(every, mine, group=group)
+                every = every.cpu().view(self.world, 128)
+            self.buckets, self.signals = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.buckets.append(self._bucket)
+                    self.signals.append(self._signal)
+                    continue
+                for i, dst in enumerate((self.buckets, self.signals)):
+                    raw = (C.c_uint8 * 64)(*every[r, 64 * i: 64 * i + 64].tolist())
+                    out = C.c_void_p()
+                    self._check(self.lib.scat_peer_open(C.cast(raw, C.c_void_p), C.byref(out)), "scat_peer_open")
+                    self._opened.append(out.value)
+                    dst.append(out.value)
+            self._bucket_arr = (C.c_void_p * self.world)(*self.buckets)
+            self._signal_arr = (C.c_void_p * self.world)(*self.signals)
+            self._holder = _DevicePtr(self._bucket, self.n_pad)
+            self.flat_padded = torch.as_tensor(self._holder, device=self.device)
+            self.flat = self.flat_padded[: self.n]
+            if self.world > 1:
+                dist.barrier(group=group)          # every peer has mapped everything before the first kernel
+            torch.cuda.synchronize()
+
+    def _alloc(self, nbytes: int) -> int:
+        out = self._C.c_void_p()
+        self._check(self.lib.scat_peer_alloc(nbytes, self._C.byref(out)), "scat_peer_alloc")
+        return out.value
+
+    def enqueue(self, stream_ptr: int, lo: int = 0, hi: int = None):
+        """Sum elements [lo, hi) (multiples of 4; hi=None: the whole bucket) over all ranks, in place, on ``stream``."""
+        hi = self.n_pad if hi is None else hi
+        self._check(self.lib.scat_peer_allreduce(self._bucket_arr, self._signal_arr, self.rank, self.world, lo, hi,
+                                                 stream_ptr), "scat_peer_allreduce")
+
+    def timed_out(self) -> bool:
+        """True when a kernel gave up waiting for a peer (synchronises the device)."""
+        out = self._C.c_int32(0)
+        self._check(self.lib.scat_peer_error(self._signal, self._C.byref(out)), "scat_peer_error")
+        return bool(out.value)
+
+    def close(self):
+        """Unmap the peers and free the local memory (every rank, after a barrier: nobody may still be reading)."""
+        if self._bucket is None:
+            return
+        torch.cuda.synchronize()
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            self.lib.scat_peer_close(p)
+        self.flat = self.flat_padded = self._holder = None
+        self.lib.scat_peer_free(self._bucket)
+        self.lib.scat_peer_free(self._signal)
+        self._bucket = self._signal = None
 
 
 def world_size(group=None) -> int:

@@ -4,7 +4,15 @@
 35 tensors, persistent input/output buffers and a caller-visible workspace.  ``step()`` runs
 
     forward -> path-length VJP -> projection + losses -> backward          (scat_head_train_step)
-    -> all-reduce(sum) of the flat gradient bucket over NCCL when world_size > 1
+    -> all-reduce(sum) of the flat gradient bucket when world_size > 1
+
+The all-reduce (``comm``): "peer" (default on GPUs of one node) keeps the bucket in CUDA-IPC peer-mapped memory and
+sums it with ONE kernel of this library over NVLink (dp.PeerMemory, csrc/dp_allreduce.cu), captured into the same CUDA
+graph as the step -- no host work, no extra launch gap, bit-identical sums on every rank.  "nccl" calls
+``torch.distributed.all_reduce`` after the step; with ``phased=True`` the step is issued in three phases
+(scat_head_train_step_phase) and the all-reduce of each finished part of the bucket runs on a communication stream
+under the next phase (measured on 8 B200s this does not beat the single NCCL call, profiles/README.md, so it is
+opt-in).
 
 Samples are independent, so data parallelism is pure batch sharding: every rank holds the
 same weights and the same host-drawn mask indices, the local loss gradient is scaled by 1/world_size inside
@@ -31,7 +39,8 @@ from ._lib import check, ptr, ptr_array
 class HeadTrainStep:
     def __init__(self, net, batch: int, l_weight_3d: float = 1e5, l_weight_2d: float = 10.0, *,
                  need_x2_grad: bool = True, need_main_feat_grad: bool = True, use_graph: bool = True,
-                 process_group=None, input_slots: int = 1):
+                 process_group=None, input_slots: int = 1, phased: Optional[bool] = None,
+                 comm: str = "auto"):
         self.net = net
         self.batch = int(batch)
         self.w3d, self.w2d = float(l_weight_3d), float(l_weight_2d)
@@ -43,7 +52,16 @@ class HeadTrainStep:
         self.pg = process_group
         self.world = dp.world_size(process_group)
         self.params = net.head_parameters()
-        self.bucket = dp.FlatGradBucket(self.params)      # p.grad are views of one flat buffer
+        if comm not in ("auto", "peer", "nccl"):
+            raise ValueError(f"comm={comm!r}: 'auto', 'peer' or 'nccl'")
+        if comm == "auto":
+            comm = "peer" if self.world in (2, 4, 8) else "nccl"
+        self.comm = comm if self.world > 1 else "none"
+        self.peer = None
+        if self.comm == "peer":                            # bucket lives in memory every rank of the node has mapped
+            self.peer = dp.PeerMemory(sum(p.numel() for p in self.params), dev, process_group)
+        # p.grad are views of one flat buffer
+        self.bucket = dp.FlatGradBucket(self.params, flat=self.peer.flat if self.peer is not None else None)
         r = net.mask_rate
         self.n_masked = int(r * net.full_content) if (r >= 0.1 and r <= 0.9) else 0
         self.cfg = net.config(self.n_masked)
@@ -65,6 +83,14 @@ class HeadTrainStep:
         self.last_mask = []
         self.use_graph = use_graph
         self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * self.n_slots
+        # phased issue (multi-rank): per slot three graphs, a communication stream, and the split points of the
+        # bucket = first element of parameter 2 (transformer layer 0) and 13 (layer 1), in state_dict order
+        self.phase_graphs: List[Optional[tuple]] = [None] * self.n_slots
+        self.phased = bool(phased) and self.peer is None
+        self.graphs_ar: List[Optional[torch.cuda.CUDAGraph]] = [None] * self.n_slots   # step + peer all-reduce
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.phased else None
+        self.split = sum(p.numel() for p in self.params[:13])
+        self.split0 = sum(p.numel() for p in self.params[:2])
 
     # single-slot views kept for callers that use one buffer set
     @property
@@ -80,20 +106,21 @@ class HeadTrainStep:
         return self.labelss[0]
 
     # ------------------------------------------------------------------------------------------
-    def _enqueue(self, slot: int = 0):
-        """Enqueue one fused step on the current stream (graph-capturable: no allocation, no sync)."""
+    def _enqueue(self, slot: int = 0, phase: int = -1):
+        """Enqueue one fused step (or one phase of it) on the current stream (graph-capturable: no allocation, no
+        sync)."""
         cfg = self.cfg
         d = cfg.desc(self.batch)
         pe = self.net.positionalEncoding.pe[0] if cfg.pos_embed else None
         labels = self.labelss[slot]
-        check(self.lib.scat_head_train_step(
+        check(self.lib.scat_head_train_step_phase(
             C.byref(d), ptr_array([p.data for p in self.params]), ptr(pe), ptr(self.net.mean_params.reshape(-1)),
             ptr(self.mask_dev) if self.n_masked else None, ptr(self.x2s[slot]), ptr(self.main_feats[slot]),
             ptr(labels), labels.shape[1], self.w3d, self.w2d, 1.0 / self.world, ptr(self.pred),
             ptr(self.feat_visual), ptr(self.pl), ptr(self.losses), ptr_array(self.bucket.views), ptr(self.x2_grad),
-            ptr(self.main_feat_grad), ptr(self.ws), self.ws.numel(), SF.stream_ptr()), "scat_head_train_step")
+            ptr(self.main_feat_grad), ptr(self.ws), self.ws.numel(), SF.stream_ptr(), phase), "scat_head_train_step")
 
-    def _capture(self, slot: int):
+    def _warm(self, slot: int):
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -101,10 +128,33 @@ class HeadTrainStep:
                 self._enqueue(slot)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+
+    def _capture(self, slot: int):
+        self._warm(slot)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._enqueue(slot)
         self.graphs[slot] = g
+
+    def _capture_ar(self, slot: int):
+        self._warm(slot)
+        self.peer.enqueue(SF.stream_ptr())                 # load the kernel outside capture (every rank does)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue(slot)
+            self.peer.enqueue(SF.stream_ptr())
+        self.graphs_ar[slot] = g
+
+    def _capture_phases(self, slot: int):
+        self._warm(slot)
+        gs = []
+        for phase in (0, 1, 2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(slot, phase)
+            gs.append(g)
+        self.phase_graphs[slot] = tuple(gs)
 
     def set_mask(self, mask_idx=None):
         """Draw (or take) the token mask on the host and stage it for the next step.  Consumes exactly one
@@ -139,17 +189,45 @@ class HeadTrainStep:
         cur = torch.cuda.current_stream()
         if self.copied[slot] is not None:
             cur.wait_event(self.copied[slot])
-        if self.use_graph:
-            if self.graphs[slot] is None:
-                self._capture(slot)
-            self.graphs[slot].replay()
+        overlap = allreduce and self.phased
+        if allreduce and self.peer is not None:            # the all-reduce kernel is part of the step's graph
+            if self.use_graph:
+                if self.graphs_ar[slot] is None:
+                    self._capture_ar(slot)
+                self.graphs_ar[slot].replay()
+            else:
+                self._enqueue(slot)
+                self.peer.enqueue(SF.stream_ptr())
+        elif not overlap:
+            if self.use_graph:
+                if self.graphs[slot] is None:
+                    self._capture(slot)
+                self.graphs[slot].replay()
+            else:
+                self._enqueue(slot)
         else:
-            self._enqueue(slot)
+            # each phase is followed by the all-reduce, on the communication stream, of the part of the bucket it
+            # finished, which overlaps the next phase
+            if self.use_graph and self.phase_graphs[slot] is None:
+                self._capture_phases(slot)
+            parts = ((self.split, None), (self.split0, self.split), (0, self.split0))
+            for phase in (0, 1, 2):
+                if self.use_graph:
+                    self.phase_graphs[slot][phase].replay()
+                else:
+                    self._enqueue(slot, phase)
+                if phase < 2:
+                    self.comm_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.comm_stream):
+                        self.bucket.all_reduce(self.pg, lo=parts[phase][0], hi=parts[phase][1])
         if self.n_slots > 1:
             ev = torch.cuda.Event()
             ev.record(cur)
             self.consumed[slot] = ev
-        if allreduce:
+        if overlap:
+            self.bucket.all_reduce(self.pg, hi=self.split0)
+            cur.wait_stream(self.comm_stream)
+        elif allreduce and self.peer is None:
             self.bucket.all_reduce(self.pg)
         return self.losses
 

@@ -152,6 +152,41 @@ def test_fused_train_step_equals_module_autograd():
         assert rel_max(ts.x2_grad, r["x2_grad"]) < 1e-6
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_phased_train_step_equals_single_call(precision):
+    """The phased issue used for data-parallel overlap (scat_head_train_step_phase 0, 1, 2; each phase leaves a
+    part of the gradient bucket final) gives the same losses and gradients as the single call (up to the summation
+    order of the split-K atomics, 1e-5 of the largest element)."""
+    from scat_b200.train_step import HeadTrainStep
+    opt, W, net, x2, mf, labels = _config2(precision, B=8)
+    out = []
+    for phased, use_graph in ((False, False), (True, False), (True, True)):
+        ts = HeadTrainStep(net, 8, use_graph=use_graph, phased=phased)
+        ts.load_inputs(torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda(), torch.from_numpy(labels).cuda())
+        ts.set_mask(list(range(ts.n_masked)))
+        if phased:
+            # after phase 0 alone the tail of the bucket (layers 1, 2, regressor) is already final
+            ts._enqueue(0, 0)
+            torch.cuda.synchronize()
+            tail = ts.bucket.flat[ts.split:].clone()
+            ts._enqueue(0, 1)                                # ... and after phase 1 layer 0 and the mask token
+            torch.cuda.synchronize()
+            mid = ts.bucket.flat[ts.split0:ts.split].clone()
+            mask_token = ts.bucket.views[0].clone()
+        for _ in range(2):
+            losses = ts.step()
+        torch.cuda.synchronize()
+        if phased:
+            assert rel_max(tail, ts.bucket.flat[ts.split:]) < 1e-5
+            assert rel_max(mid, ts.bucket.flat[ts.split0:ts.split]) < 1e-5
+            assert rel_max(mask_token, ts.bucket.views[0]) < 1e-5
+        out.append((losses.clone(), ts.bucket.flat.clone(), ts.x2_grad.clone(), ts.main_feat_grad.clone(),
+                    ts.pred.clone()))
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert rel_max(b, a) < 1e-5
+
+
 def test_full_size_properties_tf32():
     """Size-independent checks at config-2 size on the default (TF32) path."""
     opt, W, net, x2, mf, labels = _config2("tf32")
