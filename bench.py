@@ -291,6 +291,23 @@ def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
                         "; every GEMM shape of the step timed alone from a CUDA graph with the operand storage the step uses"
                         + "; weight gradients split-K with reductions in L2, as in the step"}
         kernels.insert(0, gemm)
+    # --- fused Adam over the flat head parameters: 28 B/element (p, g, m, v read; p, m, v written), HBM bound.  Buffers
+    # (4 x 15 MB) fit L2, so eight independent sets are rotated to keep the traffic in HBM ---
+    n_par = ts.flat_params.numel()
+    sets = [[torch.randn(n_par, device=dev) * 0.01, torch.randn(n_par, device=dev), torch.zeros(n_par, device=dev),
+             torch.zeros(n_par, device=dev)] for _ in range(8)]
+    turn = [0]
+
+    def adam_once():
+        a = sets[turn[0] % 8]
+        turn[0] += 1
+        check(lib.scat_adam_step(ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), n_par, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1 + turn[0],
+                                 None, None, stream_ptr()), "scat_adam_step")
+    t_adam = time_kernel(adam_once, iters=40, warm=8)
+    kernels.append({"kernel": "adam_kernel (fused optimiser step over the flat head parameters; outside the headline step)",
+                    "bound": "hbm", "achieved": 28.0 * n_par / t_adam / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "us": t_adam * 1e6, "traffic": None})
+    del sets
     for k in kernels:
         k["frac"] = k["achieved"] / k["peak"]
     dom = kernels[0]
@@ -412,6 +429,29 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = tt.tolist()
 
+    # the same step with the fused Adam update in the graph, after the all-reduce; reported
+    # next to the headline, which stays forward + backward (+ all-reduce) as BASELINE.json defines it
+    from scat_b200.optim import HeadAdam
+    keep_w = ts.flat_params.clone()
+    adam = HeadAdam(net.head_parameters(), lr=1e-4)
+    ts.attach_optimizer(adam)
+    for _ in range(3):
+        ts.set_mask(); ts.step(optimize=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ts.set_mask(); ts.step(optimize=True)
+    e1.record()
+    barrier()
+    t_opt = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_opt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_opt = float(tt.item())
+    ts.flat_params.copy_(keep_w)
+    with_opt = {"value": B * world * args.steps / t_opt, "unit": "samples/s", "ms_per_step": t_opt / args.steps * 1e3,
+                "optimizer": "fused Adam (scat_adam_step), in the step's CUDA graph"}
+
     # the other tensor-core path of BASELINE config 2 ("bf16 and TF32 paths"), device-resident, same run
     other = None
     other_prec = {"tf32": "bf16", "bf16": "tf32"}.get(args.precision)
@@ -451,7 +491,7 @@ def run_ours(args):
             "allreduce": {"none": "none", "peer": "one NVLink peer-memory kernel inside the step's CUDA graph",
                           "nccl": "NCCL, three phases overlapped with the backward" if ts.phased else
                                   "NCCL after the step"}[ts.comm],
-            "clocks": clocks, "roofline": roofline, "other_precision": other,
+            "clocks": clocks, "roofline": roofline, "other_precision": other, "with_optimizer": with_opt,
             "cpu_baseline": {"value": cpu["samples_per_s"], "unit": "samples/s", "cores": cpu["cores"], "kind": "port",
                              "sample": f"{cpu['steps']} steps of B={cpu['batch']} on {cpu_model()} (oracle port, fp32)"},
         }

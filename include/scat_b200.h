@@ -157,6 +157,16 @@ int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t
                         long long hi, void* stream);
 int scat_peer_error(const uint32_t* signal, int32_t* out);     /* synchronous read of the time-out flag */
 
+/* Fused Adam step over the head's flat parameter / gradient / moment buffers (all in the gradient bucket's order):
+ * replaces optim.Adam(self.net.parameters(), lr).step() (train.py:60,209) for the head's 35 tensors, arithmetic as
+ * torch.optim.Adam's single-tensor path (weight_decay is the coupled L2 form, no amsgrad).  `step` is the 1-based
+ * count of this update; if `step_dev` / `lr_dev` are non-null the kernel reads the count / learning rate from device
+ * memory instead (a captured CUDA graph then follows a changing schedule).  Buffers 16-byte aligned.  The scalar
+ * hyper-parameters are doubles, as torch holds them: 1 - beta is formed in double before it is rounded to fp32. */
+int scat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int32_t step, const float* lr_dev,
+                   const int32_t* step_dev, void* stream);
+
 /* Token-only transformer (HRNet-variant path up to feat.mean(dim=1), hand_net.py:193-203):
  *   tokens[B,n,dim] -> out[B,n,3], mean[B,3].  desc.channels = 0, desc.iteration = 0. */
 int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe,

@@ -215,8 +215,50 @@ def run_mano_case(name, B=6):
     print(f"[golden] {name}: oracle-vs-reference {d:.3e}; finite rows {finite.tolist()}")
 
 
+def run_adam_case(name="adam"):
+    """torch.optim.Adam itself (the reference's optimiser, train.py:60) on a few small tensors: 6 steps, the learning
+    rate changing between steps the way the warm-up schedule changes it, with and without weight decay."""
+    from oracle import adam_oracle
+    rng = np.random.Generator(np.random.PCG64(77))
+    shapes = [(1, 1, 37), (5, 8, 1, 1), (13,), (6, 11)]
+    p0 = [rng.standard_normal(s).astype(np.float32) * 0.05 for s in shapes]
+    grads = [[(rng.standard_normal(s) * (10.0 ** rng.integers(-4, 1))).astype(np.float32) for s in shapes]
+             for _ in range(6)]
+    lrs = [1e-4 * (k + 1) / 15 for k in range(3)] * 2
+    out = {"lrs": np.array(lrs), "n_tensors": np.array(len(shapes))}
+    for tag, wd in (("wd0", 0.0), ("wd1", 0.01)):
+        params = [torch.nn.Parameter(torch.from_numpy(a.copy())) for a in p0]
+        opt = torch.optim.Adam(params, lr=lrs[0], weight_decay=wd)
+        mine = [(a.copy(), np.zeros_like(a), np.zeros_like(a)) for a in p0]
+        for k in range(6):
+            for pg in opt.param_groups:
+                pg["lr"] = lrs[k]
+            for p, g in zip(params, grads[k]):
+                p.grad = torch.from_numpy(g.copy())
+            opt.step()
+            for (a, m, v), g in zip(mine, grads[k]):
+                adam_oracle.adam_step(a, g, m, v, k + 1, lrs[k], weight_decay=wd)
+        for i, p in enumerate(params):
+            ref = p.detach().numpy()
+            err = np.abs(mine[i][0] - ref).max() / np.abs(ref).max()
+            assert err < 2e-7, (tag, i, err)
+            out[f"{tag}_p{i}"] = ref
+            out[f"{tag}_m{i}"] = opt.state[p]["exp_avg"].numpy()
+            out[f"{tag}_v{i}"] = opt.state[p]["exp_avg_sq"].numpy()
+    for i, a in enumerate(p0):
+        out[f"p0_{i}"] = a
+    for k in range(6):
+        for i, g in enumerate(grads[k]):
+            out[f"g{k}_{i}"] = g
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ["adam"]:          # the optimiser fixture alone (needs torch only, not /root/reference)
+        run_adam_case("adam")
+        return
     hand_net, vt = _import_reference_head()
     # analytic anchors (SURVEY.md section 8c)
     random.seed(0)
@@ -239,6 +281,7 @@ def main():
                   pl_reg=True, mask_seed=4, in_seed=4)
     run_token_case(vt, hand_net, "tokens_n128_d196", B=2, n=128, dim=196, heads=8, mask_rate=0.2, mask_seed=5)
     run_mano_case("mano_lbs")
+    run_adam_case("adam")
 
 
 if __name__ == "__main__":

@@ -43,6 +43,8 @@ SIGNATURES = {
                                     _f, _f, _f, _sz, _f]),
     "scat_head_train_step_phase": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _i32, _fl, _fl, _fl, _f, _f, _f, _f, _pp,
                                           _f, _f, _f, _sz, _f, _i32]),
+    "scat_adam_step": (_i32, [_f, _f, _f, _f, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                             _i32, _f, _f, _f]),
     "scat_peer_signal_bytes": (_sz, []),
     "scat_peer_alloc": (_i32, [_sz, _pp]),
     "scat_peer_free": (_i32, [_f]),

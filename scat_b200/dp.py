@@ -13,28 +13,43 @@ import torch
 import torch.distributed as dist
 
 
+ALIGN = 32   # floats: every tensor of a flat buffer starts on a 128-byte boundary (TMA / 128-bit accesses need 16)
+
+
+def flat_layout(tensors, align: int = ALIGN):
+    """(offsets, total) of the tensors laid out one after the other, each start rounded up to ``align`` elements."""
+    offsets, off = [], 0
+    for t in tensors:
+        offsets.append(off)
+        off = (off + t.numel() + align - 1) // align * align
+    return offsets, off
+
+
 class FlatGradBucket:
-    """One contiguous fp32 buffer whose slices are the ``.grad`` of the given parameters.  ``flat`` lets the caller
-    supply the storage (peer-mapped memory for the NVLink all-reduce, see ``PeerMemory``)."""
+    """One contiguous fp32 buffer whose slices are the ``.grad`` of the given parameters (``flat_layout`` order and
+    alignment; the gaps stay zero).  ``flat`` lets the caller supply the storage (peer-mapped memory for the NVLink
+    all-reduce, see ``PeerMemory``)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], flat: torch.Tensor = None):
         self.params: List[torch.nn.Parameter] = list(params)
         if not self.params:
             raise ValueError("FlatGradBucket needs at least one parameter")
         dev, dt = self.params[0].device, self.params[0].dtype
-        sizes = [p.numel() for p in self.params]
+        self.offsets, total = flat_layout(self.params)
         if flat is None:
-            flat = torch.zeros(sum(sizes), device=dev, dtype=dt)
-        elif flat.numel() != sum(sizes) or flat.dtype != dt or flat.device != dev or not flat.is_contiguous():
+            flat = torch.zeros(total, device=dev, dtype=dt)
+        elif flat.numel() != total or flat.dtype != dt or flat.device != dev or not flat.is_contiguous():
             raise ValueError("FlatGradBucket: supplied storage does not match the parameters")
         self.flat = flat
         self.views: List[torch.Tensor] = []
-        off = 0
-        for p, n in zip(self.params, sizes):
-            v = self.flat[off: off + n].view_as(p)
+        for p, off in zip(self.params, self.offsets):
+            v = self.flat[off: off + p.numel()].view_as(p)
             p.grad = v
             self.views.append(v)
-            off += n
+
+    def payload_bytes(self) -> int:
+        """Bytes of actual gradients (without the alignment gaps)."""
+        return sum(p.numel() for p in self.params) * self.flat.element_size()
 
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
@@ -45,6 +60,46 @@ class FlatGradBucket:
             return None
         part = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
         return dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def _flat_view(tensors: List[torch.Tensor]):
+    """The 1-D tensor whose ``flat_layout`` slices the given tensors already are, or None."""
+    first = tensors[0]
+    offsets, total = flat_layout(tensors)
+    base = first.storage_offset()
+    for t, off in zip(tensors, offsets):
+        if (not t.is_contiguous() or t.dtype != first.dtype or t.device != first.device
+                or t.untyped_storage().data_ptr() != first.untyped_storage().data_ptr()
+                or t.storage_offset() != base + off):
+            return None
+    if (first.untyped_storage().nbytes() // first.element_size()) - base < total:
+        return None
+    return torch.empty(0, dtype=first.dtype, device=first.device).set_(first.untyped_storage(), base, (total,))
+
+
+def flatten_parameters(params: Iterable[torch.nn.Parameter]) -> torch.Tensor:
+    """Make ``p.data`` of every parameter a view of ONE flat buffer (``flat_layout`` order and alignment, zero gaps)
+    and return that buffer.  Idempotent: parameters that are already laid out that way are left alone.  Values are
+    preserved; anything that captured the old ``data_ptr`` (a CUDA graph) must be built afterwards."""
+    params = list(params)
+    flat = _flat_view([p.data for p in params])
+    if flat is not None:
+        return flat
+    offsets, total = flat_layout(params)
+    flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+    for p, off in zip(params, offsets):
+        n = p.numel()
+        flat[off: off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off: off + n].view(p.shape)
+    return flat
+
+
+def flat_gradients(params: Iterable[torch.nn.Parameter]):
+    """The flat buffer whose slices the ``.grad`` of the parameters are (a FlatGradBucket's), or None."""
+    params = list(params)
+    if any(p.grad is None for p in params):
+        return None
+    return _flat_view([p.grad for p in params])
 
 
 class _DevicePtr:

@@ -52,6 +52,8 @@ class HeadTrainStep:
         self.pg = process_group
         self.world = dp.world_size(process_group)
         self.params = net.head_parameters()
+        self.flat_params = dp.flatten_parameters(self.params)   # one buffer: the fused optimiser walks it linearly
+        self.opt = None
         if comm not in ("auto", "peer", "nccl"):
             raise ValueError(f"comm={comm!r}: 'auto', 'peer' or 'nccl'")
         if comm == "auto":
@@ -59,7 +61,7 @@ class HeadTrainStep:
         self.comm = comm if self.world > 1 else "none"
         self.peer = None
         if self.comm == "peer":                            # bucket lives in memory every rank of the node has mapped
-            self.peer = dp.PeerMemory(sum(p.numel() for p in self.params), dev, process_group)
+            self.peer = dp.PeerMemory(dp.flat_layout(self.params)[1], dev, process_group)
         # p.grad are views of one flat buffer
         self.bucket = dp.FlatGradBucket(self.params, flat=self.peer.flat if self.peer is not None else None)
         r = net.mask_rate
@@ -82,15 +84,14 @@ class HeadTrainStep:
         self.ws = SF.alloc_workspace(self.cfg, B, dev)
         self.last_mask = []
         self.use_graph = use_graph
-        self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * self.n_slots
+        self.graphs = {}      # (slot, all-reduce in graph, optimiser in graph) -> CUDAGraph
         # phased issue (multi-rank): per slot three graphs, a communication stream, and the split points of the
         # bucket = first element of parameter 2 (transformer layer 0) and 13 (layer 1), in state_dict order
         self.phase_graphs: List[Optional[tuple]] = [None] * self.n_slots
         self.phased = bool(phased) and self.peer is None
-        self.graphs_ar: List[Optional[torch.cuda.CUDAGraph]] = [None] * self.n_slots   # step + peer all-reduce
         self.comm_stream = torch.cuda.Stream(device=dev) if self.phased else None
-        self.split = sum(p.numel() for p in self.params[:13])
-        self.split0 = sum(p.numel() for p in self.params[:2])
+        self.split = self.bucket.offsets[13]
+        self.split0 = self.bucket.offsets[2]
 
     # single-slot views kept for callers that use one buffer set
     @property
@@ -129,22 +130,36 @@ class HeadTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
 
-    def _capture(self, slot: int):
-        self._warm(slot)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._enqueue(slot)
-        self.graphs[slot] = g
+    def attach_optimizer(self, opt):
+        """Make ``step(optimize=True)`` apply ``opt`` (a scat_b200.optim.HeadAdam over the same parameters) right after
+        the gradient all-reduce -- inside the step's CUDA graph whenever the all-reduce is."""
+        if opt.flat_params.data_ptr() != self.flat_params.data_ptr() or opt.n != self.flat_params.numel():
+            raise ValueError("attach_optimizer: the optimiser does not own this step's parameters")
+        self.opt = opt
+        self.graphs = {k: g for k, g in self.graphs.items() if not k[2]}
 
-    def _capture_ar(self, slot: int):
+    def _enqueue_all(self, slot: int, ar: bool, optimize: bool):
+        self._enqueue(slot)
+        if ar:
+            self.peer.enqueue(SF.stream_ptr())
+        if optimize:
+            self.opt.enqueue(self.bucket.flat)
+
+    def _capture(self, slot: int, ar: bool = False, optimize: bool = False):
         self._warm(slot)
-        self.peer.enqueue(SF.stream_ptr())                 # load the kernel outside capture (every rank does)
+        if ar:
+            self.peer.enqueue(SF.stream_ptr())             # load the kernel outside capture (every rank does)
+        if optimize:                                       # same for the optimiser kernel, without moving anything
+            keep = [t.clone() for t in (self.flat_params, self.opt.exp_avg, self.opt.exp_avg_sq)]
+            self.opt.enqueue(self.bucket.flat)
+            for dst, src in zip((self.flat_params, self.opt.exp_avg, self.opt.exp_avg_sq), keep):
+                dst.copy_(src)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._enqueue(slot)
-            self.peer.enqueue(SF.stream_ptr())
-        self.graphs_ar[slot] = g
+            self._enqueue_all(slot, ar, optimize)
+        self.graphs[(slot, ar, optimize)] = g
+        return g
 
     def _capture_phases(self, slot: int):
         self._warm(slot)
@@ -183,29 +198,22 @@ class HeadTrainStep:
             ev.record(cur)
             self.copied[slot] = ev
 
-    def step(self, allreduce: bool = True, slot: int = 0):
-        """Run fwd + pl VJP + loss + bwd on the inputs staged in ``slot``; returns the device tensor losses[4]
-        = [loss, l_3d, l_2d, l_pl] (local to this rank's shard)."""
+    def step(self, allreduce: bool = True, slot: int = 0, optimize: bool = False):
+        """Run fwd + pl VJP + loss + bwd on the inputs staged in ``slot`` (+ the gradient all-reduce, + the attached
+        optimiser's update with ``optimize``); returns the device tensor losses[4] = [loss, l_3d, l_2d, l_pl] (local
+        to this rank's shard)."""
         cur = torch.cuda.current_stream()
         if self.copied[slot] is not None:
             cur.wait_event(self.copied[slot])
-        overlap = allreduce and self.phased
-        if allreduce and self.peer is not None:            # the all-reduce kernel is part of the step's graph
-            if self.use_graph:
-                if self.graphs_ar[slot] is None:
-                    self._capture_ar(slot)
-                self.graphs_ar[slot].replay()
-            else:
-                self._enqueue(slot)
-                self.peer.enqueue(SF.stream_ptr())
-        elif not overlap:
-            if self.use_graph:
-                if self.graphs[slot] is None:
-                    self._capture(slot)
-                self.graphs[slot].replay()
-            else:
-                self._enqueue(slot)
-        else:
+        if optimize and self.opt is None:
+            raise RuntimeError("step(optimize=True): attach_optimizer first")
+        do_ar = allreduce and self.world > 1
+        ar_in_graph = do_ar and self.peer is not None       # the all-reduce kernel is part of the step's graph
+        opt_in_graph = optimize and (ar_in_graph or not do_ar)
+        overlap = do_ar and self.phased
+        if optimize:
+            self.opt.advance()
+        if overlap:
             # each phase is followed by the all-reduce, on the communication stream, of the part of the bucket it
             # finished, which overlaps the next phase
             if self.use_graph and self.phase_graphs[slot] is None:
@@ -220,6 +228,11 @@ class HeadTrainStep:
                     self.comm_stream.wait_stream(cur)
                     with torch.cuda.stream(self.comm_stream):
                         self.bucket.all_reduce(self.pg, lo=parts[phase][0], hi=parts[phase][1])
+        elif self.use_graph:
+            g = self.graphs.get((slot, ar_in_graph, opt_in_graph)) or self._capture(slot, ar_in_graph, opt_in_graph)
+            g.replay()
+        else:
+            self._enqueue_all(slot, ar_in_graph, opt_in_graph)
         if self.n_slots > 1:
             ev = torch.cuda.Event()
             ev.record(cur)
@@ -227,8 +240,10 @@ class HeadTrainStep:
         if overlap:
             self.bucket.all_reduce(self.pg, hi=self.split0)
             cur.wait_stream(self.comm_stream)
-        elif allreduce and self.peer is None:
+        elif do_ar and not ar_in_graph:
             self.bucket.all_reduce(self.pg)
+        if optimize and not opt_in_graph:
+            self.opt.enqueue(self.bucket.flat)
         return self.losses
 
 

@@ -75,6 +75,21 @@ def main():
         if ts.peer is not None:
             assert not ts.peer.timed_out()
         out[comm] = ts.bucket.flat.clone()
+        if comm == "peer":
+            # forward + backward + all-reduce + Adam in one graph: the replicas must stay bit-identical
+            from scat_b200.optim import HeadAdam
+            opt_ = HeadAdam(net.head_parameters(), lr=1e-4)
+            ts.attach_optimizer(opt_)
+            start = ts.flat_params.clone()
+            for _ in range(3):
+                ts.step(optimize=True)
+            torch.cuda.synchronize()
+            assert not ts.peer.timed_out()
+            mine = ts.flat_params.clone()
+            assert float((mine - start).abs().max()) > 0
+            theirs = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(theirs, mine)
+            assert all(torch.equal(t, mine) for t in theirs), "replicas diverged"
     a, b = out["nccl"], out["peer"]
     err = float((a - b).abs().max() / a.abs().max())
     assert err < 1e-5, err            # split-K atomics reorder sums between runs; the exchange itself is exact

@@ -55,8 +55,9 @@ def _worker(rank, world, port, out_dir):
             full = head_oracle.train_step(P, torch.from_numpy(x2), torch.from_numpy(mf), torch.from_numpy(labels),
                                           mean, mask_idx=mask, pl_reg=True)
             ref = torch.cat([full["grads"][k].reshape(-1) for k in W.keys()])
-            err = float((bucket.flat - ref).norm() / ref.norm())
-            np.save(os.path.join(out_dir, "err.npy"), np.array([err, bucket.nbytes()]))
+            got = torch.cat([v.reshape(-1) for v in bucket.views])
+            err = float((got - ref).norm() / ref.norm())
+            np.save(os.path.join(out_dir, "err.npy"), np.array([err, bucket.payload_bytes(), bucket.nbytes()]))
     finally:
         dist.destroy_process_group()
 
@@ -64,6 +65,7 @@ def _worker(rank, world, port, out_dir):
 def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    err, nbytes = np.load(tmp_path / "err.npy")
+    err, nbytes, padded = np.load(tmp_path / "err.npy")
     assert err < 1e-5
     assert int(nbytes) == 3795099 * 4          # one 15.18 MB fp32 bucket per step
+    assert 0 <= int(padded) - int(nbytes) < 35 * 128           # + alignment gaps (each tensor on a 128-byte boundary)

@@ -88,7 +88,37 @@ def test_shard_batch_partitions():
 def test_flat_grad_bucket_views():
     ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
     b = dp.FlatGradBucket(ps)
-    assert b.flat.numel() == 17 and b.nbytes() == 68
+    assert b.offsets == [0, dp.ALIGN] and b.flat.numel() == 2 * dp.ALIGN       # every tensor on a 128-byte boundary
+    assert b.payload_bytes() == 68 and b.nbytes() == 8 * dp.ALIGN
     b.flat.fill_(2.0)
-    assert torch.all(ps[0].grad == 2.0) and ps[1].grad.data_ptr() == b.flat[12:].data_ptr()
+    assert torch.all(ps[0].grad == 2.0) and ps[1].grad.data_ptr() == b.flat[dp.ALIGN:].data_ptr()
     assert b.all_reduce() is None                                   # single process: no-op
+
+
+def test_flatten_parameters_is_value_preserving_and_idempotent():
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(1, 1, 7))]
+    vals = [p.detach().clone() for p in ps]
+    flat = dp.flatten_parameters(ps)
+    A = dp.ALIGN
+    assert flat.numel() == 3 * A and all(torch.equal(p.data, v) for p, v in zip(ps, vals))
+    assert all(p.data_ptr() % (4 * A) == flat.data_ptr() % (4 * A) for p in ps)
+    assert float(flat[12:A].abs().sum()) == 0.0               # gaps are zero
+    again = dp.flatten_parameters(ps)
+    assert again.data_ptr() == flat.data_ptr() and again.numel() == 3 * A
+    flat[A] = 42.0
+    assert ps[1].data[0] == 42.0
+    bucket = dp.FlatGradBucket(ps)
+    g = dp.flat_gradients(ps)
+    assert g is not None and g.data_ptr() == bucket.flat.data_ptr() and g.numel() == 3 * A
+    ps[1].grad = torch.zeros(5)                               # a replaced .grad breaks the flat layout
+    assert dp.flat_gradients(ps) is None
+    ps[1].grad = None
+    assert dp.flat_gradients(ps) is None
+
+
+def test_head_adam_has_no_cpu_path():
+    from scat_b200.optim import HeadAdam
+    with pytest.raises(RuntimeError):
+        HeadAdam([torch.nn.Parameter(torch.zeros(4))], lr=1e-4)
+    with pytest.raises(ValueError):
+        HeadAdam([torch.nn.Parameter(torch.zeros(4))], lr=-1.0)

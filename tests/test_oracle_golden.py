@@ -113,3 +113,42 @@ def test_mano_oracle_fixture(golden_dir):
     o64 = mano_oracle.rot_pose_beta_to_mesh(g["rots"].astype(np.float64), g["poses"].astype(np.float64),
                                             g["betas"].astype(np.float64), a64)
     assert np.abs(o64 - g["out_fp64_oracle"]).max() < 1e-12
+
+
+def test_adam_oracle_matches_torch_adam_fixture(golden_dir):
+    """oracle/adam_oracle.py against tests/golden/adam.npz = torch.optim.Adam itself (train.py:60) run on the CPU:
+    6 steps, warm-up style learning-rate changes, with and without weight decay."""
+    from oracle import adam_oracle
+    g = np.load(os.path.join(golden_dir, "adam.npz"))
+    n = int(g["n_tensors"])
+    for tag, wd in (("wd0", 0.0), ("wd1", 0.01)):
+        for i in range(n):
+            p = g[f"p0_{i}"].copy()
+            m, v = np.zeros_like(p), np.zeros_like(p)
+            for k in range(6):
+                adam_oracle.adam_step(p, g[f"g{k}_{i}"], m, v, k + 1, float(g["lrs"][k]), weight_decay=wd)
+            for got, key in ((p, "p"), (m, "m"), (v, "v")):
+                ref = g[f"{tag}_{key}{i}"]
+                assert np.abs(got - ref).max() <= 2e-7 * np.abs(ref).max(), (tag, key, i)
+
+
+def test_warmup_schedule_restatement():
+    """GradualWarmupScheduler(multiplier=1, total_epoch=15, StepLR(gamma=1)) stepped with epoch + 1
+    (train.py:61-63,134): linear ramp base/15 .. base over 15 epochs, then constant.  The package itself is absent
+    (parity unpinned, oracle/adam_oracle.py); product and oracle restatements must at least agree."""
+    from oracle import adam_oracle
+    from scat_b200 import optim
+    base = 1e-4
+    for e in range(40):
+        want = base * min(e + 1, 15) / 15
+        assert adam_oracle.gradual_warmup_lr(base, e) == pytest.approx(want, rel=1e-12)
+        assert optim.gradual_warmup_lr(base, e) == adam_oracle.gradual_warmup_lr(base, e)
+
+    class Opt:
+        param_groups = [{"lr": base}]
+    o = Opt()
+    sched = optim.WarmupSchedule(o)
+    assert o.param_groups[0]["lr"] == 0.0                      # _LRScheduler.__init__ leaves last_epoch = 0
+    for e in range(20):
+        sched.step(e + 1)
+        assert o.param_groups[0]["lr"] == adam_oracle.gradual_warmup_lr(base, e)
