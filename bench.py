@@ -12,6 +12,7 @@ The ResNet backbone is outside the step (north_star: timed separately).  Prints 
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import random
@@ -345,7 +346,8 @@ def run_ours(args):
 
     opt = SimpleNamespace(vit_heads=8, pl_reg=True, iteration=3, pos_embed=True, mask_rate=0.2)
     mean = torch.from_numpy(synth.make_mean_params("hand"))
-    net = EncoderTransformer(opt, mean, precision=args.precision, backbone=Seam())
+    with contextlib.redirect_stdout(sys.stderr):       # the module prints like the reference's; stdout carries ONE JSON line
+        net = EncoderTransformer(opt, mean, precision=args.precision, backbone=Seam())
     sd = {k: torch.from_numpy(v) for k, v in synth.make_head_weights(8).items()}
     sd["positionalEncoding.pe"] = net.positionalEncoding.pe
     net.load_state_dict(sd, strict=True)
@@ -456,7 +458,8 @@ def run_ours(args):
     other = None
     other_prec = {"tf32": "bf16", "bf16": "tf32"}.get(args.precision)
     if other_prec is not None and world == 1:
-        net2 = EncoderTransformer(opt, mean, precision=other_prec, backbone=Seam())
+        with contextlib.redirect_stdout(sys.stderr):
+            net2 = EncoderTransformer(opt, mean, precision=other_prec, backbone=Seam())
         net2.load_state_dict(sd, strict=True)
         net2 = net2.to(dev)
         ts2 = HeadTrainStep(net2, B, 1e5, 10.0, use_graph=not args.no_graph)
