@@ -78,8 +78,17 @@ extern "C" int scat_adam_step(float* params, const float* grads, float* exp_avg,
                  "adam_step: betas (%g, %g) eps %g", beta1, beta2, eps);
     const uintptr_t al = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
     SCAT_REQUIRE(al % 16 == 0, kErrBadArg, "adam_step: buffers must be 16-byte aligned");
+    // exactly one resident wave (grid-stride loop): ncu showed 1.6 waves, i.e. a 0.6-wave tail, with a fixed 8 CTAs per SM
+    static int resident = 0;
+    if (resident == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        SCAT_CHECK_CUDA(cudaGetDevice(&dev));
+        SCAT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SCAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_kernel, 256, 0));
+        resident = std::max(1, sms * per_sm);
+    }
     const long long n4 = (n + 3) / 4;
-    const int grid = (int)std::min<long long>(148 * 8, (n4 + 255) / 256);
+    const int grid = (int)std::min<long long>(resident, (n4 + 255) / 256);
     SCAT_CHECK_CUDA(launch_k(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq,
                              n, lr, beta1, beta2, (float)eps, (float)weight_decay, (int)step, lr_dev, (const int*)step_dev));
     SCAT_CHECK_LAUNCH();
