@@ -336,6 +336,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     pk = peaks()
@@ -397,6 +398,8 @@ def run_ours(args):
     e1.record()
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
+    if ts.peer is not None and ts.peer.timed_out():
+        raise RuntimeError("a rank never arrived at the gradient all-reduce (20 s bounded wait): results are invalid")
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(ts.losses[0].item())
 

@@ -149,17 +149,34 @@ class PeerMemory:
                 dist.all_gather_into_tensor(every, mine, group=group)
                 every = every.cpu().view(self.world, 128)
             self.buckets, self.signals = [], []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.buckets.append(self._bucket)
-                    self.signals.append(self._signal)
-                    continue
-                for i, dst in enumerate((self.buckets, self.signals)):
-                    raw = (C.c_uint8 * 64)(*every[r, 64 * i: 64 * i + 64].tolist())
-                    out = C.c_void_p()
-                    self._check(self.lib.scat_peer_open(C.cast(raw, C.c_void_p), C.byref(out)), "scat_peer_open")
-                    self._opened.append(out.value)
-                    dst.append(out.value)
+            failure = None
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.buckets.append(self._bucket)
+                        self.signals.append(self._signal)
+                        continue
+                    peer = self._peer_device(r)
+                    if (torch.cuda.device_count() >= self.world and peer != self.device.index
+                            and not torch.cuda.can_device_access_peer(self.device.index, peer)):
+                        raise RuntimeError(f"no peer access from rank {self.rank} to rank {r}")
+                    for i, dst in enumerate((self.buckets, self.signals)):
+                        raw = (C.c_uint8 * 64)(*every[r, 64 * i: 64 * i + 64].tolist())
+                        out = C.c_void_p()
+                        self._check(self.lib.scat_peer_open(C.cast(raw, C.c_void_p), C.byref(out)), "scat_peer_open")
+                        self._opened.append(out.value)
+                        dst.append(out.value)
+            except Exception as e:               # decide together: a rank that gave up must not leave the others waiting
+                failure = e
+            if self.world > 1:
+                ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0:
+                    self._release()
+                    raise RuntimeError(f"PeerMemory: peer mapping failed on at least one rank"
+                                       f"{' (here: ' + str(failure) + ')' if failure else ''}")
+            elif failure:
+                raise failure
             self._bucket_arr = (C.c_void_p * self.world)(*self.buckets)
             self._signal_arr = (C.c_void_p * self.world)(*self.signals)
             self._holder = _DevicePtr(self._bucket, self.n_pad)
@@ -168,6 +185,20 @@ class PeerMemory:
             if self.world > 1:
                 dist.barrier(group=group)          # every peer has mapped everything before the first kernel
             torch.cuda.synchronize()
+
+    def _peer_device(self, rank: int) -> int:
+        """CUDA device index of ``rank`` on this node (one process per GPU, LOCAL_RANK == device index)."""
+        return (self.device.index - self.rank + rank) % max(torch.cuda.device_count(), 1)
+
+    def _release(self):
+        for p in self._opened:
+            self.lib.scat_peer_close(p)
+        self._opened = []
+        self.flat = self.flat_padded = self._holder = None
+        for p in (self._bucket, self._signal):
+            if p is not None:
+                self.lib.scat_peer_free(p)
+        self._bucket = self._signal = None
 
     def _alloc(self, nbytes: int) -> int:
         out = self._C.c_void_p()
@@ -193,12 +224,7 @@ class PeerMemory:
         torch.cuda.synchronize()
         if self.world > 1 and dist.is_initialized():
             dist.barrier(group=self.group)
-        for p in self._opened:
-            self.lib.scat_peer_close(p)
-        self.flat = self.flat_padded = self._holder = None
-        self.lib.scat_peer_free(self._bucket)
-        self.lib.scat_peer_free(self._signal)
-        self._bucket = self._signal = None
+        self._release()
 
 
 def world_size(group=None) -> int:

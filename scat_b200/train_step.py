@@ -56,12 +56,20 @@ class HeadTrainStep:
         self.opt = None
         if comm not in ("auto", "peer", "nccl"):
             raise ValueError(f"comm={comm!r}: 'auto', 'peer' or 'nccl'")
-        if comm == "auto":
+        auto = comm == "auto"
+        if auto:
             comm = "peer" if self.world in (2, 4, 8) else "nccl"
         self.comm = comm if self.world > 1 else "none"
         self.peer = None
         if self.comm == "peer":                            # bucket lives in memory every rank of the node has mapped
-            self.peer = dp.PeerMemory(dp.flat_layout(self.params)[1], dev, process_group)
+            try:
+                self.peer = dp.PeerMemory(dp.flat_layout(self.params)[1], dev, process_group)
+            except RuntimeError as e:                      # raised on every rank together (no peer access / IPC refused)
+                if not auto:
+                    raise
+                import sys
+                print(f"scat_b200: {e}; gradient all-reduce falls back to NCCL", file=sys.stderr)
+                self.comm = "nccl"
         # p.grad are views of one flat buffer
         self.bucket = dp.FlatGradBucket(self.params, flat=self.peer.flat if self.peer is not None else None)
         r = net.mask_rate
