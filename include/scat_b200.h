@@ -167,6 +167,26 @@ int scat_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    double beta1, double beta2, double eps, double weight_decay, int32_t step, const float* lr_dev,
                    const int32_t* step_dev, void* stream);
 
+/* ---- evaluation metrics on the device (the reference round-trips every frame to numpy,
+ * eval.py:691-753).  All joints are fp32 [batch, n_joints, 3]. ----
+ * scat_eval_procrustes: batch_compute_similarity_transform_torch (eval.py:110-161): per sample the similarity transform
+ *   (scale, rotation via 3x3 SVD with the det fix, translation) that takes `pred` closest to `gt`; writes the transformed
+ *   prediction to `aligned` (may alias pred) and the scale to `scale` (nullable).
+ * scat_eval_joint_errors: the device part of cal_PCK (eval.py:300-316) and of the MPJPE (eval.py:749):
+ *   d = || unit_scale*pred - unit_scale*gt || per joint (unit_scale 1000: metres -> millimetres, as the reference);
+ *   counts[k] = number of joints of the whole batch with d <= thresholds[k] (thresholds: HOST array of n_thresholds <= 64
+ *   doubles; counts: device, zeroed by the call) -- PCK_k = 100 * counts[k] / (batch * n_joints); mpjpe[b] (nullable) =
+ *   mean over the joints of || pred - gt ||.
+ * scat_eval_accel: compute_error_accel (data_utils/eval_utils.py:20-47) before its visibility selection:
+ *   out[i] = mean over joints of || (pred[i] - 2 pred[i+1] + pred[i+2]) - (gt[i] - 2 gt[i+1] + gt[i+2]) ||, i < n_frames-2;
+ *   gt == NULL gives compute_accel (eval_utils.py:6-17). */
+int scat_eval_procrustes(const float* pred, const float* gt, int32_t batch, int32_t n_joints, float* aligned, float* scale,
+                         void* stream);
+int scat_eval_joint_errors(const float* pred, const float* gt, int32_t batch, int32_t n_joints, float unit_scale,
+                           const double* thresholds, int32_t n_thresholds, unsigned long long* counts, float* mpjpe,
+                           void* stream);
+int scat_eval_accel(const float* pred, const float* gt, int32_t n_frames, int32_t n_joints, float* out, void* stream);
+
 /* Token-only transformer (HRNet-variant path up to feat.mean(dim=1), hand_net.py:193-203):
  *   tokens[B,n,dim] -> out[B,n,3], mean[B,3].  desc.channels = 0, desc.iteration = 0. */
 int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe,

@@ -254,8 +254,70 @@ def run_adam_case(name="adam"):
     print("wrote", name)
 
 
+def _reference_functions(path, names, extra=None):
+    """Execute only the named top-level function definitions of a reference source file (the file as a whole is not
+    importable)."""
+    import ast
+    src = open(path, encoding="utf-8").read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(n.name for n in keep) == sorted(names), [n.name for n in keep]
+    ns = {"np": np, "torch": torch}
+    ns.update(extra or {})
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def run_eval_case(name="eval_metrics"):
+    """The reference's own metric functions (eval.py:110-161,300-340; data_utils/eval_utils.py:6-47) on seeded joints."""
+    from oracle import eval_oracle
+    if not hasattr(np, "trapz"):
+        np.trapz = np.trapezoid
+    ev = _reference_functions(os.path.join(REF, "eval.py"),
+                              ["batch_compute_similarity_transform_torch", "cal_PCK", "_area_under_curve"])
+    eu = _reference_functions(os.path.join(REF, "data_utils", "eval_utils.py"), ["compute_accel", "compute_error_accel"])
+    rng = np.random.Generator(np.random.PCG64(4242))
+    B = 16
+    gt = (rng.standard_normal((B, 21, 3)) * 0.04).astype(np.float32)
+    gt -= gt[:, 1:2]
+    # predictions = a similarity transform of the target + noise, so alignment matters
+    pred = np.empty_like(gt)
+    for b in range(B):
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] *= -1
+        pred[b] = (rng.uniform(0.7, 1.4) * gt[b] @ q.T + rng.standard_normal(3) * 0.05
+                   + rng.standard_normal((21, 3)) * 0.012).astype(np.float32)
+    pt, gtt = torch.from_numpy(pred), torch.from_numpy(gt)
+    aligned = ev["batch_compute_similarity_transform_torch"](pt.clone(), gtt.clone())
+    mine = eval_oracle.similarity_transform(pt, gtt)
+    assert float((aligned - mine).abs().max()) < 2e-6, float((aligned - mine).abs().max())
+    rnge = np.arange(20, 51, 5)
+    out = {"pred": pred, "gt": gt, "aligned": aligned.numpy(), "rnge": rnge}
+    for tag, p in (("raw", pt), ("pa", aligned)):
+        pck = ev["cal_PCK"](p, gtt, rnge)
+        assert np.array_equal(pck, eval_oracle.cal_pck(p, gtt, rnge))
+        auc = ev["_area_under_curve"](rnge / rnge.max(), pck[:, -1])
+        assert abs(auc - eval_oracle.area_under_curve(rnge / rnge.max(), pck[:, -1])) < 1e-12
+        out[f"pck_{tag}"], out[f"auc_{tag}"] = pck, np.array(auc)
+    vis = np.ones(B, dtype=bool)
+    vis[[3, 9]] = False
+    out["accel"] = eu["compute_accel"](pred)
+    out["accel_err"] = eu["compute_error_accel"](joints_gt=gt, joints_pred=pred)
+    out["accel_err_vis"] = eu["compute_error_accel"](joints_gt=gt, joints_pred=pred, vis=vis)
+    out["vis"] = vis
+    assert np.allclose(out["accel"], eval_oracle.compute_accel(pred), rtol=0, atol=0)
+    assert np.array_equal(out["accel_err"], eval_oracle.compute_error_accel(gt, pred))
+    assert np.array_equal(out["accel_err_vis"], eval_oracle.compute_error_accel(gt, pred, vis))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ["eval"]:          # the evaluation-metric fixture alone
+        run_eval_case("eval_metrics")
+        return
     if sys.argv[1:] == ["adam"]:          # the optimiser fixture alone (needs torch only, not /root/reference)
         run_adam_case("adam")
         return
@@ -282,6 +344,7 @@ def main():
     run_token_case(vt, hand_net, "tokens_n128_d196", B=2, n=128, dim=196, heads=8, mask_rate=0.2, mask_seed=5)
     run_mano_case("mano_lbs")
     run_adam_case("adam")
+    run_eval_case("eval_metrics")
 
 
 if __name__ == "__main__":

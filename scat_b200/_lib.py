@@ -45,6 +45,9 @@ SIGNATURES = {
                                           _f, _f, _f, _sz, _f, _i32]),
     "scat_adam_step": (_i32, [_f, _f, _f, _f, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                              _i32, _f, _f, _f]),
+    "scat_eval_procrustes": (_i32, [_f, _f, _i32, _i32, _f, _f, _f]),
+    "scat_eval_joint_errors": (_i32, [_f, _f, _i32, _i32, _fl, C.POINTER(C.c_double), _i32, _f, _f, _f]),
+    "scat_eval_accel": (_i32, [_f, _f, _i32, _i32, _f, _f]),
     "scat_peer_signal_bytes": (_sz, []),
     "scat_peer_alloc": (_i32, [_sz, _pp]),
     "scat_peer_free": (_i32, [_f]),
