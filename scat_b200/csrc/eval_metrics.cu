@@ -44,18 +44,24 @@ __global__ void __launch_bounds__(kProcThreads) procrustes_kernel(const float* _
     for (int i = threadIdx.x; i < rows * row; i += kProcThreads) aligned[(size_t)b0 * row + i] = s1[i];
 }
 
-// one thread per (sample, joint): d = sqrt(sum_c (unit*p - unit*g)^2) with torch's rounding points (separate multiplies,
-// subtract, squares added left to right), counts[k] += d <= thresholds[k] (compared in double like numpy), and the
-// per-sample mean of the un-scaled distance
+// one thread per (sample, joint), whole samples per block (S = 256 / n of them): d = sqrt(sum_c (unit*p - unit*g)^2)
+// with torch's rounding points (separate multiplies, subtract, squares added left to right); counts[k] += d <=
+// thresholds[k] (compared in double like numpy) through per-block shared counters; mpjpe[b] = the per-sample mean of the
+// un-scaled distance, summed in joint order by one thread (deterministic)
 __global__ void __launch_bounds__(256) joint_error_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int batch,
-                                                          int n, float unit, Thresholds thr,
+                                                          int n, int S, float unit, Thresholds thr,
                                                           unsigned long long* __restrict__ counts, float* __restrict__ mpjpe) {
     pdl_sync();
-    const long long total = (long long)batch * n;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float sraw[256];
+    __shared__ unsigned int sc[kMaxThresholds];
+    if (threadIdx.x < kMaxThresholds) sc[threadIdx.x] = 0u;
+    __syncthreads();
+    const int ls = threadIdx.x / n, j = threadIdx.x - ls * n;
+    const long long b = (long long)blockIdx.x * S + ls;
+    const bool live = ls < S && b < batch;
     float d = 0.f, raw = 0.f;
-    const bool live = i < total;
     if (live) {
+        const long long i = b * n + j;
         float acc = 0.f, acc_raw = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -68,11 +74,18 @@ __global__ void __launch_bounds__(256) joint_error_kernel(const float* __restric
         d = __fsqrt_rn(acc);
         raw = __fsqrt_rn(acc_raw);
     }
+    sraw[threadIdx.x] = raw;
     for (int k = 0; k < thr.n; ++k) {
         const unsigned hit = __ballot_sync(0xffffffffu, live && (double)d <= thr.v[k]);
-        if ((threadIdx.x & 31) == 0 && hit) atomicAdd(&counts[k], (unsigned long long)__popc(hit));
+        if ((threadIdx.x & 31) == 0 && hit) atomicAdd(&sc[k], (unsigned)__popc(hit));
     }
-    if (mpjpe && live) atomicAdd(&mpjpe[i / n], raw / (float)n);
+    __syncthreads();
+    if (mpjpe && live && j == 0) {
+        float sum = 0.f;
+        for (int jj = 0; jj < n; ++jj) sum = __fadd_rn(sum, sraw[threadIdx.x + jj]);
+        mpjpe[b] = sum / (float)n;
+    }
+    if (threadIdx.x < thr.n && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
 }
 
 // one thread per (frame triple, joint): || (p[i] - 2 p[i+1] + p[i+2]) - (g[i] - 2 g[i+1] + g[i+2]) ||, averaged over
@@ -123,7 +136,8 @@ int scat_eval_joint_errors(const float* pred, const float* gt, int32_t batch, in
                            const double* thresholds, int32_t n_thresholds, unsigned long long* counts, float* mpjpe,
                            void* stream) {
     SCAT_REQUIRE(pred && gt, kErrBadArg, "eval_joint_errors: null tensor");
-    SCAT_REQUIRE(batch > 0 && n_joints > 0, kErrBadArg, "eval_joint_errors: batch %d joints %d", batch, n_joints);
+    SCAT_REQUIRE(batch > 0 && n_joints > 0 && n_joints <= 256, kErrBadArg, "eval_joint_errors: batch %d joints %d (1..256)", batch,
+                 n_joints);
     SCAT_REQUIRE(n_thresholds >= 0 && n_thresholds <= kMaxThresholds && (n_thresholds == 0 || (thresholds && counts)), kErrBadArg,
                  "eval_joint_errors: %d thresholds (at most %d, with a counts buffer)", n_thresholds, kMaxThresholds);
     cudaStream_t st = (cudaStream_t)stream;
@@ -131,10 +145,9 @@ int scat_eval_joint_errors(const float* pred, const float* gt, int32_t batch, in
     thr.n = n_thresholds;
     for (int k = 0; k < n_thresholds; ++k) thr.v[k] = thresholds[k];
     if (n_thresholds) SCAT_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * n_thresholds, st));
-    if (mpjpe) SCAT_CHECK_CUDA(cudaMemsetAsync(mpjpe, 0, sizeof(float) * batch, st));
-    const long long total = (long long)batch * n_joints;
-    SCAT_CHECK_CUDA(launch_k(joint_error_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pred, gt, (int)batch,
-                             (int)n_joints, unit_scale, thr, counts, mpjpe));
+    const int S = 256 / n_joints;                       // whole samples per block
+    SCAT_CHECK_CUDA(launch_k(joint_error_kernel, dim3((unsigned)ceil_div(batch, S)), dim3(256), 0, st, pred, gt, (int)batch,
+                             (int)n_joints, S, unit_scale, thr, counts, mpjpe));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
