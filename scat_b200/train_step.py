@@ -255,6 +255,18 @@ class HeadTrainStep:
         return self.losses
 
 
+    def close(self):
+        """Release the peer-mapped gradient bucket (multi-rank runs; every rank must call it).  The parameters'
+        ``.grad`` views die with it, so this is the last call on the object."""
+        if self.peer is not None:
+            self.graphs, self.phase_graphs = {}, [None] * self.n_slots
+            for p in self.params:
+                p.grad = None
+            self.bucket = None
+            self.peer.close()
+            self.peer = None
+
+
 class _NullCtx:
     def __enter__(self):
         return self
