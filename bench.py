@@ -374,6 +374,8 @@ def run_ours(args):
     c0 = lib.scat_launch_count()
     ts._enqueue()
     launches_per_step = int(lib.scat_launch_count() - c0)
+    if ts.peer is not None:
+        launches_per_step += 1          # the peer-memory all-reduce kernel captured behind the step
     torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
