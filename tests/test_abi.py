@@ -64,3 +64,33 @@ def test_kernels_are_blackwell_native(lib_path):
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(lib_path):
+    """Optimiser, peer all-reduce and evaluation-metric entry points reject bad arguments before touching CUDA
+    (negative SCAT_ERR_* code + message), so the checks run on a CPU-only box."""
+    from scat_b200 import _lib
+    lib = _lib.load()
+    fake = ctypes.c_void_p(0x1000)                      # never dereferenced: validation fails first
+    assert lib.scat_adam_step(None, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None) == -1
+    assert lib.scat_adam_step(fake, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None, None, None) == -1
+    assert b"step" in lib.scat_last_error_string()
+    assert lib.scat_adam_step(fake, fake, fake, fake, 16, 1e-4, 1.0, 0.999, 1e-8, 0.0, 1, None, None, None) == -1
+    misaligned = ctypes.c_void_p(0x1004)
+    assert lib.scat_adam_step(misaligned, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None) == -1
+    assert b"aligned" in lib.scat_last_error_string()
+
+    ptrs = (ctypes.c_void_p * 3)(0x1000, 0x2000, 0x3000)
+    assert lib.scat_peer_allreduce(ptrs, ptrs, 0, 3, 0, 64, None) == -3          # 1, 2, 4 or 8 ranks
+    assert lib.scat_peer_allreduce(ptrs, ptrs, 0, 2, 2, 64, None) == -1          # range not 16-byte aligned
+    assert lib.scat_peer_allreduce(ptrs, ptrs, 2, 2, 0, 64, None) == -1          # rank out of range
+    assert lib.scat_peer_allreduce(ptrs, ptrs, 0, 9, 0, 64, None) == -1
+    assert lib.scat_peer_signal_bytes() >= 296 * 8 * 4
+
+    assert lib.scat_eval_procrustes(fake, fake, 4, 2, fake, None, None) == -1     # fewer than 3 joints
+    assert lib.scat_eval_procrustes(fake, None, 4, 21, fake, None, None) == -1
+    thr = (ctypes.c_double * 65)()
+    assert lib.scat_eval_joint_errors(fake, fake, 4, 21, 1000.0, thr, 65, fake, None, None) == -1
+    assert b"thresholds" in lib.scat_last_error_string()
+    assert lib.scat_eval_accel(fake, None, 2, 21, fake, None) == -1               # needs 3 frames
+    assert lib.scat_head_train_step_phase.argtypes[-1] is ctypes.c_int32
