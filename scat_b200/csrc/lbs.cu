@@ -10,6 +10,8 @@
 //
 // derived buffer (scat_lbs_prepare), vertex dimension padded to VP = 784:
 //   J_template[16*3] | J_shapedirs[16*3*10] | vt_t[3][VP] | sd_t[10][3][VP] | pd_t[135][3][VP] | w_t[16][VP]
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace scat {
@@ -248,6 +250,254 @@ lbs_fwd_kernel(const float* __restrict__ derived, const float* __restrict__ hand
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL, off by default (SCAT_LBS_V2="S,NVT" selects it; unvalidated on hardware at the end of round 1, see
+// DESIGN.md section 9).  Same arithmetic as lbs_fwd_kernel, different blocking: S samples per CTA (8, 16 or 32) so each
+// 1.27 MB pass over the blend-shape tables in L2 serves more samples (159 KB of L2 traffic per sample at S = 8), NVT
+// vertices per thread, and the per-sample operands (pose weights, betas, skinning matrices) stored sample-minor /
+// 16-byte aligned in shared memory so they are fetched with LDS.128 instead of one LDS per FMA triple.
+template <int S>
+struct LbsSmemV2 {
+    float A[S][NJ][12];          // 48-byte rows: three float4
+    float pwT[NPW][S];           // sample-minor
+    float betaT[NB][S];
+    float Rg[S][9];
+    float root[S][3];
+    float Jtr[S][NJ][3];
+    float Rl[S][NJ][9];
+    float Jp[S][NJ][3];
+};
+
+template <int S, int NVT>
+__device__ __forceinline__ void lbs_vertices_v2(const LbsSmemV2<S>& sm, const float* __restrict__ derived, const int (&vid)[NVT],
+                                                int ns, int b0, float* __restrict__ out) {
+    const float* vt_t = derived + OFF_VT;
+    const float* sd_t = derived + OFF_SD;
+    const float* pd_t = derived + OFF_PD;
+    const float* w_t = derived + OFF_W;
+    float vp[NVT][S][3];
+#pragma unroll
+    for (int t = 0; t < NVT; ++t) {
+        const float m0 = vt_t[vid[t]], m1 = vt_t[VP + vid[t]], m2 = vt_t[2 * VP + vid[t]];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { vp[t][s][0] = m0; vp[t][s][1] = m1; vp[t][s][2] = m2; }
+    }
+#pragma unroll 1
+    for (int k = 0; k < NB + NPW; ++k) {                    // shape then pose blend shapes (tables are adjacent)
+        const float* tab = k < NB ? sd_t + (size_t)k * 3 * VP : pd_t + (size_t)(k - NB) * 3 * VP;
+        const float4* wrow = reinterpret_cast<const float4*>(k < NB ? sm.betaT[k] : sm.pwT[k - NB]);
+        float d[NVT][3];
+#pragma unroll
+        for (int t = 0; t < NVT; ++t) { d[t][0] = tab[vid[t]]; d[t][1] = tab[VP + vid[t]]; d[t][2] = tab[2 * VP + vid[t]]; }
+#pragma unroll
+        for (int s4 = 0; s4 < S / 4; ++s4) {
+            const float4 w = wrow[s4];
+            const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int t = 0; t < NVT; ++t) {
+                    vp[t][s4 * 4 + u][0] = fmaf(d[t][0], ws[u], vp[t][s4 * 4 + u][0]);
+                    vp[t][s4 * 4 + u][1] = fmaf(d[t][1], ws[u], vp[t][s4 * 4 + u][1]);
+                    vp[t][s4 * 4 + u][2] = fmaf(d[t][2], ws[u], vp[t][s4 * 4 + u][2]);
+                }
+        }
+    }
+    float wj[NVT][NJ];
+    int tip[NVT];
+#pragma unroll
+    for (int t = 0; t < NVT; ++t) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) wj[t][j] = w_t[j * VP + vid[t]];
+        tip[t] = -1;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) if (c_tips[q] == vid[t]) tip[t] = q;
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {                           // skinning (mano.py:339-348)
+        if (s >= ns) break;
+        float T[NVT][12];
+#pragma unroll
+        for (int t = 0; t < NVT; ++t)
+#pragma unroll
+            for (int q = 0; q < 12; ++q) T[t][q] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4* arow = reinterpret_cast<const float4*>(sm.A[s][j]);
+            const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2];
+            const float a[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+            for (int t = 0; t < NVT; ++t)
+#pragma unroll
+                for (int q = 0; q < 12; ++q) T[t][q] = fmaf(wj[t][j], a[q], T[t][q]);
+        }
+        const float* Rg = sm.Rg[s];
+#pragma unroll
+        for (int t = 0; t < NVT; ++t) {
+            if (vid[t] >= NV) continue;                     // padded lanes of the remainder pass
+            float x[3], y[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                x[r] = T[t][r * 4 + 0] * vp[t][s][0] + T[t][r * 4 + 1] * vp[t][s][1] + T[t][r * 4 + 2] * vp[t][s][2] + T[t][r * 4 + 3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) y[r] = Rg[r * 3 + 0] * x[0] + Rg[r * 3 + 1] * x[1] + Rg[r * 3 + 2] * x[2] - sm.root[s][r];
+            float* o = out + ((long long)(b0 + s) * 799 + 21 + vid[t]) * 3;
+            o[0] = y[0]; o[1] = y[1]; o[2] = y[2];
+            if (tip[t] >= 0) {
+                float* oj = out + ((long long)(b0 + s) * 799 + 16 + tip[t]) * 3;
+                oj[0] = y[0]; oj[1] = y[1]; oj[2] = y[2];
+            }
+        }
+    }
+}
+
+template <int S, int NVT>
+__global__ void __launch_bounds__(LBS_THREADS)
+lbs_fwd_v2_kernel(const float* __restrict__ derived, const float* __restrict__ hands_mean, const float* __restrict__ rots,
+                  const float* __restrict__ poses, const float* __restrict__ betas, float* __restrict__ out, int B) {
+    pdl_sync();
+    extern __shared__ __align__(16) unsigned char lbs_smem_raw[];
+    LbsSmemV2<S>& sm = *reinterpret_cast<LbsSmemV2<S>*>(lbs_smem_raw);
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * S;
+    const int ns = min(S, B - b0);
+
+    // ---- set-up phase: as lbs_fwd_kernel, stores re-laid out ----
+    for (int e = tid; e < S * NJ; e += LBS_THREADS) {
+        const int s = e / NJ, i = e % NJ;
+        float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (s < ns) {
+            if (i == 0) {
+                rodrigues(0.f, 0.f, 0.f, R);
+            } else {
+                const float* ps = poses + (long long)(b0 + s) * 45 + (i - 1) * 3;
+                const float* hm = hands_mean + (i - 1) * 3;
+                rodrigues(hm[0] + ps[0], hm[1] + ps[1], hm[2] + ps[2], R);
+            }
+        }
+        if (i > 0) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+                sm.pwT[(i - 1) * 9 + q][s] = s < ns ? R[q] - ((q == 0 || q == 4 || q == 8) ? 1.0f : 0.0f) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) sm.Rl[s][i][q] = R[q];
+    }
+    for (int e = tid; e < S * NB; e += LBS_THREADS) {
+        const int s = e / NB, k = e % NB;
+        sm.betaT[k][s] = s < ns ? betas[(long long)(b0 + s) * NB + k] : 0.f;
+    }
+    if (tid < S) {
+        float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (tid < ns) rodrigues(rots[(long long)(b0 + tid) * 3], rots[(long long)(b0 + tid) * 3 + 1], rots[(long long)(b0 + tid) * 3 + 2], R);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) sm.Rg[tid][q] = R[q];
+    }
+    __syncthreads();
+    for (int e = tid; e < S * NJ * 3; e += LBS_THREADS) {
+        const int s = e / (NJ * 3), jc = e % (NJ * 3);
+        float v = derived[OFF_JT + jc];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) v = fmaf(derived[OFF_JS + jc * NB + k], sm.betaT[k][s], v);
+        sm.Jp[s][jc / 3][jc % 3] = v;
+    }
+    __syncthreads();
+    if (tid < S) {
+        const int s = tid;
+        float G[NJ][12];
+#pragma unroll 1
+        for (int i = 0; i < NJ; ++i) {
+            float L[12];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) L[r * 4 + c] = sm.Rl[s][i][r * 3 + c];
+                L[r * 4 + 3] = (i == 0) ? sm.Jp[s][0][r] : sm.Jp[s][i][r] - sm.Jp[s][c_parent[i]][r];
+            }
+            if (i == 0) {
+#pragma unroll
+                for (int q = 0; q < 12; ++q) G[0][q] = L[q];
+            } else {
+                const float* Pm = G[c_parent[i]];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v = Pm[r * 4 + 0] * L[0 * 4 + c] + Pm[r * 4 + 1] * L[1 * 4 + c] + Pm[r * 4 + 2] * L[2 * 4 + c];
+                        if (c == 3) v += Pm[r * 4 + 3];
+                        G[i][r * 4 + c] = v;
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int i = 0; i < NJ; ++i) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float gj = G[i][r * 4 + 0] * sm.Jp[s][i][0] + G[i][r * 4 + 1] * sm.Jp[s][i][1] + G[i][r * 4 + 2] * sm.Jp[s][i][2];
+                sm.A[s][i][r * 4 + 0] = G[i][r * 4 + 0];
+                sm.A[s][i][r * 4 + 1] = G[i][r * 4 + 1];
+                sm.A[s][i][r * 4 + 2] = G[i][r * 4 + 2];
+                sm.A[s][i][r * 4 + 3] = G[i][r * 4 + 3] - gj;
+                sm.Jtr[s][i][r] = G[i][r * 4 + 3];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            sm.root[s][r] = sm.Rg[s][r * 3 + 0] * sm.Jtr[s][1][0] + sm.Rg[s][r * 3 + 1] * sm.Jtr[s][1][1] + sm.Rg[s][r * 3 + 2] * sm.Jtr[s][1][2];
+    }
+    __syncthreads();
+    for (int e = tid; e < ns * NJ * 3; e += LBS_THREADS) {
+        const int s = e / (NJ * 3), j = (e / 3) % NJ, r = e % 3;
+        const float* Rg = sm.Rg[s];
+        float v = Rg[r * 3 + 0] * sm.Jtr[s][j][0] + Rg[r * 3 + 1] * sm.Jtr[s][j][1] + Rg[r * 3 + 2] * sm.Jtr[s][j][2] - sm.root[s][r];
+        if (j == 1) v = 0.f;
+        out[((long long)(b0 + s) * 799 + j) * 3 + r] = v;
+    }
+
+    // ---- vertex phase: NVT vertices per thread; the table rows are padded to VP = 784, so lanes past 777 read zeros ----
+    for (int v0 = tid; v0 < VP; v0 += LBS_THREADS * NVT) {
+        int vid[NVT];
+#pragma unroll
+        for (int t = 0; t < NVT; ++t) vid[t] = min(v0 + t * LBS_THREADS, VP - 1);
+        bool any = false;
+#pragma unroll
+        for (int t = 0; t < NVT; ++t) {
+            if (v0 + t * LBS_THREADS >= NV) vid[t] = VP - 1;         // padding column: results discarded
+            any |= vid[t] < NV;
+        }
+        if (any) lbs_vertices_v2<S, NVT>(sm, derived, vid, ns, b0, out);
+    }
+}
+
+template <int S, int NVT>
+int launch_lbs_v2(const float* derived, const float* hands_mean, const float* rots, const float* poses, const float* betas,
+                  float* out, int B, cudaStream_t stream) {
+    const size_t smem = sizeof(LbsSmemV2<S>);
+    static bool raised = false;
+    if (!raised) {
+        SCAT_CHECK_CUDA(cudaFuncSetAttribute(lbs_fwd_v2_kernel<S, NVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raised = true;
+    }
+    SCAT_CHECK_CUDA(launch_k(lbs_fwd_v2_kernel<S, NVT>, dim3(ceil_div(B, S)), dim3(LBS_THREADS), smem, stream, derived, hands_mean,
+                             rots, poses, betas, out, B));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+// SCAT_LBS_V2 = "S,NVT" with S in {8, 16, 32} and NVT in {1, 2}; anything else (or unset) keeps lbs_fwd_kernel
+int lbs_v2_choice() {
+    static int choice = -1;
+    if (choice < 0) {
+        choice = 0;
+        const char* e = getenv("SCAT_LBS_V2");
+        int s = 0, n = 0;
+        if (e && sscanf(e, "%d,%d", &s, &n) == 2 && (s == 8 || s == 16 || s == 32) && (n == 1 || n == 2)) choice = s * 10 + n;
+    }
+    return choice;
+}
+
 }  // namespace
 
 size_t lbs_derived_floats() { return DERIVED_FLOATS; }
@@ -264,6 +514,14 @@ int launch_lbs_prepare_all(const float* v_template, const float* shapedirs, cons
 int launch_lbs_fwd_derived(const float* derived, const float* hands_mean, const float* rots, const float* poses,
                            const float* betas, float* out, int B, cudaStream_t stream) {
     SCAT_REQUIRE(derived && hands_mean && rots && poses && betas && out && B > 0, kErrBadArg, "lbs_fwd: bad args");
+    switch (lbs_v2_choice()) {          // experimental blockings, off unless SCAT_LBS_V2 is set
+        case 81: return launch_lbs_v2<8, 1>(derived, hands_mean, rots, poses, betas, out, B, stream);
+        case 82: return launch_lbs_v2<8, 2>(derived, hands_mean, rots, poses, betas, out, B, stream);
+        case 161: return launch_lbs_v2<16, 1>(derived, hands_mean, rots, poses, betas, out, B, stream);
+        case 162: return launch_lbs_v2<16, 2>(derived, hands_mean, rots, poses, betas, out, B, stream);
+        case 321: return launch_lbs_v2<32, 1>(derived, hands_mean, rots, poses, betas, out, B, stream);
+        default: break;
+    }
     SCAT_CHECK_CUDA(launch_k(lbs_fwd_kernel, dim3(ceil_div(B, LBS_S)), dim3(LBS_THREADS), 0, stream, derived, hands_mean, rots, poses, betas, out, B));
     SCAT_CHECK_LAUNCH();
     return 0;
