@@ -158,6 +158,7 @@ int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, con
         reinterpret_cast<__nv_bfloat16*>(dX16), lddx16))
     if (D <= 256) SCAT_LN_BWD(8);
     else if (D <= 512) SCAT_LN_BWD(16);
+    else if (D <= 800) SCAT_LN_BWD(25);    // d = 784: 25 elements per lane instead of 32 (255 registers + spills -> see -res-usage)
     else SCAT_LN_BWD(32);
 #undef SCAT_LN_BWD
     SCAT_CHECK_LAUNCH();
