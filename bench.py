@@ -242,9 +242,15 @@ def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
     x2g, wg, mg = torch.empty_like(x2d), torch.empty(21, 512, device=dev), torch.empty(784, device=dev)
     bwd_fn = lib.scat_conv_bwd_tc if tc else lib.scat_conv_bwd
 
+    seam_id = 1 if x2d.dtype == torch.bfloat16 else 0
+
     def conv_bwd():
-        check(bwd_fn(ptr(dtok), ptr(x2d), ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
-                     ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd")
+        if tc:
+            check(bwd_fn(ptr(dtok), ptr(x2d), seam_id, ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
+                         ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd_tc")
+        else:
+            check(bwd_fn(ptr(dtok), ptr(x2d), ptr(cw), ptr(idx), ts.n_masked, ptr(x2g), ptr(wg), ptr(mg),
+                         ptr(scratch), B, 512, 784, 21, stream_ptr()), "scat_conv_bwd")
     t_bwd = time_kernel(conv_bwd)
     how = "tcgen05 kind::tf32 batched GEMM" if tc else "fp32 FFMA"
     kernels = [
@@ -303,7 +309,7 @@ def measure_roofline(ts, net, lib, pk, dev, B, step_s, precision):
         a = sets[turn[0] % 8]
         turn[0] += 1
         check(lib.scat_adam_step(ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), n_par, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1 + turn[0],
-                                 None, None, stream_ptr()), "scat_adam_step")
+                                 None, None, None, stream_ptr()), "scat_adam_step")
     t_adam = time_kernel(adam_once, iters=40, warm=8)
     kernels.append({"kernel": "adam_kernel (fused optimiser step over the flat head parameters; outside the headline step)",
                     "bound": "hbm", "achieved": 28.0 * n_par / t_adam / 1e9, "peak": pk["hbm"], "unit": "GB/s",

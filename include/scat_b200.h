@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SCAT_B200_ABI_VERSION 1
+#define SCAT_B200_ABI_VERSION 2
 
 #define SCAT_ERR_BAD_ARG     (-1)
 #define SCAT_ERR_WORKSPACE   (-2)
@@ -39,6 +39,11 @@ extern "C" {
  * split; any strides, no alignment requirement.  Measured slower than the fp32 FFMA kernel on B200 (the legacy
  * mma.sync path has FFMA-class throughput there), so the head does not use it */
 #define SCAT_PREC_TF32X3 3
+
+/* dtype of the backbone seam tensors x2 / x2.grad (resnet.py:151 emits fp32, a bf16 /
+ * autocast backbone emits bf16): both are NCHW-contiguous */
+#define SCAT_DTYPE_F32  0
+#define SCAT_DTYPE_BF16 1
 /* scat_gemm only, OR-ed into SCAT_PREC_TF32: the fp32 operands are already TF32-representable (their producer
  * rounded them), so the kernel skips its in-shared-memory rounding pass -- how the head itself runs its GEMMs */
 #define SCAT_PREC_FLAG_PREROUNDED 0x100
@@ -75,6 +80,7 @@ typedef struct ScatHeadDesc {
     int32_t precision;      /* SCAT_PREC_*                                                          */
     int32_t main_feat_dim;  /* 1024 (resnet fc1)                                                    */
     int32_t n_out;          /* 66 = 3 camera + 63 joint coordinates                                 */
+    int32_t x2_dtype;       /* SCAT_DTYPE_*: storage of x2 AND x2_grad; BF16 needs precision tf32/bf16      */
 } ScatHeadDesc;
 
 int         scat_abi_version(void);
@@ -90,11 +96,12 @@ size_t scat_head_workspace_bytes(const ScatHeadDesc* desc);
 /* EncoderTransformer.forward after the backbone (hand_net.py:363-398).
  *   params[35]     device pointers, order above;  pe[T,dim] = positionalEncoding.pe[0];
  *   mean_params[66]; mask_idx[n_masked] int32 token indices drawn on the host (hand_net.py:370-372)
- *   x2[B,C,28,28], main_feat[B,1024]  ->  pred_params[B,66], feat_visual[B,T,28,28], pl_term[B,T,28,28]
+ *   x2[B,C,28,28] (fp32 or bf16 per desc.x2_dtype), main_feat[B,1024]
+ *     ->  pred_params[B,66], feat_visual[B,T,28,28], pl_term[B,T,28,28]
  *   (pl_term may be NULL iff !pl_reg).  With pos_embed==0 and masking the reference overwrites
  *   feat_visual in place (hand_net.py:364,373); that aliasing is reproduced. */
 int scat_head_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe,
-                      const float* mean_params, const int32_t* mask_idx, const float* x2,
+                      const float* mean_params, const int32_t* mask_idx, const void* x2,
                       const float* main_feat, float* pred_params, float* feat_visual, float* pl_term,
                       void* workspace, size_t workspace_bytes, void* stream);
 
@@ -102,15 +109,16 @@ int scat_head_forward(const ScatHeadDesc* desc, const float* const* params, cons
  *   feat_visual: the forward's output (only read when pos_embed==0, where it IS the token matrix)
  *   grad_pred[B,66] (required), grad_feat_visual[B,T,784] (NULL = zero)
  *   grads[35] device pointers to receive parameter gradients (overwritten, not accumulated),
- *   x2_grad[B,C,784] / main_feat_grad[B,1024]: NULL to skip. */
+ *   x2_grad[B,C,784] (dtype desc.x2_dtype) / main_feat_grad[B,1024]: NULL to skip. */
 int scat_head_backward(const ScatHeadDesc* desc, const float* const* params, const int32_t* mask_idx,
-                       const float* x2, const float* main_feat, const float* feat_visual,
+                       const void* x2, const float* main_feat, const float* feat_visual,
                        const float* grad_pred, const float* grad_feat_visual, float* const* grads,
-                       float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
+                       void* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
                        void* stream);
 
 /* projection + losses + d loss / d pred_params (train.py:112-120,165-203).
- *   labels[B,ld_labels] (63 3D + 42 2D first), pl_term NULL = no path-length term,
+ *   labels[B,ld_labels]: ld_labels = 105 -> [63 3D | 42 2D]; 166 -> [61 pose | 63 3D | 42 2D] (train.py:188-199 picks
+ *   the columns by the row width; any other width is rejected), pl_term NULL = no path-length term,
  *   losses[4] = {loss, l_3d, l_2d, l_pl} (device), grad_pred[B,66] scaled by grad_scale (1/world for DP),
  *   scratch: >= B floats. */
 int scat_proj_loss(int32_t batch, int32_t n_tokens, int32_t token_dim, const float* pred_params,
@@ -120,11 +128,11 @@ int scat_proj_loss(int32_t batch, int32_t n_tokens, int32_t token_dim, const flo
 
 /* One fused training-step body (train.py:159-206): forward, path-length VJP, losses, backward. */
 int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, const float* pe,
-                         const float* mean_params, const int32_t* mask_idx, const float* x2,
+                         const float* mean_params, const int32_t* mask_idx, const void* x2,
                          const float* main_feat, const float* labels, int32_t ld_labels,
                          float l_weight_3d, float l_weight_2d, float grad_scale, float* pred_params,
                          float* feat_visual, float* pl_term, float* losses, float* const* grads,
-                         float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
+                         void* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes,
                          void* stream);
 
 /* The same step in three launches for data-parallel callers, so the gradient all-reduce overlaps the backward:
@@ -133,10 +141,10 @@ int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, c
  * masking (parameters 0 and 2..12 and the losses are final); phase 2 = conv backward (parameter 1, x2_grad).
  * phase -1 = scat_head_train_step. */
 int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* params, const float* pe,
-                               const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                               const float* mean_params, const int32_t* mask_idx, const void* x2, const float* main_feat,
                                const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d,
                                float grad_scale, float* pred_params, float* feat_visual, float* pl_term, float* losses,
-                               float* const* grads, float* x2_grad, float* main_feat_grad, void* workspace,
+                               float* const* grads, void* x2_grad, float* main_feat_grad, void* workspace,
                                size_t workspace_bytes, void* stream, int32_t phase);
 
 /* ---- data-parallel gradient exchange over NVLink peer memory (the reference imports
@@ -146,7 +154,8 @@ int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* par
  * scat_peer_allreduce then sums elements [lo, hi) (multiples of 4) of all buckets in place, in rank order, in ONE
  * kernel on `stream` (capturable): buckets[p] / signals[p] are rank p's bucket and signal area as mapped in this
  * process (own entries = the local allocations).  Every rank must issue the same sequence of calls.
- * A peer that never arrives does not hang the GPU: after 20 s the kernel gives up and scat_peer_error reports 1. */
+ * A peer that never arrives does not hang the GPU: after 20 s the kernel gives up WITHOUT summing or storing anything,
+ * scat_peer_error reports 1 from then on, and every later exchange on this rank returns immediately. */
 size_t scat_peer_signal_bytes(void);
 int scat_peer_alloc(size_t bytes, void** out);                 /* zero-filled device memory, IPC-exportable */
 int scat_peer_free(void* ptr);
@@ -156,16 +165,21 @@ int scat_peer_close(void* ptr);
 int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
                         long long hi, void* stream);
 int scat_peer_error(const uint32_t* signal, int32_t* out);     /* synchronous read of the time-out flag */
+/* device address of that flag inside a signal area: non-zero once an exchange on this rank has given up on a peer (it
+ * stays set; later exchanges are then no-ops).  Pass it to scat_adam_step as abort_flag. */
+const uint32_t* scat_peer_error_word(const uint32_t* signal);
 
 /* Fused Adam step over the head's flat parameter / gradient / moment buffers (all in the gradient bucket's order):
  * replaces optim.Adam(self.net.parameters(), lr).step() (train.py:60,209) for the head's 35 tensors, arithmetic as
  * torch.optim.Adam's single-tensor path (weight_decay is the coupled L2 form, no amsgrad).  `step` is the 1-based
  * count of this update; if `step_dev` / `lr_dev` are non-null the kernel reads the count / learning rate from device
  * memory instead (a captured CUDA graph then follows a changing schedule).  Buffers 16-byte aligned.  The scalar
- * hyper-parameters are doubles, as torch holds them: 1 - beta is formed in double before it is rounded to fp32. */
+ * hyper-parameters are doubles, as torch holds them: 1 - beta is formed in double before it is rounded to fp32.
+ * abort_flag (nullable, device): when the word it points to is non-zero the kernel changes nothing -- wire it to
+ * scat_peer_error_word() so that a gradient exchange that gave up on a peer never reaches the weights. */
 int scat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, double lr,
                    double beta1, double beta2, double eps, double weight_decay, int32_t step, const float* lr_dev,
-                   const int32_t* step_dev, void* stream);
+                   const int32_t* step_dev, const uint32_t* abort_flag, void* stream);
 
 /* ---- evaluation metrics on the device (the reference round-trips every frame to numpy,
  * eval.py:691-753).  All joints are fp32 [batch, n_joints, 3]. ----
@@ -222,17 +236,21 @@ int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe,
                           const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
                           float* tokens_out, int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens,
                           void* stream);
-/* The same front end on the tensor cores (tcgen05 kind::tf32 through the batched GEMM kernel, one problem per
- * sample): what the head runs in SCAT_PREC_TF32 / SCAT_PREC_BF16.  x2 and d_tokens are read as fp32 and truncated
- * to TF32 by the tensor core (compensated, see csrc/conv.cu); results are TF32-grade (~3e-4 relative), masked
- * rows stay bit-exact copies of the mask token.  scratch: scat_conv_tc_scratch_floats() floats. */
+/* The same front end on the tensor cores (csrc/conv_tc.cu: three persistent tcgen05 kernels that stream x2 / x2.grad
+ * through a TMA ring, accumulators in tensor memory): what the head runs in SCAT_PREC_TF32 / SCAT_PREC_BF16.
+ * x2_dtype SCAT_DTYPE_F32: x2 and x2_grad are fp32; x2 is rounded to TF32-NEAREST in shared memory (the tensor core
+ * alone would truncate), results are TF32-grade (~3e-4 relative) for feat_visual / conv_w_grad and fp32-grade for x2_grad
+ * (exact hi/lo split of d_tokens and the weight).  SCAT_DTYPE_BF16: x2 and x2_grad are bf16; bf16 operands are exact on
+ * the tensor core and the fp32 weight / d_tokens enter as stacked bf16 split terms, so feat_visual and conv_w_grad are
+ * fp32-grade for the given bf16 x2, and x2_grad carries only its final bf16 rounding.  Masked rows stay bit-exact
+ * copies of the mask token.  T = 21, C in {256, 512}, hw % 8 == 0.  scratch: scat_conv_tc_scratch_floats() floats. */
 size_t scat_conv_tc_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens);
-int scat_conv_pe_mask_fwd_tc(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
+int scat_conv_pe_mask_fwd_tc(const void* x2, int32_t x2_dtype, const float* conv_w, const float* pe, const float* mask_token,
                              const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
                              float* tokens_out, float* scratch, int32_t batch, int32_t channels, int32_t hw,
                              int32_t n_tokens, void* stream);
-int scat_conv_bwd_tc(const float* d_tokens, const float* x2, const float* conv_w, const int32_t* mask_idx,
-                     int32_t n_masked, float* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
+int scat_conv_bwd_tc(const float* d_tokens, const void* x2, int32_t x2_dtype, const float* conv_w, const int32_t* mask_idx,
+                     int32_t n_masked, void* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
                      int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens, void* stream);
 
 /* backward of the conv: d_tokens[B,T,hw] -> x2_grad (NULL to skip), conv_w_grad[T,C], mask_token_grad[hw];

@@ -145,7 +145,10 @@ def train_loss(pred_params, labels, pl_term=None, *, l_weight_3d: float = 1e5, l
         l_pl = torch.square(pl_lengths - pl_mean).mean()
     else:
         l_pl = torch.zeros((), dtype=pred_params.dtype)
-    gt3d, gt2d = labels[:, :63], labels[:, 63:105]                              # :188-192
+    if labels.shape[1] == 105:                                                  # :188-190  MTC / RHD / STB rows
+        gt3d, gt2d = labels[:, :63], labels[:, 63:]
+    else:                                                                       # :193-196  FreiHAND / HO-3D rows: pose first
+        gt3d, gt2d = labels[:, 61:61 + 63], labels[:, 61 + 63:]
     l_3d = F.mse_loss(j3d, gt3d)
     l_2d = F.l1_loss(j2d, gt2d)
     loss = l_weight_3d * l_3d + l_weight_2d * l_2d + (10 * l_pl if pl_term is not None else 0.0)

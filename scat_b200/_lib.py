@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libscat_b200.so")
 
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2, "tf32x3": 3}
+X2_DTYPE = {"fp32": 0, "bf16": 1}       # SCAT_DTYPE_*: storage of the seam tensors x2 / x2.grad
+ABI_VERSION = 2
 EPI = {"none": 0, "bias": 1, "bias_resid": 2, "bias_gelu": 3, "dgelu": 4, "resid": 5}
 NUM_PARAMS = 35
 
@@ -19,7 +21,7 @@ NUM_PARAMS = 35
 class ScatHeadDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "n_tokens", "channels", "token_dim", "heads", "iteration", "pos_embed", "n_masked",
-        "pl_reg", "precision", "main_feat_dim", "n_out")]
+        "pl_reg", "precision", "main_feat_dim", "n_out", "x2_dtype")]
 
 
 _f = C.c_void_p      # device pointers travel as integers
@@ -44,7 +46,7 @@ SIGNATURES = {
     "scat_head_train_step_phase": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _i32, _fl, _fl, _fl, _f, _f, _f, _f, _pp,
                                           _f, _f, _f, _sz, _f, _i32]),
     "scat_adam_step": (_i32, [_f, _f, _f, _f, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
-                             _i32, _f, _f, _f]),
+                             _i32, _f, _f, _f, _f]),
     "scat_eval_procrustes": (_i32, [_f, _f, _i32, _i32, _f, _f, _f]),
     "scat_eval_joint_errors": (_i32, [_f, _f, _i32, _i32, _fl, C.POINTER(C.c_double), _i32, _f, _f, _f]),
     "scat_eval_accel": (_i32, [_f, _f, _i32, _i32, _f, _f]),
@@ -56,6 +58,7 @@ SIGNATURES = {
     "scat_peer_close": (_i32, [_f]),
     "scat_peer_allreduce": (_i32, [_pp, _pp, _i32, _i32, C.c_longlong, C.c_longlong, _f]),
     "scat_peer_error": (_i32, [_f, C.POINTER(C.c_int32)]),
+    "scat_peer_error_word": (C.c_void_p, [_f]),
     "scat_tokens_forward": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _sz, _f]),
     "scat_gemm": (_i32, [_f, _i64, _i64, _f, _i64, _i64, _f, _i32, _i32, _i32, _i32, _i32, _f, _f, _i32, _f, _i32,
                          _i32, _i32, _f]),
@@ -64,8 +67,8 @@ SIGNATURES = {
     "scat_debug_gemm_timeline": (None, [_f]),
     "scat_conv_pe_mask_fwd": (_i32, [_f, _f, _f, _f, _f, _i32, _i32, _f, _f, _i32, _i32, _i32, _i32, _f]),
     "scat_conv_tc_scratch_floats": (_sz, [_i32, _i32, _i32, _i32]),
-    "scat_conv_pe_mask_fwd_tc": (_i32, [_f, _f, _f, _f, _f, _i32, _i32, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
-    "scat_conv_bwd_tc": (_i32, [_f, _f, _f, _f, _i32, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
+    "scat_conv_pe_mask_fwd_tc": (_i32, [_f, _i32, _f, _f, _f, _f, _i32, _i32, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
+    "scat_conv_bwd_tc": (_i32, [_f, _f, _i32, _f, _f, _i32, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
     "scat_conv_bwd_scratch_floats": (_sz, [_i32, _i32, _i32, _i32]),
     "scat_conv_bwd": (_i32, [_f, _f, _f, _f, _i32, _f, _f, _f, _f, _i32, _i32, _i32, _i32, _f]),
     "scat_layernorm_fwd": (_i32, [_f, _f, _f, _f, _f, _f, _i32, _i32, _f]),
@@ -97,7 +100,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.scat_abi_version() != 1:
+    if lib.scat_abi_version() != ABI_VERSION:
         raise RuntimeError("scat_b200: ABI version mismatch between _lib.py and libscat_b200.so")
     _lib = lib
     return lib

@@ -30,9 +30,13 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, double lr, double beta1, double beta2,
                                                    float eps, float wd, int step, const float* __restrict__ lr_dev,
-                                                   const int* __restrict__ step_dev) {
+                                                   const int* __restrict__ step_dev, const uint32_t* __restrict__ abort_flag) {
     pdl_sync();
     __shared__ AdamScalars sh;
+    __shared__ uint32_t aborted;
+    if (threadIdx.x == 0) aborted = abort_flag ? *reinterpret_cast<const volatile uint32_t*>(abort_flag) : 0u;
+    __syncthreads();
+    if (aborted) return;          // the gradient exchange before this update gave up on a peer: leave the weights alone
     if (threadIdx.x == 0) {
         const double t = (double)(step_dev ? *step_dev : step);
         // betas arrive in double: 1 - (float)0.999 differs from (float)(1 - 0.999) by 1.3e-5 relative
@@ -71,7 +75,7 @@ using namespace scat;
 
 extern "C" int scat_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                               double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
-                              const float* lr_dev, const int32_t* step_dev, void* stream) {
+                              const float* lr_dev, const int32_t* step_dev, const uint32_t* abort_flag, void* stream) {
     SCAT_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0, kErrBadArg, "adam_step: null buffer or n <= 0");
     SCAT_REQUIRE(step_dev || step >= 1, kErrBadArg, "adam_step: step %d (1-based count of this update)", step);
     SCAT_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, kErrBadArg,
@@ -79,18 +83,21 @@ extern "C" int scat_adam_step(float* params, const float* grads, float* exp_avg,
     const uintptr_t al = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
     SCAT_REQUIRE(al % 16 == 0, kErrBadArg, "adam_step: buffers must be 16-byte aligned");
     // exactly one resident wave (grid-stride loop): ncu showed 1.6 waves, i.e. a 0.6-wave tail, with a fixed 8 CTAs per SM
-    static int resident = 0;
+    static int resident_of[16] = {0};                  // per device (a process may drive several GPUs)
+    int dev = 0;
+    SCAT_CHECK_CUDA(cudaGetDevice(&dev));
+    int resident = (dev >= 0 && dev < 16) ? resident_of[dev] : 0;
     if (resident == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        SCAT_CHECK_CUDA(cudaGetDevice(&dev));
+        int sms = 0, per_sm = 0;
         SCAT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         SCAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_kernel, 256, 0));
         resident = std::max(1, sms * per_sm);
+        if (dev >= 0 && dev < 16) resident_of[dev] = resident;
     }
     const long long n4 = (n + 3) / 4;
     const int grid = (int)std::min<long long>(resident, (n4 + 255) / 256);
     SCAT_CHECK_CUDA(launch_k(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq,
-                             n, lr, beta1, beta2, (float)eps, (float)weight_decay, (int)step, lr_dev, (const int*)step_dev));
+                             n, lr, beta1, beta2, (float)eps, (float)weight_decay, (int)step, lr_dev, (const int*)step_dev, abort_flag));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

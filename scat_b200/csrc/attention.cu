@@ -166,10 +166,7 @@ int launch_attention_fwd(const float* QKV, float* O, float* P, int B, int n, int
     if (round_out != OUT_F32 && attention_tc128_supported(n, heads, QKV)) return launch_attention_tc128_fwd(QKV, O, B, n, heads, round_out, stream);
     if (attention_small_supported(n)) return launch_attention_small_fwd(QKV, O, P, B, n, heads, round_out, stream);
     const size_t smem = sizeof(float) * ((size_t)3 * n * LDS + (size_t)n * (n + 1));
-    if (smem > 48 * 1024) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-    }
+    if (smem > 48 * 1024) SCAT_ENSURE_SMEM(attention_fwd_kernel, smem);
     SCAT_CHECK_CUDA(launch_k(attention_fwd_kernel, dim3(B * heads), dim3(ATT_THREADS), smem, stream, QKV, O, P, n, heads, round_out));
     SCAT_CHECK_LAUNCH();
     return 0;
@@ -182,10 +179,7 @@ int launch_attention_bwd(const float* QKV, const float* P, const float* dO, floa
     if (attention_small_supported(n)) return launch_attention_small_bwd(QKV, P, dO, dQKV, B, n, heads, round_out, stream, act_batch);
     SCAT_REQUIRE(act_batch == 0, kErrUnsupported, "attention bwd: stacked cotangents only on the n=21 path");
     const size_t smem = sizeof(float) * ((size_t)4 * n * LDS + (size_t)2 * n * (n + 1));
-    if (smem > 48 * 1024) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-    }
+    if (smem > 48 * 1024) SCAT_ENSURE_SMEM(attention_bwd_kernel, smem);
     SCAT_CHECK_CUDA(launch_k(attention_bwd_kernel, dim3(B * heads), dim3(ATT_THREADS), smem, stream, QKV, P, dO, dQKV, n, heads, round_out));
     SCAT_CHECK_LAUNCH();
     return 0;

@@ -272,11 +272,7 @@ int launch_attention_tc128_fwd(const float* QKV, float* O, int B, int n, int hea
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SCAT_REQUIRE(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, kErrUnsupported, "attention_tc128: tensor map encode failed (%d %d)",
                  (int)r1, (int)r2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        attr_done = true;
-    }
+    SCAT_ENSURE_SMEM(attention_fwd_tc128_kernel, SMEM_TOTAL);
     SCAT_CHECK_CUDA(launch_k(attention_fwd_tc128_kernel, dim3(B * heads), dim3(THREADS), SMEM_TOTAL, stream, tmK, tmV, O, heads, out_mode));
     SCAT_CHECK_LAUNCH();
     return 0;

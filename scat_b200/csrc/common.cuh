@@ -44,6 +44,11 @@ extern unsigned long long g_launch_count;
         if (_rc != 0) return _rc;                                                              \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and a
+// process may drive several GPUs from several host threads (head.cu)
+int ensure_dynamic_smem(const void* kernel, int bytes);
+#define SCAT_ENSURE_SMEM(kernel, bytes) SCAT_PROPAGATE(scat::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (int)(bytes)))
+
 constexpr int kErrBadArg = -1;
 constexpr int kErrWorkspace = -2;
 constexpr int kErrUnsupported = -3;

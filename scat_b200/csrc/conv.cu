@@ -317,12 +317,7 @@ int launch_conv_pe_mask_fwd(const float* x2, const float* Wc, const float* pe, c
     SCAT_REQUIRE(HW % 4 == 0 && C % CONV_WARPS == 0, kErrUnsupported, "conv fwd: HW%%4 / C%%8 (HW=%d C=%d)", HW, C);
     SCAT_REQUIRE(n_masked == 0 || mask_idx != nullptr, kErrBadArg, "conv fwd: mask_idx is null");
     const size_t smem = sizeof(float) * (size_t)max(C * TP, CONV_WARPS * T * 4 * 32);
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(conv_pe_mask_fwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(96 * 1024)));
-        attr_done = true;
-    }
+    SCAT_ENSURE_SMEM(conv_pe_mask_fwd_kernel<21>, 96 * 1024);
     SCAT_REQUIRE(smem <= 96 * 1024, kErrUnsupported, "conv fwd: C too large");
     const long long groups = (long long)B * (HW / 4);
     const int grid = (int)((groups + 31) / 32);
@@ -366,12 +361,7 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
                       cudaStream_t stream) {
     SCAT_REQUIRE(T == 21 && HW % 4 == 0, kErrUnsupported, "conv dgrad: T=21, HW%%4");
     const size_t smem = sizeof(float) * (size_t)C * TP;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(conv_dgrad_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(96 * 1024)));
-        attr_done = true;
-    }
+    SCAT_ENSURE_SMEM(conv_dgrad_kernel<21>, 96 * 1024);
     SCAT_REQUIRE(smem <= 96 * 1024, kErrUnsupported, "conv dgrad: C too large");
     const long long groups = (long long)B * (HW / 4);
     SCAT_CHECK_CUDA(launch_k(conv_dgrad_kernel<21>, dim3((int)((groups + 31) / 32)), dim3(CONV_THREADS), smem, stream, dFv, Wc, x2_grad, B, C, HW));
@@ -379,19 +369,8 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Tensor-core front end: the three conv passes are GEMMs with one tiny dimension (T = 21 tokens), so they ride
-// the tcgen05 GEMM kernel in batched mode, one problem per sample, and become pure HBM streams of x2 / x2.grad:
-//   fwd    Fv[b]  [T x HW]  = Wc [T x C]       . x2[b] [C x HW]       A = Wc K-major,   B = x2[b] MN-major (px contiguous)
-//   dgrad  dx2[b] [C x HW]  = Wc^T [C x T]     . dFv[b] [T x HW]      A = Wc MN-major,  B = dFv[b] MN-major
-//   wgrad  dWc    [T x C]  += dFv[b] [T x HW]  . x2[b]^T [HW x C]     A = dFv[b] K-major, B = x2[b] K-major, reduced over b
-// The seam tensors arrive in fp32 and are not ours to round: tcgen05 kind::tf32 truncates them (drops 13 mantissa
-// bits, always toward zero), which shrinks every product by E[tail/mantissa] = 3.3e-4 per truncated operand
-// (measured on B200, tools/tf32_rounding_probe.py).  out_scale multiplies that back; what is left is zero-mean
-// TF32 rounding noise.  The fp32 "parity" precision keeps the FFMA kernels above.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr float kTruncShrink = 3.3e-4f;
 
+// Operand preparation of the tensor-core conv backward (conv_tc.cu), fp32 seam.
 // dFv [B,T,HW] -> dFv3 [B,3T,HW]: rows 0..T-1 hi = the TF32-nearest part, rows T..2T-1 lo = the (TF32-rounded)
 // remainder, rows 2T..3T-1 hi again.  Every value is exactly representable on the tensor core, so against the
 // stacked weight [Wh; Wh; Wl] the conv dgrad computes Wh hi + Wh lo + Wl hi: fp32-grade (the d tokens are small:
@@ -424,54 +403,6 @@ int launch_split_tf32(const float* dFv, float* dFv2, int B, int T, int HW, cudaS
     return 0;
 }
 
-int launch_conv_pe_mask_fwd_tc(const float* x2, const float* Wc_tf32, const float* pe, const float* mask_token,
-                               const int32_t* mask_idx, int n_masked, int pos_embed, float* feat_visual, float* X0,
-                               int B, int C, int HW, int T, cudaStream_t stream) {
-    SCAT_REQUIRE(HW % 4 == 0 && C % 4 == 0 && T <= 128, kErrUnsupported, "conv fwd (tc): HW%%4, C%%4, T<=128");
-    GemmArgs g;
-    g.A = Wc_tf32; g.sam = C; g.sak = 1;                       // [T, C] K-major
-    g.B = x2; g.sbn = 1; g.sbk = HW;                            // x2[b] as B(n = px, k = c): MN-major
-    g.M = T; g.N = HW; g.K = C;
-    g.batch = B; g.b_k_z = C;                                   // sample b: k rows b*C .. b*C + C of the [B*C, HW] matrix
-    g.C = feat_visual; g.ldc = HW; g.c_z = (long long)T * HW;
-    g.epilogue = EPI_PE_MASK; g.bias = mask_token; g.mask_idx = mask_idx; g.n_masked = n_masked;
-    if (pos_embed) { g.aux_in = pe; g.ld_aux_in = HW; }
-    if (X0 != feat_visual) { g.aux_out = X0; g.ld_aux_out = HW; g.aux_out_z = (long long)T * HW; }
-    g.prerounded = 1;                                           // no in-kernel rounding pass: memory-bound stream
-    g.out_scale = 1.0f + kTruncShrink;
-    g.force_bn = 128;
-    return launch_gemm_tc(g, PREC_TF32, stream);
-}
-
-int launch_conv_dgrad_tc(const float* dFv2, const float* Wc2_tf32, float* x2_grad, int B, int C, int HW, int T,
-                         cudaStream_t stream) {
-    SCAT_REQUIRE(HW % 4 == 0 && C % 4 == 0, kErrUnsupported, "conv dgrad (tc): HW%%4, C%%4");
-    GemmArgs g;
-    g.A = Wc2_tf32; g.sam = 1; g.sak = C;                       // A(m = c, k = j) = [Wh; Wh; Wl][j, c]: MN-major
-    g.B = dFv2; g.sbn = 1; g.sbk = HW;                          // B(n = px, k = j) = [hi; lo; hi][j, px] of sample b: MN-major
-    g.M = C; g.N = HW; g.K = 3 * T;
-    g.batch = B; g.b_k_z = 3 * T;                               // rows b*3T .. of the [B*3T, HW] matrix; the k tail of a box
-                                                                // reaches into sample b+1 but meets A's zero-filled k rows
-    g.C = x2_grad; g.ldc = HW; g.c_z = (long long)C * HW;
-    g.prerounded = 1;                                           // every operand value is TF32-representable: exact products
-    g.force_bn = 128;
-    return launch_gemm_tc(g, PREC_TF32, stream);
-}
-
-int launch_conv_wgrad_tc(const float* dFv2, const float* x2, float* dWc, int B, int C, int HW, int T, cudaStream_t stream) {
-    SCAT_REQUIRE(HW % 4 == 0 && C % 4 == 0 && T <= 64, kErrUnsupported, "conv wgrad (tc): HW%%4, C%%4, T<=64");
-    GemmArgs g;
-    g.A = dFv2; g.sam = HW; g.sak = 1;                          // A(m = t, k = px): the hi rows of sample b, K-major; the rows
-    g.B = x2; g.sbn = HW; g.sbk = 1;                            // behind them (lo, next sample) land in accumulator rows >= T
-    g.M = T; g.N = C; g.K = HW;                                 // that are never stored
-    g.batch = B; g.a_row_z = 3 * T; g.b_row_z = C; g.batch_accumulate = 1;
-    g.C = dWc; g.ldc = C;
-    g.prerounded = 1;
-    g.out_scale = 1.0f + kTruncShrink;                          // x2 is truncated by the tensor core, hi is exact
-    g.force_bn = 128;
-    return launch_gemm_tc(g, PREC_TF32, stream);
-}
-
 size_t conv_wgrad_scratch_floats(int C, int T) { return (size_t)kConvWgradCtas * T * C; }
 
 int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scratch, int B, int C, int HW, int T,
@@ -480,12 +411,7 @@ int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scra
                  "conv wgrad: T=21, HW%%28, C<=512 (T=%d HW=%d C=%d)", T, HW, C);
     SCAT_REQUIRE(scratch != nullptr, kErrBadArg, "conv wgrad: scratch is null");
     const size_t smem = sizeof(float) * ((size_t)C * WG_PX + (size_t)T * WG_PX);
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_partial_kernel<21, 2>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));
-        attr_done = true;
-    }
+    SCAT_ENSURE_SMEM((conv_wgrad_partial_kernel<21, 2>), 96 * 1024);
     const int items = B * (HW / WG_PX);
     const int grid = min(items, kConvWgradCtas);
     SCAT_CHECK_CUDA(launch_k(conv_wgrad_partial_kernel<21, 2>, dim3(grid), dim3(CONV_THREADS), smem, stream, dFv, x2, scratch, B, C, HW));

@@ -54,9 +54,14 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 
 // all ranks' block `blockIdx.x` meet here; `val` increases by one per barrier.  The bar.sync orders every thread's
 // earlier stores before the flag stores of threads 0..W-1, and st.release.sys is cumulative over them, so no
-// per-thread system fence is needed.
+// per-thread system fence is needed.  Returns false (for the whole block) when a peer did not arrive within the
+// bounded wait: the error word of this rank's signal area is then set and STAYS set.
+// Forward progress: block b only waits for block b of the peers, every rank launches the same grid and the hardware
+// dispatches blocks in ascending index order, so the lowest unfinished block index is resident on every rank.
 template <int W>
-__device__ __forceinline__ void peer_barrier(const PeerSet& ps, int rank, uint32_t val) {
+__device__ __forceinline__ bool peer_barrier(const PeerSet& ps, int rank, uint32_t val) {
+    __shared__ int failed;
+    if (threadIdx.x == 0) failed = 0;
     __syncthreads();
     if (threadIdx.x < W) {
         st_release_sys(ps.sig[threadIdx.x] + kSigFlags + blockIdx.x * kMaxPeers + rank, val);
@@ -69,12 +74,14 @@ __device__ __forceinline__ void peer_barrier(const PeerSet& ps, int rank, uint32
                 if (t0 == 0) t0 = now;
                 if (now - t0 > kSpinLimitNs) {
                     ps.sig[rank][kSigError] = 1u;
+                    failed = 1;
                     break;
                 }
             }
         }
     }
     __syncthreads();
+    return failed == 0;
 }
 
 template <int W>
@@ -83,9 +90,12 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerSet ps, in
     // is not moved across the stores of the previous iteration
     constexpr int U = W >= 8 ? 1 : (W == 4 ? 2 : 4);
     pdl_sync();                                  // this rank's gradients are final from here on
+    // a wait that timed out is sticky: this and every later exchange on this rank does nothing (the partial sums of a
+    // broken exchange must never reach the weights; the optimiser kernel reads the same word and skips its update)
+    if (*reinterpret_cast<volatile uint32_t*>(ps.sig[rank] + kSigError) != 0u) return;
     uint32_t* epoch = ps.sig[rank] + kSigEpoch + blockIdx.x;
     const uint32_t e = *epoch;
-    peer_barrier<W>(ps, rank, 2 * e + 1);
+    if (!peer_barrier<W>(ps, rank, 2 * e + 1)) return;
     const long long per = (n4 + W - 1) / W;
     const long long begin = lo4 + (long long)rank * per;
     const long long end = min(begin + per, lo4 + n4);
@@ -199,6 +209,8 @@ int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t
     }
     SCAT_REQUIRE(false, kErrUnsupported, "peer_allreduce: world size %d (1, 2, 4 or 8)", world);
 }
+
+const uint32_t* scat_peer_error_word(const uint32_t* signal) { return signal ? signal + kSigError : nullptr; }
 
 int scat_peer_error(const uint32_t* signal, int32_t* out) {
     SCAT_REQUIRE(signal && out, kErrBadArg, "peer_error: null");

@@ -121,11 +121,7 @@ int scat_eval_procrustes(const float* pred, const float* gt, int32_t batch, int3
     SCAT_REQUIRE(batch > 0 && n_joints >= 3 && n_joints <= 64, kErrBadArg, "eval_procrustes: batch %d joints %d (3..64)", batch,
                  n_joints);
     const size_t smem = (size_t)2 * kProcThreads * 3 * n_joints * sizeof(float);
-    static bool raised = false;
-    if (!raised) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(procrustes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kProcThreads * 3 * 64 * 4));
-        raised = true;
-    }
+    SCAT_ENSURE_SMEM(procrustes_kernel, 2 * kProcThreads * 3 * 64 * 4);
     SCAT_CHECK_CUDA(launch_k(procrustes_kernel, dim3(ceil_div(batch, kProcThreads)), dim3(kProcThreads), smem, (cudaStream_t)stream,
                              pred, gt, (int)batch, (int)n_joints, aligned, scale));
     SCAT_CHECK_LAUNCH();

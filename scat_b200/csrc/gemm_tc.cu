@@ -21,111 +21,14 @@
 // incremental stage / phase / descriptor arithmetic: a single-lane `if (lane == 0)` loop makes the compiler wrap
 // every uniform-datapath instruction (UTMALDG, UTCHMMA, UTCBAR) in an election loop, ~150 dependent instructions
 // per k-block, which bounded the first version of this kernel at ~0.45 us per k-block.
-#include <cuda.h>
-#include <cuda_bf16.h>
-
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace scat {
 namespace {
 
 constexpr int BM = 128;
 constexpr int TC_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug must fault the kernel, never hang the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > SPIN_LIMIT) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-template <bool BF16>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                     uint32_t acc) {
-    if (BF16) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-            "setp.ne.b32 p, %6, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-            "setp.ne.b32 p, %6, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
-            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
-    }
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// 16-byte vector reduction into global memory (sm_90+): one L2 atomic transaction per 4 floats
-__device__ __forceinline__ void red_add_v4(float* dst, const float4& v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // element traits.  UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) |
@@ -168,7 +71,6 @@ struct TcParams {
     int batched;
     int a_row_z, a_k_z, b_row_z, b_k_z;
     long long c_z, aux_out_z;
-    float out_scale;                // accumulator scale applied first (1 = none): operand-truncation bias correction
     const int32_t* mask_idx; int n_masked;   // EPI_PE_MASK: rows (tokens) replaced by bias[n] (the mask token)
     int tiles_m, tiles_n, tiles_z;  // tile space walked by the CTAs (n fastest); z = split-K slice or batch index
     int persistent;                 // a CTA may own several tiles: double-buffered accumulators, dedicated scratch
@@ -218,7 +120,7 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
     for (int i = 0; i < 8; ++i) valid |= (row0 + 4 * i < p.M ? 1u : 0u) << i;
 #define SCAT_ROW_OK(i) ((valid >> (i)) & 1u)
     // the common case gets out early below: plain fp32 store of the accumulator, nothing else to do
-    const bool plain = epi == EPI_NONE && p.out_scale == 1.0f && !p.round_out && p.C16 == nullptr && !p.atomic_out &&
+    const bool plain = epi == EPI_NONE && !p.round_out && p.C16 == nullptr && !p.atomic_out &&
                        !p.accumulate && p.C != nullptr;
     const long long c_step = 4LL * p.ldc, h_step = 4LL * p.ldc16, z_step = 4LL * p.ld_aux_out, a_step = 4LL * p.ld_aux_in;
     float* cptr = p.C ? p.C + zb * p.c_z + (long long)row0 * p.ldc + n0 + csub : nullptr;
@@ -291,10 +193,6 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
                 continue;
             }
             // ---- math phase (registers only, except the saved pre-activation of BIAS_GELU) ----
-            if (p.out_scale != 1.0f) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { acc[i].x *= p.out_scale; acc[i].y *= p.out_scale; acc[i].z *= p.out_scale; acc[i].w *= p.out_scale; }
-            }
             if (epi == EPI_PE_MASK) {
                 // C <- conv output (masked rows overwritten only when the token matrix aliases it: no aux_out);
                 // aux_out <- token matrix: mask token on masked rows, else conv output (+ positional encoding)
@@ -373,7 +271,7 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
                 for (int e = 0; e < 4; ++e) {
                     const int ne = n + e;
                     if (ne >= p.N) break;
-                    float t = ov[e] * p.out_scale;
+                    float t = ov[e];
                     if (epi == EPI_PE_MASK) {
                         bool mk = false;
                         for (int k = 0; k < p.n_masked; ++k) mk |= (p.mask_idx[k] == row);
@@ -630,41 +528,6 @@ long long* g_gemm_dbg = nullptr;
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-// 2-D tensor map: inner (contiguous) extent `inner`, `outer` rows `outer_stride` elements apart
-int make_map(CUtensorMap* map, const void* base, int elem_bytes, long long inner, long long outer, long long outer_stride,
-             int box_inner, int box_outer, CUtensorMapSwizzle swizzle) {
-    EncodeTiledFn fn = get_encode_fn();
-    SCAT_REQUIRE(fn != nullptr, kErrUnsupported, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)outer_stride * elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SCAT_REQUIRE(r == CUDA_SUCCESS, kErrUnsupported, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld stride=%lld",
-                 (int)r, inner, outer, outer_stride);
-    return 0;
-}
-
 // unit stride in one direction, 16-byte aligned base and leading stride
 bool operand_ok(const void* p, long long s_row, long long s_k, int elem_bytes) {
     const long long q = 16 / elem_bytes;
@@ -679,11 +542,7 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     using E = Elem<BF16>;
     auto kern = gemm_tc_kernel<BF16, BN, A_MN, B_MN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL_PERSISTENT));
-        attr_done = true;
-    }
+    SCAT_ENSURE_SMEM(kern, L::TOTAL_PERSISTENT);
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle mn_sw = BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     // extents of the tensor maps: one problem, or (batched) the whole stack of problems along rows / k
@@ -703,7 +562,7 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     p.round_out = g.round_out;
     p.batched = g.batch > 1 ? 1 : 0;
     p.a_row_z = g.a_row_z; p.a_k_z = g.a_k_z; p.b_row_z = g.b_row_z; p.b_k_z = g.b_k_z; p.c_z = g.c_z; p.aux_out_z = g.aux_out_z;
-    p.out_scale = g.out_scale; p.mask_idx = g.mask_idx; p.n_masked = g.n_masked;
+    p.mask_idx = g.mask_idx; p.n_masked = g.n_masked;
     p.dbg = g_gemm_dbg;
     auto al16 = [](const void* q, long long ld) { return q == nullptr || (((uintptr_t)q & 15) == 0 && (ld & 3) == 0); };
     p.vec_ok = al16(g.C, g.ldc) && (g.C16 == nullptr || (((uintptr_t)g.C16 & 7) == 0 && (g.ldc16 & 3) == 0)) &&

@@ -13,6 +13,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/scat_b200.h"
 #include "kernels.h"
 
@@ -33,6 +36,20 @@ static int read_pdl_env() {
     return (e && e[0] == '0') ? 0 : 1;
 }
 int g_use_pdl = read_pdl_env();
+
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+    struct Entry { const void* fn; int dev; int bytes; };
+    static std::mutex mu;
+    static std::vector<Entry> seen;
+    int dev = 0;
+    SCAT_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : seen)
+        if (e.fn == kernel && e.dev == dev && e.bytes >= bytes) return 0;
+    SCAT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    seen.push_back(Entry{kernel, dev, bytes});
+    return 0;
+}
 
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
     // tiny problems (regressor / N=3 grads) stay on the FFMA kernel: a 128-row tensor tile would be mostly padding
@@ -58,15 +75,20 @@ int launch_gemm_exact(const GemmArgs& g, int head_precision, cudaStream_t stream
 // SMs, so independent launches overlap almost for free.  Fork / join are event record + wait pairs, which is also
 // exactly how a side stream joins a CUDA-graph capture of the caller's stream.  One side stream and a small ring
 // of events per device, created on first use (the only state this library keeps besides the launch counter);
-// SCAT_SIDE_STREAM=0 keeps everything on the caller's stream.
+// SCAT_SIDE_STREAM=0 keeps everything on the caller's stream.  Host threads: a whole-head call holds the device's
+// side-stream mutex while it ENQUEUES (SideScope), so concurrent callers on one device interleave call by call; the
+// event ring is only ever advanced under that mutex, and a stream wait binds to the event's state at the time of the
+// call, so re-recording a ring slot later cannot disturb an earlier wait.
 // ---------------------------------------------------------------------------------------------
 struct SideStream {
     cudaStream_t s = nullptr;
     cudaEvent_t ev[32];
     int next = 0;
     bool ready = false;
+    std::mutex mu;
 };
 static SideStream g_side[16];
+static std::mutex g_side_create;
 static int side_enabled() {
     static const int on = [] { const char* e = getenv("SCAT_SIDE_STREAM"); return (e && e[0] == '0') ? 0 : 1; }();
     return on;
@@ -76,6 +98,7 @@ static SideStream* get_side() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     SideStream& sd = g_side[dev];
+    std::lock_guard<std::mutex> lock(g_side_create);
     if (!sd.ready) {
         if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (int i = 0; i < 32; ++i)
@@ -84,6 +107,14 @@ static SideStream* get_side() {
     }
     return &sd;
 }
+// the device's side stream for the duration of one whole-head call (enqueue phase), exclusive among host threads
+struct SideScope {
+    SideStream* sd;
+    SideScope() : sd(get_side()) { if (sd) sd->mu.lock(); }
+    ~SideScope() { if (sd) sd->mu.unlock(); }
+    SideScope(const SideScope&) = delete;
+    SideScope& operator=(const SideScope&) = delete;
+};
 // everything enqueued on `from` so far happens before anything enqueued on `to` from now on
 static int order_after(SideStream* sd, cudaStream_t from, cudaStream_t to) {
     if (sd == nullptr || from == to) return 0;
@@ -157,6 +188,9 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
                  "desc: token_dim %d must be a multiple of 4 and <= 1024", d.token_dim);
     SCAT_REQUIRE(d.n_masked >= 0 && d.n_masked <= d.n_tokens, kErrBadArg, "desc: n_masked %d", d.n_masked);
     SCAT_REQUIRE(d.precision >= PREC_FP32 && d.precision <= PREC_BF16, kErrBadArg, "desc: precision %d", d.precision);
+    SCAT_REQUIRE(d.x2_dtype == SCAT_DTYPE_F32 || d.x2_dtype == SCAT_DTYPE_BF16, kErrBadArg, "desc: x2_dtype %d", d.x2_dtype);
+    SCAT_REQUIRE(d.x2_dtype == SCAT_DTYPE_F32 || d.precision != PREC_FP32, kErrUnsupported,
+                 "desc: the bf16 seam (x2_dtype) needs a tensor-core precision (tf32 / bf16), fp32 is the CUDA-core parity mode");
     p.B = d.batch; p.T = d.n_tokens; p.C = d.channels; p.D = d.token_dim; p.heads = d.heads;
     p.inner = kDimHead * d.heads; p.M = d.batch * d.n_tokens; p.it = d.iteration; p.F = d.main_feat_dim; p.NP = d.n_out;
     size_t cur = 0;
@@ -220,8 +254,8 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     p.dNa = take(cur, MS * dmax);
     p.dX = take(cur, MS * dmax);
     p.dX16 = p.dX1_16 = 0;
-    p.w_conv = take(cur, p.C > 0 ? (size_t)3 * p.T * p.C : 64);
-    p.dFv2 = take(cur, (p.C > 0 && d.precision != PREC_FP32) ? 3 * M * dmax : 64);
+    p.w_conv = take(cur, p.C > 0 ? conv_weight_prep_floats(p.C, p.T) : 64);
+    p.dFv2 = take(cur, (p.C > 0 && d.precision != PREC_FP32) ? conv_split_floats(p.B, dmax, p.T) : 64);
     if (d.precision == PREC_BF16) {
         p.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
         p.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
@@ -287,12 +321,12 @@ LayerW layer_weights(const HeadPlan& p, int l, const float* const* W, const floa
 }
 
 // one launch: TF32-round (and pad the leading dimension of) every weight a tensor-core GEMM reads
-// which: -1 all, 0 the transformer weights only, 1 the conv weight only
-int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st, int which = -1) {
+// (the conv weight stacks are prepared by launch_conv_weight_prep, conv_tc.cu)
+int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st) {
     RoundJobs jobs;
     int n = 0;
     const bool bf = prec == PREC_BF16;
-    for (int l = 0; l < kDepth && which != 1; ++l) {
+    for (int l = 0; l < kDepth; ++l) {
         const LayerPlan& L = p.L[l];
         jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, bf ? pad8(L.d) : L.ld_qkv};
         jobs.job[n++] = RoundJob{W[L.p_out_w], ws + L.w_out, L.d, p.inner, p.inner, p.inner};
@@ -302,11 +336,6 @@ int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec,
         }
     }
     for (int i = 0; i < n; ++i) jobs.job[i].to_bf16 = bf ? 1 : 0;
-    if (p.C > 0 && which != 0) {                                     // conv stays kind::tf32; stacked [Wh; Wh; Wl] for its dgrad
-        jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv, p.T, p.C, p.C, p.C, 0};
-        jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv + (size_t)p.T * p.C, p.T, p.C, p.C, p.C, 0};
-        jobs.job[n++] = RoundJob{W[P_CONV_W], ws + p.w_conv + (size_t)2 * p.T * p.C, p.T, p.C, p.C, p.C, 2};
-    }
     jobs.n = n;
     if (n == 0) return 0;
     return launch_round_copy(jobs, st);
@@ -518,7 +547,7 @@ int check_ws(const HeadPlan& p, void* ws, size_t bytes) {
 }
 
 int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, const float* mean_params,
-                 const int32_t* mask_idx, const float* x2, const float* main_feat, float* pred, float* fv, float* pl,
+                 const int32_t* mask_idx, const void* x2, const float* main_feat, float* pred, float* fv, float* pl,
                  void* workspace, size_t ws_bytes, cudaStream_t st, bool defer_pl = false) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
@@ -532,21 +561,22 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     // with pos_embed == 0 the reference's token matrix is a view of feat_visual (hand_net.py:364): alias it
     float* X0 = d.pos_embed ? ws + p.L[0].X : fv;
     const bool tc = d.precision != PREC_FP32;
-    SideStream* sd = get_side();
+    SideScope side_scope;
+    SideStream* sd = side_scope.sd;
     const cudaStream_t sg = sd ? sd->s : st;
     // side stream: the iteration-invariant half of the regressor (needs only main_feat) and, below, the weight copies
     SCAT_PROPAGATE(order_after(sd, st, sg));
     SCAT_PROPAGATE(launch_regressor_hoist(main_feat, W[P_REG_W], W[P_REG_B], ws + p.hreg, p.B, p.F, p.NP, sg));
     if (tc) {
-        // per-forward weight copies for the tensor cores (TF32-rounded fp32 or bf16): the conv weight first, on the
-        // main stream; the transformer's copies overlap the conv (a batched tcgen05 GEMM) on the side stream
-        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, st, /*conv=*/1));
-        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, sg, /*conv=*/0));
-        SCAT_PROPAGATE(launch_conv_pe_mask_fwd_tc(x2, ws + p.w_conv, pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed,
-                                                  fv, X0, p.B, p.C, p.D, p.T, st));
+        // per-forward weight copies for the tensor cores: the conv weight stacks first, on the main stream; the
+        // transformer's copies (TF32-rounded fp32 or bf16) overlap the conv kernel on the side stream
+        SCAT_PROPAGATE(launch_conv_weight_prep(W[P_CONV_W], ws + p.w_conv, p.C, p.T, d.x2_dtype, st));
+        SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, sg));
+        SCAT_PROPAGATE(launch_conv_pe_mask_fwd_tc(x2, d.x2_dtype, ws + p.w_conv, pe, W[P_MASK_TOKEN], mask_idx, d.n_masked,
+                                                  d.pos_embed, fv, X0, p.B, p.C, p.D, p.T, st));
     } else {
-        SCAT_PROPAGATE(launch_conv_pe_mask_fwd(x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked, d.pos_embed, fv,
-                                               X0, p.B, p.C, p.D, p.T, st));
+        SCAT_PROPAGATE(launch_conv_pe_mask_fwd((const float*)x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked,
+                                               d.pos_embed, fv, X0, p.B, p.C, p.D, p.T, st));
     }
     SCAT_PROPAGATE(order_after(sd, sg, st));       // weight copies (and the hoisted regressor product) are in place
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
@@ -563,8 +593,8 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     return 0;
 }
 
-int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* mask_idx, const float* x2,
-                  const float* main_feat, const float* g_pred, const float* g_fv, float* const* G, float* x2_grad,
+int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* mask_idx, const void* x2,
+                  const float* main_feat, const float* g_pred, const float* g_fv, float* const* G, void* x2_grad,
                   float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias,
                   float* pl_out = nullptr /* non-null: also sweep the path-length cotangent (stacked) into pl_out */,
                   int phase = -1 /* -1: everything; 0: down to transformer layer 1; 1: layer 0 and masking; 2: conv */) {
@@ -574,7 +604,8 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_REQUIRE(W && G && x2 && main_feat && g_pred, kErrBadArg, "head_backward: null tensor");
     SCAT_REQUIRE(d.pos_embed || fv_alias, kErrBadArg, "head_backward: pos_embed==0 needs the forward's feat_visual");
     float* ws = (float*)workspace;
-    SideStream* sd = get_side();
+    SideScope side_scope;
+    SideStream* sd = side_scope.sd;
     const cudaStream_t sg = sd ? sd->s : st;
     const int sweeps = pl_out ? 2 : 1;
     float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
@@ -636,15 +667,15 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     if (phase == 1) return 0;
     }
     if (d.precision != PREC_FP32) {
-        SCAT_PROPAGATE(launch_split_tf32(ws + p.dFv, ws + p.dFv2, p.B, p.T, p.D, st));
-        // the two HBM streams (x2.grad out, x2 in) are latency bound per CTA: run them side by side
-        SCAT_PROPAGATE(order_after(sd, st, sg));
-        SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, G[P_CONV_W], p.B, p.C, p.D, p.T, sg));   // G was zeroed above
-        if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad_tc(ws + p.dFv2, ws + p.w_conv, x2_grad, p.B, p.C, p.D, p.T, st));
-        SCAT_PROPAGATE(order_after(sd, sg, st));
+        SCAT_PROPAGATE(launch_conv_split(ws + p.dFv, ws + p.dFv2, p.B, p.T, p.D, d.x2_dtype, st));
+        // two persistent one-CTA-per-SM streams (x2 in, x2.grad out): back to back on the main stream
+        SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, d.x2_dtype, G[P_CONV_W], p.B, p.C, p.D, p.T, st));   // G was zeroed above
+        if (x2_grad != nullptr)
+            SCAT_PROPAGATE(launch_conv_dgrad_tc(ws + p.dFv2, ws + p.w_conv, d.x2_dtype, x2_grad, p.B, p.C, p.D, p.T, st));
     } else {
-        if (x2_grad != nullptr) SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], x2_grad, p.B, p.C, p.D, p.T, st));
-        SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
+        if (x2_grad != nullptr)
+            SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], (float*)x2_grad, p.B, p.C, p.D, p.T, st));
+        SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, (const float*)x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
     }
     return 0;
 }
@@ -671,16 +702,16 @@ size_t scat_head_workspace_bytes(const ScatHeadDesc* desc) {
 }
 
 int scat_head_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const float* mean_params,
-                      const int32_t* mask_idx, const float* x2, const float* main_feat, float* pred_params,
+                      const int32_t* mask_idx, const void* x2, const float* main_feat, float* pred_params,
                       float* feat_visual, float* pl_term, void* workspace, size_t workspace_bytes, void* stream) {
     SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
     return head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual, pl_term,
                         workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int scat_head_backward(const ScatHeadDesc* desc, const float* const* params, const int32_t* mask_idx, const float* x2,
+int scat_head_backward(const ScatHeadDesc* desc, const float* const* params, const int32_t* mask_idx, const void* x2,
                        const float* main_feat, const float* feat_visual, const float* grad_pred,
-                       const float* grad_feat_visual, float* const* grads, float* x2_grad, float* main_feat_grad,
+                       const float* grad_feat_visual, float* const* grads, void* x2_grad, float* main_feat_grad,
                        void* workspace, size_t workspace_bytes, void* stream) {
     SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
     return head_backward(*desc, params, mask_idx, x2, main_feat, grad_pred, grad_feat_visual, grads, x2_grad,
@@ -695,10 +726,10 @@ int scat_proj_loss(int32_t batch, int32_t n_tokens, int32_t token_dim, const flo
 }
 
 static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* params, const float* pe,
-                                const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                                const float* mean_params, const int32_t* mask_idx, const void* x2, const float* main_feat,
                                 const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d, float grad_scale,
                                 float* pred_params, float* feat_visual, float* pl_term, float* losses, float* const* grads,
-                                float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream,
+                                void* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream,
                                 int phase) {
     SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
     SCAT_REQUIRE(phase >= -1 && phase <= 2, kErrBadArg, "train_step: phase %d", phase);
@@ -723,20 +754,20 @@ static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* pa
 }
 
 int scat_head_train_step(const ScatHeadDesc* desc, const float* const* params, const float* pe,
-                         const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                         const float* mean_params, const int32_t* mask_idx, const void* x2, const float* main_feat,
                          const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d, float grad_scale,
                          float* pred_params, float* feat_visual, float* pl_term, float* losses, float* const* grads,
-                         float* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream) {
+                         void* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream) {
     return head_train_step_impl(desc, params, pe, mean_params, mask_idx, x2, main_feat, labels, ld_labels, l_weight_3d,
                                 l_weight_2d, grad_scale, pred_params, feat_visual, pl_term, losses, grads, x2_grad,
                                 main_feat_grad, workspace, workspace_bytes, stream, -1);
 }
 
 int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* params, const float* pe,
-                               const float* mean_params, const int32_t* mask_idx, const float* x2, const float* main_feat,
+                               const float* mean_params, const int32_t* mask_idx, const void* x2, const float* main_feat,
                                const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d,
                                float grad_scale, float* pred_params, float* feat_visual, float* pl_term, float* losses,
-                               float* const* grads, float* x2_grad, float* main_feat_grad, void* workspace,
+                               float* const* grads, void* x2_grad, float* main_feat_grad, void* workspace,
                                size_t workspace_bytes, void* stream, int32_t phase) {
     return head_train_step_impl(desc, params, pe, mean_params, mask_idx, x2, main_feat, labels, ld_labels, l_weight_3d,
                                 l_weight_2d, grad_scale, pred_params, feat_visual, pl_term, losses, grads, x2_grad,
@@ -808,45 +839,41 @@ int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe,
                                    batch, channels, hw, n_tokens, (cudaStream_t)stream);
 }
 
-// ---- tensor-core (tcgen05 kind::tf32) front end as single operators: what the head runs in TF32 / BF16 mode ----
+// ---- tensor-core front end (conv_tc.cu) as single operators: what the head runs in TF32 / BF16 mode ----
 size_t scat_conv_tc_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens) {
-    return round_up((size_t)3 * n_tokens * channels, 64) + (size_t)4 * batch * n_tokens * hw;
+    // [weight stacks][d tokens with masked rows zeroed][split d tokens]
+    return round_up(conv_weight_prep_floats(channels, n_tokens), 64) + (size_t)batch * n_tokens * hw +
+           conv_split_floats(batch, hw, n_tokens);
 }
 
-static int round_conv_weight(const float* conv_w, float* dst, int T, int C, cudaStream_t st) {
-    RoundJobs jobs;                          // [Wh; Wh; Wl]: TF32-nearest twice, then its TF32 remainder
-    jobs.job[0] = RoundJob{conv_w, dst, T, C, C, C, 0};
-    jobs.job[1] = RoundJob{conv_w, dst + (size_t)T * C, T, C, C, C, 0};
-    jobs.job[2] = RoundJob{conv_w, dst + (size_t)2 * T * C, T, C, C, C, 2};
-    jobs.n = 3;
-    return launch_round_copy(jobs, st);
-}
-
-int scat_conv_pe_mask_fwd_tc(const float* x2, const float* conv_w, const float* pe, const float* mask_token,
+int scat_conv_pe_mask_fwd_tc(const void* x2, int32_t x2_dtype, const float* conv_w, const float* pe, const float* mask_token,
                              const int32_t* mask_idx, int32_t n_masked, int32_t pos_embed, float* feat_visual,
                              float* tokens_out, float* scratch, int32_t batch, int32_t channels, int32_t hw,
                              int32_t n_tokens, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    SCAT_REQUIRE(scratch, kErrBadArg, "conv_fwd_tc: scratch is null");
-    SCAT_PROPAGATE(round_conv_weight(conv_w, scratch, n_tokens, channels, st));
-    return launch_conv_pe_mask_fwd_tc(x2, scratch, pe, mask_token, mask_idx, n_masked, pos_embed, feat_visual, tokens_out,
-                                      batch, channels, hw, n_tokens, st);
+    SCAT_REQUIRE(scratch && x2 && conv_w && feat_visual && tokens_out, kErrBadArg, "conv_fwd_tc: null argument");
+    SCAT_REQUIRE(x2_dtype == SCAT_DTYPE_F32 || x2_dtype == SCAT_DTYPE_BF16, kErrBadArg, "conv_fwd_tc: x2_dtype %d", x2_dtype);
+    SCAT_PROPAGATE(launch_conv_weight_prep(conv_w, scratch, channels, n_tokens, x2_dtype, st));
+    return launch_conv_pe_mask_fwd_tc(x2, x2_dtype, scratch, pe, mask_token, mask_idx, n_masked, pos_embed, feat_visual,
+                                      tokens_out, batch, channels, hw, n_tokens, st);
 }
 
-int scat_conv_bwd_tc(const float* d_tokens, const float* x2, const float* conv_w, const int32_t* mask_idx,
-                     int32_t n_masked, float* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
+int scat_conv_bwd_tc(const float* d_tokens, const void* x2, int32_t x2_dtype, const float* conv_w, const int32_t* mask_idx,
+                     int32_t n_masked, void* x2_grad, float* conv_w_grad, float* mask_token_grad, float* scratch,
                      int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    SCAT_REQUIRE(scratch, kErrBadArg, "conv_bwd_tc: scratch is null");
-    float* w_tf32 = scratch;
-    float* dFv = scratch + round_up((size_t)3 * n_tokens * channels, 64);
-    float* dFv2 = dFv + (size_t)batch * n_tokens * hw;
-    SCAT_PROPAGATE(round_conv_weight(conv_w, w_tf32, n_tokens, channels, st));
+    SCAT_REQUIRE(scratch && d_tokens && x2 && conv_w && conv_w_grad, kErrBadArg, "conv_bwd_tc: null argument");
+    SCAT_REQUIRE(x2_dtype == SCAT_DTYPE_F32 || x2_dtype == SCAT_DTYPE_BF16, kErrBadArg, "conv_bwd_tc: x2_dtype %d", x2_dtype);
+    float* w_prep = scratch;
+    float* dFv = scratch + round_up(conv_weight_prep_floats(channels, n_tokens), 64);
+    float* dsplit = dFv + (size_t)batch * n_tokens * hw;
+    SCAT_PROPAGATE(launch_conv_weight_prep(conv_w, w_prep, channels, n_tokens, x2_dtype, st));
     SCAT_PROPAGATE(launch_mask_bwd(d_tokens, mask_idx, n_masked, 0, dFv, mask_token_grad, batch, n_tokens, hw, st));
-    SCAT_PROPAGATE(launch_split_tf32(dFv, dFv2, batch, n_tokens, hw, st));
-    if (x2_grad) SCAT_PROPAGATE(launch_conv_dgrad_tc(dFv2, w_tf32, x2_grad, batch, channels, hw, n_tokens, st));
+    SCAT_PROPAGATE(launch_conv_split(dFv, dsplit, batch, n_tokens, hw, x2_dtype, st));
     SCAT_CHECK_CUDA(cudaMemsetAsync(conv_w_grad, 0, (size_t)n_tokens * channels * sizeof(float), st));
-    return launch_conv_wgrad_tc(dFv2, x2, conv_w_grad, batch, channels, hw, n_tokens, st);
+    SCAT_PROPAGATE(launch_conv_wgrad_tc(dsplit, x2, x2_dtype, conv_w_grad, batch, channels, hw, n_tokens, st));
+    if (x2_grad) SCAT_PROPAGATE(launch_conv_dgrad_tc(dsplit, w_prep, x2_dtype, x2_grad, batch, channels, hw, n_tokens, st));
+    return 0;
 }
 
 size_t scat_conv_bwd_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens) {

@@ -53,7 +53,6 @@ struct GemmArgs {
     int a_row_z = 0, a_k_z = 0, b_row_z = 0, b_k_z = 0;   // per-problem offsets of the operands along rows / k (elements)
     long long c_z = 0, aux_out_z = 0;                    // per-problem element offsets of C / aux_out
     int batch_accumulate = 0;    // every problem reduces into the same C (red.global.add; C pre-zeroed): K split over the batch
-    float out_scale = 1.0f;      // accumulator scale (compensates the tensor core truncating fp32 operands, see conv_tc)
     const int32_t* mask_idx = nullptr; int n_masked = 0;   // EPI_PE_MASK
     int force_bn = 0;            // 64 / 128: tile width override
 };
@@ -95,18 +94,24 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
 size_t conv_wgrad_scratch_floats(int C, int T);
 int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scratch, int B, int C, int HW, int T,
                       cudaStream_t stream);
-// Tensor-core versions (tcgen05 kind::tf32 through the batched GEMM kernel, one problem per sample, HBM bound).
-// Wc_tf32: the conv weight rounded to TF32-nearest.  x2 / d tokens are read as they are: the tensor core truncates
-// them to TF32, a ~3.3e-4 relative shrink per truncated operand that `out_scale` undoes (see conv.cu).
-int launch_conv_pe_mask_fwd_tc(const float* x2, const float* Wc_tf32, const float* pe, const float* mask_token,
+// Tensor-core versions (conv_tc.cu): three persistent tcgen05 kernels, HBM streams of x2 / x2.grad.  x2_bf16 selects
+// the seam dtype: 0 = fp32 x2 / x2.grad (kind::tf32, x2 rounded to TF32-nearest in shared memory), 1 = bf16 x2 / x2.grad
+// (kind::f16, exact operands, the fp32 weight and d tokens enter as stacked bf16 split terms).
+//   Wprep  = launch_conv_weight_prep(conv weight)   conv_weight_prep_floats(C, T) floats, once per forward
+//   dsplit = launch_conv_split(d tokens [B,T,HW], masked rows zero)   conv_split_floats(B, HW, T) floats
+size_t conv_weight_prep_floats(int C, int T);
+size_t conv_split_floats(int B, int HW, int T);
+int launch_conv_weight_prep(const float* Wc, void* Wprep, int C, int T, int x2_bf16, cudaStream_t stream);
+int launch_conv_split(const float* dFv, void* dsplit, int B, int T, int HW, int x2_bf16, cudaStream_t stream);
+int launch_conv_pe_mask_fwd_tc(const void* x2, int x2_bf16, const void* Wprep, const float* pe, const float* mask_token,
                                const int32_t* mask_idx, int n_masked, int pos_embed, float* feat_visual, float* X0,
                                int B, int C, int HW, int T, cudaStream_t stream);
-// backward: dFv2 [B,3T,HW] = launch_split_tf32(dFv) (TF32 hi / lo / hi), Wc2_tf32 [3T,C] = [Wh; Wh; Wl] (TF32 hi, hi, lo)
+// dFv [B,T,HW] -> [B,3T,HW] = TF32 hi / lo / hi (the fp32-seam split; launch_conv_split dispatches to it)
 int launch_split_tf32(const float* dFv, float* dFv2, int B, int T, int HW, cudaStream_t stream);
-int launch_conv_dgrad_tc(const float* dFv2, const float* Wc2_tf32, float* x2_grad, int B, int C, int HW, int T,
+int launch_conv_dgrad_tc(const void* dsplit, const void* Wprep, int x2_bf16, void* x2_grad, int B, int C, int HW, int T,
                          cudaStream_t stream);
-int launch_conv_wgrad_tc(const float* dFv2, const float* x2, float* dWc /* pre-zeroed */, int B, int C, int HW, int T,
-                         cudaStream_t stream);
+int launch_conv_wgrad_tc(const void* dsplit, const void* x2, int x2_bf16, float* dWc /* pre-zeroed */, int B, int C, int HW,
+                         int T, cudaStream_t stream);
 // token-only front end (config 4): X0 = tokens (+pe) with masked rows replaced
 int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mask_token, const int32_t* mask_idx,
                           int n_masked, int pos_embed, float* X0, int B, int T, int D, cudaStream_t stream);

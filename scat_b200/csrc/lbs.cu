@@ -475,11 +475,7 @@ template <int S, int NVT>
 int launch_lbs_v2(const float* derived, const float* hands_mean, const float* rots, const float* poses, const float* betas,
                   float* out, int B, cudaStream_t stream) {
     const size_t smem = sizeof(LbsSmemV2<S>);
-    static bool raised = false;
-    if (!raised) {
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(lbs_fwd_v2_kernel<S, NVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raised = true;
-    }
+    SCAT_ENSURE_SMEM((lbs_fwd_v2_kernel<S, NVT>), smem);
     SCAT_CHECK_CUDA(launch_k(lbs_fwd_v2_kernel<S, NVT>, dim3(ceil_div(B, S)), dim3(LBS_THREADS), smem, stream, derived, hands_mean,
                              rots, poses, betas, out, B));
     SCAT_CHECK_LAUNCH();

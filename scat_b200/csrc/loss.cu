@@ -49,12 +49,14 @@ proj_loss_kernel(const float* __restrict__ pred, const float* __restrict__ label
     __shared__ float scratch[LOSS_THREADS / 32];
     const int tid = threadIdx.x;
     const float inv3 = 1.0f / (63.0f * (float)B), inv2 = 1.0f / (42.0f * (float)B);
+    // train.py:188-199: 105-wide rows are [63 3D | 42 2D]; wider rows (FreiHAND / HO-3D) are [61 pose | 63 3D | 42 2D]
+    const int off3 = ld_labels == 105 ? 0 : 61;
     float a3 = 0.f, a2 = 0.f;
     // one thread per (sample, joint): 3D term for 3 coords, 2D term for 2 coords
     for (int e = tid; e < B * 21; e += LOSS_THREADS) {
         const int b = e / 21, t = e % 21;
         const float* p = pred + (long long)b * 66;
-        const float* lb = labels + (long long)b * ld_labels;
+        const float* lb = labels + (long long)b * ld_labels + off3;
         const float s = p[0], tx = p[1], ty = p[2];
         const float jx = p[3 + 3 * t], jy = p[4 + 3 * t], jz = p[5 + 3 * t];
         const float dx = jx - lb[3 * t], dy = jy - lb[3 * t + 1], dz = jz - lb[3 * t + 2];
@@ -77,7 +79,7 @@ proj_loss_kernel(const float* __restrict__ pred, const float* __restrict__ label
     if (g_pred != nullptr) {
         for (int b = tid; b < B; b += LOSS_THREADS) {
             const float* p = pred + (long long)b * 66;
-            const float* lb = labels + (long long)b * ld_labels;
+            const float* lb = labels + (long long)b * ld_labels + off3;
             const float s = p[0], tx = p[1], ty = p[2];
             float gs = 0.f, gtx = 0.f, gty = 0.f;
             for (int t = 0; t < 21; ++t) {
@@ -152,7 +154,9 @@ int launch_proj_loss(const float* pred, const float* labels, int ld_labels, cons
                      int n_tokens, float w3d, float w2d, float grad_scale, float* losses, float* g_pred,
                      float* pl_scratch, int B, cudaStream_t stream) {
     SCAT_REQUIRE(pred && labels && losses && B > 0, kErrBadArg, "proj_loss: bad args");
-    SCAT_REQUIRE(ld_labels >= 105, kErrBadArg, "proj_loss: labels need >= 105 columns (63 3D + 42 2D), got %d", ld_labels);
+    // the reference slices by width (train.py:188-199) and its L1 loss needs exactly 42 2D columns behind the 3D block
+    SCAT_REQUIRE(ld_labels == 105 || ld_labels == 166, kErrBadArg,
+                 "proj_loss: label rows are 105 wide (63 3D + 42 2D) or 166 wide (61 pose + 63 3D + 42 2D), got %d", ld_labels);
     if (pl_term != nullptr) {
         SCAT_REQUIRE(pl_scratch != nullptr, kErrBadArg, "proj_loss: pl_scratch[B] required with pl_term");
         SCAT_CHECK_CUDA(launch_k(rowsumsq_kernel, dim3(B), dim3(LOSS_THREADS), 0, stream, pl_term, pl_row_elems, pl_scratch));

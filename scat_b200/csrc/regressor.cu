@@ -159,8 +159,7 @@ int launch_regressor_hoist(const float* main_feat, const float* Wr, const float*
                  "regressor: P=%d F=%d out of range (F even, P<=96, F<=4096)", P, F);
     SCAT_REQUIRE(h_scratch != nullptr, kErrBadArg, "regressor: h scratch [B,P] required");
     const size_t smem1 = sizeof(float) * (size_t)HS * F;
-    if (smem1 > 48 * 1024)
-        SCAT_CHECK_CUDA(cudaFuncSetAttribute(regressor_hoist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    if (smem1 > 48 * 1024) SCAT_ENSURE_SMEM(regressor_hoist_kernel, smem1);
     SCAT_CHECK_CUDA(launch_k(regressor_hoist_kernel, dim3(dim3(ceil_div(B, HS), ceil_div(P, HJ))), dim3(256), smem1, stream, main_feat, Wr, br, h_scratch, B, F, P));
     SCAT_CHECK_LAUNCH();
     return 0;

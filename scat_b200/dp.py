@@ -211,6 +211,10 @@ class PeerMemory:
         self._check(self.lib.scat_peer_allreduce(self._bucket_arr, self._signal_arr, self.rank, self.world, lo, hi,
                                                  stream_ptr), "scat_peer_allreduce")
 
+    def error_word(self):
+        """Device address (ctypes void pointer) of this rank's sticky time-out flag, for scat_adam_step's abort_flag."""
+        return self._C.c_void_p(self.lib.scat_peer_error_word(self._signal))
+
     def timed_out(self) -> bool:
         """True when a kernel gave up waiting for a peer (synchronises the device)."""
         out = self._C.c_int32(0)

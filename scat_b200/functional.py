@@ -7,12 +7,13 @@ library or a non-CUDA tensor raises.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 
 import torch
 
 from . import _lib
-from ._lib import PREC, EPI, ScatHeadDesc, check, ptr, ptr_array, stream_ptr
+from ._lib import PREC, EPI, X2_DTYPE, ScatHeadDesc, check, ptr, ptr_array, stream_ptr
 
 
 @dataclass(frozen=True)
@@ -28,11 +29,23 @@ class HeadConfig:
     token_dim: int = 784
     main_feat_dim: int = 1024
     n_out: int = 66
+    x2_dtype: str = "fp32"          # seam storage of x2 and x2.grad: "fp32" (resnet.py:151) or "bf16" (autocast backbone)
 
     def desc(self, batch: int) -> ScatHeadDesc:
         return ScatHeadDesc(batch, self.n_tokens, self.channels, self.token_dim, self.heads, self.iteration,
                             int(self.pos_embed), self.n_masked, int(self.pl_reg), PREC[self.precision],
-                            self.main_feat_dim, self.n_out)
+                            self.main_feat_dim, self.n_out, X2_DTYPE[self.x2_dtype])
+
+
+def _seam(t: torch.Tensor, name: str):
+    """The backbone seam tensor x2: fp32 or bf16, NCHW contiguous.  Returns (tensor, "fp32" | "bf16")."""
+    if not t.is_cuda:
+        raise RuntimeError(f"scat_b200: {name} must be a CUDA tensor (the head has no CPU path)")
+    if t.dtype == torch.float32:
+        return t.contiguous(), "fp32"
+    if t.dtype == torch.bfloat16:
+        return t.contiguous(), "bf16"
+    raise RuntimeError(f"scat_b200: {name} must be float32 or bfloat16, got {t.dtype}")
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -62,7 +75,11 @@ class HeadFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: HeadConfig, mask_idx, mean_params, pe, x2, main_feat, *params):
         lib = _lib.load()
-        x2 = _f32c(x2, "x2")
+        x2, seam = _seam(x2, "x2")
+        if seam != cfg.x2_dtype:
+            cfg = dataclasses.replace(cfg, x2_dtype=seam)      # the seam dtype follows the tensor the backbone delivered
+        if seam == "bf16" and cfg.precision == "fp32":
+            raise RuntimeError("scat_b200: a bfloat16 x2 needs precision 'tf32' or 'bf16' (fp32 is the CUDA-core parity mode)")
         main_feat = _f32c(main_feat, "main_feat")
         B = x2.shape[0]
         params = [_f32c(p.detach(), "parameter") for p in params]
@@ -262,17 +279,20 @@ def attention_bwd(qkv, p, d_o, batch, n, heads, tc=False):
 
 
 def conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, pos_embed=True, tc=False):
-    """hand_net.py:363-373.  tc=False: fp32 FFMA kernel (parity mode); tc=True: tcgen05 kind::tf32 batched GEMM."""
+    """hand_net.py:363-373.  tc=False: fp32 FFMA kernel (parity mode); tc=True: the persistent tcgen05 kernel
+    (csrc/conv_tc.cu), x2 fp32 (kind::tf32) or bfloat16 (kind::f16)."""
     lib = _lib.load()
-    x2 = _f32c(x2, "x2")
+    x2, seam = _seam(x2, "x2")
+    if seam == "bf16" and not tc:
+        raise RuntimeError("scat_b200: a bfloat16 x2 needs the tensor-core front end (tc=True)")
     B, Cc, H, W = x2.shape
     T = conv_w.shape[0]
-    fv = torch.empty(B, T, H, W, device=x2.device)
-    tok = torch.empty(B, T, H * W, device=x2.device) if pos_embed else fv
+    fv = torch.empty(B, T, H, W, device=x2.device, dtype=torch.float32)
+    tok = torch.empty(B, T, H * W, device=x2.device, dtype=torch.float32) if pos_embed else fv
     n_masked = 0 if mask_idx is None else int(mask_idx.numel())
     if tc:
         scratch = torch.empty(lib.scat_conv_tc_scratch_floats(B, Cc, H * W, T), device=x2.device)
-        check(lib.scat_conv_pe_mask_fwd_tc(ptr(x2), ptr(_f32c(conv_w, "conv_w")), ptr(pe), ptr(mask_token), ptr(mask_idx),
+        check(lib.scat_conv_pe_mask_fwd_tc(ptr(x2), X2_DTYPE[seam], ptr(_f32c(conv_w, "conv_w")), ptr(pe), ptr(mask_token), ptr(mask_idx),
                                            n_masked, int(pos_embed), ptr(fv), ptr(tok), ptr(scratch), B, Cc, H * W, T,
                                            stream_ptr()), "scat_conv_pe_mask_fwd_tc")
         return fv, tok.view(B, T, H * W)
@@ -283,16 +303,20 @@ def conv_pe_mask_fwd(x2, conv_w, pe, mask_token, mask_idx, pos_embed=True, tc=Fa
 
 
 def conv_bwd(d_tokens, x2, conv_w, mask_idx, need_x2_grad=True, tc=False):
+    """Backward of the conv front end; x2.grad comes back in x2's dtype (fp32, or bfloat16 with tc=True)."""
     lib = _lib.load()
+    x2, seam = _seam(x2, "x2")
+    if seam == "bf16" and not tc:
+        raise RuntimeError("scat_b200: a bfloat16 x2 needs the tensor-core front end (tc=True)")
     B, Cc, H, W = x2.shape
     T = conv_w.shape[0]
     n_masked = 0 if mask_idx is None else int(mask_idx.numel())
     x2g = torch.empty_like(x2) if need_x2_grad else None
-    wg = torch.empty(T, Cc, device=x2.device)
+    wg = torch.empty(T, Cc, device=x2.device, dtype=torch.float32)
     mg = torch.zeros(H * W, device=x2.device)
     if tc:
         scratch = torch.empty(lib.scat_conv_tc_scratch_floats(B, Cc, H * W, T), device=x2.device)
-        check(lib.scat_conv_bwd_tc(ptr(_f32c(d_tokens, "d_tokens")), ptr(x2), ptr(_f32c(conv_w, "conv_w")), ptr(mask_idx),
+        check(lib.scat_conv_bwd_tc(ptr(_f32c(d_tokens, "d_tokens")), ptr(x2), X2_DTYPE[seam], ptr(_f32c(conv_w, "conv_w")), ptr(mask_idx),
                                    n_masked, ptr(x2g), ptr(wg), ptr(mg) if n_masked else None, ptr(scratch), B, Cc, H * W,
                                    T, stream_ptr()), "scat_conv_bwd_tc")
         return x2g, wg, mg

@@ -116,13 +116,14 @@ class EncoderTransformer(nn.Module):
             return masked[: int(self.mask_rate * self.full_content)]
         return []
 
-    def config(self, n_masked: int) -> SF.HeadConfig:
+    def config(self, n_masked: int, x2_dtype: str = "fp32") -> SF.HeadConfig:
         return SF.HeadConfig(heads=self.transformer.heads, iteration=int(self.iteration),
                              pos_embed=bool(self.pos_embed), n_masked=n_masked, pl_reg=bool(self.pl),
-                             precision=self.precision)
+                             precision=self.precision, x2_dtype=x2_dtype)
 
     def forward_features(self, main_feat, x2, mask_idx=None):
-        """The head proper, from the backbone seam tensors (main_feat[B,1024], x2[B,512,28,28])."""
+        """The head proper, from the backbone seam tensors (main_feat[B,1024] fp32, x2[B,512,28,28] fp32 or -- from a
+        bf16 / autocast backbone -- bfloat16, in which case x2.grad is delivered as bfloat16 too)."""
         if self.pl and not torch.is_grad_enabled():
             # same failure as the reference under no_grad (autograd.grad at hand_net.py:396)
             raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn")

@@ -9,7 +9,7 @@ keeps a PyTorch optimiser (north_star: the backbone stays a PyTorch feature prod
 
 Used with ``HeadTrainStep.attach_optimizer`` the update is captured into the same CUDA graph as forward, backward and
 the gradient all-reduce; step count and learning rate then live in device memory and are refreshed by one small
-host-to-device copy per step.
+asynchronous host-to-device copy per step (pinned staging ring, no stream synchronisation).
 """
 from __future__ import annotations
 
@@ -45,6 +45,8 @@ class WarmupSchedule:
 
 
 class HeadAdam(torch.optim.Optimizer):
+    _RING = 8          # pinned staging slots for (step, learning rate): the host may run this many steps ahead
+
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError(f"HeadAdam: lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
@@ -64,6 +66,14 @@ class HeadAdam(torch.optim.Optimizer):
         self._sched_dev = torch.zeros(2, dtype=torch.int32, device=dev)      # [step, bits of the fp32 learning rate]
         self._step_dev = self._sched_dev[0:1]
         self._lr_dev = self._sched_dev[1:2].view(torch.float32)
+        # (step, learning-rate bits) travel through a small ring of pinned host words, one asynchronous copy per step:
+        # a pageable source would make copy_ synchronise the stream, i.e. drain the device every step
+        self._sched_host = torch.zeros(self._RING, 2, dtype=torch.int32).pin_memory() if dev.type == "cuda" else None
+        self._sched_events = [None] * self._RING
+        self._sched_turn = 0
+        # device address of a word that, when non-zero, turns the update into a no-op (HeadTrainStep wires it to the
+        # gradient exchange's time-out flag)
+        self.abort_flag = None
         self._link_state()
 
     def _link_state(self):
@@ -85,7 +95,7 @@ class HeadAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         check(self.lib.scat_adam_step(ptr(self.flat_params), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n,
                                       lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], step, lr_dev,
-                                      step_dev, stream_ptr()), "scat_adam_step")
+                                      step_dev, self.abort_flag, stream_ptr()), "scat_adam_step")
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -99,9 +109,17 @@ class HeadAdam(torch.optim.Optimizer):
     def advance(self):
         """Count one step and stage (learning rate, step) for the device on the current stream."""
         self.step_count += 1
-        lr_bits = torch.tensor([float(self.param_groups[0]["lr"])], dtype=torch.float32).view(torch.int32)
-        # pageable source: the driver stages these 8 bytes before returning, so the host may run steps ahead
-        self._sched_dev.copy_(torch.cat([torch.tensor([self.step_count], dtype=torch.int32), lr_bits]))
+        k = self._sched_turn % self._RING
+        self._sched_turn += 1
+        if self._sched_events[k] is not None:
+            self._sched_events[k].synchronize()          # the copy that last read this pinned slot (RING steps ago) is done
+        slot = self._sched_host[k]
+        slot[0] = self.step_count
+        slot[1:2].view(torch.float32)[0] = float(self.param_groups[0]["lr"])
+        self._sched_dev.copy_(slot, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._sched_events[k] = ev
 
     def enqueue(self, grads: torch.Tensor = None):
         """The update with count / rate read from device memory (capturable; call advance() before each replay)."""

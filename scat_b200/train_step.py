@@ -37,10 +37,13 @@ from ._lib import check, ptr, ptr_array
 
 
 class HeadTrainStep:
+    _RING = 8            # pinned staging slots for the mask indices
+    POLL_EVERY = 256     # steps between looks at the gradient exchange's time-out flag (each look drains the device)
+
     def __init__(self, net, batch: int, l_weight_3d: float = 1e5, l_weight_2d: float = 10.0, *,
                  need_x2_grad: bool = True, need_main_feat_grad: bool = True, use_graph: bool = True,
                  process_group=None, input_slots: int = 1, phased: Optional[bool] = None,
-                 comm: str = "auto"):
+                 comm: str = "auto", x2_dtype: str = "fp32", label_width: int = 105):
         self.net = net
         self.batch = int(batch)
         self.w3d, self.w2d = float(l_weight_3d), float(l_weight_2d)
@@ -74,21 +77,36 @@ class HeadTrainStep:
         self.bucket = dp.FlatGradBucket(self.params, flat=self.peer.flat if self.peer is not None else None)
         r = net.mask_rate
         self.n_masked = int(r * net.full_content) if (r >= 0.1 and r <= 0.9) else 0
-        self.cfg = net.config(self.n_masked)
+        if x2_dtype not in ("fp32", "bf16"):
+            raise ValueError(f"x2_dtype={x2_dtype!r}: 'fp32' or 'bf16'")
+        # seam storage: x2 arrives, and x2.grad leaves, in the backbone's dtype
+        self.x2_dtype = x2_dtype
+        seam_t = torch.bfloat16 if x2_dtype == "bf16" else torch.float32
+        self.cfg = net.config(self.n_masked, x2_dtype=x2_dtype)
         B = self.batch
         self.n_slots = int(input_slots)
-        self.x2s = [torch.empty(B, 512, 28, 28, device=dev) for _ in range(self.n_slots)]
+        self.x2s = [torch.empty(B, 512, 28, 28, device=dev, dtype=seam_t) for _ in range(self.n_slots)]
         self.main_feats = [torch.empty(B, 1024, device=dev) for _ in range(self.n_slots)]
-        self.labelss = [torch.empty(B, 105, device=dev) for _ in range(self.n_slots)]
+        # train.py:188-199 slices the label rows by their width: 105 = [63 3D | 42 2D], 166 = [61 pose | 63 3D | 42 2D]
+        if label_width not in (105, 166):
+            raise ValueError(f"label_width={label_width}: the reference's label rows are 105 or 166 wide (train.py:188-199)")
+        self.label_width = int(label_width)
+        self.labelss = [torch.empty(B, self.label_width, device=dev) for _ in range(self.n_slots)]
         self.copied: List[Optional[torch.cuda.Event]] = [None] * self.n_slots     # slot contents are ready
         self.consumed: List[Optional[torch.cuda.Event]] = [None] * self.n_slots   # slot may be overwritten
         self.pred = torch.empty(B, 66, device=dev)
         self.feat_visual = torch.empty(B, 21, 28, 28, device=dev)
         self.pl = torch.empty(B, 21, 28, 28, device=dev) if self.cfg.pl_reg else None
         self.losses = torch.zeros(4, device=dev)
-        self.x2_grad = torch.empty(B, 512, 28, 28, device=dev) if need_x2_grad else None
+        self.x2_grad = torch.empty(B, 512, 28, 28, device=dev, dtype=seam_t) if need_x2_grad else None
         self.main_feat_grad = torch.empty(B, 1024, device=dev) if need_main_feat_grad else None
         self.mask_dev = torch.zeros(max(self.n_masked, 1), dtype=torch.int32, device=dev)
+        # the host-drawn indices travel through a ring of pinned slots, one asynchronous copy per step (a pageable source
+        # would make copy_ synchronise the stream every step and expose the graph-launch latency)
+        self._mask_host = torch.zeros(self._RING, max(self.n_masked, 1), dtype=torch.int32).pin_memory()
+        self._mask_events: List[Optional[torch.cuda.Event]] = [None] * self._RING
+        self._mask_turn = 0
+        self._steps_since_poll = 0
         self.ws = SF.alloc_workspace(self.cfg, B, dev)
         self.last_mask = []
         self.use_graph = use_graph
@@ -144,6 +162,8 @@ class HeadTrainStep:
         if opt.flat_params.data_ptr() != self.flat_params.data_ptr() or opt.n != self.flat_params.numel():
             raise ValueError("attach_optimizer: the optimiser does not own this step's parameters")
         self.opt = opt
+        if self.peer is not None:          # a gradient exchange that gave up on a peer must not reach the weights
+            opt.abort_flag = self.peer.error_word()
         self.graphs = {k: g for k, g in self.graphs.items() if not k[2]}
 
     def _enqueue_all(self, slot: int, ar: bool, optimize: bool):
@@ -187,7 +207,15 @@ class HeadTrainStep:
             raise ValueError(f"mask has {len(masked)} indices, configuration expects {self.n_masked}")
         self.last_mask = masked
         if self.n_masked:
-            self.mask_dev.copy_(torch.tensor(masked, dtype=torch.int32))    # pageable source: staged synchronously
+            k = self._mask_turn % self._RING
+            self._mask_turn += 1
+            if self._mask_events[k] is not None:
+                self._mask_events[k].synchronize()       # the copy that read this pinned slot _RING steps ago has finished
+            self._mask_host[k].copy_(torch.tensor(masked, dtype=torch.int32))
+            self.mask_dev.copy_(self._mask_host[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._mask_events[k] = ev
         return masked
 
     def load_inputs(self, x2, main_feat, labels, slot: int = 0, stream: Optional[torch.cuda.Stream] = None,
@@ -201,7 +229,10 @@ class HeadTrainStep:
                 cur.wait_event(self.consumed[slot])
             self.x2s[slot].copy_(x2.view_as(self.x2s[slot]), non_blocking=non_blocking)
             self.main_feats[slot].copy_(main_feat, non_blocking=non_blocking)
-            self.labelss[slot].copy_(labels[:, :105], non_blocking=non_blocking)
+            if labels.shape[1] != self.label_width:
+                raise ValueError(f"load_inputs: labels are {labels.shape[1]} wide, this step was built for label_width="
+                                 f"{self.label_width} (train.py:188-199 picks the 3D / 2D columns by the row width)")
+            self.labelss[slot].copy_(labels, non_blocking=non_blocking)
             ev = torch.cuda.Event()
             ev.record(cur)
             self.copied[slot] = ev
@@ -252,7 +283,20 @@ class HeadTrainStep:
             self.bucket.all_reduce(self.pg)
         if optimize and not opt_in_graph:
             self.opt.enqueue(self.bucket.flat)
+        if self.peer is not None and do_ar:
+            self._steps_since_poll += 1
+            if self._steps_since_poll >= self.POLL_EVERY:
+                self.check_peers()
         return self.losses
+
+    def check_peers(self):
+        """Raise if a gradient exchange gave up waiting for a peer (20 s bounded wait).  From that step on the exchange
+        and the attached optimiser are no-ops on this rank, so the weights are those of the last complete step.
+        Synchronises the device; step() calls it every POLL_EVERY steps."""
+        self._steps_since_poll = 0
+        if self.peer is not None and self.peer.timed_out():
+            raise RuntimeError("scat_b200: a rank never arrived at the gradient all-reduce (20 s bounded wait); the "
+                               "exchange and the optimiser update were skipped from that step on")
 
 
     def close(self):

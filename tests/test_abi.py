@@ -40,7 +40,7 @@ def test_ctypes_binding_covers_header(lib_path):
     from scat_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.scat_abi_version() == 1
+    assert lib.scat_abi_version() == _lib.ABI_VERSION
 
 
 def test_workspace_query_and_argument_errors_need_no_gpu(lib_path):
@@ -72,12 +72,12 @@ def test_new_entry_points_validate_arguments_without_a_gpu(lib_path):
     from scat_b200 import _lib
     lib = _lib.load()
     fake = ctypes.c_void_p(0x1000)                      # never dereferenced: validation fails first
-    assert lib.scat_adam_step(None, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None) == -1
-    assert lib.scat_adam_step(fake, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None, None, None) == -1
+    assert lib.scat_adam_step(None, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None, None) == -1
+    assert lib.scat_adam_step(fake, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, None, None, None, None) == -1
     assert b"step" in lib.scat_last_error_string()
-    assert lib.scat_adam_step(fake, fake, fake, fake, 16, 1e-4, 1.0, 0.999, 1e-8, 0.0, 1, None, None, None) == -1
+    assert lib.scat_adam_step(fake, fake, fake, fake, 16, 1e-4, 1.0, 0.999, 1e-8, 0.0, 1, None, None, None, None) == -1
     misaligned = ctypes.c_void_p(0x1004)
-    assert lib.scat_adam_step(misaligned, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None) == -1
+    assert lib.scat_adam_step(misaligned, fake, fake, fake, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None, None) == -1
     assert b"aligned" in lib.scat_last_error_string()
 
     ptrs = (ctypes.c_void_p * 3)(0x1000, 0x2000, 0x3000)

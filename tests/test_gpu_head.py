@@ -21,10 +21,12 @@ pytestmark = pytest.mark.gpu
 HEAD_CASES = ["head_kat_b2", "head_b3_mask50", "head_b2_nope_alias", "head_b2_h4_it1_nomask", "head_b2_mask90"]
 
 
-def _run_module_step(net, x2, mf, labels, mask_seed):
-    """train.py:159-206 body through the drop-in module + autograd (loss via the CUDA loss kernel)."""
+def _run_module_step(net, x2, mf, labels, mask_seed, seam="fp32"):
+    """train.py:159-206 body through the drop-in module + autograd (loss via the CUDA loss kernel).  seam="bf16": the
+    backbone hands x2 over as bfloat16 (x2 must then hold bf16-representable values) and receives a bfloat16 x2.grad."""
     from scat_b200 import functional as SF
-    x2d = torch.from_numpy(x2).cuda().requires_grad_(True)
+    x2d = torch.from_numpy(x2).cuda()
+    x2d = (x2d.bfloat16() if seam == "bf16" else x2d).requires_grad_(True)
     mfd = torch.from_numpy(mf).cuda().requires_grad_(True)
     net.main_encoder.x2, net.main_encoder.main_feat = x2d, mfd
     random.seed(mask_seed)
@@ -129,6 +131,39 @@ def test_head_config2_bf16_path_mpjpe_budget():
     worst_l2 = max([rel_l2(named[k].grad, o["grads"][k]) for k in W] + [rel_l2(r["x2_grad"], o["x2_grad"]),
                                                                        rel_l2(r["mf_grad"], o["main_feat_grad"])])
     assert worst_l2 < 3e-2, worst_l2
+
+
+@pytest.mark.parametrize("precision,seam", [("tf32", "fp32"), ("tf32", "bf16"), ("bf16", "bf16")])
+def test_head_config2_bf16_valued_seam(precision, seam):
+    """x2 as a bf16 / autocast backbone delivers it: values are bf16-representable, handed
+    over either widened to fp32 or as bfloat16 storage.  Both must meet the same bars as Gaussian fp32 input against
+    the fp64 oracle on the SAME values -- TF32-representable input is exactly where a truncation-compensation constant
+    would bias feat_visual -- and the two hand-overs must agree with each other (the conv is exact on bf16 operands)."""
+    regime = "hand" if precision == "bf16" else "unit"
+    opt, W, net, x2, mf, labels = _config2(precision, regime=regime)
+    x2 = torch.from_numpy(x2).bfloat16().float().numpy()
+    r = _run_module_step(net, x2, mf, labels, mask_seed=3, seam=seam)
+    o = oracle_step(W, x2, mf, labels, "hand", heads=8, iteration=3, pos_embed=True, mask_idx=net.last_mask,
+                    pl_reg=True, dtype=torch.float64)
+    assert r["x2_grad"].dtype == (torch.bfloat16 if seam == "bf16" else torch.float32)
+    assert torch.all(r["pred"][:, 6:9] == 0)
+    fv_err = rel_l2(r["fv"], o["feat_visual"])
+    assert fv_err < (2e-6 if seam == "bf16" else 2e-3), fv_err          # bf16 seam: exact products, 3-term weight split
+    big = o["feat_visual"].abs() > 0.5 * o["feat_visual"].abs().max()
+    bias = float(((r["fv"].double().cpu() - o["feat_visual"]) / o["feat_visual"])[big].mean())
+    assert abs(bias) < 5e-5, bias
+    named = dict(net.named_parameters())
+    g_l2 = {k: rel_l2(named[k].grad, o["grads"][k]) for k in W}
+    g_l2["main_feat"] = rel_l2(r["mf_grad"], o["main_feat_grad"])
+    x2g_l2 = rel_l2(r["x2_grad"], o["x2_grad"])
+    if precision == "tf32":
+        assert rel_max(r["pred"], o["pred"]) < 1e-4
+        assert max(g_l2.values()) < 1e-3, sorted(g_l2.items(), key=lambda kv: -kv[1])[:4]
+        assert x2g_l2 < (3e-3 if seam == "bf16" else 1e-3), x2g_l2     # bf16 x2.grad: plus its storage rounding (2^-9)
+    else:
+        j = r["pred"][:, 3:].double().cpu().view(96, 21, 3)
+        assert float((j - o["pred"][:, 3:].double().view(96, 21, 3)).norm(dim=-1).mean()) * 1e3 < 0.05
+        assert max(g_l2.values()) < 3e-2 and x2g_l2 < 3e-2
 
 
 def test_fused_train_step_equals_module_autograd():

@@ -16,14 +16,14 @@ sets = [[torch.randn(n, device="cuda") * 0.01, torch.randn(n, device="cuda"), to
 for k in range(24):
     a = sets[k % 8]
     check(lib.scat_adam_step(ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), n, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1 + k // 8, None, None,
-                             stream_ptr()), "scat_adam_step")
+                             None, stream_ptr()), "scat_adam_step")
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for k in range(80):
     a = sets[k % 8]
     check(lib.scat_adam_step(ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), n, 1e-4, 0.9, 0.999, 1e-8, 0.0, 4 + k // 8, None, None,
-                             stream_ptr()), "scat_adam_step")
+                             None, stream_ptr()), "scat_adam_step")
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / 80 * 1e3
