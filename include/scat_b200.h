@@ -296,6 +296,13 @@ int scat_lbs_prepare(const float* v_template, const float* shapedirs, const floa
                      const float* j_regressor, const float* weights, float* derived, void* stream);
 int scat_lbs_fwd(const float* derived, const float* hands_mean, const float* rots, const float* poses,
                  const float* betas, float* out, int32_t batch, void* stream);
+/* Backward of scat_lbs_fwd: mano.py:280-391 is plain differentiable PyTorch in the reference (autograd); this is its
+ * vector-Jacobian product.  grad_out[B,799,3] -> grad_rots[B,3], grad_poses[B,45], grad_betas[B,10] (overwritten).
+ * Nothing is saved by the forward: the kernel recomputes from (rots, poses, betas).  Rows whose axis-angle norm is
+ * below 1e-30 take the gradient of the Taylor branch (mano.py:258-265), where the reference's autograd returns NaN. */
+int scat_lbs_bwd(const float* derived, const float* hands_mean, const float* rots, const float* poses,
+                 const float* betas, const float* grad_out, float* grad_rots, float* grad_poses,
+                 float* grad_betas, int32_t batch, void* stream);
 
 #ifdef __cplusplus
 }

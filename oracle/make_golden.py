@@ -214,6 +214,25 @@ def run_mano_case(name, B=6):
                         finite=finite, out_fp64_oracle=o64.astype(np.float64))
     print(f"[golden] {name}: oracle-vs-reference {d:.3e}; finite rows {finite.tolist()}")
 
+    # ---- gradients: the reference function under the reference's own mechanism (autograd), generic inputs ----
+    Bg = 5
+    rots, poses, betas = synth.make_mano_inputs(Bg, 11)
+    cot = np.random.Generator(np.random.PCG64(4242)).standard_normal((Bg, 799, 3)).astype(np.float32)
+    tr, tp, tb = (torch.from_numpy(a.copy()).requires_grad_(True) for a in (rots, poses, betas))
+    out_ref = ref_mano.rot_pose_beta_to_mesh(tr, tp, tb)
+    (out_ref * torch.from_numpy(cot)).sum().backward()
+    # the differentiable restatement (float64) must give the reference's gradients
+    dr, dp_, db = (torch.from_numpy(a.astype(np.float64)).requires_grad_(True) for a in (rots, poses, betas))
+    out_o = mano_oracle.rot_pose_beta_to_mesh_torch(dr, dp_, db, asset)
+    (out_o * torch.from_numpy(cot).double()).sum().backward()
+    for nm, a, b in (("rots", tr.grad, dr.grad), ("poses", tp.grad, dp_.grad), ("betas", tb.grad, db.grad)):
+        e = float((a.double() - b).abs().max() / b.abs().max())
+        assert e < 2e-4, (nm, e)                                           # fp32 autograd of the reference vs float64
+        print(f"[golden] {name}_grad: d{nm} reference(fp32 autograd) vs oracle(fp64) rel {e:.2e}")
+    np.savez_compressed(os.path.join(GOLD, name + "_grad.npz"), rots=rots, poses=poses, betas=betas, cot_seed=np.array(4242),
+                        out=out_ref.detach().numpy(), g_rots=tr.grad.numpy(), g_poses=tp.grad.numpy(), g_betas=tb.grad.numpy(),
+                        g_rots_fp64=dr.grad.numpy(), g_poses_fp64=dp_.grad.numpy(), g_betas_fp64=db.grad.numpy())
+
 
 def run_adam_case(name="adam"):
     """torch.optim.Adam itself (the reference's optimiser, train.py:60) on a few small tensors: 6 steps, the learning
@@ -320,6 +339,9 @@ def main():
         return
     if sys.argv[1:] == ["adam"]:          # the optimiser fixture alone (needs torch only, not /root/reference)
         run_adam_case("adam")
+        return
+    if sys.argv[1:] == ["mano"]:          # the LBS fixtures alone (forward + autograd gradients of the reference)
+        run_mano_case("mano_lbs")
         return
     hand_net, vt = _import_reference_head()
     # analytic anchors

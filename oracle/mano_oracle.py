@@ -79,3 +79,67 @@ def rot_pose_beta_to_mesh(rots, poses, betas, asset) -> np.ndarray:
     Jtr = np.einsum("brc,bjc->bjr", Rg, Jtr)                                   # :383
     root = Jtr[:, 1:2].copy()                                                  # :386-388
     return np.concatenate([Jtr - root, v - root], axis=1).astype(dt)           # :391
+
+
+def rot_pose_beta_to_mesh_torch(rots, poses, betas, asset):
+    """The same function on torch tensors (any float dtype), differentiable: the checker for scat_lbs_bwd.
+
+    mano.py:280-391 is differentiable end to end (it runs under autograd in the reference); this restatement keeps
+    the reference's formulas, including rodrigues written in terms of n = r / theta (mano.py:246-253), so that its
+    autograd gradient is the reference's.  Rows with theta < 1e-30 take the Taylor branch (mano.py:255-265)."""
+    import torch
+    dt, dev = rots.dtype, rots.device
+
+    def cst(key):
+        a = asset[key]
+        if hasattr(a, "todense"):
+            a = np.asarray(a.todense())
+        return torch.as_tensor(np.asarray(a, dtype=np.float64)).to(dt).to(dev)
+
+    v_template, shapedirs, posedirs = cst("v_template"), cst("shapedirs"), cst("posedirs")
+    J_reg, weights, hands_mean = cst("J_regressor"), cst("weights"), cst("hands_mean")
+    B = rots.shape[0]
+
+    def skew(n):
+        z = torch.zeros_like(n[:, 0])
+        return torch.stack([z, -n[:, 2], n[:, 1], n[:, 2], z, -n[:, 0], -n[:, 1], n[:, 0], z], dim=1).view(-1, 3, 3)
+
+    def rodrigues_t(r):
+        theta = torch.sqrt(torch.sum(r * r, dim=1))
+        eye = torch.eye(3, dtype=dt, device=dev)[None]
+        small = theta < 1e-30
+        safe = torch.where(small, torch.ones_like(theta), theta)      # keeps 0/0 out of the autograd graph of the other rows
+        n = r / safe[:, None]
+        Sn = skew(n)
+        R = eye + torch.sin(theta)[:, None, None] * Sn + (1.0 - torch.cos(theta))[:, None, None] * (Sn @ Sn)
+        Sr = skew(r)
+        t2 = theta ** 2
+        R2 = eye + (1.0 - t2[:, None, None] / 6.0) * Sr + (0.5 - t2[:, None, None] / 24.0) * (Sr @ Sr)
+        return torch.where(small[:, None, None], R2, R)
+
+    theta = (hands_mean[None] + poses).view(B, 15, 3)
+    theta = torch.cat([torch.zeros(B, 1, 3, dtype=dt, device=dev), theta], dim=1)
+    v_shaped = v_template[None] + torch.einsum("vck,bk->bvc", shapedirs, betas)
+    Rall = rodrigues_t(theta.reshape(-1, 3)).view(B, 16, 3, 3)
+    pw = (Rall[:, 1:] - torch.eye(3, dtype=dt, device=dev)).reshape(B, 135)
+    v_posed = v_shaped + torch.einsum("vck,bk->bvc", posedirs, pw)
+    J = torch.einsum("jv,bvc->bjc", J_reg, v_shaped)
+    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=dt, device=dev).view(1, 1, 4).expand(B, 1, 4)
+    G = [None] * 16
+    for i in range(16):
+        t = J[:, i] if i == 0 else J[:, i] - J[:, PARENTS[i]]
+        local = torch.cat([torch.cat([Rall[:, i], t[:, :, None]], dim=2), bottom], dim=1)
+        G[i] = local if i == 0 else G[PARENTS[i]] @ local
+    G = torch.stack(G, dim=1)                                                     # [B,16,4,4]
+    Jh = torch.cat([J, torch.zeros(B, 16, 1, dtype=dt, device=dev)], dim=2)
+    corr = torch.einsum("bjrc,bjc->bjr", G, Jh)
+    A = torch.cat([G[..., :3], (G[..., 3] - corr)[..., None]], dim=3)
+    T = torch.einsum("vj,bjrc->bvrc", weights, A)
+    vh = torch.cat([v_posed, torch.ones(B, 778, 1, dtype=dt, device=dev)], dim=2)
+    v = torch.einsum("bvrc,bvc->bvr", T, vh)[:, :, :3]
+    Jtr = torch.cat([G[:, :, :3, 3], v[:, list(TIP_VERTS)]], dim=1)
+    Rg = rodrigues_t(rots)
+    v = torch.einsum("brc,bvc->bvr", Rg, v)
+    Jtr = torch.einsum("brc,bjc->bjr", Rg, Jtr)
+    root = Jtr[:, 1:2]
+    return torch.cat([Jtr - root, v - root], dim=1)

@@ -81,6 +81,7 @@ SIGNATURES = {
     "scat_lbs_derived_floats": (_sz, []),
     "scat_lbs_prepare": (_i32, [_f, _f, _f, _f, _f, _f, _f]),
     "scat_lbs_fwd": (_i32, [_f, _f, _f, _f, _f, _f, _i32, _f]),
+    "scat_lbs_bwd": (_i32, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _f]),
 }
 
 _lib = None

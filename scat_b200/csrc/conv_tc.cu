@@ -213,10 +213,23 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             int b, px0, nt;
             fwd_decode<TPU>(p, v, b, px0, nt);
             const int as = it & 1;
+            // everything the epilogue reads from memory is independent of the accumulator: fetch it while the MMAs of
+            // this unit are still running (a load -> add -> store chain per token would otherwise expose 21 L2 round
+            // trips per tile on the critical path of a CTA that only owns two or three units)
+            float pe_r[TPU][kT], mtok[TPU];
+#pragma unroll
+            for (int t = 0; t < TPU; ++t) {
+                const int px = px0 + t * 128 + q * 32 + lane;
+                const bool ok = t < nt && px < p.HW;
+                mtok[t] = (ok && maskbits) ? __ldg(p.mask_token + px) : 0.f;
+#pragma unroll
+                for (int j = 0; j < kT; ++j) pe_r[t][j] = (ok && p.pe) ? __ldg(p.pe + j * p.HW + px) : 0.f;
+            }
             mbar_wait(tfull_bar + 8 * as, (it >> 1) & 1);
             tc_fence_after();
-            for (int t = 0; t < nt; ++t) {
-                if (px0 + t * 128 + q * 32 >= p.HW) break;          // warp-uniform: this warp's 32 pixels are beyond the row
+#pragma unroll
+            for (int t = 0; t < TPU; ++t) {
+                if (t >= nt || px0 + t * 128 + q * 32 >= p.HW) break;   // warp-uniform: this warp's 32 pixels are beyond the row
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * TPU + t) * NR);
                 float c[NR];
                 tmem_ld32_nowait(taddr, c);
@@ -224,16 +237,14 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tmem_ld_wait();
                 const int px = px0 + t * 128 + q * 32 + lane;
                 if (px < p.HW) {
-                    const float mtok = maskbits ? __ldg(p.mask_token + px) : 0.f;
                     float* fvp = p.fv + (long long)b * kT * p.HW + px;
                     float* xp = p.X0 + (long long)b * kT * p.HW + px;
-                    const float* pep = p.pe ? p.pe + px : nullptr;
 #pragma unroll
                     for (int j = 0; j < kT; ++j) {
                         // bf16 seam: columns j, 21 + j, 42 + j hold x2 . (W1, W2, W3), smallest terms first
                         const float val = BF16 ? (c[(2 * kT + j) % NR] + c[(kT + j) % NR]) + c[j] : c[j];
                         const bool mk = (maskbits >> j) & 1u;
-                        const float tok = mk ? mtok : (pep ? val + __ldg(pep + j * p.HW) : val);
+                        const float tok = mk ? mtok[t] : val + pe_r[t][j];   // pe_r is 0 without positional encoding
                         if (alias) {
                             fvp[j * p.HW] = tok;                    // hand_net.py:364,373: the overwrite lands in feat_visual
                         } else {
@@ -435,8 +446,10 @@ __device__ __forceinline__ void dgrad_decode(const ConvDgradParams& p, int v, in
     else { b = v - nfull; px0 = p.tail_px0; }
 }
 
+constexpr int DG_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+
 template <bool BF16>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(DG_THREADS, 1)
 conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmO, const ConvDgradParams p) {
     using E = CElem<BF16>;
@@ -450,9 +463,9 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sW = sbase, ring = sbase + W_BYTES, stg = ring + DG_STAGES * A_BYTES;
-    const uint32_t full_bar = stg + 4 * 2 * STG, empty_bar = full_bar + 8 * DG_STAGES, w_bar = empty_bar + 8 * DG_STAGES;
+    const uint32_t full_bar = stg + 8 * 2 * STG, empty_bar = full_bar + 8 * DG_STAGES, w_bar = empty_bar + 8 * DG_STAGES;
     const uint32_t tfull_bar = w_bar + 8, tempty_bar = tfull_bar + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W_BYTES + DG_STAGES * A_BYTES + 4 * 2 * STG + 8 * (2 * DG_STAGES + 5));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W_BYTES + DG_STAGES * A_BYTES + 8 * 2 * STG + 8 * (2 * DG_STAGES + 5));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = blockIdx.x % p.n_half, cta = blockIdx.x / p.n_half, n_cta = gridDim.x / p.n_half;
     if (threadIdx.x == 0) {
@@ -467,7 +480,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
         mbar_init(w_bar, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar + 8 * i, 1);
-            mbar_init(tempty_bar + 8 * i, 4);
+            mbar_init(tempty_bar + 8 * i, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -534,10 +547,12 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
             if (++s == DG_STAGES) { s = 0; ph ^= 1; }
         }
     } else {
-        // ===== epilogue: lane = pixel, 32-channel column chunks -> [32 ch][32 px] box in shared memory -> TMA store =====
-        const int q = warp & 3;
-        const uint32_t my_stg = stg + q * 2 * STG;
-        uint8_t* my_stg_ptr = smem + W_BYTES + DG_STAGES * A_BYTES + q * 2 * STG;
+        // ===== epilogue: lane = pixel, 32-channel column chunks -> [32 ch][32 px] box in shared memory -> TMA store.
+        // Two warps share each TMEM lane quadrant and take alternate chunks: the chain tcgen05.ld -> 32 st.shared ->
+        // fence -> TMA store is latency bound per warp, and this kernel is one long epilogue =====
+        const int q = warp & 3, part = (warp - 2) >> 2, ew = warp - 2;
+        const uint32_t my_stg = stg + ew * 2 * STG;
+        uint8_t* my_stg_ptr = smem + W_BYTES + DG_STAGES * A_BYTES + ew * 2 * STG;
         int it = 0, nstore = 0;
         for (int v = cta; v < p.n_units; v += n_cta, ++it) {
             int b, px0;
@@ -547,7 +562,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
             tc_fence_after();
             const int pxw = px0 + q * 32;
             if (pxw < p.HW) {
-                for (int cc = 0; cc < DG_N / 32; ++cc, ++nstore) {
+                for (int cc = part; cc < DG_N / 32; cc += 2, ++nstore) {
                     const int buf = nstore & 1;
                     if (lane == 0) bulk_wait_read<1>();             // the store that last read this buffer has drained it
                     __syncwarp();
@@ -719,11 +734,11 @@ int conv_dgrad_tc_impl(const void* dsplit, const void* Wstack, void* x2_grad, in
     auto kern = conv_dgrad_tc_kernel<BF16>;
     constexpr int KH = 64 / E::BK;
     constexpr int SMEM = KH * (DG_N / E::MN_BOX) * E::BOX_BYTES + DG_STAGES * KH * (128 / E::MN_BOX) * E::BOX_BYTES +
-                         4 * 2 * 32 * 32 * (BF16 ? 2 : 4) + 256;
+                         8 * 2 * 32 * 32 * (BF16 ? 2 : 4) + 256;
     SCAT_ENSURE_SMEM(kern, SMEM);
     int grid = min(sm_count(), p.n_units * p.n_half);
     grid -= grid % p.n_half;
-    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(192), SMEM, stream, tmD, tmW, tmO, p));
+    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(DG_THREADS), SMEM, stream, tmD, tmW, tmO, p));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -4,7 +4,8 @@
 J_regressor (dense or scipy sparse), weights, hands_mean) once, derives the vertex-contiguous tables on the
 GPU and exposes ``rot_pose_beta_to_mesh(rots, poses, betas) -> [B, 21+778, 3]`` with the reference's argument
 meaning (no PCA: poses are 45 axis-angle values added to hands_mean; local root rotation forced to 0;
-joints = 16 chain joints + 5 fingertip vertices; everything relative to joint 1).  Forward only.
+joints = 16 chain joints + 5 fingertip vertices; everything relative to joint 1).  Differentiable w.r.t. rots, poses and
+betas like the reference (which runs it under autograd): the backward is the ``scat_lbs_bwd`` kernel.
 """
 from __future__ import annotations
 
@@ -13,6 +14,27 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
+
+
+class _LbsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layer, rots, poses, betas):
+        out = layer._forward(rots, poses, betas)
+        ctx.layer = layer
+        ctx.save_for_backward(rots, poses, betas)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        rots, poses, betas = ctx.saved_tensors
+        lib = _lib.load()
+        B = rots.shape[0]
+        g_out = g_out.contiguous().float()
+        g_r, g_p, g_b = torch.empty_like(rots), torch.empty_like(poses), torch.empty_like(betas)
+        layer = ctx.layer
+        check(lib.scat_lbs_bwd(ptr(layer.derived), ptr(layer.hands_mean), ptr(rots), ptr(poses), ptr(betas), ptr(g_out),
+                               ptr(g_r), ptr(g_p), ptr(g_b), B, stream_ptr()), "scat_lbs_bwd")
+        return None, g_r, g_p, g_b
 
 
 class ManoLayer:
@@ -43,17 +65,24 @@ class ManoLayer:
                                        ptr(self.J_regressor), ptr(self.weights), ptr(self.derived), stream_ptr()),
                   "scat_lbs_prepare")
 
-    def rot_pose_beta_to_mesh(self, rots, poses, betas, out=None):
+    def _forward(self, rots, poses, betas, out=None):
         lib = _lib.load()
-        for name, t, w in (("rots", rots, 3), ("poses", poses, 45), ("betas", betas, 10)):
-            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == w):
-                raise RuntimeError(f"scat_b200.mano: {name} must be a CUDA float32 [B,{w}] tensor")
         B = rots.shape[0]
         if out is None:
             out = torch.empty(B, 799, 3, device=rots.device, dtype=torch.float32)
-        check(lib.scat_lbs_fwd(ptr(self.derived), ptr(self.hands_mean), ptr(rots.contiguous()),
-                               ptr(poses.contiguous()), ptr(betas.contiguous()), ptr(out), B, stream_ptr()),
-              "scat_lbs_fwd")
+        check(lib.scat_lbs_fwd(ptr(self.derived), ptr(self.hands_mean), ptr(rots), ptr(poses), ptr(betas), ptr(out), B,
+                               stream_ptr()), "scat_lbs_fwd")
         return out
+
+    def rot_pose_beta_to_mesh(self, rots, poses, betas, out=None):
+        for name, t, w in (("rots", rots, 3), ("poses", poses, 45), ("betas", betas, 10)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == w):
+                raise RuntimeError(f"scat_b200.mano: {name} must be a CUDA float32 [B,{w}] tensor")
+        rots, poses, betas = rots.contiguous(), poses.contiguous(), betas.contiguous()
+        if torch.is_grad_enabled() and (rots.requires_grad or poses.requires_grad or betas.requires_grad):
+            if out is not None:
+                raise RuntimeError("scat_b200.mano: out= cannot be combined with autograd")
+            return _LbsFunction.apply(self, rots, poses, betas)
+        return self._forward(rots, poses, betas, out)
 
     __call__ = rot_pose_beta_to_mesh

@@ -115,6 +115,27 @@ def test_mano_oracle_fixture(golden_dir):
     assert np.abs(o64 - g["out_fp64_oracle"]).max() < 1e-12
 
 
+def test_mano_oracle_gradients_match_reference_autograd(golden_dir):
+    """The differentiable restatement (oracle/mano_oracle.py: rot_pose_beta_to_mesh_torch) against the gradients the
+    unmodified reference produced with autograd (tests/golden/mano_lbs_grad.npz)."""
+    import torch
+    g = _load(golden_dir, "mano_lbs_grad")
+    asset = synth.make_mano_asset()
+    cot = np.random.Generator(np.random.PCG64(int(g["cot_seed"]))).standard_normal((5, 799, 3)).astype(np.float32)
+    t = [torch.from_numpy(g[k].astype(np.float64)).requires_grad_(True) for k in ("rots", "poses", "betas")]
+    out = mano_oracle.rot_pose_beta_to_mesh_torch(*t, asset)
+    assert np.abs(out.detach().numpy() - g["out"]).max() < 2e-6
+    (out * torch.from_numpy(cot).double()).sum().backward()
+    for name, x in zip(("rots", "poses", "betas"), t):
+        ref = g["g_" + name]
+        assert np.abs(x.grad.numpy() - ref).max() < 1e-5 * np.abs(ref).max(), name
+        assert np.abs(x.grad.numpy() - g["g_" + name + "_fp64"]).max() < 1e-10 * np.abs(ref).max(), name
+    # and the numpy / torch restatements are the same function
+    o_np = mano_oracle.rot_pose_beta_to_mesh(g["rots"].astype(np.float64), g["poses"].astype(np.float64),
+                                             g["betas"].astype(np.float64), asset)
+    assert np.abs(o_np - out.detach().numpy()).max() < 1e-12
+
+
 def test_adam_oracle_matches_torch_adam_fixture(golden_dir):
     """oracle/adam_oracle.py against tests/golden/adam.npz = torch.optim.Adam itself (train.py:60) run on the CPU:
     6 steps, warm-up style learning-rate changes, with and without weight decay."""
