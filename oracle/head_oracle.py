@@ -108,7 +108,8 @@ def head_forward(P: Dict[str, torch.Tensor], x2: torch.Tensor, main_feat: torch.
             pe = positional_encoding(n_tok, feat.shape[-1], dtype=feat.dtype)
         feat = feat + pe[: feat.size(0), :]                                     # :75-77 (slices dim 0 of size 1)
     if mask_idx is not None and len(mask_idx) > 0:
-        feat[:, list(mask_idx), :] = P["mask_token"].to(feat.dtype)             # :373 (in place)
+        idx = mask_idx if torch.is_tensor(mask_idx) else list(mask_idx)         # (an index tensor keeps a GPU run sync-free)
+        feat[:, idx, :] = P["mask_token"].to(feat.dtype)                        # :373 (in place)
     feat_out = transformer(feat, P, heads)                                      # :375
     feat_out = feat_out.reshape(B, -1)                                          # :377
 

@@ -370,39 +370,6 @@ int launch_conv_dgrad(const float* dFv, const float* Wc, float* x2_grad, int B, 
 }
 
 
-// Operand preparation of the tensor-core conv backward (conv_tc.cu), fp32 seam.
-// dFv [B,T,HW] -> dFv3 [B,3T,HW]: rows 0..T-1 hi = the TF32-nearest part, rows T..2T-1 lo = the (TF32-rounded)
-// remainder, rows 2T..3T-1 hi again.  Every value is exactly representable on the tensor core, so against the
-// stacked weight [Wh; Wh; Wl] the conv dgrad computes Wh hi + Wh lo + Wl hi: fp32-grade (the d tokens are small:
-// 66 KB per sample against 1.6 MB of x2.grad).  hi alone feeds the weight gradient.
-__global__ void split_tf32_kernel(const float* __restrict__ dFv, float* __restrict__ dFv2, int B, int T, int HW) {
-    pdl_sync();
-    const long long n4 = (long long)B * T * (HW >> 2);
-    const int row4 = HW >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const long long bt = i / row4;
-        const int q = (int)(i - bt * row4);
-        const long long b = bt / T;
-        const int t = (int)(bt - b * T);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dFv) + i);
-        float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-        float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
-        float4* dst = reinterpret_cast<float4*>(dFv2 + ((b * 3 * T + t) * (long long)HW)) + q;
-        dst[0] = hi;
-        dst[(long long)T * row4] = lo;
-        dst[(long long)2 * T * row4] = hi;
-    }
-}
-
-int launch_split_tf32(const float* dFv, float* dFv2, int B, int T, int HW, cudaStream_t stream) {
-    SCAT_REQUIRE(HW % 4 == 0, kErrUnsupported, "split: HW%%4");
-    const long long n4 = (long long)B * T * (HW / 4);
-    const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    SCAT_CHECK_CUDA(launch_k(split_tf32_kernel, dim3(grid), dim3(256), 0, stream, dFv, dFv2, B, T, HW));
-    SCAT_CHECK_LAUNCH();
-    return 0;
-}
-
 size_t conv_wgrad_scratch_floats(int C, int T) { return (size_t)kConvWgradCtas * T * C; }
 
 int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scratch, int B, int C, int HW, int T,

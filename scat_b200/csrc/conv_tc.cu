@@ -600,7 +600,7 @@ conv_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
 }
 
 // =================================================================================================================
-// operand preparation (both small): the conv weight stacks, once per forward, and the split d-token tensor
+// operand preparation (both small): the conv weight stacks, once per forward, and the split d-token tensor (masking fused)
 // =================================================================================================================
 // fp32 seam: dst = fp32 [3T, C] = [Wh; Wh; Wl]  (Wh = TF32-nearest(W), Wl = TF32-nearest(W - Wh)); the forward reads
 //            the first T rows, the data gradient all of them against [hi; lo; hi]
@@ -626,10 +626,19 @@ __global__ void conv_weight_prep_kernel(const float* __restrict__ W, void* __res
     }
 }
 
-// d tokens [B,T,HW] fp32 (masked rows already zero) -> bf16 [B, 4T, HW] = [d1; d1; d2; d3]: the data gradient reads the
-// window of 64 rows at row 0 ([d1; d1; d2] against [W1; W2; W1]), the weight gradient the window at row T ([d1; d2; d3])
-__global__ void split_bf16_kernel(const float* __restrict__ dFv, __nv_bfloat16* __restrict__ out, int B, int T, int HW) {
+// Operand preparation of the backward, one pass over the cotangent of the token matrix dX0 [B,T,HW] (fp32):
+//   * rows of masked tokens do not depend on the conv output (hand_net.py:373): they are zeroed for the conv passes and
+//     summed over the batch into d mask_token (vector reductions in L2; d mask_token zero on entry) instead;
+//   * fp32 seam: dsplit fp32 [B,3T,HW] = [hi; lo; hi], hi = TF32-nearest(d), lo = TF32-nearest(d - hi): exact on the
+//     tensor core, against [Wh; Wh; Wl] the data gradient is fp32-grade; the weight gradient reads hi;
+//   * bf16 seam: dsplit bf16 [B,4T,HW] = [d1; d1; d2; d3] (three-term bf16 split): the data gradient reads the window of
+//     64 rows at row 0 ([d1; d1; d2] against [W1; W2; W1]), the weight gradient the window at row T ([d1; d2; d3]).
+template <bool BF16>
+__global__ void conv_bwd_prep_kernel(const float* __restrict__ dX0, const int32_t* __restrict__ mask_idx, int n_masked,
+                                     void* __restrict__ dsplit, float* __restrict__ d_mask_token, int B, int T, int HW) {
     pdl_sync();
+    uint32_t maskbits = 0;
+    for (int k = 0; k < n_masked; ++k) maskbits |= 1u << __ldg(mask_idx + k);
     const long long n4 = (long long)B * T * (HW >> 2);
     const int row4 = HW >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -637,22 +646,37 @@ __global__ void split_bf16_kernel(const float* __restrict__ dFv, __nv_bfloat16* 
         const int qd = (int)(i - bt * row4);
         const long long b = bt / T;
         const int t = (int)(bt - b * T);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dFv) + i);
-        const float in[4] = {v.x, v.y, v.z, v.w};
-        __nv_bfloat16 d1[4], d2[4], d3[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            d1[e] = __float2bfloat16_rn(in[e]);
-            const float r1 = in[e] - __bfloat162float(d1[e]);
-            d2[e] = __float2bfloat16_rn(r1);
-            d3[e] = __float2bfloat16_rn(r1 - __bfloat162float(d2[e]));
+        float4 v = __ldg(reinterpret_cast<const float4*>(dX0) + i);
+        if ((maskbits >> t) & 1u) {
+            if (d_mask_token != nullptr)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_mask_token + 4 * qd), "f"(v.x), "f"(v.y),
+                             "f"(v.z), "f"(v.w) : "memory");
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        uint2* dst = reinterpret_cast<uint2*>(out + ((b * 4 * T + t) * (long long)HW)) + qd;
         const long long step = (long long)T * row4;
-        dst[0] = *reinterpret_cast<const uint2*>(d1);
-        dst[step] = *reinterpret_cast<const uint2*>(d1);
-        dst[2 * step] = *reinterpret_cast<const uint2*>(d2);
-        dst[3 * step] = *reinterpret_cast<const uint2*>(d3);
+        if (!BF16) {
+            const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+            const float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(dsplit) + ((b * 3 * T + t) * (long long)HW)) + qd;
+            dst[0] = hi;
+            dst[step] = lo;
+            dst[2 * step] = hi;
+        } else {
+            const float in[4] = {v.x, v.y, v.z, v.w};
+            __nv_bfloat16 d1[4], d2[4], d3[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                d1[e] = __float2bfloat16_rn(in[e]);
+                const float r1 = in[e] - __bfloat162float(d1[e]);
+                d2[e] = __float2bfloat16_rn(r1);
+                d3[e] = __float2bfloat16_rn(r1 - __bfloat162float(d2[e]));
+            }
+            uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dsplit) + ((b * 4 * T + t) * (long long)HW)) + qd;
+            dst[0] = *reinterpret_cast<const uint2*>(d1);
+            dst[step] = *reinterpret_cast<const uint2*>(d1);
+            dst[2 * step] = *reinterpret_cast<const uint2*>(d2);
+            dst[3 * step] = *reinterpret_cast<const uint2*>(d3);
+        }
     }
 }
 
@@ -763,12 +787,18 @@ int launch_conv_weight_prep(const float* Wc, void* dst, int C, int T, int x2_bf1
     return 0;
 }
 
-int launch_conv_split(const float* dFv, void* dsplit, int B, int T, int HW, int x2_bf16, cudaStream_t stream) {
-    if (!x2_bf16) return launch_split_tf32(dFv, reinterpret_cast<float*>(dsplit), B, T, HW, stream);
-    SCAT_REQUIRE(HW % 4 == 0, kErrUnsupported, "split: HW%%4");
+int launch_conv_bwd_prep(const float* dX0, const int32_t* mask_idx, int n_masked, void* dsplit, float* d_mask_token, int B,
+                         int T, int HW, int x2_bf16, cudaStream_t stream) {
+    SCAT_REQUIRE(HW % 4 == 0 && T <= 32, kErrUnsupported, "conv bwd prep: HW%%4, T<=32");
+    SCAT_REQUIRE(n_masked == 0 || mask_idx != nullptr, kErrBadArg, "conv bwd prep: mask_idx is null");
     const long long n4 = (long long)B * T * (HW / 4);
     const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    SCAT_CHECK_CUDA(launch_k(split_bf16_kernel, dim3(grid), dim3(256), 0, stream, dFv, reinterpret_cast<__nv_bfloat16*>(dsplit), B, T, HW));
+    if (x2_bf16)
+        SCAT_CHECK_CUDA(launch_k(conv_bwd_prep_kernel<true>, dim3(grid), dim3(256), 0, stream, dX0, mask_idx, n_masked, dsplit,
+                                 d_mask_token, B, T, HW));
+    else
+        SCAT_CHECK_CUDA(launch_k(conv_bwd_prep_kernel<false>, dim3(grid), dim3(256), 0, stream, dX0, mask_idx, n_masked, dsplit,
+                                 d_mask_token, B, T, HW));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -655,8 +655,11 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps, sd,
                                         l_first, l_last));
     if (phase == 0) return 0;
-    // through masking / positional encoding into the conv output
-    SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st, 1));
+    // through masking / positional encoding into the conv output.  Tensor-core precisions without an external
+    // feat_visual cotangent: masking, d mask_token and the split operand of the conv passes are ONE pass (phase 2)
+    const bool fused_prep = d.precision != PREC_FP32 && g_fv == nullptr;
+    if (!fused_prep)
+        SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st, 1));
     if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
         SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX + (size_t)p.M * p.D, mask_idx, d.n_masked, d.pos_embed ? 0 : 1, pl_out,
                                        nullptr, p.B, p.T, p.D, st));
@@ -664,10 +667,17 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         SCAT_CHECK_CUDA(launch_k(add_inplace_kernel, dim3(148 * 4), dim3(256), 0, st, ws + p.dFv, g_fv, (long long)p.M * p.D));
         SCAT_CHECK_LAUNCH();
     }
+    if (phase == 1 && fused_prep)    // phased issue: the mask-token gradient belongs to the part of the bucket phase 1 completes
+        SCAT_PROPAGATE(launch_conv_bwd_prep(ws + p.dX, mask_idx, d.n_masked, ws + p.dFv2, G[P_MASK_TOKEN], p.B, p.T, p.D,
+                                            d.x2_dtype, st));
     if (phase == 1) return 0;
     }
     if (d.precision != PREC_FP32) {
-        SCAT_PROPAGATE(launch_conv_split(ws + p.dFv, ws + p.dFv2, p.B, p.T, p.D, d.x2_dtype, st));
+        if (g_fv != nullptr)          // dFv = masked dX + external cotangent was formed above: split it (nothing left to mask)
+            SCAT_PROPAGATE(launch_conv_bwd_prep(ws + p.dFv, nullptr, 0, ws + p.dFv2, nullptr, p.B, p.T, p.D, d.x2_dtype, st));
+        else if (phase != 2)          // (phase 2 of a phased issue: phase 1 already ran the fused pass)
+            SCAT_PROPAGATE(launch_conv_bwd_prep(ws + p.dX, mask_idx, d.n_masked, ws + p.dFv2, G[P_MASK_TOKEN], p.B, p.T, p.D,
+                                                d.x2_dtype, st));
         // two persistent one-CTA-per-SM streams (x2 in, x2.grad out): back to back on the main stream
         SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, d.x2_dtype, G[P_CONV_W], p.B, p.C, p.D, p.T, st));   // G was zeroed above
         if (x2_grad != nullptr)
@@ -841,9 +851,8 @@ int scat_conv_pe_mask_fwd(const float* x2, const float* conv_w, const float* pe,
 
 // ---- tensor-core front end (conv_tc.cu) as single operators: what the head runs in TF32 / BF16 mode ----
 size_t scat_conv_tc_scratch_floats(int32_t batch, int32_t channels, int32_t hw, int32_t n_tokens) {
-    // [weight stacks][d tokens with masked rows zeroed][split d tokens]
-    return round_up(conv_weight_prep_floats(channels, n_tokens), 64) + (size_t)batch * n_tokens * hw +
-           conv_split_floats(batch, hw, n_tokens);
+    // [weight stacks][split d tokens]
+    return round_up(conv_weight_prep_floats(channels, n_tokens), 64) + conv_split_floats(batch, hw, n_tokens);
 }
 
 int scat_conv_pe_mask_fwd_tc(const void* x2, int32_t x2_dtype, const float* conv_w, const float* pe, const float* mask_token,
@@ -865,11 +874,10 @@ int scat_conv_bwd_tc(const float* d_tokens, const void* x2, int32_t x2_dtype, co
     SCAT_REQUIRE(scratch && d_tokens && x2 && conv_w && conv_w_grad, kErrBadArg, "conv_bwd_tc: null argument");
     SCAT_REQUIRE(x2_dtype == SCAT_DTYPE_F32 || x2_dtype == SCAT_DTYPE_BF16, kErrBadArg, "conv_bwd_tc: x2_dtype %d", x2_dtype);
     float* w_prep = scratch;
-    float* dFv = scratch + round_up(conv_weight_prep_floats(channels, n_tokens), 64);
-    float* dsplit = dFv + (size_t)batch * n_tokens * hw;
+    float* dsplit = scratch + round_up(conv_weight_prep_floats(channels, n_tokens), 64);
     SCAT_PROPAGATE(launch_conv_weight_prep(conv_w, w_prep, channels, n_tokens, x2_dtype, st));
-    SCAT_PROPAGATE(launch_mask_bwd(d_tokens, mask_idx, n_masked, 0, dFv, mask_token_grad, batch, n_tokens, hw, st));
-    SCAT_PROPAGATE(launch_conv_split(dFv, dsplit, batch, n_tokens, hw, x2_dtype, st));
+    if (mask_token_grad) SCAT_CHECK_CUDA(cudaMemsetAsync(mask_token_grad, 0, (size_t)hw * sizeof(float), st));
+    SCAT_PROPAGATE(launch_conv_bwd_prep(d_tokens, mask_idx, n_masked, dsplit, mask_token_grad, batch, n_tokens, hw, x2_dtype, st));
     SCAT_CHECK_CUDA(cudaMemsetAsync(conv_w_grad, 0, (size_t)n_tokens * channels * sizeof(float), st));
     SCAT_PROPAGATE(launch_conv_wgrad_tc(dsplit, x2, x2_dtype, conv_w_grad, batch, channels, hw, n_tokens, st));
     if (x2_grad) SCAT_PROPAGATE(launch_conv_dgrad_tc(dsplit, w_prep, x2_dtype, x2_grad, batch, channels, hw, n_tokens, st));

@@ -98,16 +98,16 @@ int launch_conv_wgrad(const float* dFv, const float* x2, float* dWc, float* scra
 // the seam dtype: 0 = fp32 x2 / x2.grad (kind::tf32, x2 rounded to TF32-nearest in shared memory), 1 = bf16 x2 / x2.grad
 // (kind::f16, exact operands, the fp32 weight and d tokens enter as stacked bf16 split terms).
 //   Wprep  = launch_conv_weight_prep(conv weight)   conv_weight_prep_floats(C, T) floats, once per forward
-//   dsplit = launch_conv_split(d tokens [B,T,HW], masked rows zero)   conv_split_floats(B, HW, T) floats
+//   dsplit = launch_conv_bwd_prep(d token matrix [B,T,HW])   conv_split_floats(B, HW, T) floats; zeroes the masked token
+//            rows on the way and reduces them into d mask_token (nullable; zero on entry)
 size_t conv_weight_prep_floats(int C, int T);
 size_t conv_split_floats(int B, int HW, int T);
 int launch_conv_weight_prep(const float* Wc, void* Wprep, int C, int T, int x2_bf16, cudaStream_t stream);
-int launch_conv_split(const float* dFv, void* dsplit, int B, int T, int HW, int x2_bf16, cudaStream_t stream);
+int launch_conv_bwd_prep(const float* dX0, const int32_t* mask_idx, int n_masked, void* dsplit, float* d_mask_token, int B,
+                         int T, int HW, int x2_bf16, cudaStream_t stream);
 int launch_conv_pe_mask_fwd_tc(const void* x2, int x2_bf16, const void* Wprep, const float* pe, const float* mask_token,
                                const int32_t* mask_idx, int n_masked, int pos_embed, float* feat_visual, float* X0,
                                int B, int C, int HW, int T, cudaStream_t stream);
-// dFv [B,T,HW] -> [B,3T,HW] = TF32 hi / lo / hi (the fp32-seam split; launch_conv_split dispatches to it)
-int launch_split_tf32(const float* dFv, float* dFv2, int B, int T, int HW, cudaStream_t stream);
 int launch_conv_dgrad_tc(const void* dsplit, const void* Wprep, int x2_bf16, void* x2_grad, int B, int C, int HW, int T,
                          cudaStream_t stream);
 int launch_conv_wgrad_tc(const void* dsplit, const void* x2, int x2_bf16, float* dWc /* pre-zeroed */, int B, int C, int HW,
