@@ -105,7 +105,7 @@ def head_forward(P: Dict[str, torch.Tensor], x2: torch.Tensor, main_feat: torch.
     feat = feat_visual.view(B, n_tok, -1)                                       # :364 (a view)
     if pos_embed:
         if pe is None:
-            pe = positional_encoding(n_tok, feat.shape[-1], dtype=feat.dtype)
+            pe = positional_encoding(n_tok, feat.shape[-1], dtype=feat.dtype).to(feat.device)
         feat = feat + pe[: feat.size(0), :]                                     # :75-77 (slices dim 0 of size 1)
     if mask_idx is not None and len(mask_idx) > 0:
         idx = mask_idx if torch.is_tensor(mask_idx) else list(mask_idx)         # (an index tensor keeps a GPU run sync-free)

@@ -171,7 +171,7 @@ struct LayerPlan {
 struct HeadPlan {
     int B, T, C, D, heads, inner, M, it, F, NP;
     LayerPlan L[kDepth];
-    size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dX, dFv, conv_scratch, pl_scratch,
+    size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dNa2, dX, dFv, conv_scratch, pl_scratch,
         g_pred, ones, hreg, up2, dX16, dX1_16, w_conv, dFv2, total;   // w_conv: [2T,C] TF32-rounded conv weight, twice; dFv2: hi/lo split of dFv   // dX16 / dX1_16: bf16 shadows of dX / dX1 (PREC_BF16 only)
 };
 
@@ -252,6 +252,8 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     p.dO = take(cur, MS * p.inner);
     p.dQKV = take(cur, MS * 3 * p.inner);
     p.dNa = take(cur, MS * dmax);
+    p.dNa2 = take(cur, MS * dmax);     // layers alternate: the side stream may still read a layer's dNa (LayerNorm parameter
+                                       // gradients) while the next layer writes its own
     p.dX = take(cur, MS * dmax);
     p.dX16 = p.dX1_16 = 0;
     p.w_conv = take(cur, p.C > 0 ? conv_weight_prep_floats(p.C, p.T) : 64);
@@ -464,16 +466,19 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         const float* dX1 = ws + p.dNf;
         if (!L.last) {
+            // data gradient on the critical path; d gamma / d beta are column sums over the M real rows: side stream
             SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
-                                                ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d,
-                                                G ? G[L.p_nf_w] : nullptr, G ? G[L.p_nf_b] : nullptr, MR, L.d,
+                                                ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d, nullptr, nullptr, MR, L.d,
                                                 bf ? OUT_F32 : omode, st, amod, bf ? ws + p.dX1_16 : nullptr, ld_n));
             dX1 = ws + p.dX1;
         }
         const float* dX1g = bf ? ws + p.dX1_16 : dX1;           // what the GEMMs read
         if (G) {
-            // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1)
+            // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1); and the feed-forward LayerNorm's d gamma / d beta (reads dNf)
             SCAT_PROPAGATE(order_after(sd, st, sg));
+            if (!L.last)
+                SCAT_PROPAGATE(launch_layernorm_param_grads(ws + p.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
+                                                            G[L.p_nf_w], G[L.p_nf_b], M, L.d, sg));
             g = GemmArgs();
             g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
@@ -497,18 +502,26 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         }
         // dNa = dQKV Wqkv
         g = GemmArgs();
+        float* dNa = ws + ((l & 1) ? p.dNa2 : p.dNa);
         g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
-        g.C = ws + p.dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
+        g.C = dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // the next kernel overwrites dX (this layer's dY), and the next layer every other cotangent buffer the side-stream
         // parameter-gradient kernels of this layer read: join them here
         if (G) SCAT_PROPAGATE(order_after(sd, sg, st));
         // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs
         const bool feeds_gemm = tc && l > 0;
-        SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
-                                            L.d, ws + p.dX, L.d, G ? G[L.p_na_w] : nullptr,
-                                            G ? G[L.p_na_b] : nullptr, MR, L.d, (feeds_gemm && !bf) ? OUT_TF32 : OUT_F32, st,
-                                            amod, (feeds_gemm && bf) ? ws + p.dX16 : nullptr, ld_n));
+        SCAT_PROPAGATE(launch_layernorm_bwd(dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
+                                            L.d, ws + p.dX, L.d, nullptr, nullptr, MR, L.d,
+                                            (feeds_gemm && !bf) ? OUT_TF32 : OUT_F32, st, amod,
+                                            (feeds_gemm && bf) ? ws + p.dX16 : nullptr, ld_n));
+        if (G) {
+            // its parameter gradients read dNa (this layer's buffer: the next layer writes the other one) and the saved X:
+            // side stream, joined with the next layer's groups (or by the caller's final join for layer 0)
+            SCAT_PROPAGATE(order_after(sd, st, sg));
+            SCAT_PROPAGATE(launch_layernorm_param_grads(dNa, L.d, X, L.d, ws + L.mean_a, ws + L.rstd_a, G[L.p_na_w], G[L.p_na_b],
+                                                        M, L.d, sg));
+        }
         dY = ws + p.dX;
         dYg = bf ? ws + p.dX16 : dY;
         ld_dYg = bf ? ld_n : L.d;
@@ -654,7 +667,9 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     const int l_first = phase == 1 ? 0 : kDepth - 1, l_last = phase == 0 ? 1 : 0;
     SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps, sd,
                                         l_first, l_last));
-    if (phase == 0) return 0;
+    // the side stream still carries the last layer's LayerNorm parameter gradients: a phase joins them before it returns
+    // (its part of the gradient bucket is final then); the single call joins at the very end, behind the conv passes
+    if (phase == 0) return order_after(sd, sg, st);
     // through masking / positional encoding into the conv output.  Tensor-core precisions without an external
     // feat_visual cotangent: masking, d mask_token and the split operand of the conv passes are ONE pass (phase 2)
     const bool fused_prep = d.precision != PREC_FP32 && g_fv == nullptr;
@@ -670,7 +685,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     if (phase == 1 && fused_prep)    // phased issue: the mask-token gradient belongs to the part of the bucket phase 1 completes
         SCAT_PROPAGATE(launch_conv_bwd_prep(ws + p.dX, mask_idx, d.n_masked, ws + p.dFv2, G[P_MASK_TOKEN], p.B, p.T, p.D,
                                             d.x2_dtype, st));
-    if (phase == 1) return 0;
+    if (phase == 1) return order_after(sd, sg, st);
     }
     if (d.precision != PREC_FP32) {
         if (g_fv != nullptr)          // dFv = masked dX + external cotangent was formed above: split it (nothing left to mask)
@@ -687,7 +702,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
             SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], (float*)x2_grad, p.B, p.C, p.D, p.T, st));
         SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, (const float*)x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
     }
-    return 0;
+    return order_after(sd, sg, st);
 }
 
 }  // namespace

@@ -50,19 +50,22 @@ layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restri
     }
 }
 
-template <int NPL>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// PARAMS: also accumulate dgamma / dbeta (the stand-alone operator).  The head runs the data gradient alone on its
+// critical path (PARAMS = false: no per-lane accumulators, half the registers, two CTAs per SM) and the parameter
+// gradients as column sums on the side stream (layernorm_param_grad_kernel).
+template <int NPL, bool PARAMS>
+__global__ void __launch_bounds__(LN_WARPS * 32, PARAMS ? 1 : 2)
 layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ resid, int ldr, float* __restrict__ dX, int lddx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D, int round_out, int act_rows,
                      __nv_bfloat16* __restrict__ dX16, int lddx16) {
     pdl_sync();
-    __shared__ float red[LN_WARPS][32 * NPL];
+    __shared__ float red[PARAMS ? LN_WARPS : 1][PARAMS ? 32 * NPL : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float dg[NPL], db[NPL];
+    float dg[PARAMS ? NPL : 1], db[PARAMS ? NPL : 1];
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
+    for (int i = 0; i < (PARAMS ? NPL : 1); ++i) {
         dg[i] = 0.f;
         db[i] = 0.f;
     }
@@ -93,7 +96,7 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
             g[i] = dv * (c < D ? __ldg(gamma + c) : 0.f);
             s1 += g[i];
             s2 = fmaf(g[i], xh[i], s2);
-            if (real) {
+            if (PARAMS && real) {
                 dg[i] = fmaf(dv, xh[i], dg[i]);
                 db[i] += dv;
             }
@@ -111,29 +114,74 @@ layernorm_bwd_kernel(const float* __restrict__ dY, int lddy, const float* __rest
             }
         }
     }
-    if (dgamma == nullptr) return;   // dgrad-only pass (path-length VJP)
+    if constexpr (PARAMS) {
+        if (dgamma == nullptr) return;
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) red[warp][i * 32 + lane] = dg[i];
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
-        float s = 0.f;
+        for (int i = 0; i < NPL; ++i) red[warp][i * 32 + lane] = dg[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+            float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-        atomicAdd(dgamma + c, s);
+            for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+            atomicAdd(dgamma + c, s);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) red[warp][i * 32 + lane] = db[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+            atomicAdd(dbeta + c, s);
+        }
     }
+}
+
+// dgamma[c] += sum_m dY[m,c] * (X[m,c] - mean[m]) * rstd[m],  dbeta[c] += sum_m dY[m,c]   (both zero on entry).
+// lane = column, the 8 warps of a block stride the rows of the block's row slice; slices combine with atomics.
+constexpr int PG_SLICES = 12;
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_param_grad_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
+                            const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta, int M, int D) {
+    pdl_sync();
+    __shared__ float red[2][LN_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float dg = 0.f, db = 0.f;
+    if (c < D) {
+#pragma unroll 4
+        for (int r = r0 + warp; r < r1; r += LN_WARPS) {
+            const float dv = __ldg(dY + (long long)r * lddy + c);
+            const float xh = (__ldg(X + (long long)r * ldx + c) - __ldg(mean + r)) * __ldg(rstd + r);
+            dg = fmaf(dv, xh, dg);
+            db += dv;
+        }
+    }
+    red[0][warp][lane] = dg;
+    red[1][warp][lane] = db;
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) red[warp][i * 32 + lane] = db[i];
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+    if (warp < 2 && c < D) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-        atomicAdd(dbeta + c, s);
+        for (int w = 0; w < LN_WARPS; ++w) s += red[warp][w][lane];
+        atomicAdd((warp == 0 ? dgamma : dbeta) + c, s);
     }
 }
 
 }  // namespace
+
+int launch_layernorm_param_grads(const float* dY, int lddy, const float* X, int ldx, const float* mean, const float* rstd,
+                                 float* dgamma, float* dbeta, int M, int D, cudaStream_t stream) {
+    SCAT_REQUIRE(dY && X && mean && rstd && dgamma && dbeta && M > 0 && D > 0, kErrBadArg, "layernorm param grads: bad args");
+    SCAT_CHECK_CUDA(launch_k(layernorm_param_grad_kernel, dim3(ceil_div(D, 32), min(PG_SLICES, ceil_div(M, 64))), dim3(LN_WARPS * 32), 0,
+                             stream, dY, lddy, X, ldx, mean, rstd, dgamma, dbeta, M, D));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
 
 int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
                          float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream) {
@@ -152,14 +200,18 @@ int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, con
                          int lddx16) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm bwd: D=%d not in [1,1024]", D);
     SCAT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), kErrBadArg, "layernorm bwd: dgamma/dbeta must both be set or null");
-    const int grid = min(ceil_div(M, 2 * LN_WARPS), 148);     // >= 2 rows per warp: halves the atomic tail
-#define SCAT_LN_BWD(NPL) SCAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<NPL>, dim3(grid), dim3(LN_WARPS * 32), 0, stream,  \
+    const bool params = dgamma != nullptr;
+    // with parameter gradients: >= 2 rows per warp halves the atomic tail; without: one row per warp, two CTAs per SM
+    const int grid = params ? min(ceil_div(M, 2 * LN_WARPS), 148) : min(ceil_div(M, LN_WARPS), 2 * 148);
+#define SCAT_LN_BWD(NPL, PAR) SCAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<NPL, PAR>, dim3(grid), dim3(LN_WARPS * 32), 0, stream,  \
         dY, lddy, X, ldx, gamma, mean, rstd, resid, ldr, dX, lddx, dgamma, dbeta, M, D, round_out, act_rows,  \
         reinterpret_cast<__nv_bfloat16*>(dX16), lddx16))
-    if (D <= 256) SCAT_LN_BWD(8);
-    else if (D <= 512) SCAT_LN_BWD(16);
-    else if (D <= 800) SCAT_LN_BWD(25);    // d = 784: 25 elements per lane instead of 32 (255 registers + spills -> see -res-usage)
-    else SCAT_LN_BWD(32);
+#define SCAT_LN_BWD2(NPL) do { if (params) SCAT_LN_BWD(NPL, true); else SCAT_LN_BWD(NPL, false); } while (0)
+    if (D <= 256) SCAT_LN_BWD2(8);
+    else if (D <= 512) SCAT_LN_BWD2(16);
+    else if (D <= 800) SCAT_LN_BWD2(25);   // d = 784: 25 elements per lane instead of 32
+    else SCAT_LN_BWD2(32);
+#undef SCAT_LN_BWD2
 #undef SCAT_LN_BWD
     SCAT_CHECK_LAUNCH();
     return 0;
