@@ -207,6 +207,18 @@ int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, co
                         const int32_t* mask_idx, const float* tokens, float* out, float* mean,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* EncoderTransformerCoarse.forward after the backbone (hand_net.py:264-311, `--net reg_transformer_coarse`, the
+ * attention-visualisation variant used by eval.py:788-834): same conv + PE + masking front end, the transformer of
+ * models/vision_transformer_attn.py:104-113 (attention on the raw tokens, LayerNorm on the attention branch's output, then
+ * the residual), camera = Linear(1027 -> 3) applied once, joints = mean template + transformer output relative to joint 1.
+ *   params[35]: the head's layout above with slots norm_a.w / norm_a.b holding layers.i.1.norm (the post-attention norm),
+ *   norm_f / fc1 / fc2 holding layers.i.2.*, and 33 / 34 = regressor.weight[3,1027] / regressor.bias[3].
+ *   -> pred_params[B,66], feat_visual[B,21,28,28], attn[B,heads,21,21] (last layer's attention maps).
+ * Inference only (desc.pl_reg must be 0: the reference itself fails with pl_reg under no_grad); precision fp32 or tf32. */
+int scat_coarse_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const float* mean_params,
+                        const int32_t* mask_idx, const void* x2, const float* main_feat, float* pred_params,
+                        float* feat_visual, float* attn, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- single operators (used by the unit tests and by other callers of the same kernels) ------ */
 
 /* C[M,N] = epilogue(sum_k A(m,k) B(n,k)),  A(m,k)=A[m*sam+k*sak], B(n,k)=B[n*sbn+k*sbk]

@@ -128,6 +128,53 @@ def head_forward(P: Dict[str, torch.Tensor], x2: torch.Tensor, main_feat: torch.
     return pred, feat_visual
 
 
+def coarse_forward(P: Dict[str, torch.Tensor], x2, main_feat, mean_params, *, pos_embed: bool = True,
+                   mask_idx: Optional[Sequence[int]] = None, pe: Optional[torch.Tensor] = None, depth: int = 3):
+    """EncoderTransformerCoarse.forward after the backbone, without the path-length term: hand_net.py:264-311 with the
+    transformer of models/vision_transformer_attn.py:104-113 (8 heads, hand_net.py:236).
+
+    Returns (pred_params[B,66], feat_visual[B,21,28,28], attn[B,8,21,21] of the last layer)."""
+    heads = 8
+    B = x2.shape[0]
+    n_tok = P["conv1x1_channel_reduction.weight"].shape[0]
+    feat_visual = F.conv2d(x2, P["conv1x1_channel_reduction.weight"])          # :267
+    feat = feat_visual.view(B, n_tok, -1)                                       # :268 (a view)
+    if pos_embed:
+        if pe is None:
+            pe = positional_encoding(n_tok, feat.shape[-1], dtype=feat.dtype).to(feat.device)
+        feat = feat + pe[: feat.size(0), :]                                     # :272
+    if mask_idx is not None and len(mask_idx) > 0:
+        feat[:, list(mask_idx), :] = P["mask_token"].to(feat.dtype)             # :280 (in place)
+    x, attn = feat, None
+    for i in range(depth):                                                      # vision_transformer_attn.py:105-112
+        p = f"transformer.layers.{i}."
+        last = i == depth - 1
+        b, n, _ = x.shape
+        qkv = F.linear(x, P[p + "0.to_qkv.weight"])                             # attention on the RAW tokens (:106, :63)
+        q, k, v = (t.reshape(b, n, heads, DIM_HEAD).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
+        attn = (torch.matmul(q, k.transpose(-1, -2)) * (DIM_HEAD ** -0.5)).softmax(dim=-1)     # :66,76
+        o = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(b, n, heads * DIM_HEAD)          # :78-79
+        x1 = F.linear(o, P[p + "0.to_out.0.weight"], P[p + "0.to_out.0.bias"])                  # :80
+        x = F.layer_norm(x1, x1.shape[-1:], P[p + "1.norm.weight"], P[p + "1.norm.bias"], 1e-5) + x   # :107
+        if not last:                                                            # :108, PreNorm(FeedForward)
+            y = F.layer_norm(x, x.shape[-1:], P[p + "2.norm.weight"], P[p + "2.norm.bias"], 1e-5)
+            ff = p + "2.fn.net."
+        else:
+            y = x
+            ff = p + "2.net."
+        x = F.linear(F.gelu(F.linear(y, P[ff + "0.weight"], P[ff + "0.bias"])), P[ff + "2.weight"], P[ff + "2.bias"])
+    feat_out = x.reshape(B, -1)                                                 # hand_net.py:287
+    pred = mean_params.to(feat_out.dtype).repeat(B, 1).clone()                  # :289-293
+    pred[:, 3:] = pred[:, 3:] + feat_out                                        # :294
+    cameras = F.linear(torch.cat((main_feat, pred[:, :3]), dim=1), P["regressor.weight"], P["regressor.bias"])   # :296
+    pred_3d = pred[:, 3:66].view(-1, 21, 3)                                     # :298
+    root = pred_3d[:, 1].clone().unsqueeze(1)
+    pred_3d -= root                                                             # :300
+    pred[:, 3:] = pred_3d.view(-1, 63)
+    pred[:, :3] = cameras                                                       # :303
+    return pred, feat_visual, attn
+
+
 def train_loss(pred_params, labels, pl_term=None, *, l_weight_3d: float = 1e5, l_weight_2d: float = 10.0):
     """train.py:165-203 restated (train.py itself is unimportable offline: matplotlib/oss2/...).
 
@@ -157,7 +204,7 @@ def train_loss(pred_params, labels, pl_term=None, *, l_weight_3d: float = 1e5, l
 
 
 def train_step(P: Dict[str, torch.Tensor], x2, main_feat, labels, mean_params, *, heads=8, iteration=3,
-               pos_embed=True, mask_idx=None, pl_reg=True, l_weight_3d=1e5, l_weight_2d=10.0):
+               pos_embed=True, mask_idx=None, pl_reg=True, l_weight_3d=1e5, l_weight_2d=10.0, pe=None):
     """One head training step body (train.py:159-206): forward, path-length VJP, losses, backward.
 
     Returns dict(loss, l_3d, l_2d, l_pl, pred, feat_visual, pl, grads{name: tensor}, x2_grad, main_feat_grad)."""
@@ -165,7 +212,7 @@ def train_step(P: Dict[str, torch.Tensor], x2, main_feat, labels, mean_params, *
     x2 = x2.detach().clone().requires_grad_(True)
     main_feat = main_feat.detach().clone().requires_grad_(True)
     outs = head_forward(Pg, x2, main_feat, mean_params, heads=heads, iteration=iteration,
-                        pos_embed=pos_embed, mask_idx=mask_idx, pl_reg=pl_reg)
+                        pos_embed=pos_embed, mask_idx=mask_idx, pl_reg=pl_reg, pe=pe)
     pred, feat_visual = outs[0], outs[1]
     pl = outs[2] if pl_reg else None
     loss, l3, l2, lpl = train_loss(pred, labels, pl, l_weight_3d=l_weight_3d, l_weight_2d=l_weight_2d)

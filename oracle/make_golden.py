@@ -180,6 +180,42 @@ def run_token_case(vision_transformer, hand_net, name, *, B, n, dim, heads, mask
     print(f"[golden] {name}: oracle-vs-reference {d:.3e}")
 
 
+def run_coarse_case(hand_net, name, *, B, pos_embed, mask_rate, mask_seed, in_seed=7):
+    """EncoderTransformerCoarse (hand_net.py:216-311, `--net reg_transformer_coarse`) from the unmodified reference,
+    pl_reg off (the inference path of eval.py:788-834), against oracle/head_oracle.coarse_forward."""
+    opt = SimpleNamespace(vit_heads=8, pl_reg=False, iteration=3, pos_embed=pos_embed, mask_rate=mask_rate)
+    mean = torch.from_numpy(synth.make_mean_params("hand"))
+    torch.manual_seed(0)
+    net = hand_net.EncoderTransformerCoarse(opt, mean).eval()
+    W = synth.make_coarse_weights()
+    sd = net.state_dict()
+    head_keys = [k for k in sd if not k.startswith("main_encoder.") and k != "positionalEncoding.pe"]
+    assert head_keys == list(W), (head_keys[:6], list(W)[:6])                 # same keys, same order as the reference
+    for k, v in W.items():
+        assert tuple(sd[k].shape) == v.shape, (k, sd[k].shape, v.shape)
+        sd[k].copy_(torch.from_numpy(v))
+    stub = _StubBackbone()
+    net.main_encoder = stub
+    x2_np, mf_np, _ = synth.make_head_inputs(B, in_seed)
+    stub.x2, stub.main_feat = torch.from_numpy(x2_np), torch.from_numpy(mf_np)
+    random.seed(mask_seed)
+    with torch.no_grad():
+        pred, fv, attn = net(torch.zeros(B, 3, 8, 8))
+    random.seed(mask_seed)
+    mask_idx = synth.mask_indices(mask_rate)
+    P = {k: torch.from_numpy(v) for k, v in W.items()}
+    with torch.no_grad():
+        o = head_oracle.coarse_forward(P, torch.from_numpy(x2_np), torch.from_numpy(mf_np), mean, pos_embed=pos_embed,
+                                       mask_idx=mask_idx)
+    for nm, a, b in (("pred", o[0], pred), ("feat_visual", o[1], fv), ("attn", o[2], attn)):
+        d = (a - b).abs().max().item()
+        assert d <= 1e-6 * max(1.0, b.abs().max().item()), (name, nm, d)
+        print(f"[golden] {name}: oracle-vs-reference {nm} {d:.3e}")
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), B=B, pos_embed=int(pos_embed), mask_rate=mask_rate,
+                        mask_seed=mask_seed, in_seed=in_seed, mask_idx=np.array(mask_idx, dtype=np.int64),
+                        pred=pred.numpy(), feat_visual=fv.numpy().copy(), attn=attn.numpy())
+
+
 def run_mano_case(name, B=6):
     """MANO LBS: import models.mano from a temp cwd holding a synthetic MANO_RIGHT.pkl (mano.py:220)."""
     import scipy.sparse as sp
@@ -340,6 +376,11 @@ def main():
     if sys.argv[1:] == ["adam"]:          # the optimiser fixture alone (needs torch only, not /root/reference)
         run_adam_case("adam")
         return
+    if sys.argv[1:] == ["coarse"]:        # the reg_transformer_coarse fixtures alone
+        hand_net, _ = _import_reference_head()
+        run_coarse_case(hand_net, "coarse_b3_mask20", B=3, pos_embed=True, mask_rate=0.2, mask_seed=6)
+        run_coarse_case(hand_net, "coarse_b2_nope_alias", B=2, pos_embed=False, mask_rate=0.5, mask_seed=8, in_seed=9)
+        return
     if sys.argv[1:] == ["mano"]:          # the LBS fixtures alone (forward + autograd gradients of the reference)
         run_mano_case("mano_lbs")
         return
@@ -364,6 +405,8 @@ def main():
     run_head_case(hand_net, "head_b2_mask90", B=2, heads=8, iteration=3, pos_embed=True, mask_rate=0.9,
                   pl_reg=True, mask_seed=4, in_seed=4)
     run_token_case(vt, hand_net, "tokens_n128_d196", B=2, n=128, dim=196, heads=8, mask_rate=0.2, mask_seed=5)
+    run_coarse_case(hand_net, "coarse_b3_mask20", B=3, pos_embed=True, mask_rate=0.2, mask_seed=6)
+    run_coarse_case(hand_net, "coarse_b2_nope_alias", B=2, pos_embed=False, mask_rate=0.5, mask_seed=8, in_seed=9)
     run_mano_case("mano_lbs")
     run_adam_case("adam")
     run_eval_case("eval_metrics")

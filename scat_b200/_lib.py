@@ -60,6 +60,7 @@ SIGNATURES = {
     "scat_peer_error": (_i32, [_f, C.POINTER(C.c_int32)]),
     "scat_peer_error_word": (C.c_void_p, [_f]),
     "scat_tokens_forward": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _sz, _f]),
+    "scat_coarse_forward": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _f, _f, _f, _sz, _f]),
     "scat_gemm": (_i32, [_f, _i64, _i64, _f, _i64, _i64, _f, _i32, _i32, _i32, _i32, _i32, _f, _f, _i32, _f, _i32,
                          _i32, _i32, _f]),
     "scat_gemm_bf16": (_i32, [_f, _i64, _i64, _f, _i64, _i64, _f, _i32, _f, _i32, _i32, _i32, _i32, _i32, _f, _f, _i32,

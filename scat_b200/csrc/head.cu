@@ -303,6 +303,38 @@ __global__ void token_mean_kernel(const float* __restrict__ X, float* __restrict
     out[b * 3 + c] = s / (float)n;
 }
 
+// Tail of EncoderTransformerCoarse.forward (hand_net.py:289-302): joints = mean template + transformer output, made
+// relative to joint 1; camera = Linear(1027 -> 3)(cat(main_feat, mean_params[:3])), applied once.  One warp per sample.
+__global__ void coarse_tail_kernel(const float* __restrict__ main_feat, const float* __restrict__ feat_out,
+                                   const float* __restrict__ mean_params, const float* __restrict__ Wr /* [3, F + 3] */,
+                                   const float* __restrict__ br, float* __restrict__ pred, int B, int F) {
+    pdl_sync();
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float* mf = main_feat + (long long)b * F;
+    float cam[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < F; k += 32) {
+        const float v = mf[k];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cam[j] = fmaf(v, Wr[j * (F + 3) + k], cam[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        cam[j] = warp_sum(cam[j]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) cam[j] = fmaf(mean_params[q], Wr[j * (F + 3) + F + q], cam[j]);   // pred_params[:, :3] = mean here
+        cam[j] += br[j];
+    }
+    float* out = pred + (long long)b * 66;
+    if (lane < 3) out[lane] = cam[lane];
+    const float* fo = feat_out + (long long)b * 63;
+    for (int e = lane; e < 63; e += 32) {
+        const int c = e % 3;
+        const float root = mean_params[3 + 3 + c] + fo[3 + c];                 // joint 1 before the subtraction
+        out[3 + e] = (e / 3 == 1) ? 0.f : (mean_params[3 + e] + fo[e]) - root;
+    }
+}
+
 // Weight views used by the GEMMs of one layer: the caller's fp32 tensors, or the rounded/padded copies.
 struct LayerW {
     const float *qkv, *out, *fc1, *fc2;
@@ -348,8 +380,11 @@ int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec,
 //   PREC_TF32: fp32, rounded to TF32-nearest by the producing kernel
 //   PREC_BF16: bf16 in the same workspace slot (leading dimension padded to 8 elements); tensors that a
 //              non-GEMM kernel also reads in fp32 (dX, dX1) get a separate bf16 shadow
+// attn_variant: the wiring of models/vision_transformer_attn.py:104-113 (reg_transformer_coarse): attention on the RAW
+// token matrix, LayerNorm on the attention branch's OUTPUT, then the residual:  x = LN(attn(x)) + x ; x = ff(x).
+// The slot Na then holds the attention branch's output (the LayerNorm's input).  Forward only.
 int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int prec, cudaStream_t st,
-                        float* X0_override) {
+                        float* X0_override, bool attn_variant = false) {
     const int M = p.M;
     const bool tc = prec != PREC_FP32, bf = prec == PREC_BF16;
     const int omode = bf ? OUT_BF16 : tc ? OUT_TF32 : OUT_F32;
@@ -359,19 +394,35 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         const int ld_n = bf ? pad8(L.d) : pad4(L.d);       // leading dimension of Na / Nf (16-byte rows for TMA)
         const int ld_h = bf ? pad8(L.hid) : L.ldh;         // leading dimension of H as a GEMM operand
-        // PreNorm + Attention + Residual (:18,:26,:59-79)
-        SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, ld_n, ws + L.mean_a,
-                                            ws + L.rstd_a, M, L.d, omode, st));
         GemmArgs g;
-        g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
-        g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = tc;
-        SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
-        g = GemmArgs();
-        g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
-        g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
-        g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
-        SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        if (!attn_variant) {
+            // PreNorm + Attention + Residual (:18,:26,:59-79)
+            SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, ld_n, ws + L.mean_a,
+                                                ws + L.rstd_a, M, L.d, omode, st));
+            g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
+            g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = tc;
+            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+            SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
+            g = GemmArgs();
+            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
+            g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
+            g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
+            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+        } else {
+            // x1, attn = attention(x); x = pren(x1) + x (vision_transformer_attn.py:106-108): X is the caller's /
+            // previous layer's fp32 tensor, so the tensor-core GEMM rounds it to TF32-nearest in shared memory itself
+            g.A = X; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1;
+            g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = 0;
+            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+            SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
+            g = GemmArgs();
+            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1;
+            g.C = ws + L.Na; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
+            g.epilogue = EPI_BIAS; g.bias = W[L.p_out_b];
+            SCAT_PROPAGATE(launch_gemm(g, prec, st));
+            SCAT_PROPAGATE(launch_layernorm_fwd(ws + L.Na, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.X1, L.d, ws + L.mean_a,
+                                                ws + L.rstd_a, M, L.d, OUT_F32, st, X, L.d));
+        }
         // (PreNorm +) FeedForward, no residual (:44,:94 / :89)
         if (!L.last)
             SCAT_PROPAGATE(launch_layernorm_fwd(ws + L.X1, L.d, W[L.p_nf_w], W[L.p_nf_b], ws + L.Nf, ld_n,
@@ -817,6 +868,42 @@ int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, co
         SCAT_CHECK_CUDA(launch_k(token_mean_kernel, dim3(p.B), dim3(32), 0, st, ws + p.feat_out, mean, p.T));
         SCAT_CHECK_LAUNCH();
     }
+    return 0;
+}
+
+int scat_coarse_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const float* mean_params,
+                        const int32_t* mask_idx, const void* x2, const float* main_feat, float* pred_params,
+                        float* feat_visual, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+    SCAT_REQUIRE(desc && params && x2 && main_feat && pred_params && feat_visual && attn && mean_params, kErrBadArg,
+                 "coarse_forward: null argument");
+    const ScatHeadDesc& d = *desc;
+    cudaStream_t st = (cudaStream_t)stream;
+    HeadPlan p;
+    SCAT_PROPAGATE(make_plan(d, p));
+    SCAT_PROPAGATE(check_ws(p, workspace, workspace_bytes));
+    SCAT_REQUIRE(d.channels > 0 && d.n_out == 66 && d.n_tokens == 21, kErrUnsupported,
+                 "coarse_forward: needs channels>0, n_out=66, n_tokens=21");
+    SCAT_REQUIRE(!d.pl_reg, kErrUnsupported, "coarse_forward: inference path, the path-length term needs a backward (pl_reg must be 0)");
+    SCAT_REQUIRE(d.precision == PREC_FP32 || d.precision == PREC_TF32, kErrUnsupported, "coarse_forward: precision fp32 or tf32");
+    SCAT_REQUIRE(!d.pos_embed || pe, kErrBadArg, "coarse_forward: pos_embed set but pe is null");
+    float* ws = (float*)workspace;
+    float* X0 = d.pos_embed ? ws + p.L[0].X : feat_visual;       // same aliasing as hand_net.py:364,373 (here :268-269,280)
+    if (d.precision != PREC_FP32) {
+        SCAT_PROPAGATE(launch_conv_weight_prep(params[P_CONV_W], ws + p.w_conv, p.C, p.T, d.x2_dtype, st));
+        SCAT_PROPAGATE(round_weights(p, params, ws, d.precision, st));
+        SCAT_PROPAGATE(launch_conv_pe_mask_fwd_tc(x2, d.x2_dtype, ws + p.w_conv, pe, params[P_MASK_TOKEN], mask_idx, d.n_masked,
+                                                  d.pos_embed, feat_visual, X0, p.B, p.C, p.D, p.T, st));
+    } else {
+        SCAT_PROPAGATE(launch_conv_pe_mask_fwd((const float*)x2, params[P_CONV_W], pe, params[P_MASK_TOKEN], mask_idx, d.n_masked,
+                                               d.pos_embed, feat_visual, X0, p.B, p.C, p.D, p.T, st));
+    }
+    SCAT_PROPAGATE(transformer_forward(p, params, ws, d.precision, st, d.pos_embed ? nullptr : feat_visual, /*attn_variant=*/true));
+    // the attention maps of the LAST layer are the second output (vision_transformer_attn.py:113)
+    SCAT_CHECK_CUDA(cudaMemcpyAsync(attn, ws + p.L[kDepth - 1].P, (size_t)p.B * p.heads * p.T * p.T * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+    SCAT_CHECK_CUDA(launch_k(coarse_tail_kernel, dim3(ceil_div(p.B, 4)), dim3(128), 0, st, main_feat, (const float*)(ws + p.feat_out),
+                             mean_params, params[P_REG_W], params[P_REG_B], pred_params, p.B, p.F));
+    SCAT_CHECK_LAUNCH();
     return 0;
 }
 

@@ -119,8 +119,10 @@ int launch_pe_mask_tokens(const float* tokens, const float* pe, const float* mas
 // ------------------------------------------------------------------------------------------
 // LayerNorm (vision_transformer.py:23,26; eps 1e-5, affine)
 // ------------------------------------------------------------------------------------------
+// resid (nullable): Y = LayerNorm(X) + resid
 int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
-                         float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream);
+                         float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream,
+                         const float* resid = nullptr, int ldr = 0);
 // dX = LN'(dY) (+ resid); dgamma/dbeta accumulated with atomics when non-null (must be pre-zeroed)
 int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, const float* gamma, const float* mean,
                          const float* rstd, const float* resid, int ldr, float* dX, int lddx, float* dgamma,

@@ -12,7 +12,7 @@ template <int NPL>  // elements per lane (row length <= 32*NPL)
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ Y, int ldy, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int M, int D, int round_out) {
+                     float* __restrict__ rstd_out, int M, int D, int round_out, const float* __restrict__ resid, int ldr) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -40,7 +40,8 @@ layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restri
     for (int i = 0; i < NPL; ++i) {
         const int c = i * 32 + lane;
         if (c < D) {
-            const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            if (resid != nullptr) o += resid[(long long)row * ldr + c];     // x = pren(x1) + x (vision_transformer_attn.py:108)
             store_out(Y, (long long)row * ldy + c, o, round_out);
         }
     }
@@ -184,12 +185,13 @@ int launch_layernorm_param_grads(const float* dY, int lddy, const float* X, int 
 }
 
 int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
-                         float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream) {
+                         float* mean, float* rstd, int M, int D, int round_out, cudaStream_t stream, const float* resid,
+                         int ldr) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm: D=%d not in [1,1024]", D);
     const int grid = ceil_div(M, LN_WARPS);
-    if (D <= 256) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out));
-    else if (D <= 512) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out));
-    else SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<32>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out));
+    if (D <= 256) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));
+    else if (D <= 512) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));
+    else SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<32>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -120,6 +120,27 @@ class HeadFunction(torch.autograd.Function):
         return (None, None, None, None, x2_grad, mf_grad, *grads)
 
 
+def coarse_forward(cfg: HeadConfig, mask_idx, mean_params, pe, x2, main_feat, params):
+    """EncoderTransformerCoarse.forward after the backbone (hand_net.py:264-311), inference: returns
+    (pred_params[B,66], feat_visual[B,21,28,28], attn[B,heads,21,21])."""
+    lib = _lib.load()
+    x2, seam = _seam(x2, "x2")
+    if seam != cfg.x2_dtype:
+        cfg = dataclasses.replace(cfg, x2_dtype=seam)
+    main_feat = _f32c(main_feat, "main_feat")
+    params = [_f32c(p, "parameter") for p in params]
+    B, dev = x2.shape[0], x2.device
+    pred = torch.empty(B, cfg.n_out, device=dev, dtype=torch.float32)
+    fv = torch.empty(B, cfg.n_tokens, 28, 28, device=dev, dtype=torch.float32)
+    attn = torch.empty(B, cfg.heads, cfg.n_tokens, cfg.n_tokens, device=dev, dtype=torch.float32)
+    ws = alloc_workspace(cfg, B, dev)
+    d = cfg.desc(B)
+    check(lib.scat_coarse_forward(C.byref(d), ptr_array(params), ptr(pe), ptr(mean_params), ptr(mask_idx), ptr(x2),
+                                  ptr(main_feat), ptr(pred), ptr(fv), ptr(attn), ptr(ws), ws.numel(), stream_ptr()),
+          "scat_coarse_forward")
+    return pred, fv, attn
+
+
 class ProjLossFunction(torch.autograd.Function):
     """train.py:112-120,165-203: weak-perspective projection + MSE-3D + L1-2D + path-length statistic."""
 

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as SF
-from . import vision_transformer
+from . import vision_transformer, vision_transformer_attn
 
 
 def _to_gpu(t):
@@ -143,6 +143,62 @@ class EncoderTransformer(nn.Module):
 
     def forward(self, main_input):
         main_feat, x1, x2, x3, x4 = self.main_encoder(main_input)          # :356 (cuDNN)
+        return self.forward_features(main_feat, x2)
+
+
+class EncoderTransformerCoarse(nn.Module):
+    """reg_transformer_coarse head, hand_net.py:216-311: the attention-visualisation variant that eval.py:788-834 runs.
+    Same conv + positional encoding + masking front end; the transformer of models/vision_transformer_attn.py (attention
+    on the raw tokens, LayerNorm on the attention branch's output, then the residual; heads fixed at 8, :236); camera =
+    Linear(1027 -> 3) applied once (:259,298); returns (pred_params[B,66], feat_visual[B,21,28,28], attn[B,8,21,21]).
+    Inference path: the call must run under torch.no_grad() -- where the reference itself cannot return the path-length
+    term (autograd.grad at :309 fails under no_grad), so ``opt.pl_reg`` must be False."""
+
+    def __init__(self, opt, mean_params, precision: str = "tf32", backbone: nn.Module | None = None):
+        super().__init__()
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("EncoderTransformerCoarse: precision 'fp32' or 'tf32'")
+        self.mean_params = _to_gpu(mean_params)
+        self.pl = opt.pl_reg
+        self.full_content = 21
+        self.conv1x1_channel_reduction = nn.Conv2d(512, 21, 1, 1, 0, bias=False)
+        self.transformer = vision_transformer_attn.Transformer(dim=784, depth=3, heads=8, dim_head=64, mlp_dim=392,
+                                                               dropout=0.0)
+        self.main_encoder = backbone if backbone is not None else get_model("resnet50")
+        self.iteration = opt.iteration
+        self.pos_embed = opt.pos_embed
+        print("Position Encoding open" if self.pos_embed is True else "Position Encoding close")
+        self.positionalEncoding = PositionalEncoding(784, max_len=21)
+        self.mask_token = nn.Parameter(torch.randn(1, 1, 784))
+        self.mask_rate = opt.mask_rate
+        self.regressor = nn.Linear(1024 + 3, 3)
+        self.precision = precision
+        self.last_mask = []
+
+    def head_parameters(self):
+        return ([self.mask_token, self.conv1x1_channel_reduction.weight] + self.transformer.ordered_parameters()
+                + [self.regressor.weight, self.regressor.bias])
+
+    _draw_mask = EncoderTransformer._draw_mask
+
+    def forward_features(self, main_feat, x2, mask_idx=None):
+        if self.pl:
+            # hand_net.py:308-309: the path-length term is an autograd.grad call; this is the no_grad inference path
+            raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn")
+        if torch.is_grad_enabled() and (x2.requires_grad or main_feat.requires_grad
+                                        or any(p.requires_grad for p in self.head_parameters())):
+            raise RuntimeError("scat_b200.EncoderTransformerCoarse is an inference path; wrap the call in torch.no_grad()")
+        masked = self._draw_mask() if mask_idx is None else list(mask_idx)
+        self.last_mask = masked
+        mask_dev = torch.tensor(masked, dtype=torch.int32, device=x2.device) if len(masked) else None
+        pe = self.positionalEncoding.pe[0] if self.pos_embed else None
+        cfg = SF.HeadConfig(heads=8, iteration=0, pos_embed=bool(self.pos_embed), n_masked=len(masked), pl_reg=False,
+                            precision=self.precision)
+        return SF.coarse_forward(cfg, mask_dev, self.mean_params.reshape(-1), pe, x2, main_feat,
+                                 [p.detach() for p in self.head_parameters()])
+
+    def forward(self, main_input):
+        main_feat, x1, x2, x3, x4 = self.main_encoder(main_input)          # :262
         return self.forward_features(main_feat, x2)
 
 

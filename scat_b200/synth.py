@@ -66,6 +66,43 @@ def head_param_shapes(heads: int = 8, dim: int = TOKEN_DIM, depth: int = 3, chan
     return shapes
 
 
+def coarse_param_shapes(dim: int = TOKEN_DIM, depth: int = 3, channels: int = X2_CHANNELS, n_tokens: int = N_TOKENS):
+    """Ordered {state_dict key: shape} of EncoderTransformerCoarse (hand_net.py:220-259, vision_transformer_attn.py:88-104):
+    8 heads fixed, LayerNorm on the attention output (layers.i.1), camera regressor Linear(1027 -> 3)."""
+    inner = DIM_HEAD * 8
+    shapes = {"mask_token": (1, 1, dim), "conv1x1_channel_reduction.weight": (n_tokens, channels, 1, 1)}
+    for i, (d, hid, out) in enumerate(layer_dims(dim, depth)):
+        p = f"transformer.layers.{i}."
+        shapes[p + "0.to_qkv.weight"] = (3 * inner, d)
+        shapes[p + "0.to_out.0.weight"] = (d, inner)
+        shapes[p + "0.to_out.0.bias"] = (d,)
+        shapes[p + "1.norm.weight"] = (d,)
+        shapes[p + "1.norm.bias"] = (d,)
+        if i < depth - 1:
+            shapes[p + "2.norm.weight"] = (d,)
+            shapes[p + "2.norm.bias"] = (d,)
+            ff = p + "2.fn.net."
+        else:
+            ff = p + "2.net."
+        shapes[ff + "0.weight"] = (hid, d)
+        shapes[ff + "0.bias"] = (hid,)
+        shapes[ff + "2.weight"] = (out, hid)
+        shapes[ff + "2.bias"] = (out,)
+    shapes["regressor.weight"] = (3, MAIN_FEAT + 3)
+    shapes["regressor.bias"] = (3,)
+    return shapes
+
+
+def make_coarse_weights(seed: int = 20210206, dtype=np.float32):
+    """Random-init weights of the coarse head, same recipe as make_head_weights("unit")."""
+    g = _rng(seed)
+    out = {}
+    for name, shape in coarse_param_shapes().items():
+        r = g.standard_normal(size=shape)
+        out[name] = ((1.0 + 0.02 * r) if name.endswith("norm.weight") else 0.02 * r).astype(dtype)
+    return out
+
+
 def _rng(seed: int) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64(seed))
 

@@ -5,7 +5,7 @@
   * size-independent properties at full size (joint 1 == 0, masked-token zeros, linearity of the VJP).
 
 Tolerances (north_star): fp32 parity mode 2e-5 relative on outputs / 2e-4 on gradients; TF32 path 1e-4
-relative on joints, 1e-3 relative (L2) on gradients; masking and indexing bit-exact.
+relative on joints, 1e-3 relative on gradients in the L2 AND the max norm; masking and indexing bit-exact.
 """
 import random
 
@@ -84,8 +84,8 @@ def _config2(precision, B=96, regime="unit", seed=11):
     return opt, W, net, x2, mf, labels
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 2e-5, 2e-4), ("tf32", 1e-4, 1e-3)])
-def test_head_config2_against_oracle(precision, tol_out, tol_grad):
+@pytest.mark.parametrize("precision,tol_out,tol_grad,tol_grad_max", [("fp32", 2e-5, 2e-4, 3e-4), ("tf32", 1e-4, 1e-3, 1e-3)])
+def test_head_config2_against_oracle(precision, tol_out, tol_grad, tol_grad_max):
     """BASELINE config 2 (B=96, mask 0.2, pl_reg, iteration 3) against the fp64 oracle."""
     opt, W, net, x2, mf, labels = _config2(precision)
     r = _run_module_step(net, x2, mf, labels, mask_seed=3)
@@ -96,10 +96,10 @@ def test_head_config2_against_oracle(precision, tol_out, tol_grad):
     assert rel_l2(r["fv"], o["feat_visual"]) < (2e-5 if precision == "fp32" else 2e-3)
     assert rel_l2(r["pl"], o["pl"]) < (2e-5 if precision == "fp32" else 5e-3)
     np.testing.assert_allclose(r["loss"].item(), o["loss"].item(), rtol=10 * tol_out)
-    # gradients (north_star: within 1e-3 relative on the TF32 path).  Single-pass TF32 keeps 11 mantissa bits per
-    # operand, and x2.grad / the conv weight gradient sit behind 12 chained GEMMs: their L2-relative error is ~4e-4,
-    # while the max-norm statistic (worst element of up to 38 M, relative to the largest) lands at 0.9-1.05e-3, i.e. AT
-    # the budget.  The test therefore holds the L2-relative error to tol_grad and the max-norm error to 1.5 x tol_grad.
+    # gradients (north_star: within 1e-3 relative on the TF32 path), held in BOTH norms: relative L2 and max-norm (worst
+    # element relative to the largest).  Single-pass TF32 keeps 11 mantissa bits per operand and the layer-0 tensors sit
+    # behind ~24 chained GEMM / attention stages (forward + backward), each adding ~2e-4 of zero-mean rounding noise:
+    # measured 7-9e-4 in L2 and up to 9.8e-4 in the max norm (tools/grad_error_report.py, profiles/r2_grad_errors.txt).
     named = dict(net.named_parameters())
     errs_l2 = {k: rel_l2(named[k].grad, o["grads"][k]) for k in W}
     errs_l2["x2"] = rel_l2(r["x2_grad"], o["x2_grad"])
@@ -108,7 +108,7 @@ def test_head_config2_against_oracle(precision, tol_out, tol_grad):
     errs = {k: rel_max(named[k].grad, o["grads"][k]) for k in W}
     errs["x2"] = rel_max(r["x2_grad"], o["x2_grad"])
     errs["main_feat"] = rel_max(r["mf_grad"], o["main_feat_grad"])
-    assert max(errs.values()) < 1.5 * tol_grad, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    assert max(errs.values()) < tol_grad_max, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
 
 
 def test_head_config2_bf16_path_mpjpe_budget():
@@ -312,3 +312,65 @@ def test_data_parallel_shards_sum_to_full_batch():
         half.load_inputs(x2d[lo:lo + 4], mfd[lo:lo + 4], lab[lo:lo + 4]); half.set_mask([1, 5, 9, 13]); half.step(allreduce=False)
         acc += half.bucket.flat
     assert rel_l2(acc, g_full) < 1e-5
+
+
+def _coarse_net(precision, pos_embed, mask_rate):
+    from scat_b200.hand_net import EncoderTransformerCoarse
+    from tests.util import StubBackbone
+    mean = torch.from_numpy(synth.make_mean_params("hand"))
+    net = EncoderTransformerCoarse(make_opt(8, False, 3, pos_embed, mask_rate), mean, precision=precision,
+                                   backbone=StubBackbone())
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_coarse_weights().items()}
+    sd["positionalEncoding.pe"] = net.positionalEncoding.pe
+    net.load_state_dict(sd, strict=True)
+    return net.cuda()
+
+
+@pytest.mark.parametrize("name", ["coarse_b3_mask20", "coarse_b2_nope_alias"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_coarse_head_matches_reference_fixture(name, precision):
+    """reg_transformer_coarse (hand_net.py:216-311, vision_transformer_attn.py:104-113) against the fixture produced by
+    the unmodified reference: joints / camera, feat_visual and the last layer's attention maps."""
+    g = load_golden(name)
+    B = int(g["B"])
+    net = _coarse_net(precision, bool(g["pos_embed"]), float(g["mask_rate"]))
+    x2, mf, _ = synth.make_head_inputs(B, int(g["in_seed"]))
+    net.main_encoder.x2, net.main_encoder.main_feat = torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda()
+    random.seed(int(g["mask_seed"]))
+    with torch.no_grad():
+        pred, fv, attn = net(torch.zeros(B, 3, 8, 8, device="cuda"))
+    assert net.last_mask == g["mask_idx"].tolist()
+    tol = 2e-5 if precision == "fp32" else 2e-3
+    assert rel_max(pred, g["pred"]) < (2e-5 if precision == "fp32" else 1e-4)
+    assert torch.all(pred[:, 6:9] == 0)
+    idx = net.last_mask
+    keep = [t for t in range(21) if t not in idx]
+    if bool(g["pos_embed"]):
+        assert rel_max(fv, g["feat_visual"]) < tol
+    else:                                                              # aliased overwrite (hand_net.py:268,280)
+        assert rel_max(fv.view(B, 21, -1)[:, keep], torch.from_numpy(g["feat_visual"]).view(B, 21, -1)[:, keep]) < tol
+        assert torch.equal(fv.view(B, 21, -1)[:, idx].cpu(),
+                           torch.from_numpy(synth.make_coarse_weights()["mask_token"]).expand(B, len(idx), -1))
+    assert attn.shape == (B, 8, 21, 21)
+    assert rel_max(attn, g["attn"]) < (2e-5 if precision == "fp32" else 3e-3)
+    assert float((attn.sum(-1) - 1).abs().max()) < 1e-5
+
+
+def test_coarse_head_config_size_against_oracle():
+    """B = 96 against the float64 restatement, tf32 path; and the no_grad contract."""
+    from oracle import head_oracle
+    B = 96
+    net = _coarse_net("tf32", True, 0.2)
+    x2, mf, _ = synth.make_head_inputs(B, 21)
+    x2d, mfd = torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda()
+    random.seed(4)
+    with torch.no_grad():
+        pred, fv, attn = net.forward_features(mfd, x2d)
+    P = {k: torch.from_numpy(v).double() for k, v in synth.make_coarse_weights().items()}
+    with torch.no_grad():
+        o = head_oracle.coarse_forward(P, torch.from_numpy(x2).double(), torch.from_numpy(mf).double(),
+                                       torch.from_numpy(synth.make_mean_params("hand")).double(), pos_embed=True,
+                                       mask_idx=net.last_mask)
+    assert rel_max(pred, o[0]) < 1e-4 and rel_l2(fv, o[1]) < 2e-3 and rel_max(attn, o[2]) < 3e-3
+    with pytest.raises(RuntimeError, match="inference path"):
+        net.forward_features(mfd, x2d.clone().requires_grad_(True))

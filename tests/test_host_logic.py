@@ -122,3 +122,23 @@ def test_head_adam_has_no_cpu_path():
         HeadAdam([torch.nn.Parameter(torch.zeros(4))], lr=1e-4)
     with pytest.raises(ValueError):
         HeadAdam([torch.nn.Parameter(torch.zeros(4))], lr=-1.0)
+
+
+def test_coarse_module_state_dict_matches_reference_layout():
+    """EncoderTransformerCoarse (hand_net.py:216-259): key set, order and shapes as probed from the reference by
+    oracle/make_golden.py coarse (which asserts the same list against the unmodified reference's state_dict)."""
+    from scat_b200.hand_net import EncoderTransformerCoarse
+    mean = torch.from_numpy(synth.make_mean_params("hand"))
+    net = EncoderTransformerCoarse(make_opt(pl_reg=False), mean, backbone=StubBackbone())
+    expect = synth.coarse_param_shapes()
+    sd = net.state_dict()
+    assert [k for k in sd if k != "positionalEncoding.pe"] == list(expect)
+    for k, shape in expect.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert len(net.head_parameters()) == 35
+    # C-ABI slot order: post-attention LayerNorm first, then qkv / out projection (include/scat_b200.h)
+    hp = net.head_parameters()
+    assert hp[2] is net.transformer.layers[0][1].norm.weight and hp[4] is net.transformer.layers[0][0].to_qkv.weight
+    assert tuple(hp[33].shape) == (3, 1027)
+    with pytest.raises(RuntimeError, match="does not require grad"):       # pl_reg: the reference fails under no_grad too
+        EncoderTransformerCoarse(make_opt(pl_reg=True), mean, backbone=StubBackbone()).forward_features(None, None)

@@ -173,3 +173,23 @@ def test_warmup_schedule_restatement():
     for e in range(20):
         sched.step(e + 1)
         assert o.param_groups[0]["lr"] == adam_oracle.gradual_warmup_lr(base, e)
+
+
+@pytest.mark.parametrize("name", ["coarse_b3_mask20", "coarse_b2_nope_alias"])
+def test_coarse_oracle_matches_reference_fixture(golden_dir, name):
+    """oracle/head_oracle.coarse_forward against EncoderTransformerCoarse of the unmodified reference
+    (hand_net.py:216-311 + vision_transformer_attn.py:88-113; oracle/make_golden.py coarse)."""
+    import torch
+    g = _load(golden_dir, name)
+    W = synth.make_coarse_weights()
+    P = {k: torch.from_numpy(v) for k, v in W.items()}
+    x2, mf, _ = synth.make_head_inputs(int(g["B"]), int(g["in_seed"]))
+    mean = torch.from_numpy(synth.make_mean_params("hand"))
+    with torch.no_grad():
+        pred, fv, attn = head_oracle.coarse_forward(P, torch.from_numpy(x2), torch.from_numpy(mf), mean,
+                                                    pos_embed=bool(g["pos_embed"]), mask_idx=g["mask_idx"].tolist())
+    assert _rel(pred.numpy(), g["pred"]) < 2e-6
+    assert _rel(fv.numpy(), g["feat_visual"]) < 2e-6
+    assert _rel(attn.numpy(), g["attn"]) < 2e-6
+    assert np.all(pred.numpy()[:, 6:9] == 0.0)
+    assert np.allclose(attn.numpy().sum(-1), 1.0, atol=1e-5)
