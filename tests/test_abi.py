@@ -56,14 +56,35 @@ def test_workspace_query_and_argument_errors_need_no_gpu(lib_path):
 
 
 def test_kernels_are_blackwell_native(lib_path):
-    """The shipped SASS is sm_100a; once the tensor-core GEMM is in, it must contain tcgen05 (UTC*MMA) + TMA."""
+    """The shipped SASS is sm_100a and the tensor-core kernels really are tcgen05 / TMEM / TMA kernels: per kernel, the
+    SASS mnemonics of B200_PROFILING.md (UTC*MMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG / UTMASTG = TMA load / store)
+    are counted from `cuobjdump -sass` (tools/sass_summary.py; profiles/sass_summary.txt is a committed run)."""
     import shutil
     import subprocess
+    import sys
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import sass_summary
+    rows = sass_summary.summarize(lib_path)
+    names = sass_summary.demangle(list(rows))
+    by = {}
+    for nm, c in zip(names, rows.values()):
+        by.setdefault(nm.split("<")[0], []).append(c)
+    assert len(by["gemm_tc_kernel"]) == 16                              # bf16 / tf32 x BN 64 / 128 x operand majorness
+    for fam, need in (("gemm_tc_kernel", ("UTC*MMA", "UTMALDG", "LDTM")), ("conv_fwd_tc_kernel", ("UTC*MMA", "UTMALDG", "LDTM")),
+                      ("conv_wgrad_tc_kernel", ("UTC*MMA", "UTMALDG", "LDTM")),
+                      ("conv_dgrad_tc_kernel", ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM")),
+                      ("attention_fwd_tc128_kernel", ("UTC*MMA", "UTMALDG", "LDTM"))):
+        assert fam in by, fam
+        for c in by[fam]:
+            for k in need:
+                assert c.get(k, 0) > 0, (fam, k, dict(c))
+    for fam in ("attention_fwd_mma_kernel", "attention_bwd_mma_kernel"):    # n = 21: warp-level mma.sync, by design
+        assert by[fam][0].get("HMMA", 0) > 0 and by[fam][0].get("UTC*MMA", 0) == 0
 
 
 def test_new_entry_points_validate_arguments_without_a_gpu(lib_path):
