@@ -403,11 +403,12 @@ def gpu_eager_baseline(dev, B, iters=10):
     mean = torch.from_numpy(synth.make_mean_params("hand")).to(dev)
     x2, mf, labels = (torch.from_numpy(a).to(dev) for a in synth.make_head_inputs(B, 0))
     idx = torch.tensor([20, 17, 19, 11], device=dev)
+    pe = head_oracle.positional_encoding(21, 784).to(dev)      # the reference holds it as a device buffer (hand_net.py:74)
     out = {}
 
     def step():
         return head_oracle.train_step(P, x2, mf, labels, mean, heads=8, iteration=3, pos_embed=True, mask_idx=idx,
-                                      pl_reg=True)["loss"]
+                                      pl_reg=True, pe=pe)["loss"]
 
     def run(mode):
         old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
@@ -603,6 +604,31 @@ def configs_record(dev, pk, tpk):
     return rec
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and with them its pinned staging buffers, first-touch) to the CPU cores NVML reports
+    as local to its GPU: with 8 ranks on a two-socket host the end-to-end copies otherwise cross the socket link.
+    Returns (description, original affinity) -- the CPU baseline restores the original mask."""
+    try:
+        orig = os.sched_getaffinity(0)
+    except Exception:
+        return "unavailable (no sched_getaffinity)", None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = max(orig) + 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1} & set(orig)
+        if cpus and cpus != set(orig):
+            os.sched_setaffinity(0, cpus)
+            return f"rank bound to the {len(cpus)} CPU cores local to GPU {bus} (of {len(orig)})", orig
+        return f"GPU {bus}: all {len(orig)} allowed cores are local, no binding needed", orig
+    except Exception as e:           # binding is an optimisation of the end-to-end leg only
+        return f"not bound ({type(e).__name__}: {str(e)[:80]})", orig
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
@@ -619,6 +645,7 @@ def run_ours(args):
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_binding, orig_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -852,6 +879,9 @@ def run_ours(args):
         if not args.quick:
             tpk = measure_tensor_peaks(dev)
             line["roofline"] = measure_roofline(ts, net, lib, pk, dev, B, t_dev / args.steps, precision, seam, tpk)
+        if orig_affinity is not None:
+            os.sched_setaffinity(0, orig_affinity)      # the CPU baseline uses every host core again
+        line["host_binding"] = host_binding
         cpu = cpu_reference_run(steps=8, warmup=1, max_seconds=30.0)
         line["cpu_baseline"] = {"value": cpu["samples_per_s"], "unit": "samples/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": f"{cpu['steps']} steps of B={cpu['batch']} on {cpu_model()} (oracle port, fp32, fp32 x2)"}

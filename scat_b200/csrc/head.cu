@@ -612,7 +612,7 @@ int check_ws(const HeadPlan& p, void* ws, size_t bytes) {
 
 int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, const float* mean_params,
                  const int32_t* mask_idx, const void* x2, const float* main_feat, float* pred, float* fv, float* pl,
-                 void* workspace, size_t ws_bytes, cudaStream_t st, bool defer_pl = false) {
+                 void* workspace, size_t ws_bytes, cudaStream_t st, bool defer_pl = false, bool skip_regressor = false) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
     SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
@@ -644,8 +644,9 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     }
     SCAT_PROPAGATE(order_after(sd, sg, st));       // weight copies (and the hoisted regressor product) are in place
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
-    SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
-                                        ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st, /*hoisted=*/1));
+    if (!skip_regressor)     // (the fused train step runs the regressor inside its tail kernel, see head_backward)
+        SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
+                                            ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st, /*hoisted=*/1));
     if (d.pl_reg && !defer_pl) {
         // autograd.grad(sum(feat_out), feat_visual) (hand_net.py:396): dgrad-only sweep with a ones cotangent
         SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, ws + p.ones, 1.0f, (long long)p.M * 3));
@@ -657,15 +658,22 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     return 0;
 }
 
+// The fused train step hands its tail to head_backward: regressor forward, loss gradient and regressor backward are one
+// kernel per sample (launch_regressor_train), the loss values are computed on the side stream.
+struct TrainTail {
+    const float* mean_params; const float* labels; int ld_labels; float w3d, w2d, grad_scale; float* pred; float* losses;
+};
+
 int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* mask_idx, const void* x2,
                   const float* main_feat, const float* g_pred, const float* g_fv, float* const* G, void* x2_grad,
                   float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias,
                   float* pl_out = nullptr /* non-null: also sweep the path-length cotangent (stacked) into pl_out */,
-                  int phase = -1 /* -1: everything; 0: down to transformer layer 1; 1: layer 0 and masking; 2: conv */) {
+                  int phase = -1 /* -1: everything; 0: down to transformer layer 1; 1: layer 0 and masking; 2: conv */,
+                  const TrainTail* tail = nullptr) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
     SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
-    SCAT_REQUIRE(W && G && x2 && main_feat && g_pred, kErrBadArg, "head_backward: null tensor");
+    SCAT_REQUIRE(W && G && x2 && main_feat && (g_pred || tail), kErrBadArg, "head_backward: null tensor");
     SCAT_REQUIRE(d.pos_embed || fv_alias, kErrBadArg, "head_backward: pos_embed==0 needs the forward's feat_visual");
     float* ws = (float*)workspace;
     SideScope side_scope;
@@ -680,15 +688,26 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     SCAT_PROPAGATE(zero_param_grads(p, G, sg));
     cudaEvent_t zeroed = nullptr;
     SCAT_PROPAGATE(side_mark(sd, sg, &zeroed));
-    // regressor + root-relative backward
-    SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], up, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
-                                        p.NP, p.it, 1, st, /*skip_main_feat_gemm=*/1));
-    if (pl_out) {
-        SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, up + (size_t)p.M * 3, 1.0f, (long long)p.M * 3));
-        SCAT_CHECK_LAUNCH();
+    if (tail != nullptr) {
+        // regressor forward + d loss / d pred + regressor backward (+ the ones cotangent of the stacked sweep): one kernel
+        SCAT_PROPAGATE(launch_regressor_train(ws + p.feat_out, tail->mean_params, W[P_REG_W], ws + p.hreg, tail->labels,
+                                              tail->ld_labels, tail->w3d, tail->w2d, tail->grad_scale, tail->pred, ws + p.states,
+                                              up, pl_out ? up + (size_t)p.M * 3 : nullptr, ws + p.gsum, ws + p.gsteps, p.B, p.F,
+                                              p.NP, p.it, st));
+    } else {
+        // regressor + root-relative backward
+        SCAT_PROPAGATE(launch_regressor_bwd(g_pred, W[P_REG_W], up, mf_grad, ws + p.gsum, ws + p.gsteps, p.B, p.F,
+                                            p.NP, p.it, 1, st, /*skip_main_feat_gemm=*/1));
+        if (pl_out) {
+            SCAT_CHECK_CUDA(launch_k(fill_kernel, dim3(64), dim3(256), 0, st, up + (size_t)p.M * 3, 1.0f, (long long)p.M * 3));
+            SCAT_CHECK_LAUNCH();
+        }
     }
     {
-        SCAT_PROPAGATE(order_after(sd, st, sg));      // gsum / gsteps are ready
+        SCAT_PROPAGATE(order_after(sd, st, sg));      // gsum / gsteps (and pred) are ready
+        if (tail != nullptr)                          // the loss values need a batch reduction: off the critical path
+            SCAT_PROPAGATE(launch_proj_loss(tail->pred, tail->labels, tail->ld_labels, nullptr, p.T * p.D, p.T, tail->w3d,
+                                            tail->w2d, tail->grad_scale, tail->losses, nullptr, ws + p.pl_scratch, p.B, sg));
         const int ldw = p.F + p.NP;
         GemmArgs g;
         if (mf_grad != nullptr) {   // d main_feat[B,F] = gsum[B,P] Wr[:, :F]: nothing downstream reads it
@@ -816,14 +835,20 @@ static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* pa
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(*desc, p));
     float* ws = (float*)workspace;
+    // regressor forward, loss gradient and regressor backward as one kernel per sample whenever the shapes are the head's
+    const bool fused_tail = desc->iteration >= 1 && desc->n_out == 66 && (ld_labels == 105 || ld_labels == 166);
+    const TrainTail tail{mean_params, labels, ld_labels, l_weight_3d, l_weight_2d, grad_scale, pred_params, losses};
     if (phase <= 0) {
+        SCAT_REQUIRE(labels && losses && pred_params, kErrBadArg, "train_step: labels / losses / pred_params is null");
         SCAT_PROPAGATE(head_forward(*desc, params, pe, mean_params, mask_idx, x2, main_feat, pred_params, feat_visual,
-                                    pl_term, workspace, workspace_bytes, st, /*defer_pl=*/true));
-        SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, nullptr, p.T * p.D, p.T, l_weight_3d, l_weight_2d,
-                                        grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch, p.B, st));
+                                    pl_term, workspace, workspace_bytes, st, /*defer_pl=*/true, /*skip_regressor=*/fused_tail));
+        if (!fused_tail)
+            SCAT_PROPAGATE(launch_proj_loss(pred_params, labels, ld_labels, nullptr, p.T * p.D, p.T, l_weight_3d, l_weight_2d,
+                                            grad_scale, losses, ws + p.g_pred, ws + p.pl_scratch, p.B, st));
     }
     SCAT_PROPAGATE(head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
-                                 main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr, phase));
+                                 main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr, phase,
+                                 fused_tail ? &tail : nullptr));
     if (pl && (phase == -1 || phase == 1))       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
         SCAT_PROPAGATE(launch_pl_loss_add(pl_term, p.T * p.D, p.T, losses, ws + p.pl_scratch, p.B, st));
     return 0;

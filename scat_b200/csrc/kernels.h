@@ -173,6 +173,15 @@ int launch_regressor_bwd(const float* g_pred, const float* Wr, float* d_feat_out
                          float* gsteps, int B, int F, int P, int iteration, int root_relative, cudaStream_t stream,
                          int skip_main_feat_gemm = 0);   // 1: the caller computes d_main_feat = gsum Wr[:, :F] itself
 
+// fused train-step tail: recurrence, root-relative step, closed-form d loss / d pred_params and the reverse recurrence
+// in one kernel per sample (h_scratch from launch_regressor_hoist).  Writes pred, states, d_feat_out [B,P-3], gsum,
+// gsteps and, if ones_out != null, a ones cotangent [B,P-3] for the stacked path-length sweep.  The loss values are
+// launch_proj_loss(..., g_pred = nullptr) on pred, off the critical path.
+int launch_regressor_train(const float* feat_out, const float* mean_params, const float* Wr, const float* h_scratch,
+                           const float* labels, int ld_labels, float w3d, float w2d, float grad_scale, float* pred,
+                           float* states, float* d_feat_out, float* ones_out, float* gsum, float* gsteps, int B, int F, int P,
+                           int iteration, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------
 // projection + losses (train.py:112-120,165-203) with closed-form gradient w.r.t. pred_params
 // ------------------------------------------------------------------------------------------

@@ -149,7 +149,129 @@ regressor_iter_bwd_kernel(const float* __restrict__ g_pred, const float* __restr
     }
 }
 
+// The fused train step's tail (csrc/head.cu): forward recurrence, root-relative step, the closed-form gradient of the
+// scalar loss w.r.t. pred_params (train.py:112-120,188-203, same arithmetic as proj_loss_kernel in loss.cu) and the
+// reverse recurrence, in ONE kernel per sample -- the loss VALUES need a reduction over the batch, the gradient does
+// not (the batch only enters through the constants 1/(63B), 1/(42B)), so the values are computed off the critical path.
+// Replaces regressor_iter_kernel -> proj_loss_kernel -> regressor_iter_bwd_kernel (+ the ones-cotangent fill) there.
+__global__ void __launch_bounds__(128)
+regressor_train_kernel(const float* __restrict__ h_all, const float* __restrict__ feat_out,
+                       const float* __restrict__ mean_params, const float* __restrict__ Wr, const float* __restrict__ labels,
+                       int ld_labels, float w3d, float w2d, float grad_scale, float* __restrict__ pred,
+                       float* __restrict__ states, float* __restrict__ d_feat_out, float* __restrict__ ones_out,
+                       float* __restrict__ gsum_out, float* __restrict__ gsteps, int B, int F, int iteration) {
+    pdl_sync();
+    constexpr int P = 66, NJT = 21;
+    extern __shared__ float sm[];
+    float* Wp = sm;                    // [P][P+1]
+    float* h = Wp + P * (P + 1);       // [P]
+    float* p = h + P;                  // [P]
+    float* pn = p + P;                 // [P]
+    float* cam = pn + P;               // [3][NJT] per-joint camera-gradient terms
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ldw = F + P;
+    for (int i = tid; i < P * P; i += 128) Wp[(i / P) * (P + 1) + (i % P)] = __ldg(Wr + (long long)(i / P) * ldw + F + (i % P));
+    if (tid < P) {
+        float v = mean_params[tid];
+        if (tid >= 3) v += feat_out[(long long)b * (P - 3) + tid - 3];
+        p[tid] = v;
+        h[tid] = h_all[(long long)b * P + tid];
+    }
+    if (ones_out != nullptr && tid < P - 3) ones_out[(long long)b * (P - 3) + tid] = 1.0f;   // path-length cotangent (hand_net.py:396)
+    __syncthreads();
+    // ---- forward recurrence (hand_net.py:385-387) ----
+    for (int it = 0; it < iteration; ++it) {
+        if (tid < P) {
+            states[((long long)b * iteration + it) * P + tid] = p[tid];
+            float s = h[tid];
+            for (int k = 0; k < P; ++k) s = fmaf(Wp[tid * (P + 1) + k], p[k], s);
+            pn[tid] = p[tid] + s;
+        }
+        __syncthreads();
+        if (tid < P) p[tid] = pn[tid];
+        __syncthreads();
+    }
+    // ---- root-relative joints (hand_net.py:389-393) ----
+    if (tid < P) {
+        float v = p[tid];
+        if (tid >= 3) v -= p[3 + 3 + (tid - 3) % 3];
+        pred[(long long)b * P + tid] = v;
+        pn[tid] = v;
+    }
+    __syncthreads();
+    // ---- d loss / d pred_params, closed form (loss.cu: proj_loss_kernel) into p[] ----
+    const float inv3 = 1.0f / (63.0f * (float)B), inv2 = 1.0f / (42.0f * (float)B);
+    const float c2 = w2d * 112.0f * inv2 * grad_scale;
+    const float* lb = labels + (long long)b * ld_labels + (ld_labels == 105 ? 0 : 61);   // train.py:188-199
+    if (tid < NJT) {
+        const int t = tid;
+        const float s = pn[0], tx = pn[1], ty = pn[2];
+        const float jx = pn[3 + 3 * t], jy = pn[4 + 3 * t], jz = pn[5 + 3 * t];
+        const float dx = jx - lb[3 * t], dy = jy - lb[3 * t + 1], dz = jz - lb[3 * t + 2];
+        const float ux = (jx + tx) * s * 112.0f + 112.0f - lb[63 + 2 * t];
+        const float uy = (jy + ty) * s * 112.0f + 112.0f - lb[64 + 2 * t];
+        const float sx = (ux > 0.f) - (ux < 0.f), sy = (uy > 0.f) - (uy < 0.f);
+        p[3 + 3 * t] = (w3d * 2.0f * inv3 * dx) * grad_scale + c2 * s * sx;
+        p[4 + 3 * t] = (w3d * 2.0f * inv3 * dy) * grad_scale + c2 * s * sy;
+        p[5 + 3 * t] = (w3d * 2.0f * inv3 * dz) * grad_scale;
+        cam[t] = (jx + tx) * sx + (jy + ty) * sy;
+        cam[NJT + t] = sx;
+        cam[2 * NJT + t] = sy;
+    }
+    __syncthreads();
+    if (tid < 3) {                     // camera gradients: fixed order over the joints, like proj_loss_kernel
+        float a = 0.f;
+        for (int t = 0; t < NJT; ++t) a += cam[tid * NJT + t];
+        p[tid] = tid == 0 ? c2 * a : c2 * pn[0] * a;
+    }
+    __syncthreads();
+    // ---- backward through the root-relative step and the recurrence (regressor_iter_bwd_kernel) ----
+    float* g = p;
+    float* gn = pn;
+    if (tid < 3) {
+        float s = 0.f;
+        for (int t = 0; t < NJT; ++t) s += g[3 + 3 * t + tid];
+        cam[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 3) g[3 + 3 + tid] -= cam[tid];
+    __syncthreads();
+    float gsum = 0.f;
+    for (int it = iteration - 1; it >= 0; --it) {
+        if (tid < P) {
+            gsteps[((long long)b * iteration + it) * P + tid] = g[tid];
+            gsum += g[tid];
+            float s = g[tid];
+            for (int j = 0; j < P; ++j) s = fmaf(Wp[j * (P + 1) + tid], g[j], s);   // (I + Wp^T) g
+            gn[tid] = s;
+        }
+        __syncthreads();
+        if (tid < P) g[tid] = gn[tid];
+        __syncthreads();
+    }
+    if (tid < P) {
+        gsum_out[(long long)b * P + tid] = gsum;
+        if (tid >= 3) d_feat_out[(long long)b * (P - 3) + tid - 3] = g[tid];
+    }
+}
+
 }  // namespace
+
+int launch_regressor_train(const float* feat_out, const float* mean_params, const float* Wr, const float* h_scratch,
+                           const float* labels, int ld_labels, float w3d, float w2d, float grad_scale, float* pred,
+                           float* states, float* d_feat_out, float* ones_out, float* gsum, float* gsteps, int B, int F, int P,
+                           int iteration, cudaStream_t stream) {
+    SCAT_REQUIRE(P == 66 && iteration >= 1, kErrUnsupported, "regressor train kernel: P=66, iteration>=1 (got %d, %d)", P, iteration);
+    SCAT_REQUIRE(ld_labels == 105 || ld_labels == 166, kErrBadArg,
+                 "label rows are 105 wide (63 3D + 42 2D) or 166 wide (61 pose + 63 3D + 42 2D), got %d", ld_labels);
+    SCAT_REQUIRE(feat_out && mean_params && Wr && h_scratch && labels && pred && states && d_feat_out && gsum && gsteps, kErrBadArg,
+                 "regressor train kernel: null argument");
+    const size_t smem = sizeof(float) * ((size_t)P * (P + 1) + 3 * (size_t)P + 3 * 21);
+    SCAT_CHECK_CUDA(launch_k(regressor_train_kernel, dim3(B), dim3(128), smem, stream, h_scratch, feat_out, mean_params, Wr, labels,
+                             ld_labels, w3d, w2d, grad_scale, pred, states, d_feat_out, ones_out, gsum, gsteps, B, F, iteration));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
 
 // the iteration-invariant part h = main_feat Wr[:, :F]^T + br: depends on the backbone feature only, so a caller may
 // run it on another stream while the transformer computes feat_out
