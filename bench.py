@@ -565,7 +565,8 @@ def configs_record(dev, pk, tpk):
                                                "sample": "one forward of 32 samples"}}
     del tr
     # ---- config 5: MANO LBS (fwd, bwd) and the autoregressive regressor, B = 1k .. 64k ----
-    layer = ManoLayer(synth.make_mano_asset())
+    layer = ManoLayer(synth.make_mano_asset())                         # blend shapes on the tcgen05 GEMM (fp32 grade)
+    layer_ffma = ManoLayer(synth.make_mano_asset(), precision="fp32")  # everything on CUDA cores
     wr, br = torch.from_numpy(W["regressor.weight"]).to(dev), torch.from_numpy(W["regressor.bias"]).to(dev)
     meand = mean.to(dev)
     g = torch.Generator(device=dev).manual_seed(1)
@@ -576,6 +577,7 @@ def configs_record(dev, pk, tpk):
         betas = torch.randn(Bs, 10, device=dev, generator=g)
         out = torch.empty(Bs, 799, 3, device=dev)
         t_f = time_kernel(lambda: layer(rots, poses, betas, out=out), iters=10)
+        t_ff = time_kernel(lambda: layer_ffma(rots, poses, betas, out=out), iters=5)
         gout = torch.randn(Bs, 799, 3, device=dev, generator=g)
         gr, gp, gb = torch.empty_like(rots), torch.empty_like(poses), torch.empty_like(betas)
         t_b = time_kernel(lambda: check(lib.scat_lbs_bwd(ptr(layer.derived), ptr(layer.hands_mean), ptr(rots), ptr(poses),
@@ -587,7 +589,8 @@ def configs_record(dev, pk, tpk):
 
         def row(t, nbytes):
             return {"us": t * 1e6, "samples_per_s": Bs / t, "gbs": nbytes * Bs / t / 1e9, "frac_hbm": nbytes * Bs / t / 1e9 / pk["hbm"]}
-        sweep.append({"batch": Bs, "lbs_fwd": dict(row(t_f, 9820), gflops_fp32=1.19e6 * Bs / t_f / 1e9),
+        sweep.append({"batch": Bs, "lbs_fwd": dict(row(t_f, 9820), how="setup + tcgen05 blend-shape GEMM (3xTF32) + skinning kernel"),
+                      "lbs_fwd_ffma": dict(row(t_ff, 9820), gflops_fp32=1.19e6 * Bs / t_ff / 1e9),
                       "lbs_bwd": row(t_b, 9820), "regressor": row(t_r, 4624)})
         del rots, poses, betas, out, gout, mfs, fo
     r_, p_, b_ = synth.make_mano_inputs(1024, 0)
@@ -597,8 +600,8 @@ def configs_record(dev, pk, tpk):
     t_lbs_cpu = time.perf_counter() - t0
     rec["config5_lbs_regressor_sweep"] = {
         "gpu": sweep, "bytes_per_sample": {"lbs": 9820, "regressor": 4624},
-        "bound": "LBS is fp32-ALU bound on CUDA cores (1.19 MFLOP per 9.8 KB, SURVEY.md section 7); the HBM fractions are "
-                 "reported as north_star asks",
+        "bound": "LBS is fp32-ALU bound on CUDA cores (1.19 MFLOP per 9.8 KB, SURVEY.md section 7); lbs_fwd moves the two "
+                 "blend-shape contractions (0.65 MFLOP) to the tensor cores; the HBM fractions are reported as north_star asks",
         "cpu_lbs_B1024": {"samples_per_s": 1024 / t_lbs_cpu, "ms": t_lbs_cpu * 1e3, "kind": "port",
                           "how": "numpy restatement of mano.py:280-391, one call"}}
     return rec

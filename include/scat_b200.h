@@ -308,6 +308,16 @@ int scat_lbs_prepare(const float* v_template, const float* shapedirs, const floa
                      const float* j_regressor, const float* weights, float* derived, void* stream);
 int scat_lbs_fwd(const float* derived, const float* hands_mean, const float* rots, const float* poses,
                  const float* betas, float* out, int32_t batch, void* stream);
+/* The same forward with the two blend-shape contractions (0.65 of the 1.19 MFLOP per sample) on the tensor cores: one
+ * tcgen05 GEMM [B,145] x [145,2334] at fp32 grade (TF32 hi/lo split of both operands stacked along K), then a skinning
+ * kernel.  table: scat_lbs_tc_table_floats() floats filled once per asset by scat_lbs_tc_prepare; scratch:
+ * scat_lbs_tc_scratch_floats(batch) floats (a smaller scratch just means more, smaller chunks; a chunk's intermediates are
+ * sized to stay in L2).  Same output as scat_lbs_fwd to ~1e-7 m. */
+size_t scat_lbs_tc_table_floats(void);
+size_t scat_lbs_tc_scratch_floats(int32_t batch);
+int scat_lbs_tc_prepare(const float* shapedirs, const float* posedirs, float* table, void* stream);
+int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands_mean, const float* rots, const float* poses,
+                    const float* betas, float* out, int32_t batch, float* scratch, size_t scratch_floats, void* stream);
 /* Backward of scat_lbs_fwd: mano.py:280-391 is plain differentiable PyTorch in the reference (autograd); this is its
  * vector-Jacobian product.  grad_out[B,799,3] -> grad_rots[B,3], grad_poses[B,45], grad_betas[B,10] (overwritten).
  * Nothing is saved by the forward: the kernel recomputes from (rots, poses, betas).  Rows whose axis-angle norm is

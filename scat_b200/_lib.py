@@ -82,6 +82,10 @@ SIGNATURES = {
     "scat_lbs_derived_floats": (_sz, []),
     "scat_lbs_prepare": (_i32, [_f, _f, _f, _f, _f, _f, _f]),
     "scat_lbs_fwd": (_i32, [_f, _f, _f, _f, _f, _f, _i32, _f]),
+    "scat_lbs_tc_table_floats": (_sz, []),
+    "scat_lbs_tc_scratch_floats": (_sz, [_i32]),
+    "scat_lbs_tc_prepare": (_i32, [_f, _f, _f, _f]),
+    "scat_lbs_fwd_tc": (_i32, [_f, _f, _f, _f, _f, _f, _f, _i32, _f, _sz, _f]),
     "scat_lbs_bwd": (_i32, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i32, _f]),
 }
 

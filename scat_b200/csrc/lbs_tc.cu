@@ -1,0 +1,176 @@
+// MANO linear blend skinning with the blend shapes on the tensor cores (models/mano.py:280-391).
+//
+// 0.65 of the 1.19 MFLOP per sample are the two blend-shape contractions v_shaped = mu + S beta (mano.py:288-292) and
+// v_posed = v_shaped + P (R - I) (mano.py:296-300): one dense product  corr[b, 3v+c] = sum_k U[b,k] D[3v+c,k]  with
+// U = [beta (10) | pose weights (135)] and D = [shapedirs | posedirs] (2334 x 145).  Here it runs on the tcgen05 GEMM
+// kernel (gemm_tc.cu) at fp32 grade: both operands are split into TF32 hi + lo parts stacked along K,
+//   U' = [U_hi | U_lo | U_hi],  D' = [D_hi | D_hi | D_lo]   ->   U_hi D_hi + U_lo D_hi + U_hi D_lo   (K' = 3 x 148),
+// every value exactly representable on the tensor core, fp32 accumulation in TMEM (the dropped lo x lo term is 2^-22).
+// A call is cut into chunks whose intermediates (U' and the [chunk, 2336] corrections, ~10 KB per sample) stay in the
+// 126 MB L2:  set-up kernel (Rodrigues, chain, skinning matrices, U')  ->  GEMM  ->  skinning kernel (thread per vertex:
+// T = sum_j w_vj A_j, x = T (v_posed, 1), global rotation, root).  The FFMA kernel of lbs.cu stays as the fp32 form.
+#include "lbs_common.cuh"
+
+namespace scat {
+
+size_t lbs_derived_floats();
+
+namespace {
+
+constexpr int TC_KP = 148;                 // 145 blend shapes padded to 16-byte rows
+constexpr int TC_K = 3 * TC_KP;            // stacked hi / lo / hi
+constexpr int TC_N = NV * 3;               // 2334 vertex coordinates, n = 3 v + c
+constexpr int TC_LDC = 2336;
+constexpr int TC_S = 16;                   // samples per CTA in the set-up kernel
+constexpr int TC_PER_SAMPLE = TC_K + NJ * 12 + 12 + TC_LDC;   // scratch floats per sample: U', A, (Rg | root), corrections
+
+// D' [2334, 444]: rows n = 3 v + c, columns [D_hi | D_hi | D_lo], D = [shapedirs[v,c,:] | posedirs[v,c,:] | 0 0 0]
+__global__ void lbs_tc_prepare_kernel(const float* __restrict__ shapedirs, const float* __restrict__ posedirs,
+                                      float* __restrict__ Dst) {
+    pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TC_N * TC_K) return;
+    const int n = i / TC_K, kk = i - n * TC_K, third = kk / TC_KP, k = kk - third * TC_KP;
+    const float v = k < NB ? shapedirs[n * NB + k] : (k < NB + NPW ? posedirs[n * NPW + (k - NB)] : 0.f);
+    const float hi = round_tf32(v);
+    Dst[i] = third == 2 ? round_tf32(v - hi) : hi;
+}
+
+// per sample: U' row, skinning matrices A_j (rows of [R | t]), global rotation and root; joints 0..15 go straight out
+__global__ void __launch_bounds__(LBS_THREADS)
+lbs_tc_setup_kernel(const float* __restrict__ derived, const float* __restrict__ hands_mean, const float* __restrict__ rots,
+                    const float* __restrict__ poses, const float* __restrict__ betas, float* __restrict__ U,
+                    float* __restrict__ Aout, float* __restrict__ Rr, float* __restrict__ out, int b_first, int n_chunk) {
+    pdl_sync();
+    extern __shared__ __align__(16) unsigned char lbs_tc_raw[];
+    LbsSetup<TC_S>& sm = *reinterpret_cast<LbsSetup<TC_S>*>(lbs_tc_raw);
+    const int tid = threadIdx.x;
+    const int l0 = blockIdx.x * TC_S;                       // first sample of this CTA inside the chunk
+    const int ns = min(TC_S, n_chunk - l0);
+    const int b0 = b_first + l0;
+    lbs_setup<TC_S>(sm, derived, hands_mean, rots, poses, betas, b0, ns);
+    for (int e = tid; e < ns * NJ * 3; e += LBS_THREADS) {  // chain joints: rotate, subtract root (mano.py:383-388)
+        const int s = e / (NJ * 3), j = (e / 3) % NJ, r = e % 3;
+        const float* Rg = sm.Rg[s];
+        float v = Rg[r * 3 + 0] * sm.Jtr[s][j][0] + Rg[r * 3 + 1] * sm.Jtr[s][j][1] + Rg[r * 3 + 2] * sm.Jtr[s][j][2] - sm.root[s][r];
+        if (j == 1) v = 0.f;
+        out[((long long)(b0 + s) * 799 + j) * 3 + r] = v;
+    }
+    for (int e = tid; e < ns * TC_KP; e += LBS_THREADS) {   // U' = [hi | lo | hi]
+        const int s = e / TC_KP, k = e % TC_KP;
+        const float v = k < NB ? sm.betaT[k][s] : (k < NB + NPW ? sm.pwT[k - NB][s] : 0.f);
+        const float hi = round_tf32(v), lo = round_tf32(v - hi);
+        float* u = U + (long long)(l0 + s) * TC_K;
+        u[k] = hi; u[TC_KP + k] = lo; u[2 * TC_KP + k] = hi;
+    }
+    for (int e = tid; e < ns * NJ * 12; e += LBS_THREADS) {
+        const int s = e / (NJ * 12), q = e % (NJ * 12);
+        Aout[(long long)(l0 + s) * NJ * 12 + q] = (&sm.A[s][0][0])[q];
+    }
+    for (int e = tid; e < ns * 12; e += LBS_THREADS) {
+        const int s = e / 12, q = e % 12;
+        Rr[(long long)(l0 + s) * 12 + q] = q < 9 ? sm.Rg[s][q] : sm.root[s][q - 9];
+    }
+}
+
+// one CTA per sample, thread per vertex: skinning (mano.py:339-348), global rotation and root (:382-388), fingertips (:373-377)
+__global__ void __launch_bounds__(LBS_THREADS, 3)
+lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ corr, const float* __restrict__ Ain,
+                   const float* __restrict__ Rr, float* __restrict__ out, int b_first) {
+    pdl_sync();
+    __shared__ __align__(16) float A[NJ][12];
+    __shared__ float R[12];
+    const int l = blockIdx.x, tid = threadIdx.x;
+    for (int e = tid; e < NJ * 12; e += LBS_THREADS) (&A[0][0])[e] = Ain[(long long)l * NJ * 12 + e];
+    if (tid < 12) R[tid] = Rr[(long long)l * 12 + tid];
+    __syncthreads();
+    const float* vt_t = derived + OFF_VT;
+    const float* w_t = derived + OFF_W;
+    const float* cr = corr + (long long)l * TC_LDC;
+    float* o_base = out + (long long)(b_first + l) * 799 * 3;
+    for (int v = tid; v < NV; v += LBS_THREADS) {
+        const float p0 = vt_t[v] + cr[3 * v], p1 = vt_t[VP + v] + cr[3 * v + 1], p2 = vt_t[2 * VP + v] + cr[3 * v + 2];
+        float T[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) T[q] = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < NJ; ++j) {
+            const float w = w_t[j * VP + v];
+            const float4* arow = reinterpret_cast<const float4*>(A[j]);
+            const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2];
+            const float a[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+            for (int q = 0; q < 12; ++q) T[q] = fmaf(w, a[q], T[q]);
+        }
+        float x[3], y[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) x[r] = T[r * 4 + 0] * p0 + T[r * 4 + 1] * p1 + T[r * 4 + 2] * p2 + T[r * 4 + 3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) y[r] = R[r * 3 + 0] * x[0] + R[r * 3 + 1] * x[1] + R[r * 3 + 2] * x[2] - R[9 + r];
+        float* o = o_base + (21 + v) * 3;
+        o[0] = y[0]; o[1] = y[1]; o[2] = y[2];
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (c_tips[q] == v) {
+                float* oj = o_base + (16 + q) * 3;
+                oj[0] = y[0]; oj[1] = y[1]; oj[2] = y[2];
+            }
+    }
+}
+
+}  // namespace
+
+size_t lbs_tc_table_floats() { return (size_t)TC_N * TC_K; }
+
+}  // namespace scat
+
+using namespace scat;
+
+extern "C" {
+
+size_t scat_lbs_tc_table_floats(void) { return lbs_tc_table_floats(); }
+size_t scat_lbs_tc_scratch_floats(int32_t batch) {
+    const long long chunk = batch < 8192 ? (batch > 0 ? batch : 1) : 8192;        // ~10 KB per sample: 8192 samples = 97 MB, inside L2
+    return (size_t)chunk * TC_PER_SAMPLE;
+}
+
+int scat_lbs_tc_prepare(const float* shapedirs, const float* posedirs, float* table, void* stream) {
+    SCAT_REQUIRE(shapedirs && posedirs && table, kErrBadArg, "lbs_tc_prepare: null");
+    const int n = TC_N * TC_K;
+    SCAT_CHECK_CUDA(launch_k(lbs_tc_prepare_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, shapedirs, posedirs, table));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands_mean, const float* rots, const float* poses,
+                    const float* betas, float* out, int32_t batch, float* scratch, size_t scratch_floats, void* stream) {
+    SCAT_REQUIRE(derived && table && hands_mean && rots && poses && betas && out && scratch && batch > 0, kErrBadArg,
+                 "lbs_fwd_tc: bad args");
+    SCAT_REQUIRE(((uintptr_t)scratch & 15) == 0 && ((uintptr_t)table & 15) == 0, kErrBadArg, "lbs_fwd_tc: scratch / table must be 16-byte aligned");
+    const long long chunk_max = (long long)(scratch_floats / TC_PER_SAMPLE);
+    SCAT_REQUIRE(chunk_max >= 1, kErrWorkspace, "lbs_fwd_tc: scratch holds no sample (%zu floats, %d per sample)", scratch_floats,
+                 TC_PER_SAMPLE);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(LbsSetup<TC_S>);
+    SCAT_ENSURE_SMEM(lbs_tc_setup_kernel, smem);
+    for (long long b0 = 0; b0 < batch; b0 += chunk_max) {
+        const int n = (int)(batch - b0 < chunk_max ? batch - b0 : chunk_max);
+        float* U = scratch;                               // [n, 444]
+        float* A = U + (size_t)n * TC_K;                  // [n, 16, 12]
+        float* Rr = A + (size_t)n * NJ * 12;              // [n, 12]
+        float* corr = Rr + (size_t)n * 12;                // [n, 2336]
+        SCAT_CHECK_CUDA(launch_k(lbs_tc_setup_kernel, dim3(ceil_div(n, TC_S)), dim3(LBS_THREADS), smem, st, derived, hands_mean, rots,
+                                 poses, betas, U, A, Rr, out, (int)b0, n));
+        SCAT_CHECK_LAUNCH();
+        GemmArgs g;
+        g.A = U; g.sam = TC_K; g.sak = 1; g.B = table; g.sbn = TC_K; g.sbk = 1;
+        g.C = corr; g.ldc = TC_LDC; g.M = n; g.N = TC_N; g.K = TC_K; g.prerounded = 1;
+        SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
+        SCAT_CHECK_CUDA(launch_k(lbs_tc_skin_kernel, dim3(n), dim3(LBS_THREADS), 0, st, derived, (const float*)corr, (const float*)A,
+                                 (const float*)Rr, out, (int)b0));
+        SCAT_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -131,13 +131,16 @@ class EncoderTransformer(nn.Module):
         self.last_mask = masked
         dev = x2.device
         if len(masked):
-            # host-supplied index tensor: pageable -> device copy is staged by the driver before it returns,
-            # so the Python list can be reused immediately (stream-ordered with the kernels that read it)
+            # host-supplied index tensor (hand_net.py:370-372): a small pageable host-to-device copy, stream-ordered with
+            # the kernels that read it.  (It synchronises the stream; the graph-replayed HeadTrainStep stages the indices
+            # through pinned memory instead.)
             mask_dev = torch.tensor(masked, dtype=torch.int32, device=dev)
         else:
             mask_dev = None
         pe = self.positionalEncoding.pe[0] if self.pos_embed else None
         mean = self.mean_params.reshape(-1)
+        if main_feat.dtype != torch.float32:          # an autocast backbone's fc1 output: the regressor is always fp32
+            main_feat = main_feat.float()
         return SF.HeadFunction.apply(self.config(len(masked)), mask_dev, mean, pe, x2, main_feat,
                                      *self.head_parameters())
 

@@ -38,7 +38,13 @@ class _LbsFunction(torch.autograd.Function):
 
 
 class ManoLayer:
-    def __init__(self, asset: dict, device=None):
+    """``precision``: "tf32x3" (default) runs the blend-shape contractions as one tcgen05 GEMM at fp32 grade (TF32 hi/lo
+    split, csrc/lbs_tc.cu); "fp32" keeps everything on CUDA cores (csrc/lbs.cu).  Both agree to ~1e-7 m."""
+
+    def __init__(self, asset: dict, device=None, precision: str = "tf32x3"):
+        if precision not in ("tf32x3", "fp32"):
+            raise ValueError("ManoLayer: precision 'tf32x3' or 'fp32'")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise RuntimeError("scat_b200.mano needs a CUDA device; there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -60,18 +66,29 @@ class ManoLayer:
         self.weights = up("weights", (778, 16))
         self.hands_mean = up("hands_mean", (45,))
         self.derived = torch.empty(lib.scat_lbs_derived_floats(), device=self.device, dtype=torch.float32)
+        self.table = torch.empty(lib.scat_lbs_tc_table_floats(), device=self.device, dtype=torch.float32)
+        self._scratch = None
         with torch.cuda.device(self.device):
             check(lib.scat_lbs_prepare(ptr(self.v_template), ptr(self.shapedirs), ptr(self.posedirs),
                                        ptr(self.J_regressor), ptr(self.weights), ptr(self.derived), stream_ptr()),
                   "scat_lbs_prepare")
+            check(lib.scat_lbs_tc_prepare(ptr(self.shapedirs), ptr(self.posedirs), ptr(self.table), stream_ptr()),
+                  "scat_lbs_tc_prepare")
 
     def _forward(self, rots, poses, betas, out=None):
         lib = _lib.load()
         B = rots.shape[0]
         if out is None:
             out = torch.empty(B, 799, 3, device=rots.device, dtype=torch.float32)
-        check(lib.scat_lbs_fwd(ptr(self.derived), ptr(self.hands_mean), ptr(rots), ptr(poses), ptr(betas), ptr(out), B,
-                               stream_ptr()), "scat_lbs_fwd")
+        if self.precision == "fp32":
+            check(lib.scat_lbs_fwd(ptr(self.derived), ptr(self.hands_mean), ptr(rots), ptr(poses), ptr(betas), ptr(out), B,
+                                   stream_ptr()), "scat_lbs_fwd")
+            return out
+        need = lib.scat_lbs_tc_scratch_floats(B)
+        if self._scratch is None or self._scratch.numel() < need:      # grows to the largest chunk seen, then is reused
+            self._scratch = torch.empty(need, device=self.device, dtype=torch.float32)
+        check(lib.scat_lbs_fwd_tc(ptr(self.derived), ptr(self.table), ptr(self.hands_mean), ptr(rots), ptr(poses), ptr(betas),
+                                  ptr(out), B, ptr(self._scratch), self._scratch.numel(), stream_ptr()), "scat_lbs_fwd_tc")
         return out
 
     def rot_pose_beta_to_mesh(self, rots, poses, betas, out=None):

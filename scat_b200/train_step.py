@@ -43,7 +43,7 @@ class HeadTrainStep:
     def __init__(self, net, batch: int, l_weight_3d: float = 1e5, l_weight_2d: float = 10.0, *,
                  need_x2_grad: bool = True, need_main_feat_grad: bool = True, use_graph: bool = True,
                  process_group=None, input_slots: int = 1, phased: Optional[bool] = None,
-                 comm: str = "auto", x2_dtype: str = "fp32", label_width: int = 105):
+                 comm: str = "auto", x2_dtype: str = "fp32", label_width: int = 105, overlap_exchange: bool = True):
         self.net = net
         self.batch = int(batch)
         self.w3d, self.w2d = float(l_weight_3d), float(l_weight_2d)
@@ -118,6 +118,10 @@ class HeadTrainStep:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.phased else None
         self.split = self.bucket.offsets[13]
         self.split0 = self.bucket.offsets[2]
+        # peer-memory exchange hidden under the backward: the step is issued in its three phases inside ONE graph and the
+        # part of the bucket each phase completes is summed on a second stream while the next phase computes
+        self.overlap_exchange = bool(overlap_exchange) and self.peer is not None
+        self.ar_stream = torch.cuda.Stream(device=dev) if self.overlap_exchange else None
 
     # single-slot views kept for callers that use one buffer set
     @property
@@ -167,9 +171,27 @@ class HeadTrainStep:
         self.graphs = {k: g for k, g in self.graphs.items() if not k[2]}
 
     def _enqueue_all(self, slot: int, ar: bool, optimize: bool):
-        self._enqueue(slot)
-        if ar:
-            self.peer.enqueue(SF.stream_ptr())
+        if ar and self.overlap_exchange:
+            # phase 0 leaves the gradients of layers 1, 2 and of the regressor final (bucket[split:], 6 MB): their sum runs
+            # on the exchange stream under the layer-0 backward (phase 1); layer 0 (bucket[split0:split], 9 MB) is summed
+            # under the conv backward (phase 2); only the mask token and the conv weight (bucket[:split0], 46 KB: two
+            # cross-GPU flag barriers and nothing else) are exchanged after the last kernel.  All three exchanges are
+            # launches of the same kernel, in the same order on every rank, serialised among themselves.
+            cur, side = torch.cuda.current_stream(), self.ar_stream
+            side_ptr = C.c_void_p(side.cuda_stream)
+            self._enqueue(slot, 0)
+            side.wait_stream(cur)
+            self.peer.enqueue(side_ptr, lo=self.split, hi=None)
+            self._enqueue(slot, 1)
+            side.wait_stream(cur)
+            self.peer.enqueue(side_ptr, lo=self.split0, hi=self.split)
+            self._enqueue(slot, 2)
+            cur.wait_stream(side)
+            self.peer.enqueue(SF.stream_ptr(), lo=0, hi=self.split0)
+        else:
+            self._enqueue(slot)
+            if ar:
+                self.peer.enqueue(SF.stream_ptr())
         if optimize:
             self.opt.enqueue(self.bucket.flat)
 

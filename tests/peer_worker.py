@@ -60,13 +60,16 @@ def main():
     B = 8
     x2, mf, lab = synth.make_head_inputs(B, 50 + rank)
     out = {}
-    for comm in ("nccl", "peer"):
+    # "peer": the exchange in three parts hidden under the backward phases (default); "peer_serial": one exchange
+    # kernel behind the step
+    for mode in ("nccl", "peer", "peer_serial"):
+        comm = "nccl" if mode == "nccl" else "peer"
         net = EncoderTransformer(opt, mean, precision="tf32", backbone=torch.nn.Identity())
         sd["positionalEncoding.pe"] = net.positionalEncoding.pe
         net.load_state_dict(sd, strict=True)
         net = net.to(dev)
-        ts = HeadTrainStep(net, B, comm=comm)
-        assert ts.comm == comm
+        ts = HeadTrainStep(net, B, comm=comm, overlap_exchange=(mode == "peer"))
+        assert ts.comm == comm and ts.overlap_exchange == (mode == "peer")
         ts.load_inputs(*[torch.from_numpy(a).to(dev) for a in (x2, mf, lab)])
         ts.set_mask(list(range(ts.n_masked)))
         for _ in range(3):
@@ -74,7 +77,7 @@ def main():
         torch.cuda.synchronize()
         if ts.peer is not None:
             assert not ts.peer.timed_out()
-        out[comm] = ts.bucket.flat.clone()
+        out[mode] = ts.bucket.flat.clone()
         if comm == "peer":
             # forward + backward + all-reduce + Adam in one graph: the replicas must stay bit-identical
             from scat_b200.optim import HeadAdam
@@ -90,8 +93,9 @@ def main():
             theirs = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(theirs, mine)
             assert all(torch.equal(t, mine) for t in theirs), "replicas diverged"
-    a, b = out["nccl"], out["peer"]
-    err = float((a - b).abs().max() / a.abs().max())
+        ts.close()
+    a = out["nccl"]
+    err = max(float((a - out[m]).abs().max() / a.abs().max()) for m in ("peer", "peer_serial"))
     assert err < 1e-5, err            # split-K atomics reorder sums between runs; the exchange itself is exact
     dist.barrier()
     if rank == 0:

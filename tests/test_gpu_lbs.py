@@ -11,10 +11,12 @@ from tests.util import load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def layer():
+@pytest.fixture(scope="module", params=["tf32x3", "fp32"])
+def layer(request):
+    """Both forward paths: blend shapes on the tcgen05 GEMM at fp32 grade (csrc/lbs_tc.cu, the default) and the all-FFMA
+    kernel (csrc/lbs.cu); the backward kernel is the same for both."""
     from scat_b200.mano import ManoLayer
-    return ManoLayer(synth.make_mano_asset())
+    return ManoLayer(synth.make_mano_asset(), precision=request.param)
 
 
 def _run(layer, rots, poses, betas):
@@ -38,6 +40,29 @@ def test_lbs_matches_oracle_ragged_batches(layer, B):
     assert np.abs(out - ref).max() < 5e-6
     tips = list(synth.MANO_TIP_VERTS)
     assert np.array_equal(out[:, 16:21], out[:, [21 + t for t in tips]])   # fingertips ARE mesh vertices
+
+
+def test_lbs_tensor_core_path_chunks_and_matches_ffma():
+    """The tensor-core path cuts a call into L2-sized chunks (8192 samples); chunk boundaries and a deliberately small
+    scratch must not change the result, and it must agree with the FFMA kernel to fp32 rounding."""
+    from scat_b200 import _lib
+    from scat_b200._lib import check, ptr, stream_ptr
+    from scat_b200.mano import ManoLayer
+    asset = synth.make_mano_asset()
+    tc, ff = ManoLayer(asset, precision="tf32x3"), ManoLayer(asset, precision="fp32")
+    B = 8192 + 8192 + 37
+    r, p, b = (torch.from_numpy(a).cuda() for a in synth.make_mano_inputs(B, 12))
+    a, c = tc(r, p, b), ff(r, p, b)
+    assert float((a - c).abs().max()) < 5e-7
+    lib = _lib.load()
+    per = lib.scat_lbs_tc_scratch_floats(1)
+    small = torch.empty(per * 100 + 5, device="cuda")                  # 100 samples per chunk
+    out = torch.empty_like(a)
+    check(lib.scat_lbs_fwd_tc(ptr(tc.derived), ptr(tc.table), ptr(tc.hands_mean), ptr(r), ptr(p), ptr(b), ptr(out), B, ptr(small),
+                              small.numel(), stream_ptr()), "scat_lbs_fwd_tc")
+    assert torch.equal(out, a)
+    assert lib.scat_lbs_fwd_tc(ptr(tc.derived), ptr(tc.table), ptr(tc.hands_mean), ptr(r), ptr(p), ptr(b), ptr(out), B, ptr(small),
+                               10, stream_ptr()) == -2                # scratch too small for a single sample
 
 
 def test_lbs_properties_at_sweep_size(layer):
