@@ -58,6 +58,13 @@ constexpr int kErrUnsupported = -3;
 // pdl_sync() before it touches global memory: it waits for the preceding grid to complete (and flush), then lets
 // the following grid start launching.  Without the attribute both instructions are no-ops.
 extern int g_use_pdl;
+// Launch priorities: the step is a latency-bound critical chain on the caller's stream plus independent work (weight
+// gradients, column sums, weight copies, loss values) on the library's side stream.  Both compete for the same SMs, so
+// kernels that go to the side stream are launched with the LOWEST priority and everything else with the highest: the
+// block scheduler then serves the critical chain first (the attribute is recorded into CUDA-graph kernel nodes too).
+// tl_side_stream is the side stream of the whole-head call in progress on this host thread (null outside one).
+extern thread_local cudaStream_t tl_side_stream;
+extern int g_prio_low, g_prio_high;     // cudaDeviceGetStreamPriorityRange; equal when SCAT_PRIORITIES=0
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -70,11 +77,20 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (g_use_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (g_prio_low != g_prio_high) {
+        attr[n].id = cudaLaunchAttributePriority;
+        attr[n].val.priority = (tl_side_stream != nullptr && stream == tl_side_stream) ? g_prio_low : g_prio_high;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -36,6 +36,19 @@ static int read_pdl_env() {
     return (e && e[0] == '0') ? 0 : 1;
 }
 int g_use_pdl = read_pdl_env();
+thread_local cudaStream_t tl_side_stream = nullptr;
+int g_prio_low = 0, g_prio_high = 0;
+static void init_priorities() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* e = getenv("SCAT_PRIORITIES");
+        int least = 0, greatest = 0;
+        if (!(e && e[0] == '0') && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) {
+            g_prio_low = least;
+            g_prio_high = greatest;
+        }
+    });
+}
 
 int ensure_dynamic_smem(const void* kernel, int bytes) {
     struct Entry { const void* fn; int dev; int bytes; };
@@ -110,8 +123,14 @@ static SideStream* get_side() {
 // the device's side stream for the duration of one whole-head call (enqueue phase), exclusive among host threads
 struct SideScope {
     SideStream* sd;
-    SideScope() : sd(get_side()) { if (sd) sd->mu.lock(); }
-    ~SideScope() { if (sd) sd->mu.unlock(); }
+    SideScope() : sd(get_side()) {
+        init_priorities();
+        if (sd) { sd->mu.lock(); tl_side_stream = sd->s; }
+    }
+    ~SideScope() {
+        tl_side_stream = nullptr;
+        if (sd) sd->mu.unlock();
+    }
     SideScope(const SideScope&) = delete;
     SideScope& operator=(const SideScope&) = delete;
 };
@@ -171,6 +190,9 @@ struct LayerPlan {
 struct HeadPlan {
     int B, T, C, D, heads, inner, M, it, F, NP;
     LayerPlan L[kDepth];
+    // cotangent scratch of the backward, two sets: transformer layer l works in set l & 1, so the side stream may still read
+    // one layer's buffers (weight gradients, column sums) while the next layer already writes its own
+    struct CotSet { size_t dZ, dNf, dX1, dO, dQKV, dNa, dX, dX16, dX1_16; } cot[2];
     size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dNa2, dX, dFv, conv_scratch, pl_scratch,
         g_pred, ones, hreg, up2, dX16, dX1_16, w_conv, dFv2, total;   // w_conv: [2T,C] TF32-rounded conv weight, twice; dFv2: hi/lo split of dFv   // dX16 / dX1_16: bf16 shadows of dX / dX1 (PREC_BF16 only)
 };
@@ -261,6 +283,17 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     if (d.precision == PREC_BF16) {
         p.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
         p.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+    }
+    p.cot[0] = HeadPlan::CotSet{p.dZ, p.dNf, p.dX1, p.dO, p.dQKV, p.dNa, p.dX, p.dX16, p.dX1_16};
+    {
+        HeadPlan::CotSet& c = p.cot[1];
+        c.dZ = take(cur, MS * ldh_max); c.dNf = take(cur, MS * dmax); c.dX1 = take(cur, MS * dmax);
+        c.dO = take(cur, MS * p.inner); c.dQKV = take(cur, MS * 3 * p.inner); c.dNa = p.dNa2; c.dX = take(cur, MS * dmax);
+        c.dX16 = c.dX1_16 = 0;
+        if (d.precision == PREC_BF16) {
+            c.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+            c.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+        }
     }
     p.dFv = take(cur, M * dmax);
     p.conv_scratch = take(cur, p.C > 0 ? conv_wgrad_scratch_floats(p.C, p.T) : 64);
@@ -441,7 +474,10 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
         g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid; g.prerounded = fftc;
         g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
-        SCAT_PROPAGATE(L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st));
+        if (L.last && L.out == 3)     // three outputs per token: a warp per row instead of a 64 x 64 tile kernel
+            SCAT_PROPAGATE(launch_ff_out3_fwd(ws + L.H, L.ldh, W[L.p_fc2_w], W[L.p_fc2_b], Y, M, L.hid, st));
+        else
+            SCAT_PROPAGATE(L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st));
     }
     return 0;
 }
@@ -455,8 +491,9 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
                          int prec, const float* up, cudaStream_t st, const float* X0_override, int sweeps = 1,
                          SideStream* sd = nullptr, int l_first = kDepth - 1, int l_last = 0) {
-    // parameter gradients run on the side stream `sg` (== st without one): each group is forked once its inputs exist
-    // and all groups of a layer are joined before that layer's last kernel overwrites the cotangent buffers they read
+    // parameter gradients run on the side stream `sg` (== st without one): each group is forked once its inputs exist.
+    // Layer l works in cotangent set l & 1, so the side stream may lag a whole layer behind the critical chain: the main
+    // stream only waits (at the top of layer l) for the side work of layer l + 2, whose buffers it is about to overwrite
     const cudaStream_t sg = (sd != nullptr && G != nullptr) ? sd->s : st;
     const int M = p.M;
     const int MR = M * sweeps;                       // rows of every cotangent tensor
@@ -468,12 +505,16 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
     int ld_dYg = 3;
     if (l_first < kDepth - 1) {                      // resuming below the top layer: the cotangent is layer l_first+1's dX
         const int dn = p.L[l_first + 1].d;
-        dY = ws + p.dX;
-        dYg = bf ? ws + p.dX16 : dY;
+        const HeadPlan::CotSet& prev = p.cot[(l_first + 1) & 1];
+        dY = ws + prev.dX;
+        dYg = bf ? ws + prev.dX16 : dY;
         ld_dYg = bf ? pad8(dn) : dn;
     }
+    cudaEvent_t layer_done[kDepth] = {nullptr, nullptr, nullptr}, dy_read[kDepth] = {nullptr, nullptr, nullptr};
     for (int l = l_first; l >= l_last; --l) {
         const LayerPlan& L = p.L[l];
+        const HeadPlan::CotSet& c = p.cot[l & 1];
+        if (G && l + 2 <= l_first) SCAT_PROPAGATE(side_wait(st, layer_done[l + 2]));
         const LayerW w = layer_weights(p, l, W, ws, prec);
         const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         const int ffprec = L.last ? PREC_FP32 : prec;
@@ -481,7 +522,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         const int ld_n = bf ? pad8(L.d) : L.d;                 // dX1 / dX as GEMM operands
         const int ld_na = bf ? pad8(L.d) : pad4(L.d);          // saved Na / Nf (as the forward stored them)
         const int ld_h = ffbf ? pad8(L.hid) : L.ldh;           // H / dZ as GEMM operands
-        float* dZ = ws + p.dZ;
+        float* dZ = ws + c.dZ;
         GemmArgs g;
         if (G) {
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
@@ -490,6 +531,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
             SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, sg));
+            SCAT_PROPAGATE(side_mark(sd, sg, &dy_read[l]));        // dY (the other set's dX) has been consumed on the side stream
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
@@ -498,7 +540,10 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (ffbf) { g.C16 = dZ; g.ldc16 = ld_h; }
         else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod;
-        SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
+        if (L.last && L.out == 3 && !ffbf)     // K = 3: elementwise
+            SCAT_PROPAGATE(launch_ff_out3_bwd(dY, W[L.p_fc2_w], ws + L.Z, L.ldh, dZ, L.ldh, MR, L.hid, amod, st));
+        else
+            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         if (G) {
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             SCAT_PROPAGATE(order_after(sd, st, sg));
@@ -511,24 +556,24 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs)
         g = GemmArgs();
         g.A = dZ; g.sam = ld_h; g.sak = 1; g.B = w.fc1; g.sbn = 1; g.sbk = w.ld_fc1; g.operand_bf16 = ffbf;
-        g.C = ws + p.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
-        if (L.last && bf) { g.C16 = ws + p.dX1_16; g.ldc16 = ld_n; }
+        g.C = ws + c.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
+        if (L.last && bf) { g.C16 = ws + c.dX1_16; g.ldc16 = ld_n; }
         else g.round_out = (L.last && tc) ? 1 : 0;
         SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
-        const float* dX1 = ws + p.dNf;
+        const float* dX1 = ws + c.dNf;
         if (!L.last) {
             // data gradient on the critical path; d gamma / d beta are column sums over the M real rows: side stream
-            SCAT_PROPAGATE(launch_layernorm_bwd(ws + p.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
-                                                ws + L.rstd_f, nullptr, 0, ws + p.dX1, L.d, nullptr, nullptr, MR, L.d,
-                                                bf ? OUT_F32 : omode, st, amod, bf ? ws + p.dX1_16 : nullptr, ld_n));
-            dX1 = ws + p.dX1;
+            SCAT_PROPAGATE(launch_layernorm_bwd(ws + c.dNf, L.d, ws + L.X1, L.d, W[L.p_nf_w], ws + L.mean_f,
+                                                ws + L.rstd_f, nullptr, 0, ws + c.dX1, L.d, nullptr, nullptr, MR, L.d,
+                                                bf ? OUT_F32 : omode, st, amod, bf ? ws + c.dX1_16 : nullptr, ld_n));
+            dX1 = ws + c.dX1;
         }
-        const float* dX1g = bf ? ws + p.dX1_16 : dX1;           // what the GEMMs read
+        const float* dX1g = bf ? ws + c.dX1_16 : dX1;           // what the GEMMs read
         if (G) {
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1); and the feed-forward LayerNorm's d gamma / d beta (reads dNf)
             SCAT_PROPAGATE(order_after(sd, st, sg));
             if (!L.last)
-                SCAT_PROPAGATE(launch_layernorm_param_grads(ws + p.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
+                SCAT_PROPAGATE(launch_layernorm_param_grads(ws + c.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
                                                             G[L.p_nf_w], G[L.p_nf_b], M, L.d, sg));
             g = GemmArgs();
             g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
@@ -539,42 +584,41 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         // dO = dX1 Wo
         g = GemmArgs();
         g.A = dX1g; g.sam = ld_n; g.sak = 1; g.B = w.out; g.sbn = 1; g.sbk = w.ld_out; g.operand_bf16 = bf;
-        g.C = ws + p.dO; g.ldc = p.inner; g.M = MR; g.N = p.inner; g.K = L.d; g.prerounded = tc;
+        g.C = ws + c.dO; g.ldc = p.inner; g.M = MR; g.N = p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + p.dO, ws + p.dQKV, p.B * sweeps, p.T, p.heads, omode,
+        SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + c.dO, ws + c.dQKV, p.B * sweeps, p.T, p.heads, omode,
                                             st, sweeps > 1 ? p.B : 0));
         if (G) {
             // dWqkv[3inner,d] = dQKV^T Na
             SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
-            g.A = ws + p.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_na; g.operand_bf16 = bf;
+            g.A = ws + c.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_na; g.operand_bf16 = bf;
             g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, sg));
         }
         // dNa = dQKV Wqkv
         g = GemmArgs();
-        float* dNa = ws + ((l & 1) ? p.dNa2 : p.dNa);
-        g.A = ws + p.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
+        float* dNa = ws + c.dNa;
+        g.A = ws + c.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
         g.C = dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
-        // the next kernel overwrites dX (this layer's dY), and the next layer every other cotangent buffer the side-stream
-        // parameter-gradient kernels of this layer read: join them here
-        if (G) SCAT_PROPAGATE(order_after(sd, sg, st));
-        // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs
+        // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs.  It
+        // overwrites the dX of layer l + 2 = the dY that layer l + 1's first side-stream group read
+        if (G && l + 1 <= l_first) SCAT_PROPAGATE(side_wait(st, dy_read[l + 1]));
         const bool feeds_gemm = tc && l > 0;
         SCAT_PROPAGATE(launch_layernorm_bwd(dNa, L.d, X, L.d, W[L.p_na_w], ws + L.mean_a, ws + L.rstd_a, dX1,
-                                            L.d, ws + p.dX, L.d, nullptr, nullptr, MR, L.d,
+                                            L.d, ws + c.dX, L.d, nullptr, nullptr, MR, L.d,
                                             (feeds_gemm && !bf) ? OUT_TF32 : OUT_F32, st, amod,
-                                            (feeds_gemm && bf) ? ws + p.dX16 : nullptr, ld_n));
+                                            (feeds_gemm && bf) ? ws + c.dX16 : nullptr, ld_n));
         if (G) {
-            // its parameter gradients read dNa (this layer's buffer: the next layer writes the other one) and the saved X:
-            // side stream, joined with the next layer's groups (or by the caller's final join for layer 0)
+            // its parameter gradients read dNa and the saved X: side stream, joined two layers later or by the caller
             SCAT_PROPAGATE(order_after(sd, st, sg));
             SCAT_PROPAGATE(launch_layernorm_param_grads(dNa, L.d, X, L.d, ws + L.mean_a, ws + L.rstd_a, G[L.p_na_w], G[L.p_na_b],
                                                         M, L.d, sg));
+            SCAT_PROPAGATE(side_mark(sd, sg, &layer_done[l]));     // everything of layer l on the side stream is queued
         }
-        dY = ws + p.dX;
-        dYg = bf ? ws + p.dX16 : dY;
+        dY = ws + c.dX;
+        dYg = bf ? ws + c.dX16 : dY;
         ld_dYg = bf ? ld_n : L.d;
     }
     return 0;
@@ -708,25 +752,10 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
         if (tail != nullptr)                          // the loss values need a batch reduction: off the critical path
             SCAT_PROPAGATE(launch_proj_loss(tail->pred, tail->labels, tail->ld_labels, nullptr, p.T * p.D, p.T, tail->w3d,
                                             tail->w2d, tail->grad_scale, tail->losses, nullptr, ws + p.pl_scratch, p.B, sg));
-        const int ldw = p.F + p.NP;
-        GemmArgs g;
-        if (mf_grad != nullptr) {   // d main_feat[B,F] = gsum[B,P] Wr[:, :F]: nothing downstream reads it
-            g.A = ws + p.gsum; g.sam = p.NP; g.sak = 1; g.B = W[P_REG_W]; g.sbn = 1; g.sbk = ldw;
-            g.C = mf_grad; g.ldc = p.F; g.M = p.B; g.N = p.F; g.K = p.NP;
-            SCAT_PROPAGATE(launch_gemm_simt(g, sg));
-            g = GemmArgs();
-        }
-        // dWr[:, :F] = gsum^T main_feat
-        g.A = ws + p.gsum; g.sam = 1; g.sak = p.NP; g.B = main_feat; g.sbn = 1; g.sbk = p.F;
-        g.C = G[P_REG_W]; g.ldc = ldw; g.M = p.NP; g.N = p.F; g.K = p.B; g.allow_split_k = 1; g.c_zeroed = 1;
-        SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, sg));
-        if (p.it > 0) {   // dWr[:, F:] = sum over samples and steps of g_step (x) state
-            g = GemmArgs();
-            g.A = ws + p.gsteps; g.sam = 1; g.sak = p.NP; g.B = ws + p.states; g.sbn = 1; g.sbk = p.NP;
-            g.C = G[P_REG_W] + p.F; g.ldc = ldw; g.M = p.NP; g.N = p.NP; g.K = p.B * p.it; g.allow_split_k = 1; g.c_zeroed = 1;
-            SCAT_PROPAGATE(launch_gemm_exact(g, d.precision, sg));
-        }
-        SCAT_PROPAGATE(launch_colsum(ws + p.gsum, p.NP, p.B, p.NP, G[P_REG_B], 1, sg));
+        // d main_feat = gsum Wr[:, :F] (nothing downstream reads it), dWr[:, :F] = gsum^T main_feat, dWr[:, F:] = sum over
+        // samples and steps of g_step (x) state, d br = column sums of gsum: one launch
+        SCAT_PROPAGATE(launch_regressor_param_grads(ws + p.gsum, ws + p.gsteps, ws + p.states, main_feat, W[P_REG_W], mf_grad,
+                                                    G[P_REG_W], G[P_REG_B], p.B, p.F, p.NP, p.it, sg));
         SCAT_PROPAGATE(side_wait(st, zeroed));        // the main stream reduces into the gradients from here on
     }
     }

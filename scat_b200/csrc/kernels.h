@@ -182,6 +182,16 @@ int launch_regressor_train(const float* feat_out, const float* mean_params, cons
                            float* states, float* d_feat_out, float* ones_out, float* gsum, float* gsteps, int B, int F, int P,
                            int iteration, cudaStream_t stream);
 
+// d main_feat (nullable), d regressor.weight, d regressor.bias from the backward's gsum / gsteps / states: one launch
+int launch_regressor_param_grads(const float* gsum, const float* gsteps, const float* states, const float* main_feat,
+                                 const float* Wr, float* d_main_feat, float* dWr, float* dbr, int B, int F, int P, int iteration,
+                                 cudaStream_t stream);
+// the last feed-forward's second Linear (out = 3, vision_transformer.py:37-42) and its data gradient with the GELU
+// derivative fused (act_rows > 0: row m of dY / dZ uses activation row m % act_rows), always fp32
+int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2, float* Y, int M, int K, cudaStream_t stream);
+int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
+                       cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------
 // projection + losses (train.py:112-120,165-203) with closed-form gradient w.r.t. pred_params
 // ------------------------------------------------------------------------------------------

@@ -255,7 +255,139 @@ regressor_train_kernel(const float* __restrict__ h_all, const float* __restrict_
     }
 }
 
+// Everything the regressor contributes to the gradient bucket and to main_feat, in ONE launch (three FFMA GEMMs with a
+// 66-wide dimension and a column sum before: ~110 us of side-stream time for 30 MFLOP).  128 threads per block:
+//   blockIdx.y = 0   d main_feat[b, f] = sum_p gsum[b,p] Wr[p, f]                   thread = f, blockIdx.z = sample slice
+//   blockIdx.y = 1   dWr[p, f]        = sum_b gsum[b,p] main_feat[b, f]   (f < F)   thread = f, blockIdx.z = slice of p
+//   blockIdx.y = 2   dWr[p, F + q]    = sum_{b,it} gsteps[b,it,p] states[b,it,q];  dbr[p] = sum_b gsum[b,p]   (z = 0 only)
+// Every output element is written exactly once (no atomics, no dependence on the bucket having been zeroed).
+constexpr int PG_Z = 6, PG_SL = 16;      // slices; samples (y = 0) or rows p (y = 1) per slice, PG_Z * PG_SL >= 96
+__global__ void __launch_bounds__(128)
+regressor_param_grads_kernel(const float* __restrict__ gsum, const float* __restrict__ gsteps, const float* __restrict__ states,
+                             const float* __restrict__ main_feat, const float* __restrict__ Wr, float* __restrict__ d_main_feat,
+                             float* __restrict__ dWr, float* __restrict__ dbr, int B, int F, int P, int iteration) {
+    pdl_sync();
+    const int tid = threadIdx.x, ldw = F + P;
+    const int f = blockIdx.x * 128 + tid;
+    if (blockIdx.y == 0) {
+        if (d_main_feat == nullptr) return;
+        __shared__ float gs[PG_SL][MAXP];
+        for (int b0 = blockIdx.z * PG_SL; b0 < B; b0 += PG_Z * PG_SL) {         // (B <= 96: one pass)
+            const int nb = min(PG_SL, B - b0);
+            __syncthreads();
+            for (int i = tid; i < nb * P; i += 128) gs[i / P][i % P] = gsum[(long long)(b0 + i / P) * P + i % P];
+            __syncthreads();
+            if (f < F) {
+                float acc[PG_SL];
+#pragma unroll
+                for (int b = 0; b < PG_SL; ++b) acc[b] = 0.f;
+                for (int p = 0; p < P; ++p) {
+                    const float w = __ldg(Wr + (long long)p * ldw + f);
+#pragma unroll
+                    for (int b = 0; b < PG_SL; ++b) acc[b] = fmaf(gs[b][p], w, acc[b]);     // rows >= nb hold stale finite data
+                }
+#pragma unroll
+                for (int b = 0; b < PG_SL; ++b)
+                    if (b < nb) d_main_feat[(long long)(b0 + b) * F + f] = acc[b];
+            }
+        }
+    } else if (blockIdx.y == 1) {
+        const int p0 = blockIdx.z * PG_SL;
+        if (p0 >= P || f >= F) return;
+        const int np = min(PG_SL, P - p0);
+        float acc[PG_SL];
+#pragma unroll
+        for (int i = 0; i < PG_SL; ++i) acc[i] = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const float m = __ldg(main_feat + (long long)b * F + f);
+            const float* g = gsum + (long long)b * P + p0;
+#pragma unroll
+            for (int i = 0; i < PG_SL; ++i)
+                if (i < np) acc[i] = fmaf(__ldg(g + i), m, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < PG_SL; ++i)
+            if (i < np) dWr[(long long)(p0 + i) * ldw + f] = acc[i];
+    } else {
+        if (blockIdx.z != 0) return;
+        const int i = blockIdx.x * 128 + tid;
+        if (i < P * P) {
+            const int p = i / P, q = i - p * P;
+            float a = 0.f;
+            for (int r = 0; r < B * iteration; ++r) a = fmaf(__ldg(gsteps + (long long)r * P + p), __ldg(states + (long long)r * P + q), a);
+            dWr[(long long)p * ldw + F + q] = a;
+        } else if (i < P * P + P) {
+            const int p = i - P * P;
+            float a = 0.f;
+            for (int b = 0; b < B; ++b) a += __ldg(gsum + (long long)b * P + p);
+            dbr[p] = a;
+        }
+    }
+}
+
+// the last feed-forward of the head narrows to THREE outputs per token (vision_transformer.py:37-42): its second Linear
+// and that Linear's data gradient are far too thin for a tiled GEMM (N = 3 / K = 3); always fp32.
+//   Y[m, j] = b2[j] + sum_k H[m,k] W2[j,k]          one warp per row
+__global__ void __launch_bounds__(256)
+ff_out3_fwd_kernel(const float* __restrict__ H, int ldh, const float* __restrict__ W2, const float* __restrict__ b2,
+                   float* __restrict__ Y, int M, int K) {
+    pdl_sync();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* h = H + (long long)row * ldh;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float v = __ldg(h + k);
+        a0 = fmaf(v, __ldg(W2 + k), a0);
+        a1 = fmaf(v, __ldg(W2 + K + k), a1);
+        a2 = fmaf(v, __ldg(W2 + 2 * K + k), a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane < 3) Y[(long long)row * 3 + lane] = (lane == 0 ? a0 : lane == 1 ? a1 : a2) + __ldg(b2 + lane);
+}
+//   dZ[m, n] = (sum_{j<3} dY[m,j] W2[j,n]) * gelu'(Z[m % act_rows, n])      thread per element
+__global__ void __launch_bounds__(256)
+ff_out3_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ W2, const float* __restrict__ Z, int ldz,
+                   float* __restrict__ dZ, int lddz, int MR, int N, int act_rows) {
+    pdl_sync();
+    const long long total = (long long)MR * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+        const float* dy = dY + (long long)m * 3;
+        const float t = fmaf(__ldg(dy), __ldg(W2 + n), fmaf(__ldg(dy + 1), __ldg(W2 + N + n), __ldg(dy + 2) * __ldg(W2 + 2 * N + n)));
+        const int zr = act_rows > 0 ? m % act_rows : m;
+        dZ[(long long)m * lddz + n] = t * gelu_erf_grad(__ldg(Z + (long long)zr * ldz + n));
+    }
+}
+
 }  // namespace
+
+int launch_regressor_param_grads(const float* gsum, const float* gsteps, const float* states, const float* main_feat,
+                                 const float* Wr, float* d_main_feat, float* dWr, float* dbr, int B, int F, int P, int iteration,
+                                 cudaStream_t stream) {
+    SCAT_REQUIRE(gsum && gsteps && states && main_feat && Wr && dWr && dbr, kErrBadArg, "regressor param grads: null argument");
+    SCAT_REQUIRE(P >= 4 && P <= MAXP && P <= PG_Z * PG_SL && F >= 1, kErrUnsupported, "regressor param grads: P=%d F=%d", P, F);
+    const int gx = max(ceil_div(F, 128), ceil_div(P * P + P, 128));
+    SCAT_CHECK_CUDA(launch_k(regressor_param_grads_kernel, dim3(gx, 3, PG_Z), dim3(128), 0, stream, gsum, gsteps, states, main_feat, Wr,
+                             d_main_feat, dWr, dbr, B, F, P, iteration));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2, float* Y, int M, int K, cudaStream_t stream) {
+    SCAT_CHECK_CUDA(launch_k(ff_out3_fwd_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, H, ldh, W2, b2, Y, M, K));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
+                       cudaStream_t stream) {
+    const long long total = (long long)MR * N;
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    SCAT_CHECK_CUDA(launch_k(ff_out3_bwd_kernel, dim3(grid), dim3(256), 0, stream, dY, W2, Z, ldz, dZ, lddz, MR, N, act_rows));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
 
 int launch_regressor_train(const float* feat_out, const float* mean_params, const float* Wr, const float* h_scratch,
                            const float* labels, int ld_labels, float w3d, float w2d, float grad_scale, float* pred,
