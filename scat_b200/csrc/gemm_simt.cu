@@ -236,7 +236,44 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
     }
 }
 
+// fp32-grade tensor-core operands (3xTF32): every value is split into hi = TF32-nearest(v) and lo = TF32-nearest(v - hi),
+// both exact on the tensor core, and the two operands of a product are stacked along K so that ONE GEMM computes
+// A_hi B_hi + A_lo B_hi + A_hi B_lo (the dropped lo x lo term is 2^-22 relative):
+//   first operand  (mode 0): dst[r, 3 x cp] = [hi | lo | hi]           (cp = cols padded to 4, pad columns zero)
+//   second operand (mode 1): dst[r, 3 x cp] = [hi | hi | lo]           K-major second operand (forward, y = x W^T)
+//   second operand (mode 2): dst[3 x rp, cols] = [hi; hi; lo]          MN-major second operand (dgrad, dx = dy W), rp = rows padded to 4
+__global__ void split3_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int rows, int cols, int mode) {
+    pdl_sync();
+    const int cp = (cols + 3) & ~3, rp = (rows + 3) & ~3;
+    const long long total = mode == 2 ? (long long)rp * cols : (long long)rows * cp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int width = mode == 2 ? cols : cp;
+        const int r = (int)(i / width), c = (int)(i - (long long)r * width);
+        const float v = (r < rows && c < cols) ? __ldg(src + (long long)r * ld_src + c) : 0.f;
+        const float hi = round_tf32(v), lo = round_tf32(v - hi);
+        if (mode == 2) {
+            dst[i] = hi;
+            dst[(long long)rp * cols + i] = hi;
+            dst[2LL * rp * cols + i] = lo;
+        } else {
+            float* d = dst + (long long)r * 3 * cp + c;
+            d[0] = hi;
+            d[cp] = mode == 0 ? lo : hi;
+            d[2 * cp] = mode == 0 ? hi : lo;
+        }
+    }
+}
+
 }  // namespace
+
+int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, int mode, cudaStream_t stream) {
+    SCAT_REQUIRE(src && dst && rows > 0 && cols > 0 && mode >= 0 && mode <= 2, kErrBadArg, "split3: bad args");
+    const long long total = (long long)((rows + 3) & ~3) * ((cols + 3) & ~3);
+    const int grid = (int)((total + 255) / 256 < 148 * 4 ? (total + 255) / 256 : 148 * 4);
+    SCAT_CHECK_CUDA(launch_k(split3_kernel, dim3(grid), dim3(256), 0, stream, src, ld_src, dst, rows, cols, mode));
+    SCAT_CHECK_LAUNCH();
+    return 0;
+}
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 16, kErrBadArg, "round_copy: %d jobs", jobs.n);

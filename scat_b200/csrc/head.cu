@@ -182,6 +182,7 @@ struct LayerPlan {
     int d, hid, out, ldh;
     size_t X, Na, mean_a, rstd_a, QKV, P, O, X1, Nf, mean_f, rstd_f, Z, H;   // float offsets
     size_t w_qkv, w_out, w_fc1, w_fc2;   // TF32-rounded weight copies (tensor-core layers only)
+    size_t w_fc1s, w_fc1d;               // last layer: 3xTF32 split copies of fc1.weight, [hid, 3 d] (forward) and [3 hidp, d] (dgrad)
     int ld_qkv, ld_out, ld_fc1, ld_fc2;  // their leading dimensions (padded to 4 floats)
     bool last;
     int p_na_w, p_na_b, p_qkv, p_out_w, p_out_b, p_nf_w, p_nf_b, p_fc1_w, p_fc1_b, p_fc2_w, p_fc2_b;
@@ -194,7 +195,7 @@ struct HeadPlan {
     // one layer's buffers (weight gradients, column sums) while the next layer already writes its own
     struct CotSet { size_t dZ, dNf, dX1, dO, dQKV, dNa, dX, dX16, dX1_16; } cot[2];
     size_t feat_out, states, gsum, gsteps, dfeat, dZ, dNf, dX1, dO, dQKV, dNa, dNa2, dX, dFv, conv_scratch, pl_scratch,
-        g_pred, ones, hreg, up2, dX16, dX1_16, w_conv, dFv2, total;   // w_conv: [2T,C] TF32-rounded conv weight, twice; dFv2: hi/lo split of dFv   // dX16 / dX1_16: bf16 shadows of dX / dX1 (PREC_BF16 only)
+        g_pred, ones, hreg, up2, dX16, dX1_16, w_conv, dFv2, x1s, dZs, total;   // x1s / dZs: 3xTF32 split operands of the last feed-forward   // w_conv: [2T,C] TF32-rounded conv weight, twice; dFv2: hi/lo split of dFv   // dX16 / dX1_16: bf16 shadows of dX / dX1 (PREC_BF16 only)
 };
 
 size_t take(size_t& cur, size_t n) {
@@ -240,8 +241,11 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
         if (!L.last) {
             L.w_fc1 = take(cur, (size_t)L.hid * L.ld_fc1);
             L.w_fc2 = take(cur, (size_t)L.out * L.ld_fc2);
+            L.w_fc1s = L.w_fc1d = 0;
         } else {
             L.w_fc1 = L.w_fc2 = 0;
+            L.w_fc1s = take(cur, (size_t)L.hid * 3 * pad4(dim));
+            L.w_fc1d = take(cur, (size_t)3 * pad4(L.hid) * dim);
         }
         const int base = layer_base(l);
         L.p_na_w = base + L_NA_W; L.p_na_b = base + L_NA_B; L.p_qkv = base + L_QKV_W; L.p_out_w = base + L_OUT_W;
@@ -294,6 +298,11 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
             c.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
             c.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
         }
+    }
+    {
+        const LayerPlan& LL = p.L[kDepth - 1];
+        p.x1s = take(cur, M * 3 * pad4(LL.d));
+        p.dZs = take(cur, MS * 3 * pad4(LL.hid));
     }
     p.dFv = take(cur, M * dmax);
     p.conv_scratch = take(cur, p.C > 0 ? conv_wgrad_scratch_floats(p.C, p.T) : 64);
@@ -404,8 +413,13 @@ int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec,
     }
     for (int i = 0; i < n; ++i) jobs.job[i].to_bf16 = bf ? 1 : 0;
     jobs.n = n;
-    if (n == 0) return 0;
-    return launch_round_copy(jobs, st);
+    if (n > 0) SCAT_PROPAGATE(launch_round_copy(jobs, st));
+    // the last feed-forward's first Linear runs as an fp32-grade 3xTF32 product on the tensor core: split copies of its
+    // weight, K-major [hi | hi | lo] for the forward and MN-major [hi; hi; lo] for the data gradient
+    const LayerPlan& LL = p.L[kDepth - 1];
+    SCAT_PROPAGATE(launch_split3(W[LL.p_fc1_w], LL.d, ws + LL.w_fc1s, LL.hid, LL.d, 1, st));
+    SCAT_PROPAGATE(launch_split3(W[LL.p_fc1_w], LL.d, ws + LL.w_fc1d, LL.hid, LL.d, 2, st));
+    return 0;
 }
 
 // ---- forward through the transformer (vision_transformer.py:97-101) --------------------------------
@@ -468,7 +482,15 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
         else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh;
-        SCAT_PROPAGATE(L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st));
+        if (L.last && tc) {
+            // fp32-grade on the tensor core: X1 split into [hi | lo | hi] against the weight's [hi | hi | lo], K = 3 d
+            const int dp = pad4(L.d);
+            SCAT_PROPAGATE(launch_split3(ws + L.X1, L.d, ws + p.x1s, M, L.d, 0, st));
+            g.A = ws + p.x1s; g.sam = 3 * dp; g.B = ws + L.w_fc1s; g.sbn = 3 * dp; g.K = 3 * dp; g.prerounded = 1;
+            SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
+        } else {
+            SCAT_PROPAGATE(L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st));
+        }
         float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
         g = GemmArgs();
         g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
@@ -541,7 +563,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod;
         if (L.last && L.out == 3 && !ffbf)     // K = 3: elementwise
-            SCAT_PROPAGATE(launch_ff_out3_bwd(dY, W[L.p_fc2_w], ws + L.Z, L.ldh, dZ, L.ldh, MR, L.hid, amod, st));
+            SCAT_PROPAGATE(launch_ff_out3_bwd(dY, W[L.p_fc2_w], ws + L.Z, L.ldh, dZ, L.ldh, MR, L.hid, amod, tc ? ws + p.dZs : nullptr, st));
         else
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         if (G) {
@@ -559,7 +581,14 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         g.C = ws + c.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
         if (L.last && bf) { g.C16 = ws + c.dX1_16; g.ldc16 = ld_n; }
         else g.round_out = (L.last && tc) ? 1 : 0;
-        SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
+        if (L.last && tc && L.out == 3) {
+            // fp32-grade on the tensor core: dZ's [hi | lo | hi] (written by the kernel above) against fc1.weight's [hi; hi; lo]
+            const int hp = pad4(L.hid);
+            g.A = ws + p.dZs; g.sam = 3 * hp; g.B = ws + L.w_fc1d; g.sbk = L.d; g.K = 3 * hp; g.prerounded = 1;
+            SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
+        } else {
+            SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
+        }
         const float* dX1 = ws + c.dNf;
         if (!L.last) {
             // data gradient on the critical path; d gamma / d beta are column sums over the M real rows: side stream

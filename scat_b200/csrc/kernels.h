@@ -156,6 +156,10 @@ int launch_attention_tc128_fwd(const float* QKV, float* O, int B, int n, int hea
 struct RoundJob { const float* src; float* dst; int rows, cols, ld_src, ld_dst; int to_bf16 = 0; };
 struct RoundJobs { RoundJob job[16]; int n; };
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream);
+// TF32 hi / lo split of a matrix, stacked along K for an fp32-grade (3xTF32) tensor-core product.  mode 0: first operand
+// [rows, 3 cp] = [hi | lo | hi]; mode 1: K-major second operand [rows, 3 cp] = [hi | hi | lo]; mode 2: MN-major second
+// operand [3 rp, cols] = [hi; hi; lo] (cp / rp = cols / rows padded to 4, pads zero)
+int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, int mode, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
 // autoregressive regressor (hand_net.py:379-393) and its backward
@@ -189,8 +193,9 @@ int launch_regressor_param_grads(const float* gsum, const float* gsteps, const f
 // the last feed-forward's second Linear (out = 3, vision_transformer.py:37-42) and its data gradient with the GELU
 // derivative fused (act_rows > 0: row m of dY / dZ uses activation row m % act_rows), always fp32
 int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2, float* Y, int M, int K, cudaStream_t stream);
+// dZs (nullable): also the TF32 hi / lo split [MR, 3 pad4(N)] = [hi | lo | hi] of dZ (pad columns must be zero already)
 int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
-                       cudaStream_t stream);
+                       float* dZs, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
 // projection + losses (train.py:112-120,165-203) with closed-form gradient w.r.t. pred_params
