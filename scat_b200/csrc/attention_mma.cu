@@ -4,8 +4,8 @@
 //
 // A (batch, head) problem is 21x21x64: far below one tcgen05 tile (128 x N, operands through shared memory and
 // TMA), so these kernels use the warp-level mma.sync.m16n8k8 TF32 instruction with every operand fragment loaded
-// straight from global memory (each 21x64 tile is 5.4 KB and stays in L1): one warp owns one problem, there is no
-// block-level synchronisation at all, and the FFMA count of the CUDA-core version (113k per backward problem)
+// straight from global memory (each 21x64 tile is 5.4 KB and stays in L1): two warps own one problem (forward: one
+// 16-row query tile each; backward: dP/dS/dQ and dV/dK), synchronisation is at most one named barrier per pair, and the FFMA count of the CUDA-core version (113k per backward problem)
 // becomes 192 tensor instructions.  Operands are rounded to TF32-nearest (cvt.rna) as they are loaded; mma.sync
 // would otherwise truncate them.  Rows / columns 21..31 of the padded 32x24 score tile are zero-filled operands
 // and masked scores.
@@ -84,12 +84,15 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
         }
 }
 
-__global__ void __launch_bounds__(WARPS * 32, 3)
+// Forward: TWO warps per problem, each owns one 16-row tile of queries (rows 0..15 / 16..20 + padding): a row's softmax
+// and output only need that row's scores, so the two halves never talk.  (One warp per problem left 5 warps per SM for a
+// chain of ~60 dependent tensor instructions.)
+__global__ void __launch_bounds__(WARPS * 32, 4)
 attention_fwd_mma_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ P, int nprob, int heads,
                          int out_mode) {
     pdl_sync();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int prob = blockIdx.x * WARPS + warp;
+    const int prob = (blockIdx.x * WARPS + warp) >> 1, mt = warp & 1;
     if (prob >= nprob) return;
     const int b = prob / heads, h = prob % heads;
     const int inner = heads * DH;
@@ -98,107 +101,104 @@ attention_fwd_mma_kernel(const float* __restrict__ QKV, float* __restrict__ O, f
     const float* Kb = Qb + inner;
     const float* Vb = Qb + 2 * inner;
 
-    // S = Q K^T   [32 x 24], k = 64
-    float s[2][3][4];
+    // S = Q K^T   [16 x 24], k = 64
+    float s[3][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 3; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+    for (int nt = 0; nt < 3; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-        uint32_t a[2][4], bf[3][2];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) frag_a(a[mt], Qb, rs, mt * 16, ks * 8, N, DH, g, t);
+        uint32_t a[4], bf[3][2];
+        frag_a(a, Qb, rs, mt * 16, ks * 8, N, DH, g, t);
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) frag_b_n(bf[nt], Kb, rs, ks * 8, nt * 8, DH, N, g, t);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 3; ++nt) mma_tf32(s[mt][nt], a[mt], bf[nt]);
+        for (int nt = 0; nt < 3; ++nt) mma_tf32(s[nt], a, bf[nt]);
     }
     // softmax over j of S * 64^-0.5 (vision_transformer.py:51,64,74); a row lives in the 4 lanes of a quad
     float* Pg = P + (long long)prob * N * N;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int hf = 0; hf < 2; ++hf) {
+        float m = -INFINITY;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            float m = -INFINITY;
+        for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 3; ++nt)
+            for (int e = 0; e < 2; ++e) {
+                const int j = nt * 8 + 2 * t + e;
+                float v = s[nt][hf * 2 + e] * 0.125f;
+                v = j < N ? v : -INFINITY;
+                s[nt][hf * 2 + e] = v;
+                m = fmaxf(m, v);
+            }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float sum = 0.f;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = nt * 8 + 2 * t + e;
-                    float v = s[mt][nt][hf * 2 + e] * 0.125f;
-                    v = j < N ? v : -INFINITY;
-                    s[mt][nt][hf * 2 + e] = v;
-                    m = fmaxf(m, v);
-                }
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            float sum = 0.f;
+        for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 3; ++nt)
+            for (int e = 0; e < 2; ++e) {
+                const float ev = expf(s[nt][hf * 2 + e] - m);       // exp(-inf) = 0 on masked columns
+                s[nt][hf * 2 + e] = ev;
+                sum += ev;
+            }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.0f / sum;
+        const int i = mt * 16 + hf * 8 + g;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float ev = expf(s[mt][nt][hf * 2 + e] - m);       // exp(-inf) = 0 on masked columns
-                    s[mt][nt][hf * 2 + e] = ev;
-                    sum += ev;
-                }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            const float inv = 1.0f / sum;
-            const int i = mt * 16 + hf * 8 + g;
+        for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 3; ++nt)
+            for (int e = 0; e < 2; ++e) {
+                const float pv = s[nt][hf * 2 + e] * inv;
+                s[nt][hf * 2 + e] = pv;
+                const int j = nt * 8 + 2 * t + e;
+                if (i < N && j < N) Pg[i * N + j] = pv;                  // saved for the backward
+            }
+    }
+    // O = P V   [16 x 64], k = 24: P from the accumulator layout (cols 2t, 2t+1) to the A layout (cols t, t+4)
+    float o[8][4];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float pv = s[mt][nt][hf * 2 + e] * inv;
-                    s[mt][nt][hf * 2 + e] = pv;
-                    const int j = nt * 8 + 2 * t + e;
-                    if (i < N && j < N) Pg[i * N + j] = pv;                  // saved for the backward
-                }
-        }
-    // O = P V   [32 x 64], k = 24: P from the accumulator layout (cols 2t, 2t+1) to the A layout (cols t, t+4)
-    float o[2][8][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+    for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
     const int src_lo = (lane & ~3) | (t >> 1), src_hi = src_lo + 2;
     const bool odd = t & 1;
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks) {
-        uint32_t a[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const float l0 = __shfl_sync(0xffffffffu, s[mt][ks][0], src_lo), l1 = __shfl_sync(0xffffffffu, s[mt][ks][1], src_lo);
-            const float l2 = __shfl_sync(0xffffffffu, s[mt][ks][2], src_lo), l3 = __shfl_sync(0xffffffffu, s[mt][ks][3], src_lo);
-            const float h0 = __shfl_sync(0xffffffffu, s[mt][ks][0], src_hi), h1 = __shfl_sync(0xffffffffu, s[mt][ks][1], src_hi);
-            const float h2 = __shfl_sync(0xffffffffu, s[mt][ks][2], src_hi), h3 = __shfl_sync(0xffffffffu, s[mt][ks][3], src_hi);
-            a[mt][0] = to_tf32(odd ? l1 : l0);        // P[g      ][8ks + t]
-            a[mt][1] = to_tf32(odd ? l3 : l2);        // P[g + 8  ][8ks + t]
-            a[mt][2] = to_tf32(odd ? h1 : h0);        // P[g      ][8ks + t + 4]
-            a[mt][3] = to_tf32(odd ? h3 : h2);        // P[g + 8  ][8ks + t + 4]
-        }
+        uint32_t a[4];
+        const float l0 = __shfl_sync(0xffffffffu, s[ks][0], src_lo), l1 = __shfl_sync(0xffffffffu, s[ks][1], src_lo);
+        const float l2 = __shfl_sync(0xffffffffu, s[ks][2], src_lo), l3 = __shfl_sync(0xffffffffu, s[ks][3], src_lo);
+        const float h0 = __shfl_sync(0xffffffffu, s[ks][0], src_hi), h1 = __shfl_sync(0xffffffffu, s[ks][1], src_hi);
+        const float h2 = __shfl_sync(0xffffffffu, s[ks][2], src_hi), h3 = __shfl_sync(0xffffffffu, s[ks][3], src_hi);
+        a[0] = to_tf32(odd ? l1 : l0);        // P[g      ][8ks + t]
+        a[1] = to_tf32(odd ? l3 : l2);        // P[g + 8  ][8ks + t]
+        a[2] = to_tf32(odd ? h1 : h0);        // P[g      ][8ks + t + 4]
+        a[3] = to_tf32(odd ? h3 : h2);        // P[g + 8  ][8ks + t + 4]
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             uint32_t bf[2];
             frag_b_k(bf, Vb, rs, ks * 8, nt * 8, N, DH, g, t);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][nt], a[mt], bf);
+            mma_tf32(o[nt], a, bf);
         }
     }
-    store_tile(O, (long long)b * N * inner + h * DH, inner, o, g, t, out_mode);
+    const long long off = (long long)b * N * inner + h * DH;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int r0 = mt * 16 + g, c = nt * 8 + 2 * t;
+        if (r0 < N) store_out2(O, off + (long long)r0 * inner + c, o[nt][0], o[nt][1], out_mode);
+        if (r0 + 8 < N) store_out2(O, off + (long long)(r0 + 8) * inner + c, o[nt][2], o[nt][3], out_mode);
+    }
 }
 
+// Backward: TWO warps per problem.  Warp 0 computes dP = dO V^T, dS (into the pair's shared scratch) and dQ = dS K; warp 1
+// computes dV = P^T dO (which needs neither dP nor dS) while warp 0 works, then dK = dS^T Q once dS is there (one named
+// barrier per pair).  Same tensor instructions as one warp per problem, half the dependent chain, twice the warps.
 __global__ void __launch_bounds__(WARPS * 32, 3)
 attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ P, const float* __restrict__ dO,
                          float* __restrict__ dQKV, int nprob, int heads, int out_mode, int act_batch) {
     pdl_sync();
-    __shared__ float scratch[WARPS][32 * SP];
+    __shared__ float scratch[WARPS / 2][32 * SP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int prob = blockIdx.x * WARPS + warp;
-    if (prob >= nprob) return;
+    const int pair = warp >> 1, role = warp & 1;
+    const int prob = blockIdx.x * (WARPS / 2) + pair;
+    if (prob >= nprob) return;                                  // (both warps of a pair leave together)
     const int b = prob / heads, h = prob % heads;
     const int ba = act_batch > 0 ? b % act_batch : b;          // stacked cotangents share the saved activations
     const int inner = heads * DH;
@@ -208,8 +208,11 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
     const float* Vb = Qb + 2 * inner;
     const float* Pg = P + ((long long)ba * heads + h) * N * N;
     const float* Gb = dO + (long long)b * N * inner + h * DH;  // dO rows, stride inner
-    float* sc = scratch[warp];
+    float* sc = scratch[pair];
+    const long long drow = (long long)b * N * rs + h * DH;
+    float acc[2][8][4];
 
+    if (role == 0) {
     // dP = dO V^T   [32 x 24], k = 64
     float dp[2][3][4];
 #pragma unroll
@@ -253,8 +256,35 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
                     sc[i * SP + nt * 8 + 2 * t + e] = pv[nt][e] * (dp[mt][nt][hf * 2 + e] - r) * 0.125f;
         }
     __syncwarp();
-    const long long drow = (long long)b * N * rs + h * DH;
-    float acc[2][8][4];
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");     // dS is in the pair's scratch
+    // dQ[i] = sum_j dS[i,j] K[j]     A(m = i, k = j) = dS[i][j],  B(k = j, n = d) = K[j][d]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int m = mt * 16 + g, k = ks * 8 + t;
+            a[mt][0] = to_tf32(sc[m * SP + k]);
+            a[mt][1] = to_tf32(sc[(m + 8) * SP + k]);
+            a[mt][2] = to_tf32(sc[m * SP + k + 4]);
+            a[mt][3] = to_tf32(sc[(m + 8) * SP + k + 4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t bf[2];
+            frag_b_k(bf, Kb, rs, ks * 8, nt * 8, N, DH, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], a[mt], bf);
+        }
+    }
+    store_tile(dQKV, drow, rs, acc, g, t, out_mode);
+    return;
+    }
+    // ---- role 1 ----
     // dV[j] = sum_i P[i,j] dO[i]     A(m = j, k = i) = P[i][j],  B(k = i, n = d) = dO[i][d]
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -274,6 +304,7 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
         }
     }
     store_tile(dQKV, drow + 2 * inner, rs, acc, g, t, out_mode);
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");     // wait for warp 0's dS
     // dK[j] = sum_i dS[i,j] Q[i]     A(m = j, k = i) = dS[i][j] (scratch, transposed read),  B(k = i, n = d) = Q[i][d]
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -300,31 +331,6 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
         }
     }
     store_tile(dQKV, drow + inner, rs, acc, g, t, out_mode);
-    // dQ[i] = sum_j dS[i,j] K[j]     A(m = i, k = j) = dS[i][j],  B(k = j, n = d) = K[j][d]
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 3; ++ks) {
-        uint32_t a[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int m = mt * 16 + g, k = ks * 8 + t;
-            a[mt][0] = to_tf32(sc[m * SP + k]);
-            a[mt][1] = to_tf32(sc[(m + 8) * SP + k]);
-            a[mt][2] = to_tf32(sc[m * SP + k + 4]);
-            a[mt][3] = to_tf32(sc[(m + 8) * SP + k + 4]);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            uint32_t bf[2];
-            frag_b_k(bf, Kb, rs, ks * 8, nt * 8, N, DH, g, t);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], a[mt], bf);
-        }
-    }
-    store_tile(dQKV, drow, rs, acc, g, t, out_mode);
 }
 
 }  // namespace
@@ -332,7 +338,7 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
 int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int out_mode, cudaStream_t stream) {
     SCAT_REQUIRE(n == N, kErrUnsupported, "attention_mma: n=%d", n);
     const int nprob = B * heads;
-    SCAT_CHECK_CUDA(launch_k(attention_fwd_mma_kernel, dim3(ceil_div(nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, O, P, nprob,
+    SCAT_CHECK_CUDA(launch_k(attention_fwd_mma_kernel, dim3(ceil_div(2 * nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, O, P, nprob,
                              heads, out_mode));
     SCAT_CHECK_LAUNCH();
     return 0;
@@ -342,7 +348,7 @@ int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, 
                              int out_mode, cudaStream_t stream, int act_batch) {
     SCAT_REQUIRE(n == N, kErrUnsupported, "attention_mma: n=%d", n);
     const int nprob = B * heads;
-    SCAT_CHECK_CUDA(launch_k(attention_bwd_mma_kernel, dim3(ceil_div(nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, P, dO, dQKV,
+    SCAT_CHECK_CUDA(launch_k(attention_bwd_mma_kernel, dim3(ceil_div(2 * nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, P, dO, dQKV,
                              nprob, heads, out_mode, act_batch));
     SCAT_CHECK_LAUNCH();
     return 0;

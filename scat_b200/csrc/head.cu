@@ -41,9 +41,12 @@ int g_prio_low = 0, g_prio_high = 0;
 static void init_priorities() {
     static std::once_flag once;
     std::call_once(once, [] {
+        // Opt-in (SCAT_PRIORITIES=1).  Measured on B200 (profiles/README.md): with the critical chain at the highest and the
+        // side stream at the lowest launch priority the step gets SLOWER (0.785 -> 0.817 ms): the side stream starves (its
+        // first kernel stretched from ~10 to 100 us), falls behind, and the step ends with ~100 us of side-stream tail
         const char* e = getenv("SCAT_PRIORITIES");
         int least = 0, greatest = 0;
-        if (!(e && e[0] == '0') && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) {
+        if (e && e[0] == '1' && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) {
             g_prio_low = least;
             g_prio_high = greatest;
         }
@@ -94,8 +97,10 @@ int launch_gemm_exact(const GemmArgs& g, int head_precision, cudaStream_t stream
 // call, so re-recording a ring slot later cannot disturb an earlier wait.
 // ---------------------------------------------------------------------------------------------
 struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t ev[32];
+    cudaStream_t s = nullptr;      // weight-gradient GEMMs, weight copies, regressor gradients
+    cudaStream_t s2 = nullptr;     // the small reductions (bias column sums, LayerNorm parameter gradients): they fill a few SMs
+                                   // each, so they overlap the GEMMs of `s` instead of queueing behind them
+    cudaEvent_t ev[64];
     int next = 0;
     bool ready = false;
     std::mutex mu;
@@ -114,7 +119,8 @@ static SideStream* get_side() {
     std::lock_guard<std::mutex> lock(g_side_create);
     if (!sd.ready) {
         if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (int i = 0; i < 32; ++i)
+        if (cudaStreamCreateWithFlags(&sd.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 64; ++i)
             if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         sd.ready = true;
     }
@@ -138,10 +144,17 @@ struct SideScope {
 static int order_after(SideStream* sd, cudaStream_t from, cudaStream_t to) {
     if (sd == nullptr || from == to) return 0;
     cudaEvent_t e = sd->ev[sd->next];
-    sd->next = (sd->next + 1) % 32;
+    sd->next = (sd->next + 1) % 64;
     SCAT_CHECK_CUDA(cudaEventRecord(e, from));
     SCAT_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
     return 0;
+}
+
+// join both side streams into `to`
+static int join_side(SideStream* sd, cudaStream_t to) {
+    if (sd == nullptr) return 0;
+    SCAT_PROPAGATE(order_after(sd, sd->s, to));
+    return order_after(sd, sd->s2, to);
 }
 
 // split form: mark a point on `from` now, make `to` wait for it later
@@ -149,7 +162,7 @@ static int side_mark(SideStream* sd, cudaStream_t from, cudaEvent_t* out) {
     *out = nullptr;
     if (sd == nullptr) return 0;
     cudaEvent_t e = sd->ev[sd->next];
-    sd->next = (sd->next + 1) % 32;
+    sd->next = (sd->next + 1) % 64;
     SCAT_CHECK_CUDA(cudaEventRecord(e, from));
     *out = e;
     return 0;
@@ -517,6 +530,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
     // Layer l works in cotangent set l & 1, so the side stream may lag a whole layer behind the critical chain: the main
     // stream only waits (at the top of layer l) for the side work of layer l + 2, whose buffers it is about to overwrite
     const cudaStream_t sg = (sd != nullptr && G != nullptr) ? sd->s : st;
+    const cudaStream_t sb = (sd != nullptr && G != nullptr) ? sd->s2 : st;     // column sums, LayerNorm parameter gradients
     const int M = p.M;
     const int MR = M * sweeps;                       // rows of every cotangent tensor
     const int amod = sweeps > 1 ? M : 0;             // activation row = cotangent row % M
@@ -552,8 +566,10 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
-            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, sg));
-            SCAT_PROPAGATE(side_mark(sd, sg, &dy_read[l]));        // dY (the other set's dX) has been consumed on the side stream
+            SCAT_PROPAGATE(order_after(sd, st, sb));
+            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, sb));
+            SCAT_PROPAGATE(order_after(sd, sb, sg));
+            SCAT_PROPAGATE(side_mark(sd, sg, &dy_read[l]));        // dY (the other set's dX) has been consumed on the side streams
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
@@ -573,7 +589,8 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.last ? L.d : ld_na; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
-            SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, sg, ffbf));
+            SCAT_PROPAGATE(order_after(sd, st, sb));
+            SCAT_PROPAGATE(launch_colsum(dZ, ld_h, M, L.hid, G[L.p_fc1_b], 1, sb, ffbf));
         }
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs)
         g = GemmArgs();
@@ -601,14 +618,15 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (G) {
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1); and the feed-forward LayerNorm's d gamma / d beta (reads dNf)
             SCAT_PROPAGATE(order_after(sd, st, sg));
+            SCAT_PROPAGATE(order_after(sd, st, sb));
             if (!L.last)
                 SCAT_PROPAGATE(launch_layernorm_param_grads(ws + c.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
-                                                            G[L.p_nf_w], G[L.p_nf_b], M, L.d, sg));
+                                                            G[L.p_nf_w], G[L.p_nf_b], M, L.d, sb));
             g = GemmArgs();
             g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, sg));
-            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, sg));
+            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, sb));
         }
         // dO = dX1 Wo
         g = GemmArgs();
@@ -641,10 +659,11 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
                                             (feeds_gemm && bf) ? ws + c.dX16 : nullptr, ld_n));
         if (G) {
             // its parameter gradients read dNa and the saved X: side stream, joined two layers later or by the caller
-            SCAT_PROPAGATE(order_after(sd, st, sg));
+            SCAT_PROPAGATE(order_after(sd, st, sb));
             SCAT_PROPAGATE(launch_layernorm_param_grads(dNa, L.d, X, L.d, ws + L.mean_a, ws + L.rstd_a, G[L.p_na_w], G[L.p_na_b],
-                                                        M, L.d, sg));
-            SCAT_PROPAGATE(side_mark(sd, sg, &layer_done[l]));     // everything of layer l on the side stream is queued
+                                                        M, L.d, sb));
+            SCAT_PROPAGATE(order_after(sd, sb, sg));
+            SCAT_PROPAGATE(side_mark(sd, sg, &layer_done[l]));     // everything of layer l on the side streams is queued
         }
         dY = ws + c.dX;
         dYg = bf ? ws + c.dX16 : dY;
@@ -797,7 +816,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
                                         l_first, l_last));
     // the side stream still carries the last layer's LayerNorm parameter gradients: a phase joins them before it returns
     // (its part of the gradient bucket is final then); the single call joins at the very end, behind the conv passes
-    if (phase == 0) return order_after(sd, sg, st);
+    if (phase == 0) return join_side(sd, st);
     // through masking / positional encoding into the conv output.  Tensor-core precisions without an external
     // feat_visual cotangent: masking, d mask_token and the split operand of the conv passes are ONE pass (phase 2)
     const bool fused_prep = d.precision != PREC_FP32 && g_fv == nullptr;
@@ -813,7 +832,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     if (phase == 1 && fused_prep)    // phased issue: the mask-token gradient belongs to the part of the bucket phase 1 completes
         SCAT_PROPAGATE(launch_conv_bwd_prep(ws + p.dX, mask_idx, d.n_masked, ws + p.dFv2, G[P_MASK_TOKEN], p.B, p.T, p.D,
                                             d.x2_dtype, st));
-    if (phase == 1) return order_after(sd, sg, st);
+    if (phase == 1) return join_side(sd, st);
     }
     if (d.precision != PREC_FP32) {
         if (g_fv != nullptr)          // dFv = masked dX + external cotangent was formed above: split it (nothing left to mask)
@@ -830,7 +849,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
             SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], (float*)x2_grad, p.B, p.C, p.D, p.T, st));
         SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, (const float*)x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
     }
-    return order_after(sd, sg, st);
+    return join_side(sd, st);
 }
 
 }  // namespace
