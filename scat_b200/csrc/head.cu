@@ -566,8 +566,12 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
-            SCAT_PROPAGATE(order_after(sd, st, sb));
-            SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, sb));
+            // db2: layer l + 1's attention-LayerNorm parameter kernel summed its dX (= this dY) already, unless this call
+            // starts here
+            if (l == l_first) {
+                SCAT_PROPAGATE(order_after(sd, st, sb));
+                SCAT_PROPAGATE(launch_colsum(dY, L.out, M, L.out, G[L.p_fc2_b], 1, sb));
+            }
             SCAT_PROPAGATE(order_after(sd, sb, sg));
             SCAT_PROPAGATE(side_mark(sd, sg, &dy_read[l]));        // dY (the other set's dX) has been consumed on the side streams
         }
@@ -619,14 +623,14 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dWo[d,inner] = dX1^T O ; dbo = colsum(dX1); and the feed-forward LayerNorm's d gamma / d beta (reads dNf)
             SCAT_PROPAGATE(order_after(sd, st, sg));
             SCAT_PROPAGATE(order_after(sd, st, sb));
-            if (!L.last)
+            if (!L.last)     // ... with dbo = colsum(dX1) riding along
                 SCAT_PROPAGATE(launch_layernorm_param_grads(ws + c.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
-                                                            G[L.p_nf_w], G[L.p_nf_b], M, L.d, sb));
+                                                            G[L.p_nf_w], G[L.p_nf_b], M, L.d, sb, dX1, L.d, G[L.p_out_b]));
             g = GemmArgs();
             g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, sg));
-            SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, sb));
+            if (L.last) SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, sb));
         }
         // dO = dX1 Wo
         g = GemmArgs();
@@ -660,8 +664,11 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (G) {
             // its parameter gradients read dNa and the saved X: side stream, joined two layers later or by the caller
             SCAT_PROPAGATE(order_after(sd, st, sb));
+            // (and, when layer l - 1 follows in this call, its db2 = colsum of the dX just written)
+            const bool fuse_db2 = l > l_last;
             SCAT_PROPAGATE(launch_layernorm_param_grads(dNa, L.d, X, L.d, ws + L.mean_a, ws + L.rstd_a, G[L.p_na_w], G[L.p_na_b],
-                                                        M, L.d, sb));
+                                                        M, L.d, sb, fuse_db2 ? ws + c.dX : nullptr, L.d,
+                                                        fuse_db2 ? G[p.L[l - 1].p_fc2_b] : nullptr));
             SCAT_PROPAGATE(order_after(sd, sb, sg));
             SCAT_PROPAGATE(side_mark(sd, sg, &layer_done[l]));     // everything of layer l on the side streams is queued
         }

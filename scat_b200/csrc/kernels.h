@@ -130,8 +130,10 @@ int launch_layernorm_bwd(const float* dY, int lddy, const float* X, int ldx, con
                          void* dX16 = nullptr, int lddx16 = 0);   // dX16: optional bf16 shadow copy of dX
 // the parameter gradients alone, as column sums (dgamma / dbeta zero on entry): what the head runs on its side stream
 // next to launch_layernorm_bwd(..., dgamma = dbeta = nullptr, ...) on the critical path
+// E / esum (optional): a same-shaped [M, D] tensor whose column sums (a Linear bias gradient) accumulate into esum
 int launch_layernorm_param_grads(const float* dY, int lddy, const float* X, int ldx, const float* mean, const float* rstd,
-                                 float* dgamma, float* dbeta, int M, int D, cudaStream_t stream);
+                                 float* dgamma, float* dbeta, int M, int D, cudaStream_t stream, const float* E = nullptr,
+                                 int lde = 0, float* esum = nullptr);
 // act_rows > 0: dY/dX/resid have M rows, the saved activations (X, mean, rstd) have act_rows rows and row m uses
 // activation row m % act_rows; dgamma/dbeta only accumulate rows m < act_rows (the real cotangent)
 

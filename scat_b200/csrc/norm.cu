@@ -145,41 +145,56 @@ constexpr int PG_SLICES = 12;
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_param_grad_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ X, int ldx,
                             const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
-                            float* __restrict__ dbeta, int M, int D) {
+                            float* __restrict__ dbeta, int M, int D, const float* __restrict__ E, int lde,
+                            float* __restrict__ esum) {
     pdl_sync();
-    __shared__ float red[2][LN_WARPS][32];
+    __shared__ float red[3][LN_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     const int rows_per = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-    float dg = 0.f, db = 0.f;
+    float dg = 0.f, db = 0.f, de = 0.f;
     if (c < D) {
+        if (E != nullptr) {        // a bias gradient riding along: esum[c] += sum_m E[m,c]
 #pragma unroll 4
-        for (int r = r0 + warp; r < r1; r += LN_WARPS) {
-            const float dv = __ldg(dY + (long long)r * lddy + c);
-            const float xh = (__ldg(X + (long long)r * ldx + c) - __ldg(mean + r)) * __ldg(rstd + r);
-            dg = fmaf(dv, xh, dg);
-            db += dv;
+            for (int r = r0 + warp; r < r1; r += LN_WARPS) {
+                const float dv = __ldg(dY + (long long)r * lddy + c);
+                const float xh = (__ldg(X + (long long)r * ldx + c) - __ldg(mean + r)) * __ldg(rstd + r);
+                dg = fmaf(dv, xh, dg);
+                db += dv;
+                de += __ldg(E + (long long)r * lde + c);
+            }
+        } else {
+#pragma unroll 4
+            for (int r = r0 + warp; r < r1; r += LN_WARPS) {
+                const float dv = __ldg(dY + (long long)r * lddy + c);
+                const float xh = (__ldg(X + (long long)r * ldx + c) - __ldg(mean + r)) * __ldg(rstd + r);
+                dg = fmaf(dv, xh, dg);
+                db += dv;
+            }
         }
     }
     red[0][warp][lane] = dg;
     red[1][warp][lane] = db;
+    red[2][warp][lane] = de;
     __syncthreads();
-    if (warp < 2 && c < D) {
+    if (warp < (E != nullptr ? 3 : 2) && c < D) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < LN_WARPS; ++w) s += red[warp][w][lane];
-        atomicAdd((warp == 0 ? dgamma : dbeta) + c, s);
+        atomicAdd((warp == 0 ? dgamma : warp == 1 ? dbeta : esum) + c, s);
     }
 }
 
 }  // namespace
 
 int launch_layernorm_param_grads(const float* dY, int lddy, const float* X, int ldx, const float* mean, const float* rstd,
-                                 float* dgamma, float* dbeta, int M, int D, cudaStream_t stream) {
+                                 float* dgamma, float* dbeta, int M, int D, cudaStream_t stream, const float* E, int lde,
+                                 float* esum) {
     SCAT_REQUIRE(dY && X && mean && rstd && dgamma && dbeta && M > 0 && D > 0, kErrBadArg, "layernorm param grads: bad args");
+    SCAT_REQUIRE((E == nullptr) == (esum == nullptr), kErrBadArg, "layernorm param grads: E and esum go together");
     SCAT_CHECK_CUDA(launch_k(layernorm_param_grad_kernel, dim3(ceil_div(D, 32), min(PG_SLICES, ceil_div(M, 64))), dim3(LN_WARPS * 32), 0,
-                             stream, dY, lddy, X, ldx, mean, rstd, dgamma, dbeta, M, D));
+                             stream, dY, lddy, X, ldx, mean, rstd, dgamma, dbeta, M, D, E, lde, esum));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
