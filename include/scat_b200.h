@@ -147,6 +147,23 @@ int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* par
                                float* const* grads, void* x2_grad, float* main_feat_grad, void* workspace,
                                size_t workspace_bytes, void* stream, int32_t phase);
 
+/* The single-call step with a gradients-ready hook, for data-parallel callers that hide their gradient exchange under the
+ * backward without cutting the step into phases.  `ready(user, part, side_stream)` is called on the host, while the step
+ * is being ENQUEUED (also under stream capture), three times and in this order:
+ *   part 0: parameters 13..34 (transformer layers 1, 2 and the regressor) are final in the order of `side_stream`;
+ *   part 1: parameters 2..12 (transformer layer 0);
+ *   part 2: parameters 0, 1 (mask token, conv weight) -- the conv data gradient (x2_grad) is still to come.
+ * Work the hook enqueues on `side_stream` (a library-owned stream, the same for the three calls, so the hook's launches
+ * are serialised among themselves) runs beside the rest of the step; `stream` waits for it before the call returns, so
+ * the step stays one capturable unit.  A non-zero return from the hook fails the call.  ready == NULL: scat_head_train_step. */
+typedef int (*scat_grads_ready_fn)(void* user, int32_t part, void* side_stream);
+int scat_head_train_step_hooked(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                                const float* mean_params, const int32_t* mask_idx, const void* x2, const float* main_feat,
+                                const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d,
+                                float grad_scale, float* pred_params, float* feat_visual, float* pl_term, float* losses,
+                                float* const* grads, void* x2_grad, float* main_feat_grad, void* workspace,
+                                size_t workspace_bytes, scat_grads_ready_fn ready, void* ready_user, void* stream);
+
 /* ---- data-parallel gradient exchange over NVLink peer memory (the reference imports
  * DistributedDataParallel at train.py:18 and never uses it, so this has no reference counterpart to replace) ----
  * One process per GPU.  Each rank allocates its gradient bucket and a signal area with scat_peer_alloc, exports both

@@ -45,6 +45,8 @@ SIGNATURES = {
                                     _f, _f, _f, _sz, _f]),
     "scat_head_train_step_phase": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _i32, _fl, _fl, _fl, _f, _f, _f, _f, _pp,
                                           _f, _f, _f, _sz, _f, _i32]),
+    "scat_head_train_step_hooked": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _i32, _fl, _fl, _fl, _f, _f, _f, _f, _pp,
+                                           _f, _f, _f, _sz, C.c_void_p, C.c_void_p, _f]),
     "scat_adam_step": (_i32, [_f, _f, _f, _f, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                              _i32, _f, _f, _f, _f]),
     "scat_eval_procrustes": (_i32, [_f, _f, _i32, _i32, _f, _f, _f]),
@@ -90,6 +92,10 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+# int (*scat_grads_ready_fn)(void* user, int32_t part, void* side_stream)  (include/scat_b200.h)
+GRADS_READY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p)
 
 
 def load():

@@ -64,6 +64,7 @@ struct TcParams {
     int accumulate;
     int round_out;                  // 1: store C rounded to TF32-nearest (it feeds another tensor-core GEMM)
     int round_operands;             // 1: round fp32 operands to TF32 (nearest) in shared memory before the MMA
+    int stages;                     // depth of the operand ring (SmemLayout::STAGES or STAGES_DEEP)
     int kb_per_split;               // k-blocks per gridDim.z slice (split-K: weight gradients, K = B*21 rows)
     int atomic_out;                 // 1: C += tile with red.global.add (split-K slices combine in L2; C pre-zeroed)
     // batched launches (blockIdx.z = batch index instead of a split-K slice): per-batch TMA coordinate offsets of the
@@ -83,14 +84,19 @@ __device__ __forceinline__ void dbg_mark(const TcParams& p, int slot) {
 
 template <int BN>
 struct SmemLayout {
-    static constexpr int STAGES = BN >= 128 ? 3 : 4;      // 96 KB ring per CTA, two CTAs per SM
+    // ring depth is a launch parameter: 96 KB per CTA (two CTAs per SM) when the launch has more CTAs than SMs, 192 KB
+    // when every CTA has an SM to itself -- one CTA's fill rate is ring bytes / TMA latency (profiles/r1_gemm_timeline.txt:
+    // 96 KB in flight sustain ~52 B/cycle), so a lone CTA needs the deeper ring to keep its tensor core fed
+    static constexpr int STAGES = BN >= 128 ? 3 : 4;
+    static constexpr int STAGES_DEEP = 2 * STAGES;
     static constexpr int A_BYTES = BM * 128;              // 16 KB
     static constexpr int B_BYTES = BN * 128;              // 8 / 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int SCRATCH_OFF = BAR_OFF + 256;     // persistent CTAs: 4 warps x 32x32 floats of epilogue scratch
-    static constexpr int TOTAL = BAR_OFF + 256;           // barriers + tmem slot
-    static constexpr int TOTAL_PERSISTENT = SCRATCH_OFF + 4 * 32 * 32 * 4;
+    static constexpr int BAR_BYTES = 512;                 // 3 x 8 stage barriers + 4 accumulator barriers + tmem slot
+    static constexpr int bar_off(int stages) { return stages * STAGE_BYTES; }
+    static constexpr int total(int stages, bool persistent) {       // persistent CTAs: + 4 warps x 32x32 floats of epilogue scratch
+        return bar_off(stages) + BAR_BYTES + (persistent ? 4 * 32 * 32 * 4 : 0);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -319,18 +325,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using L = SmemLayout<BN>;
     using E = Elem<BF16>;
-    constexpr int STAGES = L::STAGES;
+    const int STAGES = p.stages;
     constexpr int BK = E::BK;
     // no static shared memory in this kernel: the dynamic window starts at the CTA's shared base, which is 1024-byte
     // aligned (128B swizzle atoms need it); checked below rather than paid for with a kilobyte of slack
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full_bar = smem_base + L::BAR_OFF;          // STAGES x 8 B each
+    const int bar_off = STAGES * L::STAGE_BYTES;
+    const uint32_t full_bar = smem_base + bar_off;             // STAGES x 8 B each
     const uint32_t empty_bar = full_bar + 8 * STAGES;
     const uint32_t conv_bar = empty_bar + 8 * STAGES;
     const uint32_t tfull_bar = conv_bar + 8 * STAGES;          // 2: accumulator buffer complete (MMA -> epilogue)
     const uint32_t tempty_bar = tfull_bar + 16;                // 2: accumulator buffer drained (epilogue -> MMA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (3 * STAGES + 4));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) dbg_mark(p, 0);
@@ -359,7 +366,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the preceding kernel): the first bulk load otherwise pays the descriptor miss on top of the L2 latency
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-#pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar + 8 * s, 1);
             mbar_init(empty_bar + 8 * s, 1);
@@ -473,7 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                      // a warp may only touch TMEM lanes [32*(warp%4), +32)
         // transposition scratch of the epilogue: the idle operand ring when this CTA owns a single tile, a dedicated
         // region behind the barriers when it is persistent (the ring is then busy with the next tile)
-        float* scratch = reinterpret_cast<float*>(smem + (persistent ? L::SCRATCH_OFF : 0)) + q * 32 * 32;
+        float* scratch = reinterpret_cast<float*>(smem + (persistent ? bar_off + L::BAR_BYTES : 0)) + q * 32 * 32;
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
@@ -524,6 +530,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 long long* g_gemm_dbg = nullptr;
+// A/B switch for the measurement in DESIGN.md: SCAT_GEMM_SHALLOW=1 keeps the 96 KB ring on every launch
+const bool g_shallow_ring = [] { const char* e = getenv("SCAT_GEMM_SHALLOW"); return e != nullptr && e[0] == '1'; }();
 
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps
@@ -542,7 +550,7 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     using E = Elem<BF16>;
     auto kern = gemm_tc_kernel<BF16, BN, A_MN, B_MN>;
-    SCAT_ENSURE_SMEM(kern, L::TOTAL_PERSISTENT);
+    SCAT_ENSURE_SMEM(kern, L::total(L::STAGES_DEEP, false));
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle mn_sw = BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     // extents of the tensor maps: one problem, or (batched) the whole stack of problems along rows / k
@@ -588,9 +596,10 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     constexpr int kSlots = 2 * 148;
     p.persistent = total_tiles > kSlots ? 1 : 0;
     if (p.persistent) grid = dim3(kSlots, 1, 1);
+    p.stages = (total_tiles <= 148 && !g_shallow_ring) ? L::STAGES_DEEP : L::STAGES;
     if (p.atomic_out && !g.accumulate && !g.c_zeroed)
         SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
-    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(TC_THREADS), p.persistent ? L::TOTAL_PERSISTENT : L::TOTAL, stream, tmA, tmB, p));
+    SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(TC_THREADS), L::total(p.stages, p.persistent != 0), stream, tmA, tmB, p));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -100,6 +100,7 @@ struct SideStream {
     cudaStream_t s = nullptr;      // weight-gradient GEMMs, weight copies, regressor gradients
     cudaStream_t s2 = nullptr;     // the small reductions (bias column sums, LayerNorm parameter gradients): they fill a few SMs
                                    // each, so they overlap the GEMMs of `s` instead of queueing behind them
+    cudaStream_t sx = nullptr;     // what a caller's gradients-ready hook enqueues (the data-parallel exchange)
     cudaEvent_t ev[64];
     int next = 0;
     bool ready = false;
@@ -120,6 +121,7 @@ static SideStream* get_side() {
     if (!sd.ready) {
         if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&sd.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&sd.sx, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (int i = 0; i < 64; ++i)
             if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         sd.ready = true;
@@ -155,6 +157,25 @@ static int join_side(SideStream* sd, cudaStream_t to) {
     if (sd == nullptr) return 0;
     SCAT_PROPAGATE(order_after(sd, sd->s, to));
     return order_after(sd, sd->s2, to);
+}
+
+// The caller's gradients-ready hook (scat_head_train_step_hooked): called on the host while the step is being enqueued,
+// once per part of the gradient list, with a stream that is ordered after everything that writes that part.  What it
+// enqueues there (a gradient exchange) runs beside the rest of the step; the step's end waits for it.
+struct GradHook {
+    scat_grads_ready_fn fn = nullptr;
+    void* user = nullptr;
+    bool used = false;
+};
+// `from`: the stream on which the part's last writer was enqueued (or that already waits for all of them)
+static int fire_hook(GradHook* h, SideStream* sd, cudaStream_t from, int part) {
+    if (h == nullptr || h->fn == nullptr) return 0;
+    const cudaStream_t sx = sd ? sd->sx : from;
+    SCAT_PROPAGATE(order_after(sd, from, sx));
+    h->used = true;
+    const int rc = h->fn(h->user, part, (void*)sx);
+    SCAT_REQUIRE(rc == 0, kErrBadArg, "train_step: the gradients-ready hook failed for part %d (rc=%d)", part, rc);
+    return 0;
 }
 
 // split form: mark a point on `from` now, make `to` wait for it later
@@ -525,7 +546,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
 // only see the first M rows.
 int transformer_backward(const HeadPlan& p, const float* const* W, float* const* G /* null = dgrad only */, float* ws,
                          int prec, const float* up, cudaStream_t st, const float* X0_override, int sweeps = 1,
-                         SideStream* sd = nullptr, int l_first = kDepth - 1, int l_last = 0) {
+                         SideStream* sd = nullptr, int l_first = kDepth - 1, int l_last = 0, GradHook* hook = nullptr) {
     // parameter gradients run on the side stream `sg` (== st without one): each group is forked once its inputs exist.
     // Layer l works in cotangent set l & 1, so the side stream may lag a whole layer behind the critical chain: the main
     // stream only waits (at the top of layer l) for the side work of layer l + 2, whose buffers it is about to overwrite
@@ -671,6 +692,9 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
                                                         fuse_db2 ? G[p.L[l - 1].p_fc2_b] : nullptr));
             SCAT_PROPAGATE(order_after(sd, sb, sg));
             SCAT_PROPAGATE(side_mark(sd, sg, &layer_done[l]));     // everything of layer l on the side streams is queued
+            // `sg` now follows every writer of the gradients of layers >= l (and of the regressor, queued on it before):
+            // layers 1.. are part 0 of the hook, layer 0 is part 1
+            if (l == 1 || l == 0) SCAT_PROPAGATE(fire_hook(hook, sd, sg, l == 1 ? 0 : 1));
         }
         dY = ws + c.dX;
         dYg = bf ? ws + c.dX16 : dY;
@@ -768,7 +792,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
                   float* mf_grad, void* workspace, size_t ws_bytes, cudaStream_t st, const float* fv_alias,
                   float* pl_out = nullptr /* non-null: also sweep the path-length cotangent (stacked) into pl_out */,
                   int phase = -1 /* -1: everything; 0: down to transformer layer 1; 1: layer 0 and masking; 2: conv */,
-                  const TrainTail* tail = nullptr) {
+                  const TrainTail* tail = nullptr, GradHook* hook = nullptr) {
     HeadPlan p;
     SCAT_PROPAGATE(make_plan(d, p));
     SCAT_PROPAGATE(check_ws(p, workspace, ws_bytes));
@@ -820,7 +844,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     if (phase != 2) {
     const int l_first = phase == 1 ? 0 : kDepth - 1, l_last = phase == 0 ? 1 : 0;
     SCAT_PROPAGATE(transformer_backward(p, W, G, ws, d.precision, up, st, d.pos_embed ? nullptr : fv_alias, sweeps, sd,
-                                        l_first, l_last));
+                                        l_first, l_last, hook));
     // the side stream still carries the last layer's LayerNorm parameter gradients: a phase joins them before it returns
     // (its part of the gradient bucket is final then); the single call joins at the very end, behind the conv passes
     if (phase == 0) return join_side(sd, st);
@@ -849,13 +873,16 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
                                                 d.x2_dtype, st));
         // two persistent one-CTA-per-SM streams (x2 in, x2.grad out): back to back on the main stream
         SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, d.x2_dtype, G[P_CONV_W], p.B, p.C, p.D, p.T, st));   // G was zeroed above
+        SCAT_PROPAGATE(fire_hook(hook, sd, st, 2));      // mask token + conv weight are final: exchanged under the dgrad stream
         if (x2_grad != nullptr)
             SCAT_PROPAGATE(launch_conv_dgrad_tc(ws + p.dFv2, ws + p.w_conv, d.x2_dtype, x2_grad, p.B, p.C, p.D, p.T, st));
     } else {
         if (x2_grad != nullptr)
             SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], (float*)x2_grad, p.B, p.C, p.D, p.T, st));
         SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, (const float*)x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
+        SCAT_PROPAGATE(fire_hook(hook, sd, st, 2));
     }
+    if (hook != nullptr && hook->used && sd != nullptr) SCAT_PROPAGATE(order_after(sd, sd->sx, st));
     return join_side(sd, st);
 }
 
@@ -909,7 +936,7 @@ static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* pa
                                 const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d, float grad_scale,
                                 float* pred_params, float* feat_visual, float* pl_term, float* losses, float* const* grads,
                                 void* x2_grad, float* main_feat_grad, void* workspace, size_t workspace_bytes, void* stream,
-                                int phase) {
+                                int phase, GradHook* hook = nullptr) {
     SCAT_REQUIRE(desc, kErrBadArg, "desc is null");
     SCAT_REQUIRE(phase >= -1 && phase <= 2, kErrBadArg, "train_step: phase %d", phase);
     cudaStream_t st = (cudaStream_t)stream;
@@ -932,7 +959,7 @@ static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* pa
     }
     SCAT_PROPAGATE(head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
                                  main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr, phase,
-                                 fused_tail ? &tail : nullptr));
+                                 fused_tail ? &tail : nullptr, hook));
     if (pl && (phase == -1 || phase == 1))       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
         SCAT_PROPAGATE(launch_pl_loss_add(pl_term, p.T * p.D, p.T, losses, ws + p.pl_scratch, p.B, st));
     return 0;
@@ -957,6 +984,19 @@ int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* par
     return head_train_step_impl(desc, params, pe, mean_params, mask_idx, x2, main_feat, labels, ld_labels, l_weight_3d,
                                 l_weight_2d, grad_scale, pred_params, feat_visual, pl_term, losses, grads, x2_grad,
                                 main_feat_grad, workspace, workspace_bytes, stream, phase);
+}
+
+int scat_head_train_step_hooked(const ScatHeadDesc* desc, const float* const* params, const float* pe,
+                                const float* mean_params, const int32_t* mask_idx, const void* x2, const float* main_feat,
+                                const float* labels, int32_t ld_labels, float l_weight_3d, float l_weight_2d,
+                                float grad_scale, float* pred_params, float* feat_visual, float* pl_term, float* losses,
+                                float* const* grads, void* x2_grad, float* main_feat_grad, void* workspace,
+                                size_t workspace_bytes, scat_grads_ready_fn ready, void* ready_user, void* stream) {
+    GradHook hook;
+    hook.fn = ready; hook.user = ready_user;
+    return head_train_step_impl(desc, params, pe, mean_params, mask_idx, x2, main_feat, labels, ld_labels, l_weight_3d,
+                                l_weight_2d, grad_scale, pred_params, feat_visual, pl_term, losses, grads, x2_grad,
+                                main_feat_grad, workspace, workspace_bytes, stream, -1, ready ? &hook : nullptr);
 }
 
 int scat_tokens_forward(const ScatHeadDesc* desc, const float* const* params, const float* pe, const int32_t* mask_idx,

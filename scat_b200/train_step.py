@@ -121,7 +121,6 @@ class HeadTrainStep:
         # peer-memory exchange hidden under the backward: the step is issued in its three phases inside ONE graph and the
         # part of the bucket each phase completes is summed on a second stream while the next phase computes
         self.overlap_exchange = bool(overlap_exchange) and self.peer is not None
-        self.ar_stream = torch.cuda.Stream(device=dev) if self.overlap_exchange else None
 
     # single-slot views kept for callers that use one buffer set
     @property
@@ -137,13 +136,36 @@ class HeadTrainStep:
         return self.labelss[0]
 
     # ------------------------------------------------------------------------------------------
-    def _enqueue(self, slot: int = 0, phase: int = -1):
+    def _enqueue(self, slot: int = 0, phase: int = -1, ready=None):
         """Enqueue one fused step (or one phase of it) on the current stream (graph-capturable: no allocation, no
-        sync)."""
+        sync).  ``ready(part, stream_ptr)``: the gradients-ready hook of scat_head_train_step_hooked (single call only)."""
         cfg = self.cfg
         d = cfg.desc(self.batch)
         pe = self.net.positionalEncoding.pe[0] if cfg.pos_embed else None
         labels = self.labelss[slot]
+        if ready is not None:
+            if phase != -1:
+                raise ValueError("_enqueue: the gradients-ready hook belongs to the single-call step")
+            failure = []
+
+            def _cb(_user, part, stream):
+                try:
+                    ready(int(part), C.c_void_p(stream))
+                    return 0
+                except Exception as e:               # an exception must not unwind through the C frames
+                    failure.append(e)
+                    return 1
+            cb = _lib.GRADS_READY_FN(_cb)
+            rc = self.lib.scat_head_train_step_hooked(
+                C.byref(d), ptr_array([p.data for p in self.params]), ptr(pe), ptr(self.net.mean_params.reshape(-1)),
+                ptr(self.mask_dev) if self.n_masked else None, ptr(self.x2s[slot]), ptr(self.main_feats[slot]),
+                ptr(labels), labels.shape[1], self.w3d, self.w2d, 1.0 / self.world, ptr(self.pred),
+                ptr(self.feat_visual), ptr(self.pl), ptr(self.losses), ptr_array(self.bucket.views), ptr(self.x2_grad),
+                ptr(self.main_feat_grad), ptr(self.ws), self.ws.numel(), C.cast(cb, C.c_void_p), None, SF.stream_ptr())
+            if failure:
+                raise failure[0]
+            check(rc, "scat_head_train_step_hooked")
+            return
         check(self.lib.scat_head_train_step_phase(
             C.byref(d), ptr_array([p.data for p in self.params]), ptr(pe), ptr(self.net.mean_params.reshape(-1)),
             ptr(self.mask_dev) if self.n_masked else None, ptr(self.x2s[slot]), ptr(self.main_feats[slot]),
@@ -172,22 +194,14 @@ class HeadTrainStep:
 
     def _enqueue_all(self, slot: int, ar: bool, optimize: bool):
         if ar and self.overlap_exchange:
-            # phase 0 leaves the gradients of layers 1, 2 and of the regressor final (bucket[split:], 6 MB): their sum runs
-            # on the exchange stream under the layer-0 backward (phase 1); layer 0 (bucket[split0:split], 9 MB) is summed
-            # under the conv backward (phase 2); only the mask token and the conv weight (bucket[:split0], 46 KB: two
-            # cross-GPU flag barriers and nothing else) are exchanged after the last kernel.  All three exchanges are
-            # launches of the same kernel, in the same order on every rank, serialised among themselves.
-            cur, side = torch.cuda.current_stream(), self.ar_stream
-            side_ptr = C.c_void_p(side.cuda_stream)
-            self._enqueue(slot, 0)
-            side.wait_stream(cur)
-            self.peer.enqueue(side_ptr, lo=self.split, hi=None)
-            self._enqueue(slot, 1)
-            side.wait_stream(cur)
-            self.peer.enqueue(side_ptr, lo=self.split0, hi=self.split)
-            self._enqueue(slot, 2)
-            cur.wait_stream(side)
-            self.peer.enqueue(SF.stream_ptr(), lo=0, hi=self.split0)
+            # The library calls back, while it enqueues the step, each time a part of the bucket is final: layers 1, 2 and
+            # the regressor (bucket[split:], 6 MB) once layer 1's weight gradients are queued -- their sum runs under the
+            # layer-0 backward; layer 0 (bucket[split0:split], 9 MB) -- summed under the conv passes; the mask token and the
+            # conv weight (bucket[:split0], 46 KB: two cross-GPU flag barriers and little else) -- under the conv data
+            # gradient, the last kernel of the step.  The three exchanges are launches of the same kernel on the library's
+            # exchange stream: same order on every rank, serialised among themselves, no phase joins on the main stream.
+            parts = ((self.split, None), (self.split0, self.split), (0, self.split0))
+            self._enqueue(slot, ready=lambda part, stream: self.peer.enqueue(stream, lo=parts[part][0], hi=parts[part][1]))
         else:
             self._enqueue(slot)
             if ar:

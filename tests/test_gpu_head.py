@@ -222,6 +222,62 @@ def test_phased_train_step_equals_single_call(precision):
             assert rel_max(b, a) < 1e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_hooked_train_step_reports_final_gradient_parts(precision):
+    """scat_head_train_step_hooked: the gradients-ready hook fires for parts 0, 1, 2 in order, and what it enqueues on the
+    stream it is handed sees that part of the gradient bucket final (snapshot copies == the bucket after the step); the
+    step itself equals the plain single call.  Eager and captured in a CUDA graph."""
+    from scat_b200.train_step import HeadTrainStep
+    opt, W, net, x2, mf, labels = _config2(precision, B=8)
+    ts = HeadTrainStep(net, 8, use_graph=False)
+    ts.load_inputs(torch.from_numpy(x2).cuda(), torch.from_numpy(mf).cuda(), torch.from_numpy(labels).cuda())
+    ts.set_mask(list(range(ts.n_masked)))
+    ts._enqueue(0)
+    torch.cuda.synchronize()
+    ref = (ts.bucket.flat.clone(), ts.x2_grad.clone(), ts.losses.clone())
+    bounds = ((ts.split, ts.bucket.flat.numel()), (ts.split0, ts.split), (0, ts.split0))
+    snap = torch.zeros_like(ts.bucket.flat)
+    seen = []
+
+    def ready(part, stream):
+        seen.append(part)
+        lo, hi = bounds[part]
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream.value or 0)):
+            snap[lo:hi].copy_(ts.bucket.flat[lo:hi])
+
+    def check():
+        torch.cuda.synchronize()
+        assert seen == [0, 1, 2]
+        for a, b in zip(ref, (ts.bucket.flat, ts.x2_grad, ts.losses)):
+            assert rel_max(b, a) < 1e-5
+        for lo, hi in bounds:
+            assert rel_max(snap[lo:hi], ts.bucket.flat[lo:hi]) < 1e-5 and snap[lo:hi].abs().max() > 0
+        seen.clear(); snap.zero_()
+
+    ts._enqueue(0, ready=ready)
+    check()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ts._enqueue(0, ready=ready)
+    assert seen == [0, 1, 2]                      # the hook runs at capture time
+    ts.bucket.flat.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(ref, (ts.bucket.flat, ts.x2_grad, ts.losses)):
+        assert rel_max(b, a) < 1e-5
+    for lo, hi in bounds:
+        assert rel_max(snap[lo:hi], ts.bucket.flat[lo:hi]) < 1e-5
+
+    def failing(part, stream):
+        raise KeyError("boom")
+    with pytest.raises(KeyError):
+        ts._enqueue(0, ready=failing)
+    torch.cuda.synchronize()
+
+
 def test_full_size_properties_tf32():
     """Size-independent checks at config-2 size on the default (TF32) path."""
     opt, W, net, x2, mf, labels = _config2("tf32")
