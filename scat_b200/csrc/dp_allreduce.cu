@@ -19,8 +19,14 @@ namespace scat {
 namespace {
 
 constexpr int kMaxPeers = 8;
-constexpr int kMaxBlocks = 296;                 // 2 per SM
-constexpr int kThreads = 512;
+constexpr int kMaxBlocks = 296;                 // size of the per-block flag arrays in the signal area
+// The exchange runs BESIDE the backward's kernels (HeadTrainStep hides it there), so it has to fit next to them: one
+// 256-thread block per SM is 16 K of the SM's 64 K registers.  Round 2 measured the first form (two 512-thread blocks per
+// SM = the whole register file): the persistent conv kernels could not get their SMs until the exchange had left
+// (conv wgrad 22 -> 46 us, profiles/r2_exchange_probe.txt).  148 x 256 threads x 4 x 16 B = 2.4 MB of loads in flight
+// is still several NVLink round trips' worth.
+constexpr int kLaunchBlocks = 148;
+constexpr int kThreads = 256;
 // signal area (uint32 words): flags[kMaxBlocks][kMaxPeers], epoch[kMaxBlocks], error
 constexpr int kSigFlags = 0;
 constexpr int kSigEpoch = kMaxBlocks * kMaxPeers;
@@ -135,7 +141,8 @@ template <int W>
 int launch_w(const PeerSet& ps, int rank, long long lo4, long long n4, cudaStream_t st) {
     constexpr int U = W >= 8 ? 1 : (W == 4 ? 2 : 4);        // as in the kernel
     const long long per = (n4 + W - 1) / W, per_block = (long long)kThreads * U;
-    const int grid = (int)std::min<long long>(kMaxBlocks, std::max<long long>(1, (per + per_block - 1) / per_block));
+    static_assert(kLaunchBlocks <= kMaxBlocks, "flag arrays");
+    const int grid = (int)std::min<long long>(kLaunchBlocks, std::max<long long>(1, (per + per_block - 1) / per_block));
     SCAT_CHECK_CUDA(launch_k(peer_allreduce_kernel<W>, dim3(grid), dim3(kThreads), 0, st, ps, rank, lo4, n4));
     SCAT_CHECK_LAUNCH();
     return 0;
