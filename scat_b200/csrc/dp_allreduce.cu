@@ -20,12 +20,15 @@ namespace {
 
 constexpr int kMaxPeers = 8;
 constexpr int kMaxBlocks = 296;                 // size of the per-block flag arrays in the signal area
-// The exchange runs BESIDE the backward's kernels (HeadTrainStep hides it there), so it has to fit next to them: one
-// 256-thread block per SM is 16 K of the SM's 64 K registers.  Round 2 measured the first form (two 512-thread blocks per
-// SM = the whole register file): the persistent conv kernels could not get their SMs until the exchange had left
-// (conv wgrad 22 -> 46 us, profiles/r2_exchange_probe.txt).  148 x 256 threads x 4 x 16 B = 2.4 MB of loads in flight
-// is still several NVLink round trips' worth.
-constexpr int kLaunchBlocks = 148;
+// The exchange runs BESIDE the backward's kernels (HeadTrainStep hides it there), so it has to fit next to them.  A
+// tensor-core GEMM CTA holds 32 K of an SM's 64 K registers (two CTAs per SM), a persistent conv CTA 41 K: wherever a
+// block of this kernel sits, one GEMM CTA does not fit until it leaves -- and it spends most of its life waiting for NVLink
+// round trips and for the peers.  Measured at 2 GPUs (profiles/r2_exchange_probe.txt): 296 x 512 threads (round 1, the
+// whole register file of every SM) made conv wgrad 22 -> 46 us and the GEMM beside it 18 -> 35 us; 148 x 256 still
+// touched every SM.  So: few blocks (kLaunchBlocks SMs lose one CTA slot, the rest of the GPU does not notice), 256
+// threads x up to 4 x 16 B of loads in flight each = 1 MB over NVLink, several round trips' worth.
+// SCAT_PEER_BLOCKS overrides the block count (every rank must use the same value).
+constexpr int kLaunchBlocksDefault = 64;
 constexpr int kThreads = 256;
 // signal area (uint32 words): flags[kMaxBlocks][kMaxPeers], epoch[kMaxBlocks], error
 constexpr int kSigFlags = 0;
@@ -141,8 +144,12 @@ template <int W>
 int launch_w(const PeerSet& ps, int rank, long long lo4, long long n4, cudaStream_t st) {
     constexpr int U = W >= 8 ? 1 : (W == 4 ? 2 : 4);        // as in the kernel
     const long long per = (n4 + W - 1) / W, per_block = (long long)kThreads * U;
-    static_assert(kLaunchBlocks <= kMaxBlocks, "flag arrays");
-    const int grid = (int)std::min<long long>(kLaunchBlocks, std::max<long long>(1, (per + per_block - 1) / per_block));
+    static const int launch_blocks = [] {
+        const char* e = getenv("SCAT_PEER_BLOCKS");
+        const int v = e ? atoi(e) : kLaunchBlocksDefault;
+        return std::max(1, std::min(v, kMaxBlocks));
+    }();
+    const int grid = (int)std::min<long long>(launch_blocks, std::max<long long>(1, (per + per_block - 1) / per_block));
     SCAT_CHECK_CUDA(launch_k(peer_allreduce_kernel<W>, dim3(grid), dim3(kThreads), 0, st, ps, rank, lo4, n4));
     SCAT_CHECK_LAUNCH();
     return 0;

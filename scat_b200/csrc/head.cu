@@ -101,7 +101,7 @@ struct SideStream {
     cudaStream_t s2 = nullptr;     // the small reductions (bias column sums, LayerNorm parameter gradients): they fill a few SMs
                                    // each, so they overlap the GEMMs of `s` instead of queueing behind them
     cudaStream_t sx = nullptr;     // what a caller's gradients-ready hook enqueues (the data-parallel exchange)
-    cudaEvent_t ev[64];
+    cudaEvent_t ev[128];
     int next = 0;
     bool ready = false;
     std::mutex mu;
@@ -122,7 +122,7 @@ static SideStream* get_side() {
         if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&sd.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&sd.sx, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (int i = 0; i < 64; ++i)
+        for (int i = 0; i < 128; ++i)
             if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         sd.ready = true;
     }
@@ -146,7 +146,7 @@ struct SideScope {
 static int order_after(SideStream* sd, cudaStream_t from, cudaStream_t to) {
     if (sd == nullptr || from == to) return 0;
     cudaEvent_t e = sd->ev[sd->next];
-    sd->next = (sd->next + 1) % 64;
+    sd->next = (sd->next + 1) % 128;
     SCAT_CHECK_CUDA(cudaEventRecord(e, from));
     SCAT_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
     return 0;
@@ -183,7 +183,7 @@ static int side_mark(SideStream* sd, cudaStream_t from, cudaEvent_t* out) {
     *out = nullptr;
     if (sd == nullptr) return 0;
     cudaEvent_t e = sd->ev[sd->next];
-    sd->next = (sd->next + 1) % 64;
+    sd->next = (sd->next + 1) % 128;
     SCAT_CHECK_CUDA(cudaEventRecord(e, from));
     *out = e;
     return 0;
@@ -804,6 +804,7 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     const cudaStream_t sg = sd ? sd->s : st;
     const int sweeps = pl_out ? 2 : 1;
     float* up = pl_out ? ws + p.up2 : ws + p.dfeat;        // [sweeps*M, 3]: real cotangent first
+    cudaEvent_t loss_done = nullptr;
     if (phase <= 0) {
     // every parameter gradient is accumulated into (split-K / column-sum / LayerNorm reductions): clear them once,
     // on the side stream, which then also carries the regressor weight gradients
@@ -829,8 +830,11 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     {
         SCAT_PROPAGATE(order_after(sd, st, sg));      // gsum / gsteps (and pred) are ready
         if (tail != nullptr)                          // the loss values need a batch reduction: off the critical path
+        {
             SCAT_PROPAGATE(launch_proj_loss(tail->pred, tail->labels, tail->ld_labels, nullptr, p.T * p.D, p.T, tail->w3d,
                                             tail->w2d, tail->grad_scale, tail->losses, nullptr, ws + p.pl_scratch, p.B, sg));
+            SCAT_PROPAGATE(side_mark(sd, sg, &loss_done));
+        }
         // d main_feat = gsum Wr[:, :F] (nothing downstream reads it), dWr[:, :F] = gsum^T main_feat, dWr[:, F:] = sum over
         // samples and steps of g_step (x) state, d br = column sums of gsum: one launch
         SCAT_PROPAGATE(launch_regressor_param_grads(ws + p.gsum, ws + p.gsteps, ws + p.states, main_feat, W[P_REG_W], mf_grad,
@@ -856,6 +860,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
         SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX + (size_t)p.M * p.D, mask_idx, d.n_masked, d.pos_embed ? 0 : 1, pl_out,
                                        nullptr, p.B, p.T, p.D, st));
+    if (pl_out && tail != nullptr) {
+        // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201): two small reductions behind the loss kernel on the
+        // second side stream, under the conv passes instead of after them
+        const cudaStream_t sb = sd ? sd->s2 : st;
+        SCAT_PROPAGATE(order_after(sd, st, sb));
+        SCAT_PROPAGATE(side_wait(sb, loss_done));     // the loss kernel wrote losses[0..2] (and used the same scratch)
+        SCAT_PROPAGATE(launch_pl_loss_add(pl_out, p.T * p.D, p.T, tail->losses, ws + p.pl_scratch, p.B, sb));
+    }
     if (g_fv != nullptr) {
         SCAT_CHECK_CUDA(launch_k(add_inplace_kernel, dim3(148 * 4), dim3(256), 0, st, ws + p.dFv, g_fv, (long long)p.M * p.D));
         SCAT_CHECK_LAUNCH();
@@ -960,7 +972,7 @@ static int head_train_step_impl(const ScatHeadDesc* desc, const float* const* pa
     SCAT_PROPAGATE(head_backward(*desc, params, mask_idx, x2, main_feat, ws + p.g_pred, nullptr, grads, x2_grad,
                                  main_feat_grad, workspace, workspace_bytes, st, feat_visual, pl ? pl_term : nullptr, phase,
                                  fused_tail ? &tail : nullptr, hook));
-    if (pl && (phase == -1 || phase == 1))       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
+    if (pl && !fused_tail && (phase == -1 || phase == 1))       // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201)
         SCAT_PROPAGATE(launch_pl_loss_add(pl_term, p.T * p.D, p.T, losses, ws + p.pl_scratch, p.B, st));
     return 0;
 }
