@@ -25,10 +25,12 @@ constexpr int kMaxBlocks = 296;                 // size of the per-block flag ar
 // block of this kernel sits, one GEMM CTA does not fit until it leaves -- and it spends most of its life waiting for NVLink
 // round trips and for the peers.  Measured at 2 GPUs (profiles/r2_exchange_probe.txt): 296 x 512 threads (round 1, the
 // whole register file of every SM) made conv wgrad 22 -> 46 us and the GEMM beside it 18 -> 35 us; 148 x 256 still
-// touched every SM.  So: few blocks (kLaunchBlocks SMs lose one CTA slot, the rest of the GPU does not notice), 256
-// threads x up to 4 x 16 B of loads in flight each = 1 MB over NVLink, several round trips' worth.
+// touched every SM.  So: few blocks (that many SMs lose one CTA slot, the rest of the GPU does not notice), 256 threads x
+// up to 4 x 16 B of loads in flight each.  Block-count sweep at 2 GPUs, step with the exchange hidden / exposed after the
+// last kernel: 32 blocks 0.796 / 0.840 ms, 64: 0.805 / 0.826, 148: 0.802 / 0.829 (no exchange: 0.775) -- the default serves
+// the hidden form.
 // SCAT_PEER_BLOCKS overrides the block count (every rank must use the same value).
-constexpr int kLaunchBlocksDefault = 64;
+constexpr int kLaunchBlocksDefault = 32;
 constexpr int kThreads = 256;
 // signal area (uint32 words): flags[kMaxBlocks][kMaxPeers], epoch[kMaxBlocks], error
 constexpr int kSigFlags = 0;
