@@ -65,6 +65,7 @@ struct TcParams {
     int round_out;                  // 1: store C rounded to TF32-nearest (it feeds another tensor-core GEMM)
     int round_operands;             // 1: round fp32 operands to TF32 (nearest) in shared memory before the MMA
     int stages;                     // depth of the operand ring (SmemLayout::STAGES or STAGES_DEEP)
+    int b_static;                   // 1: B does not depend on the preceding kernel (a weight): prefetched before the PDL wait
     int kb_per_split;               // k-blocks per gridDim.z slice (split-K: weight gradients, K = B*21 rows)
     int atomic_out;                 // 1: C += tile with red.global.add (split-K slices combine in L2; C pre-zeroed)
     // batched launches (blockIdx.z = batch index instead of a split-K slice): per-batch TMA coordinate offsets of the
@@ -383,6 +384,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // B operands the caller declares independent of the preceding kernel (weights): the first ring-full of their stages
+    // is requested BEFORE the dependency wait, so the L2 / HBM latency of the weight tile hides under that kernel's tail
+    int b_prefetched = 0;
+    if (warp == 0 && p.b_static && tile_first < total_tiles) {
+        int z, m0, n0;
+        decode_tile(tile_first, z, m0, n0);
+        const int zb = p.batched ? z : 0;
+        const int kb_begin = p.batched ? 0 : z * p.kb_per_split;
+        const int num_kb = min(kb_all, kb_begin + p.kb_per_split) - kb_begin;
+        const int bn0 = n0 + zb * p.b_row_z, bk_off = zb * p.b_k_z;
+        b_prefetched = min(STAGES, num_kb);
+        if (elect_one()) {
+            for (int kb = 0; kb < b_prefetched; ++kb) {
+                const uint32_t fb = full_bar + 8 * kb;
+                const uint32_t sb = smem_base + kb * L::STAGE_BYTES + L::A_BYTES;
+                const int k0 = (kb_begin + kb) * BK;
+                mbar_expect_tx(fb, L::STAGE_BYTES);           // A's bytes arrive after the wait below
+                if (!B_MN) {
+                    tma_load_2d(&tmB, fb, sb, k0 + bk_off, bn0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BN / E::MN_BOX; ++i)
+                        tma_load_2d(&tmB, fb, sb + i * E::MN_LBO, bn0 + E::MN_BOX * i, k0 + bk_off);
+                }
+            }
+        }
+        __syncwarp();
+    }
     // everything above (barrier init, TMEM allocation) overlapped the previous kernel's tail; operands and the
     // output buffer may only be touched once that kernel has completed
     pdl_sync();
@@ -401,10 +430,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int k0 = kb_begin * BK;
             const int am0 = m0 + zb * p.a_row_z, ak_off = zb * p.a_k_z, bn0 = n0 + zb * p.b_row_z, bk_off = zb * p.b_k_z;
             for (int kb = 0; kb < num_kb; ++kb) {
+                const bool b_done = tile == tile_first && kb < b_prefetched;      // (first pass of the ring: slots are free)
                 mbar_wait(empty_bar + 8 * s, ph ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = full_bar + 8 * s;
-                    mbar_expect_tx(fb, L::STAGE_BYTES);
+                    if (!b_done) mbar_expect_tx(fb, L::STAGE_BYTES);
                     const uint32_t sa = smem_base + s * L::STAGE_BYTES;
                     const uint32_t sb = sa + L::A_BYTES;
                     if (!A_MN) {
@@ -414,7 +444,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < BM / E::MN_BOX; ++i)
                             tma_load_2d(&tmA, fb, sa + i * E::MN_LBO, am0 + E::MN_BOX * i, k0 + ak_off);    // box {MN_BOX rows, BK k}
                     }
-                    if (!B_MN) {
+                    if (b_done) {
+                    } else if (!B_MN) {
                         tma_load_2d(&tmB, fb, sb, k0 + bk_off, bn0);                              // box {BK k, BN rows}
                     } else {
 #pragma unroll
@@ -531,6 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 long long* g_gemm_dbg = nullptr;
 // A/B switch for the measurement in DESIGN.md: SCAT_GEMM_SHALLOW=1 keeps the 96 KB ring on every launch
+const bool g_no_b_prefetch = [] { const char* e = getenv("SCAT_GEMM_NO_B_PREFETCH"); return e != nullptr && e[0] == '1'; }();
 const bool g_shallow_ring = [] { const char* e = getenv("SCAT_GEMM_SHALLOW"); return e != nullptr && e[0] == '1'; }();
 
 // ---------------------------------------------------------------------------------------------
@@ -568,6 +600,7 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     p.ld_aux_out = g.ld_aux_out; p.accumulate = g.accumulate;
     p.round_operands = (BF16 || g.prerounded) ? 0 : 1;
     p.round_out = g.round_out;
+    p.b_static = (g.b_static && (BF16 || g.prerounded) && !g_no_b_prefetch) ? 1 : 0;     // (the in-kernel rounding pass owns un-rounded stages)
     p.batched = g.batch > 1 ? 1 : 0;
     p.a_row_z = g.a_row_z; p.a_k_z = g.a_k_z; p.b_row_z = g.b_row_z; p.b_k_z = g.b_k_z; p.c_z = g.c_z; p.aux_out_z = g.aux_out_z;
     p.mask_idx = g.mask_idx; p.n_masked = g.n_masked;

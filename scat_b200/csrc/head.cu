@@ -480,24 +480,24 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
             // PreNorm + Attention + Residual (:18,:26,:59-79)
             SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, ld_n, ws + L.mean_a,
                                                 ws + L.rstd_a, M, L.d, omode, st));
-            g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
+            g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
             g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
             SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
             g = GemmArgs();
-            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
+            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.b_static = 1; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
             g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
             g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
         } else {
             // x1, attn = attention(x); x = pren(x1) + x (vision_transformer_attn.py:106-108): X is the caller's /
             // previous layer's fp32 tensor, so the tensor-core GEMM rounds it to TF32-nearest in shared memory itself
-            g.A = X; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.sbn = w.ld_qkv; g.sbk = 1;
+            g.A = X; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.sbn = w.ld_qkv; g.sbk = 1;
             g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = 0;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
             SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
             g = GemmArgs();
-            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.sbn = w.ld_out; g.sbk = 1;
+            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.b_static = 1; g.sbn = w.ld_out; g.sbk = 1;
             g.C = ws + L.Na; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
             g.epilogue = EPI_BIAS; g.bias = W[L.p_out_b];
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
@@ -511,7 +511,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         const int ffprec = L.last ? PREC_FP32 : prec;   // last FF stays fp32
         const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
         g = GemmArgs();
-        g.A = ws + L.Nf; g.sam = L.last ? L.d : ld_n; g.sak = 1; g.B = w.fc1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
+        g.A = ws + L.Nf; g.sam = L.last ? L.d : ld_n; g.sak = 1; g.B = w.fc1; g.b_static = 1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
         g.M = M; g.N = L.hid; g.K = L.d; g.prerounded = fftc;
         if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
         else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
@@ -527,7 +527,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         }
         float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
         g = GemmArgs();
-        g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
+        g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.b_static = 1; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
         g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid; g.prerounded = fftc;
         g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
         if (L.last && L.out == 3)     // three outputs per token: a warp per row instead of a 64 x 64 tile kernel
@@ -584,7 +584,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (G) {
             // dW2[out,hid] = dY^T H ; db2 = colsum(dY)
             SCAT_PROPAGATE(order_after(sd, st, sg));
-            g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
+            g.A = dYg; g.sam = 1; g.sak = ld_dYg; g.B = ws + L.H; g.b_static = 1; g.sbn = 1; g.sbk = ld_h; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc2_w]; g.ldc = L.hid; g.M = L.out; g.N = L.hid; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
             // db2: layer l + 1's attention-LayerNorm parameter kernel summed its dX (= this dY) already, unless this call
@@ -598,7 +598,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         }
         // dZ = (dY W2) * gelu'(Z)
         g = GemmArgs();
-        g.A = dYg; g.sam = ld_dYg; g.sak = 1; g.B = w.fc2; g.sbn = 1; g.sbk = w.ld_fc2; g.operand_bf16 = ffbf;
+        g.A = dYg; g.sam = ld_dYg; g.sak = 1; g.B = w.fc2; g.b_static = 1; g.sbn = 1; g.sbk = w.ld_fc2; g.operand_bf16 = ffbf;
         g.M = MR; g.N = L.hid; g.K = L.out; g.prerounded = fftc;
         if (ffbf) { g.C16 = dZ; g.ldc16 = ld_h; }
         else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
@@ -611,7 +611,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dW1[hid,d] = dZ^T Nf ; db1 = colsum(dZ)
             SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
-            g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.sbn = 1; g.sbk = L.last ? L.d : ld_na; g.operand_bf16 = ffbf;
+            g.A = dZ; g.sam = 1; g.sak = ld_h; g.B = ws + L.Nf; g.b_static = 1; g.sbn = 1; g.sbk = L.last ? L.d : ld_na; g.operand_bf16 = ffbf;
             g.C = G[L.p_fc1_w]; g.ldc = L.d; g.M = L.hid; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = fftc;
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, sg) : launch_gemm(g, ffprec, sg)));
             SCAT_PROPAGATE(order_after(sd, st, sb));
@@ -619,7 +619,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         }
         // dNf = dZ W1   (for the last layer this IS dX1 and feeds the tensor-core out-projection GEMMs)
         g = GemmArgs();
-        g.A = dZ; g.sam = ld_h; g.sak = 1; g.B = w.fc1; g.sbn = 1; g.sbk = w.ld_fc1; g.operand_bf16 = ffbf;
+        g.A = dZ; g.sam = ld_h; g.sak = 1; g.B = w.fc1; g.b_static = 1; g.sbn = 1; g.sbk = w.ld_fc1; g.operand_bf16 = ffbf;
         g.C = ws + c.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
         if (L.last && bf) { g.C16 = ws + c.dX1_16; g.ldc16 = ld_n; }
         else g.round_out = (L.last && tc) ? 1 : 0;
@@ -648,14 +648,14 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
                 SCAT_PROPAGATE(launch_layernorm_param_grads(ws + c.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
                                                             G[L.p_nf_w], G[L.p_nf_b], M, L.d, sb, dX1, L.d, G[L.p_out_b]));
             g = GemmArgs();
-            g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
+            g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.b_static = 1; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, sg));
             if (L.last) SCAT_PROPAGATE(launch_colsum(dX1, L.d, M, L.d, G[L.p_out_b], 1, sb));
         }
         // dO = dX1 Wo
         g = GemmArgs();
-        g.A = dX1g; g.sam = ld_n; g.sak = 1; g.B = w.out; g.sbn = 1; g.sbk = w.ld_out; g.operand_bf16 = bf;
+        g.A = dX1g; g.sam = ld_n; g.sak = 1; g.B = w.out; g.b_static = 1; g.sbn = 1; g.sbk = w.ld_out; g.operand_bf16 = bf;
         g.C = ws + c.dO; g.ldc = p.inner; g.M = MR; g.N = p.inner; g.K = L.d; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         SCAT_PROPAGATE(launch_attention_bwd(ws + L.QKV, ws + L.P, ws + c.dO, ws + c.dQKV, p.B * sweeps, p.T, p.heads, omode,
@@ -664,14 +664,14 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             // dWqkv[3inner,d] = dQKV^T Na
             SCAT_PROPAGATE(order_after(sd, st, sg));
             g = GemmArgs();
-            g.A = ws + c.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.sbn = 1; g.sbk = ld_na; g.operand_bf16 = bf;
+            g.A = ws + c.dQKV; g.sam = 1; g.sak = 3 * p.inner; g.B = ws + L.Na; g.b_static = 1; g.sbn = 1; g.sbk = ld_na; g.operand_bf16 = bf;
             g.C = G[L.p_qkv]; g.ldc = L.d; g.M = 3 * p.inner; g.N = L.d; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, sg));
         }
         // dNa = dQKV Wqkv
         g = GemmArgs();
         float* dNa = ws + c.dNa;
-        g.A = ws + c.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
+        g.A = ws + c.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
         g.C = dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs.  It

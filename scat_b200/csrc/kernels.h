@@ -55,6 +55,8 @@ struct GemmArgs {
     int batch_accumulate = 0;    // every problem reduces into the same C (red.global.add; C pre-zeroed): K split over the batch
     const int32_t* mask_idx = nullptr; int n_masked = 0;   // EPI_PE_MASK
     int force_bn = 0;            // 64 / 128: tile width override
+    int b_static = 0;            // tensor-core kernel: B was NOT written by the kernel preceding this launch on its stream (a
+                                 // weight, a saved activation): its first stages are requested before the PDL dependency wait
 };
 
 #ifdef __CUDACC__

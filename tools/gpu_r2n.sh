@@ -19,3 +19,6 @@ python bench.py --steps 2 --warmup 3 --quick > /dev/null 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2n_launches.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/r2n_ncu_launches.log 2>&1
 python tools/summarize_launches.py gpurun_out/r2n_launches.csv > gpurun_out/r2n_launches.txt 2>&1
 ls -la /tmp/*.ncu-rep; tail -n 3 gpurun_out/r2n_plain_*.log; grep -c "^==" gpurun_out/r2n_*_metrics.txt; head -30 gpurun_out/r2n_launches.txt
+timeout 300 python tools/config4_timeline.py tf32 > gpurun_out/r2n_config4_timeline_tf32.txt 2>&1
+timeout 300 python tools/config4_timeline.py bf16 > gpurun_out/r2n_config4_timeline_bf16.txt 2>&1
+head -3 gpurun_out/r2n_config4_timeline_tf32.txt
