@@ -199,15 +199,26 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(job.dst);
         if (((job.cols | job.ld_src | job.ld_dst) & 3) == 0) {       // 4 values per thread: float4 in, 8 bytes out
             const int c4n = job.ld_dst >> 2, total = job.rows * c4n;
-            for (int i = tid; i < total; i += nthr) {
-                const int r = i / c4n, c4 = i - r * c4n;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c4 * 4 < job.cols) v = __ldg(reinterpret_cast<const float4*>(job.src + (size_t)r * job.ld_src) + c4);
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                reinterpret_cast<uint2*>(dst)[i] = pk;
+            for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * nthr;
+                    const int r = i / c4n, c4 = i - r * c4n;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < total && c4 * 4 < job.cols) v[u] = __ldg(reinterpret_cast<const float4*>(job.src + (size_t)r * job.ld_src) + c4);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * nthr;
+                    if (i < total) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                        reinterpret_cast<uint2*>(dst)[i] = pk;
+                    }
+                }
             }
             return;
         }
@@ -219,13 +230,27 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
         return;
     }
     if (((job.cols | job.ld_src | job.ld_dst) & 3) == 0) {          // float4 path (every weight but fc2 of layer 1)
+        // four loads in flight per thread before the first store (dst may alias src as far as the compiler knows, so a
+        // one-element loop body waits a DRAM round trip per element: 37 us in the step's timeline for 15 MB)
         const int c4n = job.ld_dst >> 2, total = job.rows * c4n;
-        for (int i = tid; i < total; i += nthr) {
-            const int r = i / c4n, c4 = i - r * c4n;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c4 * 4 < job.cols) v = __ldg(reinterpret_cast<const float4*>(job.src + (size_t)r * job.ld_src) + c4);
-            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-            reinterpret_cast<float4*>(job.dst)[i] = v;
+        for (int i0 = tid; i0 < total; i0 += 4 * nthr) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr;
+                const int r = i / c4n, c4 = i - r * c4n;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total && c4 * 4 < job.cols) v[u] = __ldg(reinterpret_cast<const float4*>(job.src + (size_t)r * job.ld_src) + c4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr;
+                if (i < total) {
+                    float4 w = v[u];
+                    w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w);
+                    reinterpret_cast<float4*>(job.dst)[i] = w;
+                }
+            }
         }
     } else {
         const int total = job.rows * job.ld_dst;
@@ -245,6 +270,23 @@ __global__ void round_copy_kernel(const RoundJobs jobs) {
 __global__ void split3_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int rows, int cols, int mode) {
     pdl_sync();
     const int cp = (cols + 3) & ~3, rp = (rows + 3) & ~3;
+    if (mode != 2 && ((cols | ld_src) & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        // activations (the step's critical chain): one float4 in, three float4 out per thread
+        const int c4n = cols >> 2;
+        const long long total4 = (long long)rows * c4n;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / c4n), c4 = (int)(i - (long long)r * c4n);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld_src) + c4);
+            float4 hi, lo;
+            hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+            lo.x = round_tf32(v.x - hi.x); lo.y = round_tf32(v.y - hi.y); lo.z = round_tf32(v.z - hi.z); lo.w = round_tf32(v.w - hi.w);
+            float4* d = reinterpret_cast<float4*>(dst + (long long)r * 3 * cp) + c4;
+            d[0] = hi;
+            d[c4n] = mode == 0 ? lo : hi;
+            d[2 * c4n] = mode == 0 ? hi : lo;
+        }
+        return;
+    }
     const long long total = mode == 2 ? (long long)rp * cols : (long long)rows * cp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int width = mode == 2 ? cols : cp;
@@ -269,7 +311,9 @@ __global__ void split3_kernel(const float* __restrict__ src, int ld_src, float* 
 int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, int mode, cudaStream_t stream) {
     SCAT_REQUIRE(src && dst && rows > 0 && cols > 0 && mode >= 0 && mode <= 2, kErrBadArg, "split3: bad args");
     const long long total = (long long)((rows + 3) & ~3) * ((cols + 3) & ~3);
-    const int grid = (int)((total + 255) / 256 < 148 * 4 ? (total + 255) / 256 : 148 * 4);
+    const bool vec = mode != 2 && ((cols | ld_src) & 3) == 0;
+    const long long work = vec ? total / 4 : total;
+    const int grid = (int)((work + 255) / 256 < 148 * 4 ? (work + 255) / 256 : 148 * 4);
     SCAT_CHECK_CUDA(launch_k(split3_kernel, dim3(grid), dim3(256), 0, stream, src, ld_src, dst, rows, cols, mode));
     SCAT_CHECK_LAUNCH();
     return 0;
@@ -277,7 +321,7 @@ int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, 
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 16, kErrBadArg, "round_copy: %d jobs", jobs.n);
-    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(dim3(60, jobs.n)), dim3(256), 0, stream, jobs));
+    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(dim3(74, jobs.n)), dim3(256), 0, stream, jobs));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

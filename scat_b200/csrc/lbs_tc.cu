@@ -73,48 +73,77 @@ lbs_tc_setup_kernel(const float* __restrict__ derived, const float* __restrict__
     }
 }
 
-// one CTA per sample, thread per vertex: skinning (mano.py:339-348), global rotation and root (:382-388), fingertips (:373-377)
-__global__ void __launch_bounds__(LBS_THREADS, 3)
+// one CTA per sample, FOUR consecutive vertices per thread: skinning (mano.py:339-348), global rotation and root (:382-388),
+// fingertips (:373-377).  A thread per vertex was bound by the load/store unit (per joint one weight load and three
+// broadcast LDS.128 of A_j for 12 FMAs: ncu 134 us per 8192 samples, 25 % of the FMA peak); with four vertices a joint
+// costs one LDG.128 of weights and the same three LDS.128 for 48 FMAs.  Per vertex the arithmetic (and its order) is
+// unchanged.  Results leave through a shared-memory row so that the 9.3 KB of a sample's vertices are written coalesced.
+constexpr int SKIN_VPT = 4;
+static_assert(VP % SKIN_VPT == 0 && (OFF_VT % 4) == 0 && (OFF_W % 4) == 0 && (TC_LDC % 4) == 0, "float4 table reads");
+static_assert((NV + SKIN_VPT - 1) / SKIN_VPT <= LBS_THREADS, "one pass over the vertices");
+__global__ void __launch_bounds__(LBS_THREADS, 2)
 lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ corr, const float* __restrict__ Ain,
                    const float* __restrict__ Rr, float* __restrict__ out, int b_first) {
     pdl_sync();
     __shared__ __align__(16) float A[NJ][12];
     __shared__ float R[12];
+    __shared__ __align__(16) float stage[NV * 3 + 2];
     const int l = blockIdx.x, tid = threadIdx.x;
     for (int e = tid; e < NJ * 12; e += LBS_THREADS) (&A[0][0])[e] = Ain[(long long)l * NJ * 12 + e];
     if (tid < 12) R[tid] = Rr[(long long)l * 12 + tid];
     __syncthreads();
     const float* vt_t = derived + OFF_VT;
     const float* w_t = derived + OFF_W;
-    const float* cr = corr + (long long)l * TC_LDC;
-    float* o_base = out + (long long)(b_first + l) * 799 * 3;
-    for (int v = tid; v < NV; v += LBS_THREADS) {
-        const float p0 = vt_t[v] + cr[3 * v], p1 = vt_t[VP + v] + cr[3 * v + 1], p2 = vt_t[2 * VP + v] + cr[3 * v + 2];
-        float T[12];
+    const int v0 = tid * SKIN_VPT;
+    if (v0 < NV) {
+        const float* cr = corr + (long long)l * TC_LDC + 3 * v0;       // 12 corrections of vertices v0 .. v0 + 3
+        float c[12];
 #pragma unroll
-        for (int q = 0; q < 12; ++q) T[q] = 0.f;
-#pragma unroll 4
+        for (int k = 0; k < 3; ++k) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (3 * v0 + 4 * k < TC_LDC) t4 = __ldg(reinterpret_cast<const float4*>(cr) + k);     // (row end: vertices >= NV)
+            c[4 * k] = t4.x; c[4 * k + 1] = t4.y; c[4 * k + 2] = t4.z; c[4 * k + 3] = t4.w;
+        }
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(vt_t + v0));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(vt_t + VP + v0));
+        const float4 t2 = __ldg(reinterpret_cast<const float4*>(vt_t + 2 * VP + v0));
+        const float tx[4] = {t0.x, t0.y, t0.z, t0.w}, ty[4] = {t1.x, t1.y, t1.z, t1.w}, tz[4] = {t2.x, t2.y, t2.z, t2.w};
+        float T[SKIN_VPT][12];
+#pragma unroll
+        for (int u = 0; u < SKIN_VPT; ++u)
+#pragma unroll
+            for (int q = 0; q < 12; ++q) T[u][q] = 0.f;
+#pragma unroll 2
         for (int j = 0; j < NJ; ++j) {
-            const float w = w_t[j * VP + v];
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_t + j * VP + v0));
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
             const float4* arow = reinterpret_cast<const float4*>(A[j]);
             const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2];
             const float a[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-            for (int q = 0; q < 12; ++q) T[q] = fmaf(w, a[q], T[q]);
+            for (int u = 0; u < SKIN_VPT; ++u)
+#pragma unroll
+                for (int q = 0; q < 12; ++q) T[u][q] = fmaf(w[u], a[q], T[u][q]);
         }
-        float x[3], y[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) x[r] = T[r * 4 + 0] * p0 + T[r * 4 + 1] * p1 + T[r * 4 + 2] * p2 + T[r * 4 + 3];
+        for (int u = 0; u < SKIN_VPT; ++u) {
+            if (v0 + u < NV) {
+                const float p0 = tx[u] + c[3 * u], p1 = ty[u] + c[3 * u + 1], p2 = tz[u] + c[3 * u + 2];
+                float x[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) y[r] = R[r * 3 + 0] * x[0] + R[r * 3 + 1] * x[1] + R[r * 3 + 2] * x[2] - R[9 + r];
-        float* o = o_base + (21 + v) * 3;
-        o[0] = y[0]; o[1] = y[1]; o[2] = y[2];
+                for (int r = 0; r < 3; ++r) x[r] = T[u][r * 4 + 0] * p0 + T[u][r * 4 + 1] * p1 + T[u][r * 4 + 2] * p2 + T[u][r * 4 + 3];
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-            if (c_tips[q] == v) {
-                float* oj = o_base + (16 + q) * 3;
-                oj[0] = y[0]; oj[1] = y[1]; oj[2] = y[2];
+                for (int r = 0; r < 3; ++r)
+                    stage[3 * (v0 + u) + r] = R[r * 3 + 0] * x[0] + R[r * 3 + 1] * x[1] + R[r * 3 + 2] * x[2] - R[9 + r];
             }
+        }
+    }
+    __syncthreads();
+    float* o_base = out + (long long)(b_first + l) * 799 * 3;
+    for (int i = tid; i < NV * 3; i += LBS_THREADS) o_base[21 * 3 + i] = stage[i];
+    if (tid < 15) {
+        const int q = tid / 3, r = tid - 3 * q;
+        o_base[(16 + q) * 3 + r] = stage[c_tips[q] * 3 + r];
     }
 }
 

@@ -8,8 +8,8 @@ namespace {
 constexpr float kEps = 1e-5f;
 constexpr int LN_WARPS = 8;
 
-template <int NPL>  // elements per lane (row length <= 32*NPL)
-__global__ void __launch_bounds__(LN_WARPS * 32)
+template <int NPL, bool RESID>  // elements per lane (row length <= 32*NPL); RESID: Y = LN(X) + resid (coarse variant)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ Y, int ldy, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int D, int round_out, const float* __restrict__ resid, int ldr) {
@@ -18,14 +18,22 @@ layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restri
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const float* x = X + (long long)row * ldx;
-    float v[NPL];
+    const float* rr = RESID ? resid + (long long)row * ldr : nullptr;
+    // every global read of the row (x, gamma, beta, residual) is issued before the first store: Y may alias any of them as
+    // far as the compiler knows (store_out also writes through a bf16 pointer), and a load placed after a store waits one L2
+    // round trip per element -- ncu had this kernel at 17 us for 6 MB with 25 long-scoreboard stalls per issue
+    float v[NPL], gm[NPL], bt[NPL], rv[RESID ? NPL : 1];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
         const int c = i * 32 + lane;
-        v[i] = c < D ? x[c] : 0.f;
-        s += v[i];
+        v[i] = c < D ? __ldg(x + c) : 0.f;
+        gm[i] = c < D ? __ldg(gamma + c) : 0.f;
+        bt[i] = c < D ? __ldg(beta + c) : 0.f;
+        if (RESID) rv[i] = c < D ? __ldg(rr + c) : 0.f;             // x = pren(x1) + x (vision_transformer_attn.py:108)
     }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) s += v[i];
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
@@ -40,8 +48,8 @@ layernorm_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restri
     for (int i = 0; i < NPL; ++i) {
         const int c = i * 32 + lane;
         if (c < D) {
-            float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
-            if (resid != nullptr) o += resid[(long long)row * ldr + c];     // x = pren(x1) + x (vision_transformer_attn.py:108)
+            float o = (v[i] - mean) * rstd * gm[i] + bt[i];
+            if (RESID) o += rv[i];
             store_out(Y, (long long)row * ldy + c, o, round_out);
         }
     }
@@ -204,9 +212,20 @@ int launch_layernorm_fwd(const float* X, int ldx, const float* gamma, const floa
                          int ldr) {
     SCAT_REQUIRE(D >= 1 && D <= 1024, kErrUnsupported, "layernorm: D=%d not in [1,1024]", D);
     const int grid = ceil_div(M, LN_WARPS);
-    if (D <= 256) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));
-    else if (D <= 512) SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));
-    else SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<32>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));
+#define SCAT_LN_FWD(NPL)                                                                                                      \
+    do {                                                                                                                      \
+        if (resid != nullptr)                                                                                                 \
+            SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<NPL, true>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, \
+                                     beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));                                   \
+        else                                                                                                                  \
+            SCAT_CHECK_CUDA(launch_k(layernorm_fwd_kernel<NPL, false>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, X, ldx, gamma, \
+                                     beta, Y, ldy, mean, rstd, M, D, round_out, resid, ldr));                                   \
+    } while (0)
+    if (D <= 256) SCAT_LN_FWD(8);
+    else if (D <= 512) SCAT_LN_FWD(16);
+    else if (D <= 800) SCAT_LN_FWD(25);
+    else SCAT_LN_FWD(32);
+#undef SCAT_LN_FWD
     SCAT_CHECK_LAUNCH();
     return 0;
 }

@@ -13,3 +13,8 @@ import json
 for f in ('r2p_bench_quick','r2p_bench_quick_bf16'):
     d=json.load(open('gpurun_out/'+f+'.json')); print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'], d['roofline']['frac'])
 "
+NCU="ncu --set full --clock-control none --import-source on"
+timeout 900 $NCU -k regex:"attention_fwd_tc128|gemm_simt|gemm_tc|lbs_|peer_allreduce|proj_loss|regressor_" -s 0 -c 45 -o /tmp/misc python tools/prof_misc.py > gpurun_out/r2p_ncu_misc.log 2>&1
+python tools/ncu_metrics.py /tmp/misc.ncu-rep > gpurun_out/r2p_misc_metrics.txt 2>&1
+python tools/ncu_top_stalls.py /tmp/misc.ncu-rep 10 > gpurun_out/r2p_misc_stalls.txt 2>&1
+grep -c "^==" gpurun_out/r2p_misc_metrics.txt
