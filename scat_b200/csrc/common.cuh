@@ -47,6 +47,8 @@ extern unsigned long long g_launch_count;
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and a
 // process may drive several GPUs from several host threads (head.cu)
 int ensure_dynamic_smem(const void* kernel, int bytes);
+extern int g_carveout;
+void ensure_carveout(const void* kernel);
 #define SCAT_ENSURE_SMEM(kernel, bytes) SCAT_PROPAGATE(scat::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (int)(bytes)))
 
 constexpr int kErrBadArg = -1;
@@ -89,6 +91,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
         attr[n].val.priority = (tl_side_stream != nullptr && stream == tl_side_stream) ? g_prio_low : g_prio_high;
         ++n;
     }
+    if (g_carveout) ensure_carveout(reinterpret_cast<const void*>(kernel));
     cfg.attrs = attr;
     cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -67,6 +67,22 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     return 0;
 }
 
+// SCAT_CARVEOUT=1 (experiment): every kernel asks for the maximum shared-memory carve-out, so that
+// consecutive kernels of the chain never make an SM change its L1 / shared split between them
+int g_carveout = [] { const char* e = getenv("SCAT_CARVEOUT"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+void ensure_carveout(const void* kernel) {
+    struct Entry { const void* fn; int dev; };
+    static std::mutex mu;
+    static std::vector<Entry> seen;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : seen)
+        if (e.fn == kernel && e.dev == dev) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    seen.push_back(Entry{kernel, dev});
+}
+
 int launch_gemm(const GemmArgs& g, int precision, cudaStream_t stream) {
     // tiny problems (regressor / N=3 grads) stay on the FFMA kernel: a 128-row tensor tile would be mostly padding
     if (g.operand_bf16) return launch_gemm_tc(g, precision, stream);     // bf16 operands only exist for the tensor core

@@ -80,8 +80,9 @@ lbs_tc_setup_kernel(const float* __restrict__ derived, const float* __restrict__
 // unchanged.  Results leave through a shared-memory row so that the 9.3 KB of a sample's vertices are written coalesced.
 constexpr int SKIN_VPT = 4;
 static_assert(VP % SKIN_VPT == 0 && (OFF_VT % 4) == 0 && (OFF_W % 4) == 0 && (TC_LDC % 4) == 0, "float4 table reads");
-static_assert((NV + SKIN_VPT - 1) / SKIN_VPT <= LBS_THREADS, "one pass over the vertices");
-__global__ void __launch_bounds__(LBS_THREADS, 2)
+constexpr int SKIN_THREADS = 224;             // 7 warps: 195 threads own vertices
+static_assert((NV + SKIN_VPT - 1) / SKIN_VPT <= SKIN_THREADS, "one pass over the vertices");
+__global__ void __launch_bounds__(SKIN_THREADS, 3)
 lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ corr, const float* __restrict__ Ain,
                    const float* __restrict__ Rr, float* __restrict__ out, int b_first) {
     pdl_sync();
@@ -89,7 +90,7 @@ lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ 
     __shared__ float R[12];
     __shared__ __align__(16) float stage[NV * 3 + 2];
     const int l = blockIdx.x, tid = threadIdx.x;
-    for (int e = tid; e < NJ * 12; e += LBS_THREADS) (&A[0][0])[e] = Ain[(long long)l * NJ * 12 + e];
+    for (int e = tid; e < NJ * 12; e += SKIN_THREADS) (&A[0][0])[e] = Ain[(long long)l * NJ * 12 + e];
     if (tid < 12) R[tid] = Rr[(long long)l * 12 + tid];
     __syncthreads();
     const float* vt_t = derived + OFF_VT;
@@ -97,17 +98,9 @@ lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ 
     const int v0 = tid * SKIN_VPT;
     if (v0 < NV) {
         const float* cr = corr + (long long)l * TC_LDC + 3 * v0;       // 12 corrections of vertices v0 .. v0 + 3
-        float c[12];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (3 * v0 + 4 * k < TC_LDC) t4 = __ldg(reinterpret_cast<const float4*>(cr) + k);     // (row end: vertices >= NV)
-            c[4 * k] = t4.x; c[4 * k + 1] = t4.y; c[4 * k + 2] = t4.z; c[4 * k + 3] = t4.w;
-        }
-        const float4 t0 = __ldg(reinterpret_cast<const float4*>(vt_t + v0));
-        const float4 t1 = __ldg(reinterpret_cast<const float4*>(vt_t + VP + v0));
-        const float4 t2 = __ldg(reinterpret_cast<const float4*>(vt_t + 2 * VP + v0));
-        const float tx[4] = {t0.x, t0.y, t0.z, t0.w}, ty[4] = {t1.x, t1.y, t1.z, t1.w}, tz[4] = {t2.x, t2.y, t2.z, t2.w};
+        // (read after the joint loop, so that they are not live across it: three CTAs per SM; requested now)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr + 8));
         float T[SKIN_VPT][12];
 #pragma unroll
         for (int u = 0; u < SKIN_VPT; ++u)
@@ -125,6 +118,17 @@ lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ 
 #pragma unroll
                 for (int q = 0; q < 12; ++q) T[u][q] = fmaf(w[u], a[q], T[u][q]);
         }
+        float c[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (3 * v0 + 4 * k < TC_LDC) t4 = __ldg(reinterpret_cast<const float4*>(cr) + k);     // (row end: vertices >= NV)
+            c[4 * k] = t4.x; c[4 * k + 1] = t4.y; c[4 * k + 2] = t4.z; c[4 * k + 3] = t4.w;
+        }
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(vt_t + v0));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(vt_t + VP + v0));
+        const float4 t2 = __ldg(reinterpret_cast<const float4*>(vt_t + 2 * VP + v0));
+        const float tx[4] = {t0.x, t0.y, t0.z, t0.w}, ty[4] = {t1.x, t1.y, t1.z, t1.w}, tz[4] = {t2.x, t2.y, t2.z, t2.w};
 #pragma unroll
         for (int u = 0; u < SKIN_VPT; ++u) {
             if (v0 + u < NV) {
@@ -140,7 +144,7 @@ lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ 
     }
     __syncthreads();
     float* o_base = out + (long long)(b_first + l) * 799 * 3;
-    for (int i = tid; i < NV * 3; i += LBS_THREADS) o_base[21 * 3 + i] = stage[i];
+    for (int i = tid; i < NV * 3; i += SKIN_THREADS) o_base[21 * 3 + i] = stage[i];
     if (tid < 15) {
         const int q = tid / 3, r = tid - 3 * q;
         o_base[(16 + q) * 3 + r] = stage[c_tips[q] * 3 + r];
@@ -195,7 +199,7 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
         g.A = U; g.sam = TC_K; g.sak = 1; g.B = table; g.sbn = TC_K; g.sbk = 1;
         g.C = corr; g.ldc = TC_LDC; g.M = n; g.N = TC_N; g.K = TC_K; g.prerounded = 1;
         SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
-        SCAT_CHECK_CUDA(launch_k(lbs_tc_skin_kernel, dim3(n), dim3(LBS_THREADS), 0, st, derived, (const float*)corr, (const float*)A,
+        SCAT_CHECK_CUDA(launch_k(lbs_tc_skin_kernel, dim3(n), dim3(SKIN_THREADS), 0, st, derived, (const float*)corr, (const float*)A,
                                  (const float*)Rr, out, (int)b0));
         SCAT_CHECK_LAUNCH();
     }

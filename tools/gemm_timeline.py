@@ -9,7 +9,7 @@ from scat_b200._lib import ptr
 lib = _lib.load()
 buf = torch.zeros(8, dtype=torch.int64, device="cuda")
 names = ["entry", "setup+dep wait done", "first stage landed", "accumulator ready", "chunk0 tmem ld", "chunk0 transposed", "chunk0 stored", "all tiles done"]
-shapes = [(128, 64, 32), (128, 64, 2048), (128, 128, 2048), (2016, 784, 512), (2016, 1536, 784)]
+shapes = [(128, 64, 32), (128, 128, 2048), (2016, 784, 512), (2016, 1536, 784), (2016, 588, 784), (2016, 392, 588), (4032, 784, 1536)]
 # output-bound persistent case shaped like the conv dgrad: 2352 tiles of 128x128 with 2 k-blocks, MN-major operands
 M, N, K = 512, 96 * 784, 64
 At = torch.randn(K, M, device="cuda"); Bt = torch.randn(K, N, device="cuda"); out = torch.empty(M, N, device="cuda")
@@ -27,7 +27,7 @@ for prec in ("tf32", "bf16"):
         dt = torch.bfloat16 if prec == "bf16" else torch.float32
         A = torch.randn(M, K, device="cuda").to(dt); B = torch.randn(N, K, device="cuda").to(dt)
         out = torch.empty(M, N, device="cuda")
-        fn = (lambda: SF.gemm_bf16(A, B, out=out)) if prec == "bf16" else (lambda: SF.gemm(A, B, precision="tf32", out=out))
+        fn = (lambda: SF.gemm_bf16(A, B, out=out)) if prec == "bf16" else (lambda: SF.gemm(A, B, precision="tf32", out=out, prerounded=True))
         for _ in range(3): fn()
         torch.cuda.synchronize()
         lib.scat_debug_gemm_timeline(ptr(buf))
