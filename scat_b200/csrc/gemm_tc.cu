@@ -65,6 +65,7 @@ struct TcParams {
     int round_out;                  // 1: store C rounded to TF32-nearest (it feeds another tensor-core GEMM)
     int round_operands;             // 1: round fp32 operands to TF32 (nearest) in shared memory before the MMA
     int stages;                     // depth of the operand ring (SmemLayout::STAGES or STAGES_DEEP)
+    int exp_skip_gelu;              // timing experiment only (SCAT_EXP_SKIP_GELU=1): GELU / dGELU math replaced by a copy
     int b_static;                   // 1: B does not depend on the preceding kernel (a weight): prefetched before the PDL wait
     int kb_per_split;               // k-blocks per gridDim.z slice (split-K: weight gradients, K = B*21 rows)
     int atomic_out;                 // 1: C += tile with red.global.add (split-K slices combine in L2; C pre-zeroed)
@@ -224,7 +225,7 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
             } else if (epi == EPI_DGELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if (SCAT_ROW_OK(i)) {
+                    if (SCAT_ROW_OK(i) && !p.exp_skip_gelu) {
                         acc[i].x *= gelu_erf_grad(ext[i].x); acc[i].y *= gelu_erf_grad(ext[i].y);
                         acc[i].z *= gelu_erf_grad(ext[i].z); acc[i].w *= gelu_erf_grad(ext[i].w);
                     }
@@ -232,6 +233,7 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (SCAT_ROW_OK(i)) *reinterpret_cast<float4*>(zptr + i * z_step) = acc[i];
+                    if (p.exp_skip_gelu) continue;
                     acc[i].x = gelu_erf(acc[i].x); acc[i].y = gelu_erf(acc[i].y);
                     acc[i].z = gelu_erf(acc[i].z); acc[i].w = gelu_erf(acc[i].w);
                 }
@@ -563,6 +565,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 long long* g_gemm_dbg = nullptr;
 // A/B switch for the measurement in DESIGN.md: SCAT_GEMM_SHALLOW=1 keeps the 96 KB ring on every launch
 const bool g_no_b_prefetch = [] { const char* e = getenv("SCAT_GEMM_NO_B_PREFETCH"); return e != nullptr && e[0] == '1'; }();
+const bool g_exp_skip_gelu = [] { const char* e = getenv("SCAT_EXP_SKIP_GELU"); return e != nullptr && e[0] == '1'; }();
 const bool g_shallow_ring = [] { const char* e = getenv("SCAT_GEMM_SHALLOW"); return e != nullptr && e[0] == '1'; }();
 
 // ---------------------------------------------------------------------------------------------
@@ -605,6 +608,7 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     p.a_row_z = g.a_row_z; p.a_k_z = g.a_k_z; p.b_row_z = g.b_row_z; p.b_k_z = g.b_k_z; p.c_z = g.c_z; p.aux_out_z = g.aux_out_z;
     p.mask_idx = g.mask_idx; p.n_masked = g.n_masked;
     p.dbg = g_gemm_dbg;
+    p.exp_skip_gelu = g_exp_skip_gelu ? 1 : 0;
     auto al16 = [](const void* q, long long ld) { return q == nullptr || (((uintptr_t)q & 15) == 0 && (ld & 3) == 0); };
     p.vec_ok = al16(g.C, g.ldc) && (g.C16 == nullptr || (((uintptr_t)g.C16 & 7) == 0 && (g.ldc16 & 3) == 0)) &&
                al16(g.aux_in, g.ld_aux_in) && al16(g.aux_out, g.ld_aux_out) && al16(g.bias, 0);

@@ -67,9 +67,11 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     return 0;
 }
 
-// SCAT_CARVEOUT=1 (experiment): every kernel asks for the maximum shared-memory carve-out, so that
-// consecutive kernels of the chain never make an SM change its L1 / shared split between them
-int g_carveout = [] { const char* e = getenv("SCAT_CARVEOUT"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+// Every kernel asks for the maximum shared-memory carve-out, so that consecutive kernels of the chain never make an SM
+// change its L1 / shared split between them: a GEMM CTA (96-192 KB of shared memory) cannot become resident on an SM that
+// is still configured for a kernel without shared memory, which defeats the programmatic-launch overlap.  Measured on the
+// B=96 step: 0.742 -> 0.722 ms.  SCAT_CARVEOUT=0 restores the driver's per-kernel choice.
+int g_carveout = [] { const char* e = getenv("SCAT_CARVEOUT"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
 void ensure_carveout(const void* kernel) {
     struct Entry { const void* fn; int dev; };
     static std::mutex mu;
