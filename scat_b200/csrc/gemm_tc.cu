@@ -89,8 +89,9 @@ struct SmemLayout {
     // ring depth is a launch parameter: 96 KB per CTA (two CTAs per SM) when the launch has more CTAs than SMs, 192 KB
     // when every CTA has an SM to itself -- one CTA's fill rate is ring bytes / TMA latency (profiles/r1_gemm_timeline.txt:
     // 96 KB in flight sustain ~52 B/cycle), so a lone CTA needs the deeper ring to keep its tensor core fed
-    static constexpr int STAGES = BN >= 128 ? 3 : 4;
-    static constexpr int STAGES_DEEP = 2 * STAGES;
+    // Tiles wider than 128 (BN = 192, 256) only ever run one CTA per SM with the deep ring (single-wave launches).
+    static constexpr int STAGES = BN == 64 ? 4 : 3;
+    static constexpr int STAGES_DEEP = BN == 64 ? 8 : BN == 128 ? 6 : BN == 192 ? 5 : 4;    // 192 / 192 / 200 / 192 KB
     static constexpr int A_BYTES = BM * 128;              // 16 KB
     static constexpr int B_BYTES = BN * 128;              // 8 / 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -362,7 +363,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             z = blockIdx.z; m0 = blockIdx.y * BM; n0 = blockIdx.x * BN;
         }
     };
-    const uint32_t tmem_cols = persistent ? 2 * BN : BN;
+    // (allocations are powers of two >= 32 columns; the host never makes a wide-tile launch persistent)
+    const uint32_t tmem_cols = BN > 128 ? 256u : (persistent ? 2u * BN : (uint32_t)BN);
 
     if (warp == 0 && lane == 0) {
         // fetch the two TMA descriptors while the barriers are set up (they are kernel parameters, not data of
@@ -566,6 +568,7 @@ long long* g_gemm_dbg = nullptr;
 // A/B switch for the measurement in DESIGN.md: SCAT_GEMM_SHALLOW=1 keeps the 96 KB ring on every launch
 const bool g_no_b_prefetch = [] { const char* e = getenv("SCAT_GEMM_NO_B_PREFETCH"); return e != nullptr && e[0] == '1'; }();
 const bool g_exp_skip_gelu = [] { const char* e = getenv("SCAT_EXP_SKIP_GELU"); return e != nullptr && e[0] == '1'; }();
+const bool g_no_wide_tiles = [] { const char* e = getenv("SCAT_GEMM_NO_WIDE"); return e != nullptr && e[0] == '1'; }();
 const bool g_shallow_ring = [] { const char* e = getenv("SCAT_GEMM_SHALLOW"); return e != nullptr && e[0] == '1'; }();
 
 // ---------------------------------------------------------------------------------------------
@@ -633,7 +636,8 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     constexpr int kSlots = 2 * 148;
     p.persistent = total_tiles > kSlots ? 1 : 0;
     if (p.persistent) grid = dim3(kSlots, 1, 1);
-    p.stages = (total_tiles <= 148 && !g_shallow_ring) ? L::STAGES_DEEP : L::STAGES;
+    p.stages = (BN > 128 || (total_tiles <= 148 && !g_shallow_ring)) ? L::STAGES_DEEP : L::STAGES;
+    SCAT_REQUIRE(BN <= 128 || (total_tiles <= 148 && !p.persistent), kErrUnsupported, "gemm_tc: wide tiles need a single-wave launch");
     if (p.atomic_out && !g.accumulate && !g.c_zeroed)
         SCAT_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, stream));
     SCAT_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(TC_THREADS), L::total(p.stages, p.persistent != 0), stream, tmA, tmB, p));
@@ -667,14 +671,39 @@ int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
     SCAT_REQUIRE(operand_ok(g.A, g.sam, g.sak, eb) && operand_ok(g.B, g.sbn, g.sbk, eb), kErrUnsupported,
                  "gemm_tc: operands need a unit stride, 16-byte aligned base and 16-byte multiple leading stride");
     SCAT_REQUIRE(g.C != nullptr || g.C16 != nullptr, kErrBadArg, "gemm_tc: no output");
-    // The main loop is bound by the shared-memory fill (L2 -> SMEM), so pick the tile width that minimises the
-    // bytes staged per SM: waves x (BM + BN) rows of K.
+    // The main loop is bound by the shared-memory fill (one SM takes ~64 B per cycle from L2, measured with
+    // tools/gemm_timeline.py: 500 cycles per 32 KB k-block whether one deep-ring CTA or two shallow ones share the SM), so
+    // pick the tile width that minimises what the busiest SM has to stage, plus the (serial) epilogue of its last tile:
+    //   cycles(BN) = waves x k-blocks x (BM + BN) x 128 B / 64 B + (BN / 32) x 450,   waves = ceil(tiles / 148).
+    // 192- and 256-wide tiles only when the launch then fits one wave (one CTA per SM, deep ring) and needs no split-K:
+    // M = 2016 x N = 1536 (every qkv projection) is 192 tiles of 128 = 1.3 waves but 128 tiles of 192; the stacked
+    // 4032-row dgrads with N = 784 / 588 are 224 / 160 tiles of 128 but 128 tiles of 256 / 192.
     const int tm = ceil_div(g.M, BM);
-    const long long cost64 = (long long)ceil_div(tm * ceil_div(g.N, 64), 148) * (BM + 64);
-    const long long cost128 = (long long)ceil_div(tm * ceil_div(g.N, 128), 148) * (BM + 128);
-    const bool wide = g.force_bn ? g.force_bn == 128 : (g.N > 64 && cost128 <= cost64);
-    if (g.operand_bf16) return wide ? launch_major<true, 128>(g, stream) : launch_major<true, 64>(g, stream);
-    return wide ? launch_major<false, 128>(g, stream) : launch_major<false, 64>(g, stream);
+    const int kb = ceil_div(g.K, g.operand_bf16 ? 64 : 32);
+    auto cycles = [&](int bn) {
+        const long long tiles = (long long)tm * ceil_div(g.N, bn);
+        return ceil_div((int)tiles, 148) * (long long)kb * (BM + bn) * 2 + (bn / 32) * 450LL;
+    };
+    int bn = 64;
+    if (g.force_bn) {
+        bn = g.force_bn;
+    } else if (g.N > 64) {
+        bn = cycles(128) <= cycles(64) ? 128 : 64;
+        const bool wide_ok = !g_no_wide_tiles && g.batch <= 1 && !g.allow_split_k;
+        for (int cand : {192, 256})
+            if (wide_ok && g.N > cand - 64 && (long long)tm * ceil_div(g.N, cand) <= 148 && cycles(cand) < cycles(bn)) bn = cand;
+    }
+    SCAT_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, kErrBadArg, "gemm_tc: tile width %d", bn);
+#define SCAT_TC_DISPATCH(BF)                                               \
+    switch (bn) {                                                          \
+        case 64: return launch_major<BF, 64>(g, stream);                   \
+        case 128: return launch_major<BF, 128>(g, stream);                 \
+        case 192: return launch_major<BF, 192>(g, stream);                 \
+        default: return launch_major<BF, 256>(g, stream);                  \
+    }
+    if (g.operand_bf16) { SCAT_TC_DISPATCH(true) }
+    SCAT_TC_DISPATCH(false)
+#undef SCAT_TC_DISPATCH
 }
 
 }  // namespace scat

@@ -74,7 +74,7 @@ def test_kernels_are_blackwell_native(lib_path):
     by = {}
     for nm, c in zip(names, rows.values()):
         by.setdefault(nm.split("<")[0], []).append(c)
-    assert len(by["gemm_tc_kernel"]) == 16                              # bf16 / tf32 x BN 64 / 128 x operand majorness
+    assert len(by["gemm_tc_kernel"]) == 32                              # bf16 / tf32 x BN 64 / 128 / 192 / 256 x operand majorness
     for fam, need in (("gemm_tc_kernel", ("UTC*MMA", "UTMALDG", "LDTM")), ("conv_fwd_tc_kernel", ("UTC*MMA", "UTMALDG", "LDTM")),
                       ("conv_wgrad_tc_kernel", ("UTC*MMA", "UTMALDG", "LDTM")),
                       ("conv_dgrad_tc_kernel", ("UTC*MMA", "UTMALDG", "UTMASTG", "LDTM")),

@@ -30,6 +30,8 @@ def _err(x, ref):
     (2016, 784, 512, "k", "mn"), (2016, 392, 1536, "k", "mn"), (2016, 588, 392, "k", "mn"),
     (1536, 784, 2016, "mn", "mn"), (588, 784, 2016, "mn", "mn"), (196, 294, 2016, "mn", "mn"),
     (300, 200, 100, "mn", "k"), (1, 8, 8, "k", "k"), (129, 65, 33, "k", "k"), (4032, 1536, 196, "k", "k"),
+    # single-wave launches on 192- / 256-wide tiles: the stacked dgrads of layer 0 (B operand MN-major) and a ragged N
+    (4032, 784, 1536, "k", "mn"), (4032, 588, 392, "k", "mn"), (4032, 784, 588, "k", "mn"), (2016, 1000, 64, "k", "k"),
 ])
 def test_tc_gemm_layouts(M, N, K, a, b):
     from scat_b200 import functional as SF
@@ -69,6 +71,26 @@ def test_tc_gemm_epilogues_and_padded_ld():
     acc = torch.ones(M, N, device="cuda")
     SF.gemm(Ad, Bd, precision="tf32", out=acc, accumulate=True)
     assert _err(acc, ref + 1.0) < TOL
+
+
+def test_tc_gemm_epilogues_on_wide_tiles():
+    """The 192-wide single-wave launch of the stacked dZ GEMM of layer 0 (4032 x 588 x 392, B MN-major, dGELU with a saved
+    pre-activation of 2016 rows read modulo) and the 192-wide qkv shape with a bias."""
+    from scat_b200 import functional as SF
+    M, N, K = 4032, 588, 392
+    A, B, Ad, Bd, sa, sb = _mk(M, N, K, "k", "mn", seed=5)
+    g = np.random.Generator(np.random.PCG64(11))
+    z = torch.from_numpy(g.standard_normal((M, N)).astype(np.float32))
+    ref = A.double() @ B.double().t()
+    zz = z.double().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    d = SF.gemm(Ad, Bd, a_strides=sa, b_strides=sb, m=M, n=N, k=K, epilogue="dgelu", aux_in=z.cuda(), precision="tf32")
+    assert _err(d, ref * zz.grad) < TOL
+    M, N, K = 2016, 1536, 784
+    A, B, Ad, Bd, sa, sb = _mk(M, N, K, "k", "k", seed=6)
+    bias = torch.from_numpy(g.standard_normal(N).astype(np.float32))
+    y = SF.gemm(Ad, Bd, epilogue="bias", bias=bias.cuda(), precision="tf32")
+    assert _err(y, A.double() @ B.double().t() + bias.double()) < TOL
 
 
 def test_tc_gemm_is_linear_and_exact_on_tf32_representable_inputs():
@@ -111,6 +133,7 @@ def _mk16(M, N, K, a, b, seed=1):
     (2016, 784, 512, "k", "mn"), (4032, 392, 1536, "k", "mn"), (2016, 588, 392, "k", "mn"), (2016, 294, 196, "k", "mn"),
     (1536, 784, 2016, "mn", "mn"), (588, 784, 2016, "mn", "mn"), (196, 294, 2016, "mn", "mn"), (392, 512, 2016, "mn", "mn"),
     (300, 200, 100, "mn", "k"), (1, 8, 8, "k", "k"), (129, 65, 33, "k", "k"),
+    (4032, 784, 1536, "k", "mn"), (4032, 588, 392, "k", "mn"), (2016, 1000, 64, "k", "k"),      # 256- / 192-wide tiles
 ])
 def test_bf16_gemm_layouts(M, N, K, a, b):
     """bf16 x bf16 products are exact in fp32, so the only error is fp32 accumulation order: tight tolerance."""
