@@ -689,7 +689,7 @@ int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
         bn = g.force_bn;
     } else if (g.N > 64) {
         bn = cycles(128) <= cycles(64) ? 128 : 64;
-        const bool wide_ok = !g_no_wide_tiles && g.batch <= 1 && !g.allow_split_k;
+        const bool wide_ok = g.allow_wide && !g_no_wide_tiles && g.batch <= 1 && !g.allow_split_k;
         for (int cand : {192, 256})
             if (wide_ok && g.N > cand - 64 && (long long)tm * ceil_div(g.N, cand) <= 148 && cycles(cand) < cycles(bn)) bn = cand;
     }

@@ -498,24 +498,24 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
             // PreNorm + Attention + Residual (:18,:26,:59-79)
             SCAT_PROPAGATE(launch_layernorm_fwd(X, L.d, W[L.p_na_w], W[L.p_na_b], ws + L.Na, ld_n, ws + L.mean_a,
                                                 ws + L.rstd_a, M, L.d, omode, st));
-            g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
+            g.A = ws + L.Na; g.sam = ld_n; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.allow_wide = 1; g.sbn = w.ld_qkv; g.sbk = 1; g.operand_bf16 = bf;
             g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = tc;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
             SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
             g = GemmArgs();
-            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.b_static = 1; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
+            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.b_static = 1; g.allow_wide = 1; g.sbn = w.ld_out; g.sbk = 1; g.operand_bf16 = bf;
             g.C = ws + L.X1; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
             g.epilogue = EPI_BIAS_RESID; g.bias = W[L.p_out_b]; g.aux_in = X; g.ld_aux_in = L.d;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
         } else {
             // x1, attn = attention(x); x = pren(x1) + x (vision_transformer_attn.py:106-108): X is the caller's /
             // previous layer's fp32 tensor, so the tensor-core GEMM rounds it to TF32-nearest in shared memory itself
-            g.A = X; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.sbn = w.ld_qkv; g.sbk = 1;
+            g.A = X; g.sam = L.d; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.allow_wide = 1; g.sbn = w.ld_qkv; g.sbk = 1;
             g.C = ws + L.QKV; g.ldc = 3 * p.inner; g.M = M; g.N = 3 * p.inner; g.K = L.d; g.prerounded = 0;
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
             SCAT_PROPAGATE(launch_attention_fwd(ws + L.QKV, ws + L.O, ws + L.P, p.B, p.T, p.heads, omode, st));
             g = GemmArgs();
-            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.b_static = 1; g.sbn = w.ld_out; g.sbk = 1;
+            g.A = ws + L.O; g.sam = p.inner; g.sak = 1; g.B = w.out; g.b_static = 1; g.allow_wide = 1; g.sbn = w.ld_out; g.sbk = 1;
             g.C = ws + L.Na; g.ldc = L.d; g.M = M; g.N = L.d; g.K = p.inner; g.prerounded = tc;
             g.epilogue = EPI_BIAS; g.bias = W[L.p_out_b];
             SCAT_PROPAGATE(launch_gemm(g, prec, st));
@@ -529,7 +529,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         const int ffprec = L.last ? PREC_FP32 : prec;   // last FF stays fp32
         const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
         g = GemmArgs();
-        g.A = ws + L.Nf; g.sam = L.last ? L.d : ld_n; g.sak = 1; g.B = w.fc1; g.b_static = 1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
+        g.A = ws + L.Nf; g.sam = L.last ? L.d : ld_n; g.sak = 1; g.B = w.fc1; g.b_static = 1; g.allow_wide = 1; g.sbn = w.ld_fc1; g.sbk = 1; g.operand_bf16 = ffbf;
         g.M = M; g.N = L.hid; g.K = L.d; g.prerounded = fftc;
         if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
         else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
@@ -545,7 +545,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         }
         float* Y = L.last ? ws + p.feat_out : ws + p.L[l + 1].X;
         g = GemmArgs();
-        g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.b_static = 1; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
+        g.A = ws + L.H; g.sam = ffbf ? ld_h : L.ldh; g.sak = 1; g.B = w.fc2; g.b_static = 1; g.allow_wide = 1; g.sbn = w.ld_fc2; g.sbk = 1; g.operand_bf16 = ffbf;
         g.C = Y; g.ldc = L.out; g.M = M; g.N = L.out; g.K = L.hid; g.prerounded = fftc;
         g.epilogue = EPI_BIAS; g.bias = W[L.p_fc2_b];
         if (L.last && L.out == 3)     // three outputs per token: a warp per row instead of a 64 x 64 tile kernel
@@ -1096,6 +1096,7 @@ int scat_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
     g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
     g.aux_out = aux_out; g.ld_aux_out = ld_aux_out; g.accumulate = accumulate;
     g.prerounded = (precision & SCAT_PREC_FLAG_PREROUNDED) ? 1 : 0;
+    g.allow_wide = 1;
     if (precision & SCAT_PREC_FLAG_SPLIT_K) { g.allow_split_k = 1; g.c_zeroed = 1; }
     precision &= ~(SCAT_PREC_FLAG_PREROUNDED | SCAT_PREC_FLAG_SPLIT_K);
     if (precision == PREC_FP32) return launch_gemm_simt(g, (cudaStream_t)stream);
@@ -1117,6 +1118,7 @@ int scat_gemm_bf16(const void* A, int64_t sam, int64_t sak, const void* B, int64
     g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.bias = bias; g.aux_in = aux_in; g.ld_aux_in = ld_aux_in;
     g.aux_out = aux_out; g.ld_aux_out = ld_aux_out;
     g.allow_split_k = split_k ? 1 : 0; g.c_zeroed = split_k ? 1 : 0;
+    g.allow_wide = 1;
     SCAT_REQUIRE(gemm_tc_supported(g), kErrUnsupported,
                  "scat_gemm_bf16: operand layout not expressible as TMA tensor maps (16-byte strides, unit inner stride)");
     return launch_gemm_tc(g, PREC_BF16, (cudaStream_t)stream);

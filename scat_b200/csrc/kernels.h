@@ -55,6 +55,9 @@ struct GemmArgs {
     int batch_accumulate = 0;    // every problem reduces into the same C (red.global.add; C pre-zeroed): K split over the batch
     const int32_t* mask_idx = nullptr; int n_masked = 0;   // EPI_PE_MASK
     int force_bn = 0;            // 64 / 128: tile width override
+    int allow_wide = 0;          // tensor-core kernel: 192- / 256-wide single-wave tiles may be chosen (one 200 KB CTA per SM:
+                                 // only where nothing runs beside this GEMM -- measured slower in the backward, where the
+                                 // weight-gradient GEMMs of the side stream then cannot share the SMs)
     int b_static = 0;            // tensor-core kernel: B was NOT written by the kernel preceding this launch on its stream (a
                                  // weight, a saved activation): its first stages are requested before the PDL dependency wait
 };
