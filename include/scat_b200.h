@@ -181,6 +181,11 @@ int scat_peer_open(const uint8_t* handle64, void** out);
 int scat_peer_close(void* ptr);
 int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
                         long long hi, void* stream);
+/* One of SEVERAL exchanges a step issues on the same stream (disjoint ranges, same order on every rank): with last == 0
+ * the closing cross-GPU barrier is left to a later exchange of that stream -- the sums of this range may only be read,
+ * and the gradients only be rewritten, after an exchange with last != 0 (or scat_peer_allreduce) on the same stream. */
+int scat_peer_allreduce_part(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
+                             long long hi, int32_t last, void* stream);
 int scat_peer_error(const uint32_t* signal, int32_t* out);     /* synchronous read of the time-out flag */
 /* device address of that flag inside a signal area: non-zero once an exchange on this rank has given up on a peer (it
  * stays set; later exchanges are then no-ops).  Pass it to scat_adam_step as abort_flag. */

@@ -59,6 +59,7 @@ SIGNATURES = {
     "scat_peer_open": (_i32, [_f, _pp]),
     "scat_peer_close": (_i32, [_f]),
     "scat_peer_allreduce": (_i32, [_pp, _pp, _i32, _i32, C.c_longlong, C.c_longlong, _f]),
+    "scat_peer_allreduce_part": (_i32, [_pp, _pp, _i32, _i32, C.c_longlong, C.c_longlong, _i32, _f]),
     "scat_peer_error": (_i32, [_f, C.POINTER(C.c_int32)]),
     "scat_peer_error_word": (C.c_void_p, [_f]),
     "scat_tokens_forward": (_i32, [_desc, _pp, _f, _f, _f, _f, _f, _f, _sz, _f]),

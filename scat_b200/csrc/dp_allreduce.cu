@@ -96,7 +96,7 @@ __device__ __forceinline__ bool peer_barrier(const PeerSet& ps, int rank, uint32
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerSet ps, int rank, long long lo4, long long n4) {
+__global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerSet ps, int rank, long long lo4, long long n4, int last) {
     // loads of U grid-strides are issued together: an NVLink round trip is several microseconds, and a volatile load
     // is not moved across the stores of the previous iteration
     constexpr int U = W >= 8 ? 1 : (W == 4 ? 2 : 4);
@@ -138,21 +138,22 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerSet ps, in
             }
         }
     }
-    peer_barrier<W>(ps, rank, 2 * e + 2);
+    // the closing barrier (every peer has stored its sums into this rank's bucket) may be left to a LATER exchange of the
+    // same stream: its opening barrier is reached by a rank only after that rank's earlier exchanges have stored, and
+    // nothing reads the sums or rewrites the gradients before the last exchange of the step has closed
+    if (last) peer_barrier<W>(ps, rank, 2 * e + 2);
     if (threadIdx.x == 0) *epoch = e + 1;
 }
 
 template <int W>
-int launch_w(const PeerSet& ps, int rank, long long lo4, long long n4, cudaStream_t st) {
+int launch_w(const PeerSet& ps, int rank, long long lo4, long long n4, int last, cudaStream_t st) {
     constexpr int U = W >= 8 ? 1 : (W == 4 ? 2 : 4);        // as in the kernel
     const long long per = (n4 + W - 1) / W, per_block = (long long)kThreads * U;
-    static const int launch_blocks = [] {
-        const char* e = getenv("SCAT_PEER_BLOCKS");
-        const int v = e ? atoi(e) : kLaunchBlocksDefault;
-        return std::max(1, std::min(v, kMaxBlocks));
-    }();
+    static const int env_blocks = [] { const char* e = getenv("SCAT_PEER_BLOCKS"); return e ? atoi(e) : 0; }();
+    // more ranks = more NVLink round trips per byte of this rank's share: the block count grows with the world size
+    const int launch_blocks = std::max(1, std::min(env_blocks > 0 ? env_blocks : kLaunchBlocksDefault * (W >= 8 ? 4 : W >= 4 ? 2 : 1), kMaxBlocks));
     const int grid = (int)std::min<long long>(launch_blocks, std::max<long long>(1, (per + per_block - 1) / per_block));
-    SCAT_CHECK_CUDA(launch_k(peer_allreduce_kernel<W>, dim3(grid), dim3(kThreads), 0, st, ps, rank, lo4, n4));
+    SCAT_CHECK_CUDA(launch_k(peer_allreduce_kernel<W>, dim3(grid), dim3(kThreads), 0, st, ps, rank, lo4, n4, last));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
@@ -201,8 +202,8 @@ int scat_peer_close(void* ptr) {
     return 0;
 }
 
-int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
-                        long long hi, void* stream) {
+static int peer_allreduce_impl(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
+                               long long hi, int last, void* stream) {
     SCAT_REQUIRE(buckets && signals, kErrBadArg, "peer_allreduce: null");
     SCAT_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, kErrBadArg,
                  "peer_allreduce: rank %d of %d (at most %d peers)", rank, world, kMaxPeers);
@@ -217,13 +218,23 @@ int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     const long long lo4 = lo / 4, n4 = (hi - lo) / 4;
     switch (world) {
-        case 1: return launch_w<1>(ps, rank, lo4, n4, st);
-        case 2: return launch_w<2>(ps, rank, lo4, n4, st);
-        case 4: return launch_w<4>(ps, rank, lo4, n4, st);
-        case 8: return launch_w<8>(ps, rank, lo4, n4, st);
+        case 1: return launch_w<1>(ps, rank, lo4, n4, last, st);
+        case 2: return launch_w<2>(ps, rank, lo4, n4, last, st);
+        case 4: return launch_w<4>(ps, rank, lo4, n4, last, st);
+        case 8: return launch_w<8>(ps, rank, lo4, n4, last, st);
         default: break;
     }
     SCAT_REQUIRE(false, kErrUnsupported, "peer_allreduce: world size %d (1, 2, 4 or 8)", world);
+}
+
+int scat_peer_allreduce(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
+                        long long hi, void* stream) {
+    return peer_allreduce_impl(buckets, signals, rank, world, lo, hi, 1, stream);
+}
+
+int scat_peer_allreduce_part(float* const* buckets, uint32_t* const* signals, int32_t rank, int32_t world, long long lo,
+                             long long hi, int32_t last, void* stream) {
+    return peer_allreduce_impl(buckets, signals, rank, world, lo, hi, last ? 1 : 0, stream);
 }
 
 const uint32_t* scat_peer_error_word(const uint32_t* signal) { return signal ? signal + kSigError : nullptr; }

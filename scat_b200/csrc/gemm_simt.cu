@@ -182,10 +182,15 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ld, 
     }
 }
 
-__global__ void round_copy_kernel(const RoundJobs jobs) {
+// One block per SM walks every job: the copies run beside the conv forward, whose persistent CTAs (54 K registers) only
+// become resident on an SM that holds at most one of these 256-thread blocks
+__device__ __forceinline__ void round_copy_job(const RoundJob& job, int tid, int nthr);
+__global__ void __launch_bounds__(256) round_copy_kernel(const RoundJobs jobs) {
     pdl_sync();
-    const RoundJob job = jobs.job[blockIdx.y];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int j = 0; j < jobs.n; ++j) round_copy_job(jobs.job[j], tid, nthr);
+}
+__device__ __forceinline__ void round_copy_job(const RoundJob& job, int tid, int nthr) {
     if (job.to_bf16 == 2) {                                          // TF32 remainder: src - round(src), itself rounded
         const int total = job.rows * job.ld_dst;
         for (int i = tid; i < total; i += nthr) {
@@ -321,7 +326,7 @@ int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, 
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 16, kErrBadArg, "round_copy: %d jobs", jobs.n);
-    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(dim3(74, jobs.n)), dim3(256), 0, stream, jobs));
+    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(148), dim3(256), 0, stream, jobs));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

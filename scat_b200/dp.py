@@ -205,11 +205,12 @@ class PeerMemory:
         self._check(self.lib.scat_peer_alloc(nbytes, self._C.byref(out)), "scat_peer_alloc")
         return out.value
 
-    def enqueue(self, stream_ptr: int, lo: int = 0, hi: int = None):
-        """Sum elements [lo, hi) (multiples of 4; hi=None: the whole bucket) over all ranks, in place, on ``stream``."""
+    def enqueue(self, stream_ptr: int, lo: int = 0, hi: int = None, last: bool = True):
+        """Sum elements [lo, hi) (multiples of 4; hi=None: the whole bucket) over all ranks, in place, on ``stream``.
+        ``last=False``: another exchange follows on the same stream and closes this one too (scat_peer_allreduce_part)."""
         hi = self.n_pad if hi is None else hi
-        self._check(self.lib.scat_peer_allreduce(self._bucket_arr, self._signal_arr, self.rank, self.world, lo, hi,
-                                                 stream_ptr), "scat_peer_allreduce")
+        self._check(self.lib.scat_peer_allreduce_part(self._bucket_arr, self._signal_arr, self.rank, self.world, lo, hi,
+                                                      1 if last else 0, stream_ptr), "scat_peer_allreduce_part")
 
     def error_word(self):
         """Device address (ctypes void pointer) of this rank's sticky time-out flag, for scat_adam_step's abort_flag."""

@@ -201,7 +201,9 @@ class HeadTrainStep:
             # gradient, the last kernel of the step.  The three exchanges are launches of the same kernel on the library's
             # exchange stream: same order on every rank, serialised among themselves, no phase joins on the main stream.
             parts = ((self.split, None), (self.split0, self.split), (0, self.split0))
-            self._enqueue(slot, ready=lambda part, stream: self.peer.enqueue(stream, lo=parts[part][0], hi=parts[part][1]))
+            # (the first two leave their closing cross-GPU barrier to the third)
+            self._enqueue(slot, ready=lambda part, stream: self.peer.enqueue(stream, lo=parts[part][0], hi=parts[part][1],
+                                                                               last=(part == 2)))
         else:
             self._enqueue(slot)
             if ar:
