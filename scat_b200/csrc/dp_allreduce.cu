@@ -30,7 +30,8 @@ constexpr int kMaxBlocks = 296;                 // size of the per-block flag ar
 // last kernel: 32 blocks 0.796 / 0.840 ms, 64: 0.805 / 0.826, 148: 0.802 / 0.829 (no exchange: 0.775) -- the default serves
 // the hidden form.
 // SCAT_PEER_BLOCKS overrides the block count (every rank must use the same value).
-constexpr int kLaunchBlocksDefault = 32;
+// (defaults per world size in launch_w: 48 / 64 / 128 blocks for 2 / 4 / 8 ranks -- the 9 MB layer-0 part has ~70 us of conv
+// backward to hide under, and more ranks mean longer round trips for the same bytes)
 constexpr int kThreads = 256;
 // signal area (uint32 words): flags[kMaxBlocks][kMaxPeers], epoch[kMaxBlocks], error
 constexpr int kSigFlags = 0;
@@ -151,7 +152,7 @@ int launch_w(const PeerSet& ps, int rank, long long lo4, long long n4, int last,
     const long long per = (n4 + W - 1) / W, per_block = (long long)kThreads * U;
     static const int env_blocks = [] { const char* e = getenv("SCAT_PEER_BLOCKS"); return e ? atoi(e) : 0; }();
     // more ranks = more NVLink round trips per byte of this rank's share: the block count grows with the world size
-    const int launch_blocks = std::max(1, std::min(env_blocks > 0 ? env_blocks : kLaunchBlocksDefault * (W >= 8 ? 4 : W >= 4 ? 2 : 1), kMaxBlocks));
+    const int launch_blocks = std::max(1, std::min(env_blocks > 0 ? env_blocks : (W >= 8 ? 128 : W >= 4 ? 64 : 48), kMaxBlocks));
     const int grid = (int)std::min<long long>(launch_blocks, std::max<long long>(1, (per + per_block - 1) / per_block));
     SCAT_CHECK_CUDA(launch_k(peer_allreduce_kernel<W>, dim3(grid), dim3(kThreads), 0, st, ps, rank, lo4, n4, last));
     SCAT_CHECK_LAUNCH();

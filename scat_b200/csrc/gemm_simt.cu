@@ -182,10 +182,11 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ld, 
     }
 }
 
-// One block per SM walks every job: the copies run beside the conv forward, whose persistent CTAs (54 K registers) only
-// become resident on an SM that holds at most one of these 256-thread blocks
+// One 128-thread block per SM walks every job: the copies run beside the conv forward, whose persistent CTAs hold 54 K of
+// an SM's 64 K registers -- whichever of the two kernels arrives second only becomes resident if the other left room
+// (with 256-thread blocks the timeline showed them taking turns: 18 us of the copies' 30 behind the conv kernel)
 __device__ __forceinline__ void round_copy_job(const RoundJob& job, int tid, int nthr);
-__global__ void __launch_bounds__(256) round_copy_kernel(const RoundJobs jobs) {
+__global__ void __launch_bounds__(128) round_copy_kernel(const RoundJobs jobs) {
     pdl_sync();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     for (int j = 0; j < jobs.n; ++j) round_copy_job(jobs.job[j], tid, nthr);
@@ -326,7 +327,7 @@ int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, 
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 16, kErrBadArg, "round_copy: %d jobs", jobs.n);
-    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(148), dim3(256), 0, stream, jobs));
+    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(148), dim3(128), 0, stream, jobs));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
