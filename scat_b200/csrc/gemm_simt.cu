@@ -182,14 +182,13 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ld, 
     }
 }
 
-// One 128-thread block per SM walks every job: the copies run beside the conv forward, whose persistent CTAs hold 54 K of
-// an SM's 64 K registers -- whichever of the two kernels arrives second only becomes resident if the other left room
-// (with 256-thread blocks the timeline showed them taking turns: 18 us of the copies' 30 behind the conv kernel)
+// grid (x, job): block column x strides job blockIdx.y.  (Measured alternatives, r2v2 / r2x timelines: ONE 256- or 128-thread
+// block per SM walking every job, launched so that the conv forward gets the SMs first -- the copies then start 15 us
+// after the conv kernel and finish 47 us into the step, delaying the first GEMM; the kernels do not overlap either way.)
 __device__ __forceinline__ void round_copy_job(const RoundJob& job, int tid, int nthr);
-__global__ void __launch_bounds__(128) round_copy_kernel(const RoundJobs jobs) {
+__global__ void __launch_bounds__(256) round_copy_kernel(const RoundJobs jobs) {
     pdl_sync();
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    for (int j = 0; j < jobs.n; ++j) round_copy_job(jobs.job[j], tid, nthr);
+    round_copy_job(jobs.job[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 __device__ __forceinline__ void round_copy_job(const RoundJob& job, int tid, int nthr) {
     if (job.to_bf16 == 2) {                                          // TF32 remainder: src - round(src), itself rounded
@@ -327,7 +326,7 @@ int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, 
 
 int launch_round_copy(const RoundJobs& jobs, cudaStream_t stream) {
     SCAT_REQUIRE(jobs.n > 0 && jobs.n <= 16, kErrBadArg, "round_copy: %d jobs", jobs.n);
-    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(148), dim3(128), 0, stream, jobs));
+    SCAT_CHECK_CUDA(launch_k(round_copy_kernel, dim3(dim3(74, jobs.n)), dim3(256), 0, stream, jobs));
     SCAT_CHECK_LAUNCH();
     return 0;
 }

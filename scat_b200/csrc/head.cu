@@ -769,11 +769,11 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
     SideScope side_scope;
     SideStream* sd = side_scope.sd;
     const cudaStream_t sg = sd ? sd->s : st;
-    // side stream: the weight copies and, once the conv kernel has left the SMs, the iteration-invariant half of the
-    // regressor (needs only main_feat).  Anything resident beside the conv forward delays it: its persistent CTAs need
-    // 54 K of an SM's 64 K registers, so the copies run as ONE 256-thread block per SM and the regressor product waits
+    // side stream: the iteration-invariant half of the regressor (needs only main_feat) and, below, the weight copies.
+    // (They and the conv forward do not overlap on the GPU: whichever is dispatched first holds the SMs for 10-15 us.
+    // Copies first is the better order -- they are needed by the first GEMM, 35 us into the step.)
     SCAT_PROPAGATE(order_after(sd, st, sg));
-    if (!tc) SCAT_PROPAGATE(launch_regressor_hoist(main_feat, W[P_REG_W], W[P_REG_B], ws + p.hreg, p.B, p.F, p.NP, sg));
+    SCAT_PROPAGATE(launch_regressor_hoist(main_feat, W[P_REG_W], W[P_REG_B], ws + p.hreg, p.B, p.F, p.NP, sg));
     if (tc) {
         // per-forward weight copies for the tensor cores: the conv weight stacks first, on the main stream; the
         // transformer's copies (TF32-rounded fp32 or bf16) overlap the conv kernel on the side stream
@@ -781,16 +781,12 @@ int head_forward(const ScatHeadDesc& d, const float* const* W, const float* pe, 
         SCAT_PROPAGATE(round_weights(p, W, ws, d.precision, sg));
         SCAT_PROPAGATE(launch_conv_pe_mask_fwd_tc(x2, d.x2_dtype, ws + p.w_conv, pe, W[P_MASK_TOKEN], mask_idx, d.n_masked,
                                                   d.pos_embed, fv, X0, p.B, p.C, p.D, p.T, st));
-        const cudaStream_t sb = sd ? sd->s2 : st;         // (behind the conv kernel; joined with `sg` below)
-        SCAT_PROPAGATE(order_after(sd, st, sb));
-        SCAT_PROPAGATE(launch_regressor_hoist(main_feat, W[P_REG_W], W[P_REG_B], ws + p.hreg, p.B, p.F, p.NP, sb));
     } else {
         SCAT_PROPAGATE(launch_conv_pe_mask_fwd((const float*)x2, W[P_CONV_W], pe, W[P_MASK_TOKEN], mask_idx, d.n_masked,
                                                d.pos_embed, fv, X0, p.B, p.C, p.D, p.T, st));
     }
     SCAT_PROPAGATE(order_after(sd, sg, st));       // weight copies (and the hoisted regressor product) are in place
     SCAT_PROPAGATE(transformer_forward(p, W, ws, d.precision, st, d.pos_embed ? nullptr : fv));
-    if (tc && sd != nullptr) SCAT_PROPAGATE(order_after(sd, sd->s2, st));      // the hoisted regressor product (long finished)
     if (!skip_regressor)     // (the fused train step runs the regressor inside its tail kernel, see head_backward)
         SCAT_PROPAGATE(launch_regressor_fwd(main_feat, ws + p.feat_out, mean_params, W[P_REG_W], W[P_REG_B], pred,
                                             ws + p.states, ws + p.hreg, p.B, p.F, p.NP, p.it, 1, st, /*hoisted=*/1));
