@@ -10,6 +10,7 @@
 // 126 MB L2:  set-up kernel (Rodrigues, chain, skinning matrices, U')  ->  GEMM  ->  skinning kernel (thread per vertex:
 // T = sum_j w_vj A_j, x = T (v_posed, 1), global rotation, root).  The FFMA kernel of lbs.cu stays as the fp32 form.
 #include "lbs_common.cuh"
+#include <mutex>
 
 namespace scat {
 
@@ -22,7 +23,35 @@ constexpr int TC_K = 3 * TC_KP;            // stacked hi / lo / hi
 constexpr int TC_N = NV * 3;               // 2334 vertex coordinates, n = 3 v + c
 constexpr int TC_LDC = 2336;
 constexpr int TC_S = 16;                   // samples per CTA in the set-up kernel
-constexpr int TC_PER_SAMPLE = TC_K + NJ * 12 + 12 + TC_LDC;   // scratch floats per sample: U', A, (Rg | root), corrections
+constexpr int TC_SETUP_FLOATS = TC_K + NJ * 12 + 12;          // per sample: U', A, (Rg | root)
+// scratch floats per sample: TWO set-up sets (the set-up of chunk c + 1 runs on a second stream beside the GEMM and the
+// skinning of chunk c) + the corrections
+constexpr int TC_PER_SAMPLE = 2 * TC_SETUP_FLOATS + TC_LDC;
+
+// second stream + events of scat_lbs_fwd_tc, per device (created on first use; a call holds the mutex while it enqueues)
+struct LbsSide {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[8];
+    int next = 0;
+    bool ready = false;
+    std::mutex mu;
+};
+LbsSide g_lbs_side[16];
+std::mutex g_lbs_side_create;
+LbsSide* lbs_side() {
+    static const int on = [] { const char* e = getenv("SCAT_LBS_PIPELINE"); return (e && e[0] == '0') ? 0 : 1; }();
+    int dev = 0;
+    if (!on || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    LbsSide& sd = g_lbs_side[dev];
+    std::lock_guard<std::mutex> lock(g_lbs_side_create);
+    if (!sd.ready) {
+        if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 8; ++i)
+            if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sd.ready = true;
+    }
+    return &sd;
+}
 
 // D' [2334, 444]: rows n = 3 v + c, columns [D_hi | D_hi | D_lo], D = [shapedirs[v,c,:] | posedirs[v,c,:] | 0 0 0]
 __global__ void lbs_tc_prepare_kernel(const float* __restrict__ shapedirs, const float* __restrict__ posedirs,
@@ -163,7 +192,7 @@ extern "C" {
 
 size_t scat_lbs_tc_table_floats(void) { return lbs_tc_table_floats(); }
 size_t scat_lbs_tc_scratch_floats(int32_t batch) {
-    const long long chunk = batch < 8192 ? (batch > 0 ? batch : 1) : 8192;        // ~10 KB per sample: 8192 samples = 97 MB, inside L2
+    const long long chunk = batch < 8192 ? (batch > 0 ? batch : 1) : 8192;        // ~10 KB per sample: 8192 samples: 76 MB of corrections through L2
     return (size_t)chunk * TC_PER_SAMPLE;
 }
 
@@ -186,15 +215,47 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(LbsSetup<TC_S>);
     SCAT_ENSURE_SMEM(lbs_tc_setup_kernel, smem);
-    for (long long b0 = 0; b0 < batch; b0 += chunk_max) {
-        const int n = (int)(batch - b0 < chunk_max ? batch - b0 : chunk_max);
-        float* U = scratch;                               // [n, 444]
-        float* A = U + (size_t)n * TC_K;                  // [n, 16, 12]
-        float* Rr = A + (size_t)n * NJ * 12;              // [n, 12]
-        float* corr = Rr + (size_t)n * 12;                // [n, 2336]
-        SCAT_CHECK_CUDA(launch_k(lbs_tc_setup_kernel, dim3(ceil_div(n, TC_S)), dim3(LBS_THREADS), smem, st, derived, hands_mean, rots,
+    // chunk c: set-up (Rodrigues, chain, U') -> GEMM -> skinning.  The set-up of chunk c + 1 only needs its own buffers, so
+    // it runs on a second stream beside the GEMM / skinning of chunk c (two set-up sets alternate); the main stream waits
+    // for it just before the GEMM that reads it.  Everything is joined again before the call returns (capturable).
+    const long long chunk = batch < chunk_max ? batch : chunk_max;
+    float* set_base[2] = {scratch, scratch + (size_t)chunk * TC_SETUP_FLOATS};
+    float* corr = scratch + 2 * (size_t)chunk * TC_SETUP_FLOATS;         // [chunk, 2336]
+    const int n_chunks = (int)((batch + chunk - 1) / chunk);
+    LbsSide* sd = n_chunks > 1 ? lbs_side() : nullptr;
+    std::unique_lock<std::mutex> lock;
+    if (sd) lock = std::unique_lock<std::mutex>(sd->mu);
+    auto next_event = [&]() { cudaEvent_t e = sd->ev[sd->next]; sd->next = (sd->next + 1) % 8; return e; };
+    auto setup = [&](int c, cudaStream_t s) -> int {
+        const long long b0 = (long long)c * chunk;
+        const int n = (int)(batch - b0 < chunk ? batch - b0 : chunk);
+        float* U = set_base[c & 1];
+        float* A = U + (size_t)chunk * TC_K;
+        float* Rr = A + (size_t)chunk * NJ * 12;
+        SCAT_CHECK_CUDA(launch_k(lbs_tc_setup_kernel, dim3(ceil_div(n, TC_S)), dim3(LBS_THREADS), smem, s, derived, hands_mean, rots,
                                  poses, betas, U, A, Rr, out, (int)b0, n));
         SCAT_CHECK_LAUNCH();
+        return 0;
+    };
+    SCAT_PROPAGATE(setup(0, st));
+    cudaEvent_t ready = nullptr;
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long b0 = (long long)c * chunk;
+        const int n = (int)(batch - b0 < chunk ? batch - b0 : chunk);
+        float* U = set_base[c & 1];
+        float* A = U + (size_t)chunk * TC_K;
+        float* Rr = A + (size_t)chunk * NJ * 12;
+        cudaEvent_t ready_next = nullptr;
+        if (c + 1 < n_chunks && sd) {
+            // set (c + 1) & 1 was last read by the GEMM / skinning of chunk c - 1: everything on `st` so far
+            cudaEvent_t e_free = next_event();
+            SCAT_CHECK_CUDA(cudaEventRecord(e_free, st));
+            SCAT_CHECK_CUDA(cudaStreamWaitEvent(sd->s, e_free, 0));
+            SCAT_PROPAGATE(setup(c + 1, sd->s));
+            ready_next = next_event();
+            SCAT_CHECK_CUDA(cudaEventRecord(ready_next, sd->s));
+        }
+        if (ready != nullptr) SCAT_CHECK_CUDA(cudaStreamWaitEvent(st, ready, 0));
         GemmArgs g;
         g.A = U; g.sam = TC_K; g.sak = 1; g.B = table; g.sbn = TC_K; g.sbk = 1;
         g.C = corr; g.ldc = TC_LDC; g.M = n; g.N = TC_N; g.K = TC_K; g.prerounded = 1;
@@ -202,6 +263,8 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
         SCAT_CHECK_CUDA(launch_k(lbs_tc_skin_kernel, dim3(n), dim3(SKIN_THREADS), 0, st, derived, (const float*)corr, (const float*)A,
                                  (const float*)Rr, out, (int)b0));
         SCAT_CHECK_LAUNCH();
+        if (c + 1 < n_chunks && !sd) SCAT_PROPAGATE(setup(c + 1, st));
+        ready = ready_next;
     }
     return 0;
 }
