@@ -101,16 +101,26 @@ attention_fwd_mma_kernel(const float* __restrict__ QKV, float* __restrict__ O, f
     const float* Kb = Qb + inner;
     const float* Vb = Qb + 2 * inner;
 
-    // S = Q K^T   [16 x 24], k = 64
+    // S = Q K^T   [16 x 24], k = 64.  The k index inside an 8-wide MMA step is permuted the same way for both operands
+    // (lane t holds k = 2t, 2t + 1 instead of t, t + 4: a dot product does not care), so that a lane's two k values are
+    // adjacent in memory: one 8-byte load per fragment row instead of two 4-byte loads.
     float s[3][4];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    const int qr0 = mt * 16 + g, qr1 = qr0 + 8;
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-        uint32_t a[4], bf[3][2];
-        frag_a(a, Qb, rs, mt * 16, ks * 8, N, DH, g, t);
+        const int kc = ks * 8 + 2 * t;
+        const float2 q0 = qr0 < N ? __ldg(reinterpret_cast<const float2*>(Qb + (long long)qr0 * rs + kc)) : make_float2(0.f, 0.f);
+        const float2 q1 = qr1 < N ? __ldg(reinterpret_cast<const float2*>(Qb + (long long)qr1 * rs + kc)) : make_float2(0.f, 0.f);
+        const uint32_t a[4] = {to_tf32(q0.x), to_tf32(q1.x), to_tf32(q0.y), to_tf32(q1.y)};
+        uint32_t bf[3][2];
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) frag_b_n(bf[nt], Kb, rs, ks * 8, nt * 8, DH, N, g, t);
+        for (int nt = 0; nt < 3; ++nt) {
+            const int j = nt * 8 + g;
+            const float2 kv = j < N ? __ldg(reinterpret_cast<const float2*>(Kb + (long long)j * rs + kc)) : make_float2(0.f, 0.f);
+            bf[nt][0] = to_tf32(kv.x); bf[nt][1] = to_tf32(kv.y);
+        }
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) mma_tf32(s[nt], a, bf[nt]);
     }
@@ -154,27 +164,20 @@ attention_fwd_mma_kernel(const float* __restrict__ QKV, float* __restrict__ O, f
                 if (i < N && j < N) Pg[i * N + j] = pv;                  // saved for the backward
             }
     }
-    // O = P V   [16 x 64], k = 24: P from the accumulator layout (cols 2t, 2t+1) to the A layout (cols t, t+4)
+    // O = P V   [16 x 64], k = 24.  With the same permutation (lane t holds k = 2t, 2t + 1) the accumulator layout of P
+    // (columns 2t, 2t + 1 of rows g, g + 8) IS the A-fragment layout: no shuffles; V rows 2t, 2t + 1 of the k step feed B.
     float o[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
-    const int src_lo = (lane & ~3) | (t >> 1), src_hi = src_lo + 2;
-    const bool odd = t & 1;
 #pragma unroll
     for (int ks = 0; ks < 3; ++ks) {
-        uint32_t a[4];
-        const float l0 = __shfl_sync(0xffffffffu, s[ks][0], src_lo), l1 = __shfl_sync(0xffffffffu, s[ks][1], src_lo);
-        const float l2 = __shfl_sync(0xffffffffu, s[ks][2], src_lo), l3 = __shfl_sync(0xffffffffu, s[ks][3], src_lo);
-        const float h0 = __shfl_sync(0xffffffffu, s[ks][0], src_hi), h1 = __shfl_sync(0xffffffffu, s[ks][1], src_hi);
-        const float h2 = __shfl_sync(0xffffffffu, s[ks][2], src_hi), h3 = __shfl_sync(0xffffffffu, s[ks][3], src_hi);
-        a[0] = to_tf32(odd ? l1 : l0);        // P[g      ][8ks + t]
-        a[1] = to_tf32(odd ? l3 : l2);        // P[g + 8  ][8ks + t]
-        a[2] = to_tf32(odd ? h1 : h0);        // P[g      ][8ks + t + 4]
-        a[3] = to_tf32(odd ? h3 : h2);        // P[g + 8  ][8ks + t + 4]
+        const uint32_t a[4] = {to_tf32(s[ks][0]), to_tf32(s[ks][2]), to_tf32(s[ks][1]), to_tf32(s[ks][3])};
+        const int j0 = ks * 8 + 2 * t, j1 = j0 + 1;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             uint32_t bf[2];
-            frag_b_k(bf, Vb, rs, ks * 8, nt * 8, N, DH, g, t);
+            bf[0] = ld_tf32(Vb, rs, j0, nt * 8 + g, N, DH);
+            bf[1] = ld_tf32(Vb, rs, j1, nt * 8 + g, N, DH);
             mma_tf32(o[nt], a, bf);
         }
     }
