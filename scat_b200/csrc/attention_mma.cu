@@ -222,13 +222,24 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) dp[mt][nt][0] = dp[mt][nt][1] = dp[mt][nt][2] = dp[mt][nt][3] = 0.f;
+    // (k permuted inside each MMA step as in the forward: lane t holds k = 2t, 2t + 1 of both operands, 8-byte loads)
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
         uint32_t a[2][4], bf[3][2];
+        const int kc = ks * 8 + 2 * t;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) frag_a(a[mt], Gb, inner, mt * 16, ks * 8, N, DH, g, t);
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const float2 x0 = r0 < N ? __ldg(reinterpret_cast<const float2*>(Gb + (long long)r0 * inner + kc)) : make_float2(0.f, 0.f);
+            const float2 x1 = r1 < N ? __ldg(reinterpret_cast<const float2*>(Gb + (long long)r1 * inner + kc)) : make_float2(0.f, 0.f);
+            a[mt][0] = to_tf32(x0.x); a[mt][1] = to_tf32(x1.x); a[mt][2] = to_tf32(x0.y); a[mt][3] = to_tf32(x1.y);
+        }
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) frag_b_n(bf[nt], Vb, rs, ks * 8, nt * 8, DH, N, g, t);
+        for (int nt = 0; nt < 3; ++nt) {
+            const int j = nt * 8 + g;
+            const float2 v = j < N ? __ldg(reinterpret_cast<const float2*>(Vb + (long long)j * rs + kc)) : make_float2(0.f, 0.f);
+            bf[nt][0] = to_tf32(v.x); bf[nt][1] = to_tf32(v.y);
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
