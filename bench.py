@@ -699,8 +699,8 @@ def run_ours(args):
     c0 = lib.scat_launch_count()
     ts._enqueue()
     launches_per_step = int(lib.scat_launch_count() - c0)
-    if ts.peer is not None:
-        launches_per_step += 1          # the peer-memory all-reduce kernel captured behind the step
+    if ts.peer is not None:             # the peer-memory all-reduce kernel(s) captured with the step: one launch per part
+        launches_per_step += 4 if ts.overlap_exchange else 1
     torch.cuda.synchronize()
 
     def barrier():
@@ -868,7 +868,8 @@ def run_ours(args):
                                             "slots) + step(), losses copied back every step"},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "loss": loss_val,
-            "allreduce": {"none": "none", "peer": "one NVLink peer-memory kernel inside the step's CUDA graph",
+            "allreduce": {"none": "none", "peer": ("NVLink peer-memory exchange in four parts hidden under the backward (gradients-ready hook), inside the step's CUDA graph"
+                                   if getattr(ts, "overlap_exchange", False) else "one NVLink peer-memory kernel inside the step's CUDA graph"),
                           "nccl": "NCCL, three phases overlapped with the backward" if ts.phased else
                                   "NCCL after the step"}[ts.comm],
             "clocks": clocks, "with_optimizer": with_opt,

@@ -149,11 +149,12 @@ int scat_head_train_step_phase(const ScatHeadDesc* desc, const float* const* par
 
 /* The single-call step with a gradients-ready hook, for data-parallel callers that hide their gradient exchange under the
  * backward without cutting the step into phases.  `ready(user, part, side_stream)` is called on the host, while the step
- * is being ENQUEUED (also under stream capture), three times and in this order:
+ * is being ENQUEUED (also under stream capture), four times and in this order:
  *   part 0: parameters 13..34 (transformer layers 1, 2 and the regressor) are final in the order of `side_stream`;
- *   part 1: parameters 2..12 (transformer layer 0);
- *   part 2: parameters 0, 1 (mask token, conv weight) -- the conv data gradient (x2_grad) is still to come.
- * Work the hook enqueues on `side_stream` (a library-owned stream, the same for the three calls, so the hook's launches
+ *   part 1: parameters 7..12 (the feed-forward half of transformer layer 0: its LayerNorm, fc1, fc2);
+ *   part 2: parameters 2..6 (the attention half of layer 0: its LayerNorm, to_qkv, to_out);
+ *   part 3: parameters 0, 1 (mask token, conv weight) -- the conv data gradient (x2_grad) is still to come.
+ * Work the hook enqueues on `side_stream` (a library-owned stream, the same for the four calls, so the hook's launches
  * are serialised among themselves) runs beside the rest of the step; `stream` waits for it before the call returns, so
  * the step stays one capturable unit.  A non-zero return from the hook fails the call.  ready == NULL: scat_head_train_step. */
 typedef int (*scat_grads_ready_fn)(void* user, int32_t part, void* side_stream);

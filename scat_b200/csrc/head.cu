@@ -67,6 +67,8 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     return 0;
 }
 
+// experiment switch: bit 0 / 1 / 2 lets the dZ / dNf / dNa GEMM of the backward use the wide single-wave tiles
+int g_exp_wide_bwd = [] { const char* e = getenv("SCAT_EXP_WIDE_BWD"); return e ? atoi(e) : 0; }();
 // Every kernel asks for the maximum shared-memory carve-out, so that consecutive kernels of the chain never make an SM
 // change its L1 / shared split between them: a GEMM CTA (96-192 KB of shared memory) cannot become resident on an SM that
 // is still configured for a kernel without shared memory, which defeats the programmatic-launch overlap.  Measured on the
@@ -621,6 +623,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         if (ffbf) { g.C16 = dZ; g.ldc16 = ld_h; }
         else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
         g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod;
+        g.allow_wide = g_exp_wide_bwd & 1;
         if (L.last && L.out == 3 && !ffbf)     // K = 3: elementwise
             SCAT_PROPAGATE(launch_ff_out3_bwd(dY, W[L.p_fc2_w], ws + L.Z, L.ldh, dZ, L.ldh, MR, L.hid, amod, tc ? ws + p.dZs : nullptr, st));
         else
@@ -641,6 +644,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         g.C = ws + c.dNf; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = L.hid; g.prerounded = fftc;
         if (L.last && bf) { g.C16 = ws + c.dX1_16; g.ldc16 = ld_n; }
         else g.round_out = (L.last && tc) ? 1 : 0;
+        g.allow_wide = (g_exp_wide_bwd >> 1) & 1;
         if (L.last && tc && L.out == 3) {
             // fp32-grade on the tensor core: dZ's [hi | lo | hi] (written by the kernel above) against fc1.weight's [hi; hi; lo]
             const int hp = pad4(L.hid);
@@ -665,6 +669,12 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             if (!L.last)     // ... with dbo = colsum(dX1) riding along
                 SCAT_PROPAGATE(launch_layernorm_param_grads(ws + c.dNf, L.d, ws + L.X1, L.d, ws + L.mean_f, ws + L.rstd_f,
                                                             G[L.p_nf_w], G[L.p_nf_b], M, L.d, sb, dX1, L.d, G[L.p_out_b]));
+            if (l == 0 && hook != nullptr && hook->fn != nullptr) {
+                // layer 0's feed-forward half (parameters 7..12: its LayerNorm, fc1, fc2) is final once the kernels queued
+                // so far on the two side streams have run: part 1 of the hook, ~60 us before the attention half
+                SCAT_PROPAGATE(order_after(sd, sb, sg));
+                SCAT_PROPAGATE(fire_hook(hook, sd, sg, 1));
+            }
             g = GemmArgs();
             g.A = dX1g; g.sam = 1; g.sak = ld_n; g.B = ws + L.O; g.b_static = 1; g.sbn = 1; g.sbk = p.inner; g.operand_bf16 = bf;
             g.C = G[L.p_out_w]; g.ldc = p.inner; g.M = L.d; g.N = p.inner; g.K = M; g.allow_split_k = 1; g.c_zeroed = 1; g.prerounded = tc;
@@ -691,6 +701,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         float* dNa = ws + c.dNa;
         g.A = ws + c.dQKV; g.sam = 3 * p.inner; g.sak = 1; g.B = w.qkv; g.b_static = 1; g.sbn = 1; g.sbk = w.ld_qkv; g.operand_bf16 = bf;
         g.C = dNa; g.ldc = L.d; g.M = MR; g.N = L.d; g.K = 3 * p.inner; g.prerounded = tc;
+        g.allow_wide = (g_exp_wide_bwd >> 2) & 1;
         SCAT_PROPAGATE(launch_gemm(g, prec, st));
         // dX = LN_a'(dNa) + dX1 (residual, vision_transformer.py:18); it is the dY of layer l-1's tensor-core GEMMs.  It
         // overwrites the dX of layer l + 2 = the dY that layer l + 1's first side-stream group read
@@ -711,8 +722,8 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
             SCAT_PROPAGATE(order_after(sd, sb, sg));
             SCAT_PROPAGATE(side_mark(sd, sg, &layer_done[l]));     // everything of layer l on the side streams is queued
             // `sg` now follows every writer of the gradients of layers >= l (and of the regressor, queued on it before):
-            // layers 1.. are part 0 of the hook, layer 0 is part 1
-            if (l == 1 || l == 0) SCAT_PROPAGATE(fire_hook(hook, sd, sg, l == 1 ? 0 : 1));
+            // layers 1.. are part 0 of the hook, the attention half of layer 0 (parameters 2..6) is part 2
+            if (l == 1 || l == 0) SCAT_PROPAGATE(fire_hook(hook, sd, sg, l == 1 ? 0 : 2));
         }
         dY = ws + c.dX;
         dYg = bf ? ws + c.dX16 : dY;
@@ -905,14 +916,14 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
                                                 d.x2_dtype, st));
         // two persistent one-CTA-per-SM streams (x2 in, x2.grad out): back to back on the main stream
         SCAT_PROPAGATE(launch_conv_wgrad_tc(ws + p.dFv2, x2, d.x2_dtype, G[P_CONV_W], p.B, p.C, p.D, p.T, st));   // G was zeroed above
-        SCAT_PROPAGATE(fire_hook(hook, sd, st, 2));      // mask token + conv weight are final: exchanged under the dgrad stream
+        SCAT_PROPAGATE(fire_hook(hook, sd, st, 3));      // mask token + conv weight are final: exchanged under the dgrad stream
         if (x2_grad != nullptr)
             SCAT_PROPAGATE(launch_conv_dgrad_tc(ws + p.dFv2, ws + p.w_conv, d.x2_dtype, x2_grad, p.B, p.C, p.D, p.T, st));
     } else {
         if (x2_grad != nullptr)
             SCAT_PROPAGATE(launch_conv_dgrad(ws + p.dFv, W[P_CONV_W], (float*)x2_grad, p.B, p.C, p.D, p.T, st));
         SCAT_PROPAGATE(launch_conv_wgrad(ws + p.dFv, (const float*)x2, G[P_CONV_W], ws + p.conv_scratch, p.B, p.C, p.D, p.T, st));
-        SCAT_PROPAGATE(fire_hook(hook, sd, st, 2));
+        SCAT_PROPAGATE(fire_hook(hook, sd, st, 3));
     }
     if (hook != nullptr && hook->used && sd != nullptr) SCAT_PROPAGATE(order_after(sd, sd->sx, st));
     return join_side(sd, st);

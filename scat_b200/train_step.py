@@ -118,6 +118,7 @@ class HeadTrainStep:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.phased else None
         self.split = self.bucket.offsets[13]
         self.split0 = self.bucket.offsets[2]
+        self.split_ff = self.bucket.offsets[7]      # first element of layer 0's feed-forward half (its PreNorm weight)
         # peer-memory exchange hidden under the backward: the step is issued in its three phases inside ONE graph and the
         # part of the bucket each phase completes is summed on a second stream while the next phase computes
         self.overlap_exchange = bool(overlap_exchange) and self.peer is not None
@@ -196,14 +197,15 @@ class HeadTrainStep:
         if ar and self.overlap_exchange:
             # The library calls back, while it enqueues the step, each time a part of the bucket is final: layers 1, 2 and
             # the regressor (bucket[split:], 6 MB) once layer 1's weight gradients are queued -- their sum runs under the
-            # layer-0 backward; layer 0 (bucket[split0:split], 9 MB) -- summed under the conv passes; the mask token and the
-            # conv weight (bucket[:split0], 46 KB: two cross-GPU flag barriers and little else) -- under the conv data
-            # gradient, the last kernel of the step.  The three exchanges are launches of the same kernel on the library's
-            # exchange stream: same order on every rank, serialised among themselves, no phase joins on the main stream.
-            parts = ((self.split, None), (self.split0, self.split), (0, self.split0))
-            # (the first two leave their closing cross-GPU barrier to the third)
+            # layer-0 backward; layer 0's feed-forward half (bucket[split_ff:split], 2.8 MB) in the middle of layer 0; its
+            # attention half (bucket[split0:split_ff], 6.4 MB) -- summed under the conv passes; the mask token and the conv
+            # weight (bucket[:split0], 46 KB: two cross-GPU flag barriers and little else) -- under the conv data gradient,
+            # the last kernel of the step.  The exchanges are launches of the same kernel on the library's exchange
+            # stream: same order on every rank, serialised among themselves, no phase joins on the main stream; all but the
+            # last leave their closing cross-GPU barrier to the last.
+            parts = ((self.split, None), (self.split_ff, self.split), (self.split0, self.split_ff), (0, self.split0))
             self._enqueue(slot, ready=lambda part, stream: self.peer.enqueue(stream, lo=parts[part][0], hi=parts[part][1],
-                                                                               last=(part == 2)))
+                                                                               last=(part == 3)))
         else:
             self._enqueue(slot)
             if ar:

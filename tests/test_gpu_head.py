@@ -224,7 +224,7 @@ def test_phased_train_step_equals_single_call(precision):
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_hooked_train_step_reports_final_gradient_parts(precision):
-    """scat_head_train_step_hooked: the gradients-ready hook fires for parts 0, 1, 2 in order, and what it enqueues on the
+    """scat_head_train_step_hooked: the gradients-ready hook fires for parts 0, 1, 2, 3 in order, and what it enqueues on the
     stream it is handed sees that part of the gradient bucket final (snapshot copies == the bucket after the step); the
     step itself equals the plain single call.  Eager and captured in a CUDA graph."""
     from scat_b200.train_step import HeadTrainStep
@@ -235,7 +235,7 @@ def test_hooked_train_step_reports_final_gradient_parts(precision):
     ts._enqueue(0)
     torch.cuda.synchronize()
     ref = (ts.bucket.flat.clone(), ts.x2_grad.clone(), ts.losses.clone())
-    bounds = ((ts.split, ts.bucket.flat.numel()), (ts.split0, ts.split), (0, ts.split0))
+    bounds = ((ts.split, ts.bucket.flat.numel()), (ts.split_ff, ts.split), (ts.split0, ts.split_ff), (0, ts.split0))
     snap = torch.zeros_like(ts.bucket.flat)
     seen = []
 
@@ -247,7 +247,7 @@ def test_hooked_train_step_reports_final_gradient_parts(precision):
 
     def check():
         torch.cuda.synchronize()
-        assert seen == [0, 1, 2]
+        assert seen == [0, 1, 2, 3]
         for a, b in zip(ref, (ts.bucket.flat, ts.x2_grad, ts.losses)):
             assert rel_max(b, a) < 1e-5
         for lo, hi in bounds:
@@ -262,7 +262,7 @@ def test_hooked_train_step_reports_final_gradient_parts(precision):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             ts._enqueue(0, ready=ready)
-    assert seen == [0, 1, 2]                      # the hook runs at capture time
+    assert seen == [0, 1, 2, 3]                   # the hook runs at capture time
     ts.bucket.flat.zero_()
     g.replay()
     torch.cuda.synchronize()
