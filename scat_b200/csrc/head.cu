@@ -888,16 +888,18 @@ int head_backward(const ScatHeadDesc& d, const float* const* W, const int32_t* m
     const bool fused_prep = d.precision != PREC_FP32 && g_fv == nullptr;
     if (!fused_prep)
         SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX, mask_idx, d.n_masked, 0, ws + p.dFv, G[P_MASK_TOKEN], p.B, p.T, p.D, st, 1));
-    if (pl_out)   // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396)
+    if (pl_out) {
+        // second half of the stacked sweep is d(sum feat_out)/d feat_visual (hand_net.py:396); nothing on the chain reads
+        // it, so it (and, in the fused step, loss += 10 * l_pl, losses[3] = l_pl, train.py:178-183,201) runs on the second
+        // side stream under the conv passes
+        const cudaStream_t sp = (sd && tail != nullptr) ? sd->s2 : st;
+        SCAT_PROPAGATE(order_after(sd, st, sp));
         SCAT_PROPAGATE(launch_mask_bwd(ws + p.dX + (size_t)p.M * p.D, mask_idx, d.n_masked, d.pos_embed ? 0 : 1, pl_out,
-                                       nullptr, p.B, p.T, p.D, st));
-    if (pl_out && tail != nullptr) {
-        // loss += 10 * l_pl, losses[3] = l_pl (train.py:178-183,201): two small reductions behind the loss kernel on the
-        // second side stream, under the conv passes instead of after them
-        const cudaStream_t sb = sd ? sd->s2 : st;
-        SCAT_PROPAGATE(order_after(sd, st, sb));
-        SCAT_PROPAGATE(side_wait(sb, loss_done));     // the loss kernel wrote losses[0..2] (and used the same scratch)
-        SCAT_PROPAGATE(launch_pl_loss_add(pl_out, p.T * p.D, p.T, tail->losses, ws + p.pl_scratch, p.B, sb));
+                                       nullptr, p.B, p.T, p.D, sp));
+        if (tail != nullptr) {
+            SCAT_PROPAGATE(side_wait(sp, loss_done));     // the loss kernel wrote losses[0..2] (and used the same scratch)
+            SCAT_PROPAGATE(launch_pl_loss_add(pl_out, p.T * p.D, p.T, tail->losses, ws + p.pl_scratch, p.B, sp));
+        }
     }
     if (g_fv != nullptr) {
         SCAT_CHECK_CUDA(launch_k(add_inplace_kernel, dim3(148 * 4), dim3(256), 0, st, ws + p.dFv, g_fv, (long long)p.M * p.D));
