@@ -192,7 +192,9 @@ extern "C" {
 
 size_t scat_lbs_tc_table_floats(void) { return lbs_tc_table_floats(); }
 size_t scat_lbs_tc_scratch_floats(int32_t batch) {
-    const long long chunk = batch < 8192 ? (batch > 0 ? batch : 1) : 8192;        // ~10 KB per sample: 8192 samples: 76 MB of corrections through L2
+    // ~14 KB per sample, 74 MB of corrections through L2 per chunk.  7936 samples = 62 row tiles x 19 column tiles = 1178
+    // GEMM tiles = 3.98 rounds of the 296 persistent CTAs (8192 samples are 1216 tiles = 4.1 rounds, i.e. five)
+    const long long chunk = batch < 7936 ? (batch > 0 ? batch : 1) : 7936;
     return (size_t)chunk * TC_PER_SAMPLE;
 }
 

@@ -43,7 +43,7 @@ def test_lbs_matches_oracle_ragged_batches(layer, B):
 
 
 def test_lbs_tensor_core_path_chunks_and_matches_ffma():
-    """The tensor-core path cuts a call into L2-sized chunks (8192 samples); chunk boundaries and a deliberately small
+    """The tensor-core path cuts a call into L2-sized chunks (7936 samples); chunk boundaries and a deliberately small
     scratch must not change the result, and it must agree with the FFMA kernel to fp32 rounding."""
     from scat_b200 import _lib
     from scat_b200._lib import check, ptr, stream_ptr
