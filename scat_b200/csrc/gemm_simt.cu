@@ -269,19 +269,19 @@ __device__ __forceinline__ void round_copy_job(const RoundJob& job, int tid, int
 // fp32-grade tensor-core operands (3xTF32): every value is split into hi = TF32-nearest(v) and lo = TF32-nearest(v - hi),
 // both exact on the tensor core, and the two operands of a product are stacked along K so that ONE GEMM computes
 // A_hi B_hi + A_lo B_hi + A_hi B_lo (the dropped lo x lo term is 2^-22 relative):
-//   first operand  (mode 0): dst[r, 3 x cp] = [hi | lo | hi]           (cp = cols padded to 4, pad columns zero)
+//   first operand  (mode 0): dst[r, 3 x cp] = [hi | lo | hi]           (cp = cols padded to 8, pad columns zero)
 //   second operand (mode 1): dst[r, 3 x cp] = [hi | hi | lo]           K-major second operand (forward, y = x W^T)
-//   second operand (mode 2): dst[3 x rp, cols] = [hi; hi; lo]          MN-major second operand (dgrad, dx = dy W), rp = rows padded to 4
+//   second operand (mode 2): dst[3 x rp, cols] = [hi; hi; lo]          MN-major second operand (dgrad, dx = dy W), rp = rows padded to 8
 __global__ void split3_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int rows, int cols, int mode) {
     pdl_sync();
-    const int cp = (cols + 3) & ~3, rp = (rows + 3) & ~3;
+    const int cp = (cols + 7) & ~7, rp = (rows + 7) & ~7;          // operand pitches: 32-byte rows (head.cu: padp)
     if (mode != 2 && ((cols | ld_src) & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
-        // activations (the step's critical chain): one float4 in, three float4 out per thread
-        const int c4n = cols >> 2;
+        // activations (the step's critical chain): one float4 in, three float4 out per thread; pad columns written as zeros
+        const int c4n = cp >> 2;
         const long long total4 = (long long)rows * c4n;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
             const int r = (int)(i / c4n), c4 = (int)(i - (long long)r * c4n);
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld_src) + c4);
+            const float4 v = c4 * 4 < cols ? __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld_src) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 hi, lo;
             hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
             lo.x = round_tf32(v.x - hi.x); lo.y = round_tf32(v.y - hi.y); lo.z = round_tf32(v.z - hi.z); lo.w = round_tf32(v.w - hi.w);
@@ -315,7 +315,7 @@ __global__ void split3_kernel(const float* __restrict__ src, int ld_src, float* 
 
 int launch_split3(const float* src, int ld_src, float* dst, int rows, int cols, int mode, cudaStream_t stream) {
     SCAT_REQUIRE(src && dst && rows > 0 && cols > 0 && mode >= 0 && mode <= 2, kErrBadArg, "split3: bad args");
-    const long long total = (long long)((rows + 3) & ~3) * ((cols + 3) & ~3);
+    const long long total = (long long)((rows + 7) & ~7) * ((cols + 7) & ~7);
     const bool vec = mode != 2 && ((cols | ld_src) & 3) == 0;
     const long long work = vec ? total / 4 : total;
     const int grid = (int)((work + 255) / 256 < 148 * 4 ? (work + 255) / 256 : 148 * 4);

@@ -229,7 +229,10 @@ enum ParamIdx {
     P_REG_W = 33, P_REG_B = 34,
 };
 inline int layer_base(int l) { return 2 + 11 * l; }
-inline int pad4(int x) { return (x + 3) / 4 * 4; }
+// leading dimension (in floats) of an fp32 tensor-core operand: rows start on 32-byte sectors.  TMA accepts any 16-byte
+// pitch, but a pitch that is an odd multiple of 16 bytes (d = 196, hidden 588 / 147, the LBS K = 444) costs the bulk
+// loads dearly: tools/gemm_pitch_probe.py, 8192 x 2334 x 444: 68.8 us at pitch 444, 44.7 us at pitch 448
+inline int padp(int x) { return (x + 7) / 8 * 8; }
 inline int pad8(int x) { return (x + 7) / 8 * 8; }
 
 struct LayerPlan {
@@ -276,20 +279,20 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     for (int l = 0; l < kDepth; ++l) {
         LayerPlan& L = p.L[l];
         L.last = (l == kDepth - 1);
-        L.d = dim; L.hid = (dim * 3) / 4; L.out = L.last ? 3 : dim / 2; L.ldh = pad4(L.hid);
+        L.d = dim; L.hid = (dim * 3) / 4; L.out = L.last ? 3 : dim / 2; L.ldh = padp(L.hid);
         ldh_max = L.ldh > ldh_max ? L.ldh : ldh_max;
         L.X = take(cur, M * dim);
-        L.Na = take(cur, M * pad4(dim));     // GEMM operand: rows padded to 16 bytes (TMA), e.g. dim 98 of the token variant
+        L.Na = take(cur, M * padp(dim));     // GEMM operand: rows padded to 16 bytes (TMA), e.g. dim 98 of the token variant
         L.mean_a = take(cur, M); L.rstd_a = take(cur, M);
         L.QKV = take(cur, M * 3 * p.inner);
         L.P = take(cur, (size_t)p.B * p.heads * p.T * p.T);
         L.O = take(cur, M * p.inner);
         L.X1 = take(cur, M * dim);
-        if (!L.last) { L.Nf = take(cur, M * pad4(dim)); L.mean_f = take(cur, M); L.rstd_f = take(cur, M); }
+        if (!L.last) { L.Nf = take(cur, M * padp(dim)); L.mean_f = take(cur, M); L.rstd_f = take(cur, M); }
         else { L.Nf = L.X1; L.mean_f = L.rstd_f = 0; }
         L.Z = take(cur, M * L.ldh);
         L.H = take(cur, M * L.ldh);
-        L.ld_qkv = pad4(dim); L.ld_out = p.inner; L.ld_fc1 = pad4(dim); L.ld_fc2 = pad4(L.hid);
+        L.ld_qkv = padp(dim); L.ld_out = p.inner; L.ld_fc1 = padp(dim); L.ld_fc2 = padp(L.hid);
         L.w_qkv = take(cur, (size_t)3 * p.inner * L.ld_qkv);
         L.w_out = take(cur, (size_t)dim * L.ld_out);
         if (!L.last) {
@@ -298,8 +301,8 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
             L.w_fc1s = L.w_fc1d = 0;
         } else {
             L.w_fc1 = L.w_fc2 = 0;
-            L.w_fc1s = take(cur, (size_t)L.hid * 3 * pad4(dim));
-            L.w_fc1d = take(cur, (size_t)3 * pad4(L.hid) * dim);
+            L.w_fc1s = take(cur, (size_t)L.hid * 3 * padp(dim));
+            L.w_fc1d = take(cur, (size_t)3 * padp(L.hid) * dim);
         }
         const int base = layer_base(l);
         L.p_na_w = base + L_NA_W; L.p_na_b = base + L_NA_B; L.p_qkv = base + L_QKV_W; L.p_out_w = base + L_OUT_W;
@@ -355,8 +358,8 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     }
     {
         const LayerPlan& LL = p.L[kDepth - 1];
-        p.x1s = take(cur, M * 3 * pad4(LL.d));
-        p.dZs = take(cur, MS * 3 * pad4(LL.hid));
+        p.x1s = take(cur, M * 3 * padp(LL.d));
+        p.dZs = take(cur, MS * 3 * padp(LL.hid));
     }
     p.dFv = take(cur, M * dmax);
     p.conv_scratch = take(cur, p.C > 0 ? conv_wgrad_scratch_floats(p.C, p.T) : 64);
@@ -493,7 +496,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         const LayerPlan& L = p.L[l];
         const LayerW w = layer_weights(p, l, W, ws, prec);
         float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
-        const int ld_n = bf ? pad8(L.d) : pad4(L.d);       // leading dimension of Na / Nf (16-byte rows for TMA)
+        const int ld_n = bf ? pad8(L.d) : padp(L.d);       // leading dimension of Na / Nf (16-byte rows for TMA)
         const int ld_h = bf ? pad8(L.hid) : L.ldh;         // leading dimension of H as a GEMM operand
         GemmArgs g;
         if (!attn_variant) {
@@ -538,7 +541,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh;
         if (L.last && tc) {
             // fp32-grade on the tensor core: X1 split into [hi | lo | hi] against the weight's [hi | hi | lo], K = 3 d
-            const int dp = pad4(L.d);
+            const int dp = padp(L.d);
             SCAT_PROPAGATE(launch_split3(ws + L.X1, L.d, ws + p.x1s, M, L.d, 0, st));
             g.A = ws + p.x1s; g.sam = 3 * dp; g.B = ws + L.w_fc1s; g.sbn = 3 * dp; g.K = 3 * dp; g.prerounded = 1;
             SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
@@ -597,7 +600,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         const int ffprec = L.last ? PREC_FP32 : prec;
         const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
         const int ld_n = bf ? pad8(L.d) : L.d;                 // dX1 / dX as GEMM operands
-        const int ld_na = bf ? pad8(L.d) : pad4(L.d);          // saved Na / Nf (as the forward stored them)
+        const int ld_na = bf ? pad8(L.d) : padp(L.d);          // saved Na / Nf (as the forward stored them)
         const int ld_h = ffbf ? pad8(L.hid) : L.ldh;           // H / dZ as GEMM operands
         float* dZ = ws + c.dZ;
         GemmArgs g;
@@ -647,7 +650,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         g.allow_wide = (g_exp_wide_bwd >> 1) & 1;
         if (L.last && tc && L.out == 3) {
             // fp32-grade on the tensor core: dZ's [hi | lo | hi] (written by the kernel above) against fc1.weight's [hi; hi; lo]
-            const int hp = pad4(L.hid);
+            const int hp = padp(L.hid);
             g.A = ws + p.dZs; g.sam = 3 * hp; g.B = ws + L.w_fc1d; g.sbk = L.d; g.K = 3 * hp; g.prerounded = 1;
             SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
         } else {

@@ -200,7 +200,7 @@ int launch_regressor_param_grads(const float* gsum, const float* gsteps, const f
 // the last feed-forward's second Linear (out = 3, vision_transformer.py:37-42) and its data gradient with the GELU
 // derivative fused (act_rows > 0: row m of dY / dZ uses activation row m % act_rows), always fp32
 int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2, float* Y, int M, int K, cudaStream_t stream);
-// dZs (nullable): also the TF32 hi / lo split [MR, 3 pad4(N)] = [hi | lo | hi] of dZ (pad columns must be zero already)
+// dZs (nullable): also the TF32 hi / lo split [MR, 3 x (N padded to 8)] = [hi | lo | hi] of dZ (pad columns must be zero already)
 int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
                        float* dZs, cudaStream_t stream);
 

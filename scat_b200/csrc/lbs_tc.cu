@@ -20,10 +20,13 @@ namespace {
 
 constexpr int TC_KP = 148;                 // 145 blend shapes padded to 16-byte rows
 constexpr int TC_K = 3 * TC_KP;            // stacked hi / lo / hi
+constexpr int TC_LD = 448;                 // row pitch of U' and D' in floats: 128-byte rows (at pitch 444 = 1776 bytes the GEMM
+                                           // takes 68.8 us per 8192 samples, at 448 44.7 us: tools/gemm_pitch_probe.py)
 constexpr int TC_N = NV * 3;               // 2334 vertex coordinates, n = 3 v + c
 constexpr int TC_LDC = 2336;
 constexpr int TC_S = 16;                   // samples per CTA in the set-up kernel
-constexpr int TC_SETUP_FLOATS = TC_K + NJ * 12 + 12;          // per sample: U', A, (Rg | root)
+constexpr int TC_SETUP_FLOATS = 672;                          // per sample: U' (448), A (192), (Rg | root) (12), padded to 128 bytes
+static_assert(TC_SETUP_FLOATS >= TC_LD + NJ * 12 + 12 && TC_SETUP_FLOATS % 32 == 0, "set-up set layout");
 // scratch floats per sample: TWO set-up sets (the set-up of chunk c + 1 runs on a second stream beside the GEMM and the
 // skinning of chunk c) + the corrections
 constexpr int TC_PER_SAMPLE = 2 * TC_SETUP_FLOATS + TC_LDC;
@@ -53,7 +56,7 @@ LbsSide* lbs_side() {
     return &sd;
 }
 
-// D' [2334, 444]: rows n = 3 v + c, columns [D_hi | D_hi | D_lo], D = [shapedirs[v,c,:] | posedirs[v,c,:] | 0 0 0]
+// D' [2334, 444] at row pitch 448: rows n = 3 v + c, columns [D_hi | D_hi | D_lo], D = [shapedirs[v,c,:] | posedirs[v,c,:] | 0 0 0]
 __global__ void lbs_tc_prepare_kernel(const float* __restrict__ shapedirs, const float* __restrict__ posedirs,
                                       float* __restrict__ Dst) {
     pdl_sync();
@@ -62,7 +65,7 @@ __global__ void lbs_tc_prepare_kernel(const float* __restrict__ shapedirs, const
     const int n = i / TC_K, kk = i - n * TC_K, third = kk / TC_KP, k = kk - third * TC_KP;
     const float v = k < NB ? shapedirs[n * NB + k] : (k < NB + NPW ? posedirs[n * NPW + (k - NB)] : 0.f);
     const float hi = round_tf32(v);
-    Dst[i] = third == 2 ? round_tf32(v - hi) : hi;
+    Dst[(long long)n * TC_LD + kk] = third == 2 ? round_tf32(v - hi) : hi;       // (columns 444..447 of a row are never read)
 }
 
 // per sample: U' row, skinning matrices A_j (rows of [R | t]), global rotation and root; joints 0..15 go straight out
@@ -89,7 +92,7 @@ lbs_tc_setup_kernel(const float* __restrict__ derived, const float* __restrict__
         const int s = e / TC_KP, k = e % TC_KP;
         const float v = k < NB ? sm.betaT[k][s] : (k < NB + NPW ? sm.pwT[k - NB][s] : 0.f);
         const float hi = round_tf32(v), lo = round_tf32(v - hi);
-        float* u = U + (long long)(l0 + s) * TC_K;
+        float* u = U + (long long)(l0 + s) * TC_LD;
         u[k] = hi; u[TC_KP + k] = lo; u[2 * TC_KP + k] = hi;
     }
     for (int e = tid; e < ns * NJ * 12; e += LBS_THREADS) {
@@ -182,7 +185,7 @@ lbs_tc_skin_kernel(const float* __restrict__ derived, const float* __restrict__ 
 
 }  // namespace
 
-size_t lbs_tc_table_floats() { return (size_t)TC_N * TC_K; }
+size_t lbs_tc_table_floats() { return (size_t)TC_N * TC_LD; }
 
 }  // namespace scat
 
@@ -232,7 +235,7 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
         const long long b0 = (long long)c * chunk;
         const int n = (int)(batch - b0 < chunk ? batch - b0 : chunk);
         float* U = set_base[c & 1];
-        float* A = U + (size_t)chunk * TC_K;
+        float* A = U + (size_t)chunk * TC_LD;
         float* Rr = A + (size_t)chunk * NJ * 12;
         SCAT_CHECK_CUDA(launch_k(lbs_tc_setup_kernel, dim3(ceil_div(n, TC_S)), dim3(LBS_THREADS), smem, s, derived, hands_mean, rots,
                                  poses, betas, U, A, Rr, out, (int)b0, n));
@@ -245,7 +248,7 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
         const long long b0 = (long long)c * chunk;
         const int n = (int)(batch - b0 < chunk ? batch - b0 : chunk);
         float* U = set_base[c & 1];
-        float* A = U + (size_t)chunk * TC_K;
+        float* A = U + (size_t)chunk * TC_LD;
         float* Rr = A + (size_t)chunk * NJ * 12;
         cudaEvent_t ready_next = nullptr;
         if (c + 1 < n_chunks && sd) {
@@ -259,7 +262,7 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
         }
         if (ready != nullptr) SCAT_CHECK_CUDA(cudaStreamWaitEvent(st, ready, 0));
         GemmArgs g;
-        g.A = U; g.sam = TC_K; g.sak = 1; g.B = table; g.sbn = TC_K; g.sbk = 1;
+        g.A = U; g.sam = TC_LD; g.sak = 1; g.B = table; g.sbn = TC_LD; g.sbk = 1;
         g.C = corr; g.ldc = TC_LDC; g.M = n; g.N = TC_N; g.K = TC_K; g.prerounded = 1;
         SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
         SCAT_CHECK_CUDA(launch_k(lbs_tc_skin_kernel, dim3(n), dim3(SKIN_THREADS), 0, st, derived, (const float*)corr, (const float*)A,

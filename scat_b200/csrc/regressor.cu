@@ -346,12 +346,12 @@ ff_out3_fwd_kernel(const float* __restrict__ H, int ldh, const float* __restrict
     if (lane < 3) Y[(long long)row * 3 + lane] = (lane == 0 ? a0 : lane == 1 ? a1 : a2) + __ldg(b2 + lane);
 }
 //   dZ[m, n] = (sum_{j<3} dY[m,j] W2[j,n]) * gelu'(Z[m % act_rows, n])      thread per element; the pad columns n >= N of a row
-//   (lddz = pad4(N)) are written as zeros so that the row can feed a tensor-core GEMM
+//   (lddz = N padded to 8 floats, head.cu: padp) are written as zeros so that the row can feed a tensor-core GEMM
 __global__ void __launch_bounds__(256)
 ff_out3_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ W2, const float* __restrict__ Z, int ldz,
                    float* __restrict__ dZ, int lddz, int MR, int N, int act_rows, float* __restrict__ dZs) {
     pdl_sync();
-    const int np = (N + 3) & ~3;
+    const int np = (N + 7) & ~7;
     const long long total = (long long)MR * np;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(i / np), n = (int)(i - (long long)m * np);
@@ -393,7 +393,7 @@ int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2
 
 int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
                        float* dZs, cudaStream_t stream) {
-    const long long total = (long long)MR * ((N + 3) & ~3);
+    const long long total = (long long)MR * ((N + 7) & ~7);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     SCAT_CHECK_CUDA(launch_k(ff_out3_bwd_kernel, dim3(grid), dim3(256), 0, stream, dY, W2, Z, ldz, dZ, lddz, MR, N, act_rows, dZs));
     SCAT_CHECK_LAUNCH();
