@@ -349,9 +349,14 @@ attention_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict_
 
 }  // namespace
 
+// experiment switch: SCAT_EXP_ATTN_L1=1 lets the two warp-level attention kernels prefer L1 over the
+// maximum shared-memory carve-out (their fragment loads re-read Q / K / V lines)
+static const bool g_exp_attn_l1 = [] { const char* e = getenv("SCAT_EXP_ATTN_L1"); return e != nullptr && e[0] == '1'; }();
+
 int launch_attention_mma_fwd(const float* QKV, float* O, float* P, int B, int n, int heads, int out_mode, cudaStream_t stream) {
     SCAT_REQUIRE(n == N, kErrUnsupported, "attention_mma: n=%d", n);
     const int nprob = B * heads;
+    if (g_exp_attn_l1) ensure_carveout(reinterpret_cast<const void*>(attention_fwd_mma_kernel), 25);
     SCAT_CHECK_CUDA(launch_k(attention_fwd_mma_kernel, dim3(ceil_div(2 * nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, O, P, nprob,
                              heads, out_mode));
     SCAT_CHECK_LAUNCH();
@@ -362,6 +367,7 @@ int launch_attention_mma_bwd(const float* QKV, const float* P, const float* dO, 
                              int out_mode, cudaStream_t stream, int act_batch) {
     SCAT_REQUIRE(n == N, kErrUnsupported, "attention_mma: n=%d", n);
     const int nprob = B * heads;
+    if (g_exp_attn_l1) ensure_carveout(reinterpret_cast<const void*>(attention_bwd_mma_kernel), 25);
     SCAT_CHECK_CUDA(launch_k(attention_bwd_mma_kernel, dim3(ceil_div(2 * nprob, WARPS)), dim3(WARPS * 32), 0, stream, QKV, P, dO, dQKV,
                              nprob, heads, out_mode, act_batch));
     SCAT_CHECK_LAUNCH();

@@ -48,7 +48,7 @@ extern unsigned long long g_launch_count;
 // process may drive several GPUs from several host threads (head.cu)
 int ensure_dynamic_smem(const void* kernel, int bytes);
 extern int g_carveout;
-void ensure_carveout(const void* kernel);
+void ensure_carveout(const void* kernel, int pct = 100);
 #define SCAT_ENSURE_SMEM(kernel, bytes) SCAT_PROPAGATE(scat::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (int)(bytes)))
 
 constexpr int kErrBadArg = -1;

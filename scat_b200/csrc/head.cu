@@ -74,7 +74,9 @@ int g_exp_wide_bwd = [] { const char* e = getenv("SCAT_EXP_WIDE_BWD"); return e 
 // is still configured for a kernel without shared memory, which defeats the programmatic-launch overlap.  Measured on the
 // B=96 step: 0.742 -> 0.722 ms.  SCAT_CARVEOUT=0 restores the driver's per-kernel choice.
 int g_carveout = [] { const char* e = getenv("SCAT_CARVEOUT"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
-void ensure_carveout(const void* kernel) {
+// pct: preferred shared-memory share of the SM's 256 KB (100 = everything a kernel may get).  The first request for a
+// kernel wins, so a launcher that wants L1 instead (table-reading FFMA kernels: the LBS skinning) asks before it launches.
+void ensure_carveout(const void* kernel, int pct) {
     struct Entry { const void* fn; int dev; };
     static std::mutex mu;
     static std::vector<Entry> seen;
@@ -83,7 +85,7 @@ void ensure_carveout(const void* kernel) {
     std::lock_guard<std::mutex> lock(mu);
     for (const Entry& e : seen)
         if (e.fn == kernel && e.dev == dev) return;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct >= 100 ? (int)cudaSharedmemCarveoutMaxShared : pct);
     seen.push_back(Entry{kernel, dev});
 }
 

@@ -265,6 +265,9 @@ int scat_lbs_fwd_tc(const float* derived, const float* table, const float* hands
         g.A = U; g.sam = TC_LD; g.sak = 1; g.B = table; g.sbn = TC_LD; g.sbk = 1;
         g.C = corr; g.ldc = TC_LDC; g.M = n; g.N = TC_N; g.K = TC_K; g.prerounded = 1;
         SCAT_PROPAGATE(launch_gemm_tc(g, PREC_TF32, st));
+        // the skinning kernel re-reads the 50 KB weight table and the 9 KB template per sample: it wants them in L1, not the
+        // maximum shared-memory carve-out every other kernel of the library asks for (11 KB of shared memory per CTA)
+        ensure_carveout(reinterpret_cast<const void*>(lbs_tc_skin_kernel), 25);
         SCAT_CHECK_CUDA(launch_k(lbs_tc_skin_kernel, dim3(n), dim3(SKIN_THREADS), 0, st, derived, (const float*)corr, (const float*)A,
                                  (const float*)Rr, out, (int)b0));
         SCAT_CHECK_LAUNCH();
