@@ -108,6 +108,15 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 #ifdef __CUDACC__
+// packed fp32 FMA (FFMA2, sm_100): (d0, d1) += w * (b0, b1); each lane is an ordinary fma.rn, one issue slot for two
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float w, float b0, float b1) {
+    unsigned long long d, a, b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

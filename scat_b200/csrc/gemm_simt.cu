@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 4; j += 2) ffma2(acc[i][j], acc[i][j + 1], av[i], bv[j], bv[j + 1]);   // packed FMA: same values
         }
     }
 

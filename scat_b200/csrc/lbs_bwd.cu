@@ -131,10 +131,10 @@ lbs_bwd_kernel(const float* __restrict__ derived, const float* __restrict__ hand
                 const float4 w = wrow[s4];
                 const float ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    vp[s4 * 4 + u][0] = fmaf(d0, ws[u], vp[s4 * 4 + u][0]);
-                    vp[s4 * 4 + u][1] = fmaf(d1, ws[u], vp[s4 * 4 + u][1]);
-                    vp[s4 * 4 + u][2] = fmaf(d2, ws[u], vp[s4 * 4 + u][2]);
+                for (int u = 0; u < 4; u += 2) {              // two samples per packed FMA (same values as fmaf)
+                    ffma2(vp[s4 * 4 + u][0], vp[s4 * 4 + u + 1][0], d0, ws[u], ws[u + 1]);
+                    ffma2(vp[s4 * 4 + u][1], vp[s4 * 4 + u + 1][1], d1, ws[u], ws[u + 1]);
+                    ffma2(vp[s4 * 4 + u][2], vp[s4 * 4 + u + 1][2], d2, ws[u], ws[u + 1]);
                 }
             }
         }
@@ -163,7 +163,7 @@ lbs_bwd_kernel(const float* __restrict__ derived, const float* __restrict__ hand
                     const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2];
                     const float a[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-                    for (int q = 0; q < 12; ++q) T[q] = fmaf(wj[j], a[q], T[q]);
+                    for (int q = 0; q < 12; q += 2) ffma2(T[q], T[q + 1], wj[j], a[q], a[q + 1]);
                 }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) x[r] = T[r * 4 + 0] * vp[s][0] + T[r * 4 + 1] * vp[s][1] + T[r * 4 + 2] * vp[s][2] + T[r * 4 + 3];
@@ -252,8 +252,11 @@ lbs_bwd_kernel(const float* __restrict__ derived, const float* __restrict__ hand
         for (int v = lane; v < NV; v += 32) {
             const float d0 = tab[v], d1 = tab[VP + v], d2 = tab[2 * VP + v];
 #pragma unroll
-            for (int s = 0; s < BW_S; ++s)
-                acc[s] = fmaf(d0, sm.vp[s][v][0], fmaf(d1, sm.vp[s][v][1], fmaf(d2, sm.vp[s][v][2], acc[s])));
+            for (int s = 0; s < BW_S; s += 2) {               // acc = d0 p0 + (d1 p1 + (d2 p2 + acc)), two samples per packed FMA
+                ffma2(acc[s], acc[s + 1], d2, sm.vp[s][v][2], sm.vp[s + 1][v][2]);
+                ffma2(acc[s], acc[s + 1], d1, sm.vp[s][v][1], sm.vp[s + 1][v][1]);
+                ffma2(acc[s], acc[s + 1], d0, sm.vp[s][v][0], sm.vp[s + 1][v][0]);
+            }
         }
 #pragma unroll
         for (int s = 0; s < BW_S; ++s) {

@@ -16,6 +16,7 @@ constexpr int OFF_JT = 0, OFF_JS = OFF_JT + NJ * 3, OFF_VT = 528 /* 16*3 + 16*3*
 __constant__ int c_parent[NJ] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14};   // mano.py:221-223
 __constant__ int c_tips[5] = {320, 443, 671, 554, 744};                                    // mano.py:373-377
 
+
 // R = I + sin(t) S(n) + (1 - cos(t)) S(n)^2, n = r/t; Taylor form only where t < 1e-30 (mano.py:236-267)
 __device__ inline void rodrigues(float rx, float ry, float rz, float* R) {
     const float t2 = rx * rx + ry * ry + rz * rz;

@@ -110,15 +110,6 @@ lbs_tc_setup_kernel(const float* __restrict__ derived, const float* __restrict__
 // broadcast LDS.128 of A_j for 12 FMAs: ncu 134 us per 8192 samples, 25 % of the FMA peak); with four vertices a joint
 // costs one LDG.128 of weights and the same three LDS.128 for 48 FMAs.  Per vertex the arithmetic (and its order) is
 // unchanged.  Results leave through a shared-memory row so that the 9.3 KB of a sample's vertices are written coalesced.
-// (d0, d1) += w * (b0, b1)
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float w, float b0, float b1) {
-    unsigned long long d, a, b;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(w));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
-}
 constexpr int SKIN_VPT = 4;
 static_assert(VP % SKIN_VPT == 0 && (OFF_VT % 4) == 0 && (OFF_W % 4) == 0 && (TC_LDC % 4) == 0, "float4 table reads");
 constexpr int SKIN_THREADS = 224;             // 7 warps: 195 threads own vertices
