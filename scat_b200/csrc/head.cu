@@ -235,7 +235,8 @@ inline int layer_base(int l) { return 2 + 11 * l; }
 // pitch, but a pitch that is an odd multiple of 16 bytes (d = 196, hidden 588 / 147, the LBS K = 444) costs the bulk
 // loads dearly: tools/gemm_pitch_probe.py, 8192 x 2334 x 444: 68.8 us at pitch 444, 44.7 us at pitch 448
 inline int padp(int x) { return (x + 7) / 8 * 8; }
-inline int pad8(int x) { return (x + 7) / 8 * 8; }
+// the same for a bf16 operand (16 elements = 32 bytes); the bf16 tensor lives in the first half of an fp32-sized slot
+inline int padh(int x) { return (x + 15) / 16 * 16; }
 
 struct LayerPlan {
     int d, hid, out, ldh;
@@ -344,8 +345,8 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
     p.w_conv = take(cur, p.C > 0 ? conv_weight_prep_floats(p.C, p.T) : 64);
     p.dFv2 = take(cur, (p.C > 0 && d.precision != PREC_FP32) ? conv_split_floats(p.B, dmax, p.T) : 64);
     if (d.precision == PREC_BF16) {
-        p.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
-        p.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+        p.dX16 = take(cur, (MS * padh(dmax) + 1) / 2);
+        p.dX1_16 = take(cur, (MS * padh(dmax) + 1) / 2);
     }
     p.cot[0] = HeadPlan::CotSet{p.dZ, p.dNf, p.dX1, p.dO, p.dQKV, p.dNa, p.dX, p.dX16, p.dX1_16};
     {
@@ -354,8 +355,8 @@ int make_plan(const ScatHeadDesc& d, HeadPlan& p) {
         c.dO = take(cur, MS * p.inner); c.dQKV = take(cur, MS * 3 * p.inner); c.dNa = p.dNa2; c.dX = take(cur, MS * dmax);
         c.dX16 = c.dX1_16 = 0;
         if (d.precision == PREC_BF16) {
-            c.dX16 = take(cur, (MS * pad8(dmax) + 1) / 2);
-            c.dX1_16 = take(cur, (MS * pad8(dmax) + 1) / 2);
+            c.dX16 = take(cur, (MS * padh(dmax) + 1) / 2);
+            c.dX1_16 = take(cur, (MS * padh(dmax) + 1) / 2);
         }
     }
     {
@@ -447,11 +448,11 @@ LayerW layer_weights(const HeadPlan& p, int l, const float* const* W, const floa
     const bool tc = prec != PREC_FP32, bf = prec == PREC_BF16;
     // tensor-core modes read the per-forward copies in the workspace: TF32-rounded fp32 (leading dimension padded to
     // 4) or bf16 (padded to 8, stored in the first half of the same slot)
-    w.qkv = tc ? ws + L.w_qkv : W[L.p_qkv];   w.ld_qkv = bf ? pad8(L.d) : tc ? L.ld_qkv : L.d;
+    w.qkv = tc ? ws + L.w_qkv : W[L.p_qkv];   w.ld_qkv = bf ? padh(L.d) : tc ? L.ld_qkv : L.d;
     w.out = tc ? ws + L.w_out : W[L.p_out_w]; w.ld_out = p.inner;
     const bool tc_ff = tc && !L.last;         // last feed-forward stays fp32 on the caller's weights
-    w.fc1 = tc_ff ? ws + L.w_fc1 : W[L.p_fc1_w]; w.ld_fc1 = !tc_ff ? L.d : bf ? pad8(L.d) : L.ld_fc1;
-    w.fc2 = tc_ff ? ws + L.w_fc2 : W[L.p_fc2_w]; w.ld_fc2 = !tc_ff ? L.hid : bf ? pad8(L.hid) : L.ld_fc2;
+    w.fc1 = tc_ff ? ws + L.w_fc1 : W[L.p_fc1_w]; w.ld_fc1 = !tc_ff ? L.d : bf ? padh(L.d) : L.ld_fc1;
+    w.fc2 = tc_ff ? ws + L.w_fc2 : W[L.p_fc2_w]; w.ld_fc2 = !tc_ff ? L.hid : bf ? padh(L.hid) : L.ld_fc2;
     return w;
 }
 
@@ -463,11 +464,11 @@ int round_weights(const HeadPlan& p, const float* const* W, float* ws, int prec,
     const bool bf = prec == PREC_BF16;
     for (int l = 0; l < kDepth; ++l) {
         const LayerPlan& L = p.L[l];
-        jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, bf ? pad8(L.d) : L.ld_qkv};
+        jobs.job[n++] = RoundJob{W[L.p_qkv], ws + L.w_qkv, 3 * p.inner, L.d, L.d, bf ? padh(L.d) : L.ld_qkv};
         jobs.job[n++] = RoundJob{W[L.p_out_w], ws + L.w_out, L.d, p.inner, p.inner, p.inner};
         if (!L.last) {
-            jobs.job[n++] = RoundJob{W[L.p_fc1_w], ws + L.w_fc1, L.hid, L.d, L.d, bf ? pad8(L.d) : L.ld_fc1};
-            jobs.job[n++] = RoundJob{W[L.p_fc2_w], ws + L.w_fc2, L.out, L.hid, L.hid, bf ? pad8(L.hid) : L.ld_fc2};
+            jobs.job[n++] = RoundJob{W[L.p_fc1_w], ws + L.w_fc1, L.hid, L.d, L.d, bf ? padh(L.d) : L.ld_fc1};
+            jobs.job[n++] = RoundJob{W[L.p_fc2_w], ws + L.w_fc2, L.out, L.hid, L.hid, bf ? padh(L.hid) : L.ld_fc2};
         }
     }
     for (int i = 0; i < n; ++i) jobs.job[i].to_bf16 = bf ? 1 : 0;
@@ -498,8 +499,8 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         const LayerPlan& L = p.L[l];
         const LayerW w = layer_weights(p, l, W, ws, prec);
         float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
-        const int ld_n = bf ? pad8(L.d) : padp(L.d);       // leading dimension of Na / Nf (16-byte rows for TMA)
-        const int ld_h = bf ? pad8(L.hid) : L.ldh;         // leading dimension of H as a GEMM operand
+        const int ld_n = bf ? padh(L.d) : padp(L.d);       // leading dimension of Na / Nf (16-byte rows for TMA)
+        const int ld_h = bf ? padh(L.hid) : L.ldh;         // leading dimension of H as a GEMM operand
         GemmArgs g;
         if (!attn_variant) {
             // PreNorm + Attention + Residual (:18,:26,:59-79)
@@ -590,7 +591,7 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         const HeadPlan::CotSet& prev = p.cot[(l_first + 1) & 1];
         dY = ws + prev.dX;
         dYg = bf ? ws + prev.dX16 : dY;
-        ld_dYg = bf ? pad8(dn) : dn;
+        ld_dYg = bf ? padh(dn) : dn;
     }
     cudaEvent_t layer_done[kDepth] = {nullptr, nullptr, nullptr}, dy_read[kDepth] = {nullptr, nullptr, nullptr};
     for (int l = l_first; l >= l_last; --l) {
@@ -601,9 +602,9 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         const float* X = (l == 0 && X0_override) ? X0_override : ws + L.X;
         const int ffprec = L.last ? PREC_FP32 : prec;
         const bool fftc = ffprec != PREC_FP32, ffbf = ffprec == PREC_BF16;
-        const int ld_n = bf ? pad8(L.d) : L.d;                 // dX1 / dX as GEMM operands
-        const int ld_na = bf ? pad8(L.d) : padp(L.d);          // saved Na / Nf (as the forward stored them)
-        const int ld_h = ffbf ? pad8(L.hid) : L.ldh;           // H / dZ as GEMM operands
+        const int ld_n = bf ? padh(L.d) : L.d;                 // dX1 / dX as GEMM operands
+        const int ld_na = bf ? padh(L.d) : padp(L.d);          // saved Na / Nf (as the forward stored them)
+        const int ld_h = ffbf ? padh(L.hid) : L.ldh;           // H / dZ as GEMM operands
         float* dZ = ws + c.dZ;
         GemmArgs g;
         if (G) {
