@@ -154,6 +154,13 @@ __device__ __forceinline__ void store_out4(float* base, long long idx, float4 v,
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// gelu(x) and gelu'(x) from one erf: the same expressions as gelu_erf / gelu_erf_grad (0.5 x (1 + e) == x (0.5 (1 + e)) exactly)
+__device__ __forceinline__ float gelu_erf_both(float x, float& grad) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    grad = cdf + x * pdf;
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);

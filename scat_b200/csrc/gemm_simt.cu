@@ -131,10 +131,19 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g, int kt_p
                 case EPI_BIAS_RESID: v += g.bias[n] + g.aux_in[ma * g.ld_aux_in + n]; break;
                 case EPI_BIAS_GELU: {
                     v += g.bias[n];
-                    g.aux_out[(long long)m * g.ld_aux_out + n] = v;
-                    v = gelu_erf(v);
+                    if (g.gelu_saves_grad) {
+                        float dg;
+                        v = gelu_erf_both(v, dg);
+                        g.aux_out[(long long)m * g.ld_aux_out + n] = dg;
+                    } else {
+                        g.aux_out[(long long)m * g.ld_aux_out + n] = v;
+                        v = gelu_erf(v);
+                    }
                 } break;
-                case EPI_DGELU: v *= gelu_erf_grad(g.aux_in[ma * g.ld_aux_in + n]); break;
+                case EPI_DGELU: {
+                    const float z = g.aux_in[ma * g.ld_aux_in + n];
+                    v *= g.gelu_saves_grad ? z : gelu_erf_grad(z);
+                } break;
                 case EPI_RESID: v += g.aux_in[ma * g.ld_aux_in + n]; break;
                 default: break;
             }

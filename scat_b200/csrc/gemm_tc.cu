@@ -65,6 +65,7 @@ struct TcParams {
     int round_out;                  // 1: store C rounded to TF32-nearest (it feeds another tensor-core GEMM)
     int round_operands;             // 1: round fp32 operands to TF32 (nearest) in shared memory before the MMA
     int stages;                     // depth of the operand ring (SmemLayout::STAGES or STAGES_DEEP)
+    int gelu_saves_grad;            // GemmArgs::gelu_saves_grad
     int exp_skip_gelu;              // timing experiment only (SCAT_EXP_SKIP_GELU=1): GELU / dGELU math replaced by a copy
     int b_static;                   // 1: B does not depend on the preceding kernel (a weight): prefetched before the PDL wait
     int kb_per_split;               // k-blocks per gridDim.z slice (split-K: weight gradients, K = B*21 rows)
@@ -227,12 +228,23 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (SCAT_ROW_OK(i) && !p.exp_skip_gelu) {
-                        acc[i].x *= gelu_erf_grad(ext[i].x); acc[i].y *= gelu_erf_grad(ext[i].y);
-                        acc[i].z *= gelu_erf_grad(ext[i].z); acc[i].w *= gelu_erf_grad(ext[i].w);
+                        if (p.gelu_saves_grad) {       // the forward stored gelu'(z)
+                            acc[i].x *= ext[i].x; acc[i].y *= ext[i].y; acc[i].z *= ext[i].z; acc[i].w *= ext[i].w;
+                        } else {
+                            acc[i].x *= gelu_erf_grad(ext[i].x); acc[i].y *= gelu_erf_grad(ext[i].y);
+                            acc[i].z *= gelu_erf_grad(ext[i].z); acc[i].w *= gelu_erf_grad(ext[i].w);
+                        }
                     }
             } else if (epi == EPI_BIAS_GELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
+                    if (p.gelu_saves_grad && !p.exp_skip_gelu) {
+                        float4 dg;
+                        acc[i].x = gelu_erf_both(acc[i].x, dg.x); acc[i].y = gelu_erf_both(acc[i].y, dg.y);
+                        acc[i].z = gelu_erf_both(acc[i].z, dg.z); acc[i].w = gelu_erf_both(acc[i].w, dg.w);
+                        if (SCAT_ROW_OK(i)) *reinterpret_cast<float4*>(zptr + i * z_step) = dg;
+                        continue;
+                    }
                     if (SCAT_ROW_OK(i)) *reinterpret_cast<float4*>(zptr + i * z_step) = acc[i];
                     if (p.exp_skip_gelu) continue;
                     acc[i].x = gelu_erf(acc[i].x); acc[i].y = gelu_erf(acc[i].y);
@@ -292,8 +304,17 @@ __device__ __forceinline__ void epilogue_tile_impl(const TcParams& p, uint32_t t
                     switch (epi) {
                         case EPI_BIAS: t += p.bias[ne]; break;
                         case EPI_BIAS_RESID: t += p.bias[ne] + p.aux_in[ar * p.ld_aux_in + ne]; break;
-                        case EPI_BIAS_GELU: t += p.bias[ne]; p.aux_out[(long long)row * p.ld_aux_out + ne] = t; t = gelu_erf(t); break;
-                        case EPI_DGELU: t *= gelu_erf_grad(p.aux_in[ar * p.ld_aux_in + ne]); break;
+                        case EPI_BIAS_GELU: {
+                            t += p.bias[ne];
+                            float dg = t;
+                            if (p.gelu_saves_grad) t = gelu_erf_both(t, dg);
+                            else t = gelu_erf(t);
+                            p.aux_out[(long long)row * p.ld_aux_out + ne] = dg;
+                        } break;
+                        case EPI_DGELU: {
+                            const float z = p.aux_in[ar * p.ld_aux_in + ne];
+                            t *= p.gelu_saves_grad ? z : gelu_erf_grad(z);
+                        } break;
                         case EPI_RESID: t += p.aux_in[ar * p.ld_aux_in + ne]; break;
                         default: break;
                     }
@@ -612,6 +633,7 @@ int launch_variant(const GemmArgs& g, cudaStream_t stream) {
     p.mask_idx = g.mask_idx; p.n_masked = g.n_masked;
     p.dbg = g_gemm_dbg;
     p.exp_skip_gelu = g_exp_skip_gelu ? 1 : 0;
+    p.gelu_saves_grad = g.gelu_saves_grad;
     auto al16 = [](const void* q, long long ld) { return q == nullptr || (((uintptr_t)q & 15) == 0 && (ld & 3) == 0); };
     p.vec_ok = al16(g.C, g.ldc) && (g.C16 == nullptr || (((uintptr_t)g.C16 & 7) == 0 && (g.ldc16 & 3) == 0)) &&
                al16(g.aux_in, g.ld_aux_in) && al16(g.aux_out, g.ld_aux_out) && al16(g.bias, 0);

@@ -54,6 +54,8 @@ struct GemmArgs {
     long long c_z = 0, aux_out_z = 0;                    // per-problem element offsets of C / aux_out
     int batch_accumulate = 0;    // every problem reduces into the same C (red.global.add; C pre-zeroed): K split over the batch
     const int32_t* mask_idx = nullptr; int n_masked = 0;   // EPI_PE_MASK
+    int gelu_saves_grad = 0;     // EPI_BIAS_GELU: aux_out receives gelu'(z) instead of z;  EPI_DGELU: aux_in already IS gelu'(z)
+                                 // (the head: the backward's epilogue becomes a multiply, the erf is evaluated once, in the forward)
     int force_bn = 0;            // 64 / 128: tile width override
     int allow_wide = 0;          // tensor-core kernel: 192- / 256-wide single-wave tiles may be chosen (one 200 KB CTA per SM:
                                  // only where nothing runs beside this GEMM -- measured slower in the backward, where the
@@ -202,7 +204,7 @@ int launch_regressor_param_grads(const float* gsum, const float* gsteps, const f
 int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2, float* Y, int M, int K, cudaStream_t stream);
 // dZs (nullable): also the TF32 hi / lo split [MR, 3 x (N padded to 8)] = [hi | lo | hi] of dZ (pad columns must be zero already)
 int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
-                       float* dZs, cudaStream_t stream);
+                       float* dZs, cudaStream_t stream, int z_is_grad = 0);      // z_is_grad: Z holds gelu'(z) (see GemmArgs)
 
 // ------------------------------------------------------------------------------------------
 // projection + losses (train.py:112-120,165-203) with closed-form gradient w.r.t. pred_params

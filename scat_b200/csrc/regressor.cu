@@ -349,7 +349,7 @@ ff_out3_fwd_kernel(const float* __restrict__ H, int ldh, const float* __restrict
 //   (lddz = N padded to 8 floats, head.cu: padp) are written as zeros so that the row can feed a tensor-core GEMM
 __global__ void __launch_bounds__(256)
 ff_out3_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ W2, const float* __restrict__ Z, int ldz,
-                   float* __restrict__ dZ, int lddz, int MR, int N, int act_rows, float* __restrict__ dZs) {
+                   float* __restrict__ dZ, int lddz, int MR, int N, int act_rows, float* __restrict__ dZs, int z_is_grad) {
     pdl_sync();
     const int np = (N + 7) & ~7;
     const long long total = (long long)MR * np;
@@ -360,7 +360,8 @@ ff_out3_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ W2, c
             const float* dy = dY + (long long)m * 3;
             const float t = fmaf(__ldg(dy), __ldg(W2 + n), fmaf(__ldg(dy + 1), __ldg(W2 + N + n), __ldg(dy + 2) * __ldg(W2 + 2 * N + n)));
             const int zr = act_rows > 0 ? m % act_rows : m;
-            v = t * gelu_erf_grad(__ldg(Z + (long long)zr * ldz + n));
+            const float z = __ldg(Z + (long long)zr * ldz + n);
+            v = t * (z_is_grad ? z : gelu_erf_grad(z));       // z_is_grad: the forward saved gelu'(z) (GemmArgs::gelu_saves_grad)
         }
         if (n < lddz) dZ[(long long)m * lddz + n] = v;
         if (dZs != nullptr) {           // [hi | lo | hi], thirds of np columns: first operand of the 3xTF32 dgrad GEMM
@@ -392,10 +393,10 @@ int launch_ff_out3_fwd(const float* H, int ldh, const float* W2, const float* b2
 }
 
 int launch_ff_out3_bwd(const float* dY, const float* W2, const float* Z, int ldz, float* dZ, int lddz, int MR, int N, int act_rows,
-                       float* dZs, cudaStream_t stream) {
+                       float* dZs, cudaStream_t stream, int z_is_grad) {
     const long long total = (long long)MR * ((N + 7) & ~7);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    SCAT_CHECK_CUDA(launch_k(ff_out3_bwd_kernel, dim3(grid), dim3(256), 0, stream, dY, W2, Z, ldz, dZ, lddz, MR, N, act_rows, dZs));
+    SCAT_CHECK_CUDA(launch_k(ff_out3_bwd_kernel, dim3(grid), dim3(256), 0, stream, dY, W2, Z, ldz, dZ, lddz, MR, N, act_rows, dZs, z_is_grad));
     SCAT_CHECK_LAUNCH();
     return 0;
 }
