@@ -67,6 +67,8 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     return 0;
 }
 
+// SCAT_SAVE_DGELU=0 (A/B switch): the forward saves z and the backward evaluates gelu'(z) itself, as in round 1
+int g_save_dgelu = [] { const char* e = getenv("SCAT_SAVE_DGELU"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
 // experiment switch: bit 0 / 1 / 2 lets the dZ / dNf / dNa GEMM of the backward use the wide single-wave tiles
 int g_exp_wide_bwd = [] { const char* e = getenv("SCAT_EXP_WIDE_BWD"); return e ? atoi(e) : 0; }();
 // Every kernel asks for the maximum shared-memory carve-out, so that consecutive kernels of the chain never make an SM
@@ -542,7 +544,7 @@ int transformer_forward(const HeadPlan& p, const float* const* W, float* ws, int
         if (ffbf) { g.C16 = ws + L.H; g.ldc16 = ld_h; }                         // H exists only as bf16
         else { g.C = ws + L.H; g.ldc = L.ldh; g.round_out = fftc; }
         // (the slot Z holds gelu'(z), not z: the only reader is the backward's dGELU epilogue, which then is a multiply)
-        g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh; g.gelu_saves_grad = 1;
+        g.epilogue = EPI_BIAS_GELU; g.bias = W[L.p_fc1_b]; g.aux_out = ws + L.Z; g.ld_aux_out = L.ldh; g.gelu_saves_grad = g_save_dgelu;
         if (L.last && tc) {
             // fp32-grade on the tensor core: X1 split into [hi | lo | hi] against the weight's [hi | hi | lo], K = 3 d
             const int dp = padp(L.d);
@@ -629,10 +631,10 @@ int transformer_backward(const HeadPlan& p, const float* const* W, float* const*
         g.M = MR; g.N = L.hid; g.K = L.out; g.prerounded = fftc;
         if (ffbf) { g.C16 = dZ; g.ldc16 = ld_h; }
         else { g.C = dZ; g.ldc = L.ldh; g.round_out = fftc; }
-        g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod; g.gelu_saves_grad = 1;
+        g.epilogue = EPI_DGELU; g.aux_in = ws + L.Z; g.ld_aux_in = L.ldh; g.aux_row_mod = amod; g.gelu_saves_grad = g_save_dgelu;
         g.allow_wide = g_exp_wide_bwd & 1;
         if (L.last && L.out == 3 && !ffbf)     // K = 3: elementwise
-            SCAT_PROPAGATE(launch_ff_out3_bwd(dY, W[L.p_fc2_w], ws + L.Z, L.ldh, dZ, L.ldh, MR, L.hid, amod, tc ? ws + p.dZs : nullptr, st, /*z_is_grad=*/1));
+            SCAT_PROPAGATE(launch_ff_out3_bwd(dY, W[L.p_fc2_w], ws + L.Z, L.ldh, dZ, L.ldh, MR, L.hid, amod, tc ? ws + p.dZs : nullptr, st, /*z_is_grad=*/g_save_dgelu));
         else
             SCAT_PROPAGATE((L.last ? launch_gemm_exact(g, prec, st) : launch_gemm(g, ffprec, st)));
         if (G) {
