@@ -106,6 +106,10 @@ def test_new_entry_points_validate_arguments_without_a_gpu(lib_path):
     assert lib.scat_peer_allreduce(ptrs, ptrs, 0, 2, 2, 64, None) == -1          # range not 16-byte aligned
     assert lib.scat_peer_allreduce(ptrs, ptrs, 2, 2, 0, 64, None) == -1          # rank out of range
     assert lib.scat_peer_allreduce(ptrs, ptrs, 0, 9, 0, 64, None) == -1
+    assert lib.scat_peer_allreduce_part(ptrs, ptrs, 0, 2, 2, 64, 0, None) == -1  # the per-part form checks the same way
+    assert lib.scat_peer_allreduce_part(ptrs, ptrs, 0, 3, 0, 64, 1, None) == -3
+    assert lib.scat_head_train_step_hooked(None, None, None, None, None, None, None, None, 105, 1.0, 1.0, 1.0, None, None, None,
+                                           None, None, None, None, None, 0, None, None, None) == -1        # desc is null
     assert lib.scat_peer_signal_bytes() >= 296 * 8 * 4
 
     assert lib.scat_eval_procrustes(fake, fake, 4, 2, fake, None, None) == -1     # fewer than 3 joints
